@@ -1,0 +1,698 @@
+// libnpe_cuda.so: C ABI over the sm_100a NPE kernels (see include/npe_cuda.h).
+// Host side: handle/state management, buffer growth, launch sequencing on one stream.  No CPU fallback anywhere:
+// every compute entry point launches CUDA kernels or returns an error.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/npe_cuda.h"
+#include "npe_kernels.cuh"
+#include "npe_rollout.cuh"
+
+using namespace npe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- NCCL through dlopen (libnccl.so.2; the torch-bundled copy is reused when already loaded) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(lib, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl symbols missing"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+constexpr int NCCL_FLOAT32 = 7, NCCL_SUM = 0;
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct npe_handle {
+    npe_config cfg;
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    cudaEvent_t events[16] = {};
+
+    // model + optimiser state
+    float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr, *rms_m = nullptr;
+    float* allreduce_buf = nullptr;   // NPARAM + 4 floats: gradient + {sum_v, sum_w, F}
+    int adam_t = 0;
+    float rms_m_init = 0.f;
+    float* partial = nullptr;         // [num_sms][NPARAM]
+    float* loss3_dev = nullptr;
+    double* loss_sums_dev = nullptr;
+
+    // scenes / foci
+    DevBuf<float> states;
+    DevBuf<int> n_obj;
+    int S = 0, Nmax = 0, T = 0;
+    std::vector<std::vector<int>> scene_foci;   // non-obstacle objects per scene
+    int64_t scene_pred_objects = 0;
+    DevBuf<int> foc_scene, foc_obj, foc_t0;
+    std::vector<int> win_start;                 // prefix of foci per window (size W + 1)
+    int foc_first = 0, F = 0;
+    bool batch_form = false;
+    bool have_y = false;
+
+    // per-batch buffers
+    DevBuf<float> y, pred, loss_ex, s_sum, ds, this_rows;
+    DevBuf<u64> keep, nbr;
+    u64* active_total = nullptr;
+    bool pairs_valid = false, fwd_valid = false;
+    DevBuf<int> ctx_idx_out, cnt_out;
+    DevBuf<unsigned char> mask_out;
+
+    // rollout
+    DevBuf<float> traj;
+    DevBuf<double> metrics;
+
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    FocusSrc src() const {
+        FocusSrc s;
+        s.states = states.p; s.n_obj = n_obj.p; s.Nmax = Nmax; s.T = T;
+        s.foc_scene = foc_scene.p + foc_first; s.foc_obj = foc_obj.p + foc_first; s.foc_t0 = foc_t0.p + foc_first;
+        s.F = F;
+        return s;
+    }
+};
+
+namespace {
+
+int fail(npe_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(h, NPE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define CKL()                                                                                             \
+    do {                                                                                                  \
+        h->launches++;                                                                                    \
+        cudaError_t e__ = cudaGetLastError();                                                             \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define NEED(h)                                      \
+    do {                                             \
+        if (!(h)) return NPE_ERR_INVALID;            \
+        cudaError_t e0__ = cudaSetDevice((h)->device); \
+        if (e0__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e0__)); \
+    } while (0)
+
+__global__ void k_batch_foci(int* scene, int* obj, int* t0, int* n_obj, int B, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { scene[i] = i; obj[i] = 0; t0[i] = 0; n_obj[i] = N; }
+}
+
+int ensure_batch_buffers(npe_handle* h, int F) {
+    CK(h->y.ensure((size_t)F * OUT));
+    CK(h->pred.ensure((size_t)F * OUT));
+    CK(h->loss_ex.ensure((size_t)F * 3));
+    CK(h->s_sum.ensure((size_t)F * 52));
+    CK(h->ds.ensure((size_t)F * 52));
+    CK(h->keep.ensure(F));
+    CK(h->nbr.ensure(F));
+    return NPE_OK;
+}
+
+int build_pairs(npe_handle* h) {
+    if (h->pairs_valid) return NPE_OK;
+    if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
+    CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));
+    const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
+    const int kmax = h->cfg.nbrhd ? h->cfg.max_ctx : h->cfg.max_ctx;
+    k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), kmax, h->cfg.nbrhd ? thr : INFINITY, h->keep.p,
+                                                        h->nbr.p, h->active_total);
+    CKL();
+    h->pairs_valid = true;
+    return NPE_OK;
+}
+
+int run_forward(npe_handle* h, bool training) {
+    int rc = build_pairs(h);
+    if (rc) return rc;
+    const int ntiles = (h->F + TILE - 1) / TILE;
+    const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
+    k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->have_y ? h->y.p : nullptr,
+                                                        h->pred.p, h->have_y ? h->loss_ex.p : nullptr,
+                                                        training ? h->s_sum.p : nullptr);
+    CKL();
+    h->fwd_valid = training;
+    return NPE_OK;
+}
+
+int run_loss_reduce(npe_handle* h) {
+    k_loss_reduce<<<1, 256, 0, h->stream>>>(h->loss_ex.p, h->F, h->loss3_dev, h->loss_sums_dev);
+    CKL();
+    return NPE_OK;
+}
+
+int run_backward(npe_handle* h, int divisor_batch) {
+    if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
+    if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+    const int B = divisor_batch > 0 ? divisor_batch : h->F;
+    // d_vel = 2 (p - y) * vlambda / (2B); d_ang_vel = 2 (p - y) * lambda / B   (npe.lua:304-315)
+    const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
+    const float sw = 2.f * h->cfg.lambda / (float)B;
+    const int nt_d = (h->F + TILE - 1) / TILE, nt_p = (h->F + FT_B - 1) / FT_B;
+    const int gd = nt_d < h->num_sms ? nt_d : h->num_sms;
+    const int gp = nt_p < h->num_sms ? nt_p : h->num_sms;
+    k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->params, h->y.p, h->s_sum.p, h->ds.p,
+                                                              h->partial, sv, sw);
+    CKL();
+    k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->ds.p, h->partial);
+    CKL();
+    k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
+    CKL();
+    return NPE_OK;
+}
+
+int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
+    h->adam_t += 1;
+    const double t = (double)h->adam_t;
+    const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
+    k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, NPARAM, b1, b2, eps, step);
+    CKL();
+    return NPE_OK;
+}
+
+int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
+    k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, NPARAM, alpha, eps, lr);
+    CKL();
+    return NPE_OK;
+}
+
+int run_allreduce(npe_handle* h) {
+    if (!h->comm) return NPE_OK;
+    ncclResult_t r = g_nccl.AllReduce(h->grads, h->grads, NPARAM, NCCL_FLOAT32, NCCL_SUM, h->comm, h->stream);
+    if (r != 0) return fail(h, NPE_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    return NPE_OK;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int npe_abi_version(void) { return NPE_ABI_VERSION; }
+
+void npe_default_config(npe_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = (int32_t)sizeof(npe_config);
+    cfg->device = 0;
+    cfg->rnn_dim = 50; cfg->layers = 5; cfg->num_past = 2; cfg->num_future = 1; cfg->object_dim = 22;
+    cfg->nbrhd = 1; cfg->nbrhdsize = 3.5f; cfg->max_ctx = 12; cfg->vlambda = 1.f; cfg->lambda = 1.f;
+    cfg->ball_zero_mode = 1;
+}
+
+const char* npe_last_error(const npe_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int npe_create(const npe_config* cfg, npe_handle** out) {
+    npe_handle* h = nullptr;
+    if (!cfg || !out) return fail(h, NPE_ERR_INVALID, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(npe_config)) return fail(h, NPE_ERR_INVALID, "npe_config size mismatch");
+    if (cfg->rnn_dim != H || cfg->layers != NL || cfg->num_past != 2 || cfg->num_future != 1 || cfg->object_dim != D)
+        return fail(h, NPE_ERR_UNSUPPORTED,
+                    "only the north-star configuration is built: rnn_dim 50, layers 5, num_past 2, num_future 1, object_dim 22");
+    if (!cfg->nbrhd) return fail(h, NPE_ERR_UNSUPPORTED, "only -nbrhd (bias-free pairwise layers) is built");
+    if (cfg->max_ctx > 63) return fail(h, NPE_ERR_INVALID, "max_ctx must be <= 63");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, NPE_ERR_CUDA, "no CUDA device: %s (libnpe_cuda has no CPU path)", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(h, NPE_ERR_INVALID, "device %d out of range", cfg->device);
+    npe_handle* hh = new npe_handle();
+    hh->cfg = *cfg;
+    hh->device = cfg->device;
+    h = hh;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+        delete hh;
+        return NPE_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(h->device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    h->num_sms = prop.multiProcessorCount;
+    if ((size_t)prop.sharedMemPerBlockOptin < sizeof(PairBwdSmem)) {
+        g_create_error = "device shared memory per block too small (needs an sm_100-class GPU)";
+        delete hh;
+        return NPE_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (auto& ev : h->events)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+    float** bufs[] = {&h->params, &h->grads, &h->adam_m, &h->adam_v, &h->rms_m};
+    for (float** b : bufs) {
+        if ((e = cudaMalloc((void**)b, NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemset(*b, 0, NPARAM * sizeof(float));
+    }
+    if ((e = cudaMalloc((void**)&h->partial, (size_t)h->num_sms * NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(h->active_total, 0, sizeof(u64));
+    if ((e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess)
+        return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
+    *out = h;
+    return NPE_OK;
+}
+
+int npe_destroy(npe_handle* h) {
+    if (!h) return NPE_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf};
+    for (float* b : bufs) if (b) cudaFree(b);
+    if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
+    if (h->active_total) cudaFree(h->active_total);
+    h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
+    h->y.release(); h->pred.release(); h->loss_ex.release(); h->s_sum.release(); h->ds.release(); h->this_rows.release();
+    h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
+    h->traj.release(); h->metrics.release();
+    for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NPE_OK;
+}
+
+int npe_param_count(const npe_handle* h) { (void)h; return NPARAM; }
+
+int npe_params_set(npe_handle* h, const float* host, int32_t n) {
+    NEED(h);
+    if (!host || n != NPARAM) return fail(h, NPE_ERR_INVALID, "params_set: expected %d floats", NPARAM);
+    CK(cudaMemcpyAsync(h->params, host, NPARAM * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fwd_valid = false;
+    return NPE_OK;
+}
+int npe_params_get(npe_handle* h, float* host, int32_t n) {
+    NEED(h);
+    if (!host || n != NPARAM) return fail(h, NPE_ERR_INVALID, "params_get: expected %d floats", NPARAM);
+    CK(cudaMemcpyAsync(host, h->params, NPARAM * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+int npe_grads_get(npe_handle* h, float* host, int32_t n) {
+    NEED(h);
+    if (!host || n != NPARAM) return fail(h, NPE_ERR_INVALID, "grads_get: expected %d floats", NPARAM);
+    CK(cudaMemcpyAsync(host, h->grads, NPARAM * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+int npe_grads_set(npe_handle* h, const float* host, int32_t n) {
+    NEED(h);
+    if (!host || n != NPARAM) return fail(h, NPE_ERR_INVALID, "grads_set: expected %d floats", NPARAM);
+    CK(cudaMemcpyAsync(h->grads, host, NPARAM * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_batch_upload(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C) {
+    NEED(h);
+    if (!this_past || B <= 0 || C < 0 || (C > 0 && !context)) return fail(h, NPE_ERR_INVALID, "batch_upload: bad arguments");
+    if (C + 1 > MAXOBJ) return fail(h, NPE_ERR_INVALID, "batch_upload: at most %d contexts", MAXOBJ - 1);
+    const int N = C + 1;
+    CK(h->states.ensure((size_t)B * N * IN));
+    CK(h->n_obj.ensure(B));
+    CK(h->foc_scene.ensure(B)); CK(h->foc_obj.ensure(B)); CK(h->foc_t0.ensure(B));
+    int rc = ensure_batch_buffers(h, B);
+    if (rc) return rc;
+    // scene b = [this_b | context_b,0 | ... | context_b,C-1], T = 2  (== `past` of eval.lua:283)
+    CK(cudaMemcpy2DAsync(h->states.p, (size_t)N * IN * sizeof(float), this_past, IN * sizeof(float), IN * sizeof(float), B,
+                         cudaMemcpyHostToDevice, h->stream));
+    if (C > 0)
+        CK(cudaMemcpy2DAsync(h->states.p + IN, (size_t)N * IN * sizeof(float), context, (size_t)C * IN * sizeof(float),
+                             (size_t)C * IN * sizeof(float), B, cudaMemcpyHostToDevice, h->stream));
+    if (y) CK(cudaMemcpyAsync(h->y.p, y, (size_t)B * OUT * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    k_batch_foci<<<(B + 255) / 256, 256, 0, h->stream>>>(h->foc_scene.p, h->foc_obj.p, h->foc_t0.p, h->n_obj.p, B, N);
+    CKL();
+    h->S = B; h->Nmax = N; h->T = 2;
+    h->foc_first = 0; h->F = B;
+    h->batch_form = true; h->have_y = (y != nullptr);
+    h->pairs_valid = false; h->fwd_valid = false;
+    h->win_start.clear();
+    h->scene_foci.clear();
+    return NPE_OK;
+}
+
+int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, int32_t S, int32_t Nmax, int32_t T) {
+    NEED(h);
+    if (!states || !n_obj || S <= 0 || Nmax <= 0 || T < 2) return fail(h, NPE_ERR_INVALID, "scenes_upload: bad arguments");
+    if (Nmax > MAXOBJ) return fail(h, NPE_ERR_INVALID, "scenes_upload: at most %d objects per scene", MAXOBJ);
+    const size_t n = (size_t)S * Nmax * T * D;
+    CK(h->states.ensure(n));
+    CK(h->n_obj.ensure(S));
+    CK(cudaMemcpyAsync(h->states.p, states, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->n_obj.p, n_obj, (size_t)S * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->scene_foci.assign(S, {});
+    h->scene_pred_objects = 0;
+    for (int s = 0; s < S; ++s) {
+        if (n_obj[s] < 1 || n_obj[s] > Nmax) return fail(h, NPE_ERR_INVALID, "scenes_upload: n_obj[%d] = %d out of range", s, n_obj[s]);
+        for (int o = 0; o < n_obj[s]; ++o) {
+            const float* st = states + (((size_t)s * Nmax + o) * T) * D;
+            if (st[11] != 1.f) h->scene_foci[s].push_back(o);   // oid one-hot col 11 = obstacle: never a focus
+        }
+        h->scene_pred_objects += (int64_t)h->scene_foci[s].size();
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->S = S; h->Nmax = Nmax; h->T = T;
+    h->F = 0; h->foc_first = 0;
+    h->batch_form = false; h->have_y = false;
+    h->pairs_valid = false; h->fwd_valid = false;
+    h->win_start.clear();
+    return NPE_OK;
+}
+
+int npe_windows_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* t0, int32_t W) {
+    NEED(h);
+    if (h->batch_form || h->S == 0 || h->scene_foci.empty()) return fail(h, NPE_ERR_STATE, "windows_upload: upload scenes first");
+    if (!scene_ids || !t0 || W <= 0) return fail(h, NPE_ERR_INVALID, "windows_upload: bad arguments");
+    std::vector<int> fs, fo, ft;
+    h->win_start.assign(1, 0);
+    for (int w = 0; w < W; ++w) {
+        const int s = scene_ids[w];
+        if (s < 0 || s >= h->S || t0[w] < 0 || t0[w] + 3 > h->T)
+            return fail(h, NPE_ERR_INVALID, "windows_upload: window %d (scene %d, t0 %d) out of range", w, s, t0[w]);
+        for (int o : h->scene_foci[s]) { fs.push_back(s); fo.push_back(o); ft.push_back(t0[w]); }
+        h->win_start.push_back((int)fs.size());
+    }
+    const size_t n = fs.size();
+    if (n == 0) return fail(h, NPE_ERR_INVALID, "windows_upload: no focus objects");
+    CK(h->foc_scene.ensure(n)); CK(h->foc_obj.ensure(n)); CK(h->foc_t0.ensure(n));
+    CK(cudaMemcpyAsync(h->foc_scene.p, fs.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->foc_obj.p, fo.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->foc_t0.p, ft.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->F = 0;
+    h->pairs_valid = false; h->fwd_valid = false;
+    return NPE_OK;
+}
+
+int npe_select_windows(npe_handle* h, int32_t first, int32_t count) {
+    NEED(h);
+    const int W = (int)h->win_start.size() - 1;
+    if (W <= 0) return fail(h, NPE_ERR_STATE, "select_windows: no window schedule uploaded");
+    if (first < 0 || count <= 0 || first + count > W) return fail(h, NPE_ERR_INVALID, "select_windows: range out of bounds");
+    h->foc_first = h->win_start[first];
+    h->F = h->win_start[first + count] - h->foc_first;
+    if (h->F <= 0) return fail(h, NPE_ERR_INVALID, "select_windows: empty batch");
+    int rc = ensure_batch_buffers(h, h->F);
+    if (rc) return rc;
+    k_window_targets<<<((size_t)h->F * IN + 255) / 256, 256, 0, h->stream>>>(h->src(), h->y.p, nullptr);
+    CKL();
+    h->have_y = true;
+    h->pairs_valid = false; h->fwd_valid = false;
+    return NPE_OK;
+}
+
+int npe_num_foci(const npe_handle* h) { return h ? h->F : 0; }
+int npe_ctx_slots(const npe_handle* h) {
+    if (!h) return 0;
+    const int cn = h->Nmax - 1;
+    return (h->cfg.max_ctx > 0 && h->cfg.max_ctx < cn) ? h->cfg.max_ctx : cn;
+}
+
+int npe_batch_download(npe_handle* h, float* this_past_out, float* y_out) {
+    NEED(h);
+    if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
+    if (this_past_out) {
+        CK(h->this_rows.ensure((size_t)h->F * IN));
+        k_window_targets<<<((size_t)h->F * IN + 255) / 256, 256, 0, h->stream>>>(h->src(), nullptr, h->this_rows.p);
+        CKL();
+        CK(cudaMemcpyAsync(this_past_out, h->this_rows.p, (size_t)h->F * IN * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (y_out) {
+        if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+        CK(cudaMemcpyAsync(y_out, h->y.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_build_pairs(npe_handle* h, int32_t* ctx_idx_out, uint8_t* mask_out, int32_t* cnt_out) {
+    NEED(h);
+    int rc = build_pairs(h);
+    if (rc) return rc;
+    if (ctx_idx_out || mask_out || cnt_out) {
+        const int K = npe_ctx_slots(h);
+        const size_t n = (size_t)h->F * (K > 0 ? K : 1);
+        CK(h->ctx_idx_out.ensure(n)); CK(h->mask_out.ensure(n)); CK(h->cnt_out.ensure(h->F));
+        k_expand_pairs<<<(h->F + 255) / 256, 256, 0, h->stream>>>(h->keep.p, h->nbr.p, h->F, K, h->ctx_idx_out.p,
+                                                                  h->mask_out.p, h->cnt_out.p);
+        CKL();
+        if (ctx_idx_out && K > 0) CK(cudaMemcpyAsync(ctx_idx_out, h->ctx_idx_out.p, (size_t)h->F * K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        if (mask_out && K > 0) CK(cudaMemcpyAsync(mask_out, h->mask_out.p, (size_t)h->F * K, cudaMemcpyDeviceToHost, h->stream));
+        if (cnt_out) CK(cudaMemcpyAsync(cnt_out, h->cnt_out.p, (size_t)h->F * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return NPE_OK;
+}
+
+int npe_forward(npe_handle* h, float* pred_out, float* loss3_out) {
+    NEED(h);
+    if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
+    int rc = run_forward(h, true);
+    if (rc) return rc;
+    if (loss3_out) {
+        if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+        if ((rc = run_loss_reduce(h))) return rc;
+        CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (pred_out) CK(cudaMemcpyAsync(pred_out, h->pred.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (pred_out || loss3_out) CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_forward_per_example(npe_handle* h, float* pred_out, float* loss_out) {
+    NEED(h);
+    if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
+    int rc = run_forward(h, false);
+    if (rc) return rc;
+    if (loss_out) {
+        if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+        CK(cudaMemcpyAsync(loss_out, h->loss_ex.p, (size_t)h->F * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (pred_out) CK(cudaMemcpyAsync(pred_out, h->pred.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (pred_out || loss_out) CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_backward(npe_handle* h, int32_t divisor_batch) {
+    NEED(h);
+    return run_backward(h, divisor_batch);
+}
+
+int npe_adam_step(npe_handle* h, float lr, float beta1, float beta2, float eps) {
+    NEED(h);
+    return run_adam(h, lr, beta1, beta2, eps);
+}
+int npe_rmsprop_step(npe_handle* h, float lr, float alpha, float eps) {
+    NEED(h);
+    return run_rmsprop(h, lr, alpha, eps);
+}
+int npe_optim_reset(npe_handle* h, float rmsprop_m_init) {
+    NEED(h);
+    h->adam_t = 0;
+    h->rms_m_init = rmsprop_m_init;
+    CK(cudaMemsetAsync(h->adam_m, 0, NPARAM * sizeof(float), h->stream));
+    CK(cudaMemsetAsync(h->adam_v, 0, NPARAM * sizeof(float), h->stream));
+    k_fill<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->rms_m, NPARAM, rmsprop_m_init);
+    CKL();
+    return NPE_OK;
+}
+
+int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out) {
+    NEED(h);
+    if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
+    int rc;
+    if ((rc = run_forward(h, true))) return rc;
+    if (loss3_out && (rc = run_loss_reduce(h))) return rc;
+    if ((rc = run_backward(h, divisor_batch))) return rc;
+    if ((rc = run_allreduce(h))) return rc;
+    if (opt == 0) rc = run_adam(h, lr, 0.9f, 0.999f, 1e-8f);
+    else if (opt == 1) rc = run_rmsprop(h, lr, 0.99f, 1e-8f);
+    else return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
+    if (rc) return rc;
+    h->fwd_valid = false;   // parameters changed
+    if (loss3_out) {
+        CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return NPE_OK;
+}
+
+static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teacher, bool want_traj, bool want_metrics) {
+    if (h->batch_form || h->S == 0) return fail(h, NPE_ERR_STATE, "rollout: upload scenes first");
+    if (steps <= 0 || t0 < 0 || t0 + 2 > h->T) return fail(h, NPE_ERR_INVALID, "rollout: bad t0/steps");
+    if (use_gt && t0 + 2 + steps > h->T)
+        return fail(h, NPE_ERR_INVALID, "rollout: %d steps need %d frames of ground truth, scenes have %d", steps, t0 + 2 + steps, h->T);
+    RollArgs A;
+    A.states = h->states.p; A.n_obj = h->n_obj.p; A.S = h->S; A.Nmax = h->Nmax; A.T = h->T;
+    A.t0 = t0; A.steps = steps; A.use_gt = use_gt; A.teacher = teacher;
+    A.kmax = h->cfg.max_ctx; A.ball_zero = h->cfg.ball_zero_mode;
+    A.thr_px = h->cfg.nbrhdsize * 60.f;
+    A.params = h->params;
+    A.traj = nullptr; A.metrics = nullptr;
+    if (want_traj) {
+        CK(h->traj.ensure((size_t)h->S * h->Nmax * steps * D));
+        CK(cudaMemsetAsync(h->traj.p, 0, (size_t)h->S * h->Nmax * steps * D * sizeof(float), h->stream));
+        A.traj = h->traj.p;
+    }
+    if (want_metrics) {
+        CK(h->metrics.ensure((size_t)steps * 7));
+        CK(cudaMemsetAsync(h->metrics.p, 0, (size_t)steps * 7 * sizeof(double), h->stream));
+        A.metrics = h->metrics.p;
+    }
+    const int G = TILE / h->Nmax;
+    const int ngroups = (h->S + G - 1) / G;
+    const int grid = ngroups < h->num_sms ? ngroups : h->num_sms;
+    k_rollout<<<grid, NT, sizeof(RollSmem), h->stream>>>(A);
+    CKL();
+    return NPE_OK;
+}
+
+int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* metrics_out) {
+    NEED(h);
+    int rc = rollout_impl(h, t0, steps, use_gt, teacher, traj_out != nullptr, metrics_out != nullptr);
+    if (rc) return rc;
+    if (traj_out) CK(cudaMemcpyAsync(traj_out, h->traj.p, (size_t)h->S * h->Nmax * steps * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (metrics_out) CK(cudaMemcpyAsync(metrics_out, h->metrics.p, (size_t)steps * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out) {
+    NEED(h);
+    int rc = rollout_impl(h, t0, steps, 0, 0, false, false);
+    if (rc) return rc;
+    if (object_steps_out) *object_steps_out = h->scene_pred_objects * (int64_t)steps;
+    return NPE_OK;
+}
+
+int npe_comm_unique_id(void* id128_out) {
+    std::string err;
+    if (!id128_out) return NPE_ERR_INVALID;
+    if (!g_nccl.load(err)) { g_create_error = err; return NPE_ERR_NCCL; }
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return NPE_ERR_NCCL; }
+    memcpy(id128_out, &id, sizeof id);
+    return NPE_OK;
+}
+
+int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128) {
+    NEED(h);
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, NPE_ERR_INVALID, "comm_init: bad arguments");
+    std::string err;
+    if (!g_nccl.load(err)) return fail(h, NPE_ERR_NCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (r != 0) return fail(h, NPE_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    h->rank = rank; h->nranks = nranks;
+    return NPE_OK;
+}
+
+int npe_allreduce_grads(npe_handle* h) {
+    NEED(h);
+    if (!h->comm) return fail(h, NPE_ERR_STATE, "allreduce_grads: no communicator (npe_comm_init)");
+    return run_allreduce(h);
+}
+
+int npe_sync(npe_handle* h) {
+    NEED(h);
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_event_record(npe_handle* h, int32_t slot) {
+    NEED(h);
+    if (slot < 0 || slot >= 16) return fail(h, NPE_ERR_INVALID, "event slot out of range");
+    CK(cudaEventRecord(h->events[slot], h->stream));
+    return NPE_OK;
+}
+int npe_event_elapsed_ms(npe_handle* h, int32_t a, int32_t b, float* ms_out) {
+    NEED(h);
+    if (a < 0 || a >= 16 || b < 0 || b >= 16 || !ms_out) return fail(h, NPE_ERR_INVALID, "event slot out of range");
+    CK(cudaEventSynchronize(h->events[b]));
+    CK(cudaEventElapsedTime(ms_out, h->events[a], h->events[b]));
+    return NPE_OK;
+}
+
+int64_t npe_launch_count(const npe_handle* h) { return h ? h->launches : 0; }
+
+int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out) {
+    NEED(h);
+    int rc = build_pairs(h);
+    if (rc) return rc;
+    u64 tot = 0;
+    CK(cudaMemcpyAsync(&tot, h->active_total, sizeof tot, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (foci_out) *foci_out = h->F;
+    if (active_pairs_out) *active_pairs_out = (int64_t)tot;
+    return NPE_OK;
+}
+
+}  // extern "C"

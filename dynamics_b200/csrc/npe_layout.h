@@ -1,0 +1,59 @@
+// Shared host/device constants: model dimensions, the flat (reference) parameter layout and the padded
+// shared-memory weight layout used by the sm_100a kernels.
+//
+// Flat layout == nn.Module:getParameters() of init_network (reference src/lua/npe.lua:14-61,
+// modules.lua:10-26,46-88) with -nbrhd; see include/npe_cuda.h.
+#pragma once
+
+namespace npe {
+
+constexpr int D = 22;        // object_dim                (config.lua:25)
+constexpr int IN = 44;       // input_dim = 2 * 22        (main.lua:122)
+constexpr int H = 50;        // rnn_dim                   (main.lua:37)
+constexpr int H2 = 25;       // encoder half width        (modules.lua:17,19)
+constexpr int NL = 5;        // layers                    (main.lua:40)
+constexpr int OUT = 22;      // out_dim                   (main.lua:123)
+constexpr int DEC_IN = 94;   // rnn_dim + input_dim       (modules.lua:54)
+
+// ---- flat offsets (floats) ----
+constexpr int OFF_ENC_T = 0;
+constexpr int OFF_ENC_C = 1100;
+constexpr int OFF_PAIR = 2200;      // + 2500 * l
+constexpr int OFF_DEC1_W = 14700;   // 50 x 94
+constexpr int OFF_DEC1_B = 19400;
+constexpr int OFF_DEC2_W = 19450;   // dec layers 2..4: W at 19450 + 2550*(i-2), b at W + 2500
+constexpr int OFF_DEC5_W = 27100;   // 22 x 50
+constexpr int OFF_DEC5_B = 28200;
+constexpr int NPARAM = 28222;
+constexpr int NPARAM_PAIR = 14700;  // [0, 14700) = encoder + pairwise layers; [14700, 28222) = decoder
+__host__ __device__ constexpr int off_dec_w(int i) { return OFF_DEC2_W + 2550 * (i - 2); }  // i = 2..4
+__host__ __device__ constexpr int off_dec_b(int i) { return off_dec_w(i) + 2500; }
+
+// ---- padded shared-memory layout ----
+// Activations are row-major [row][LD]; weights keep the reference (out,in) orientation [n][LDW] so that ONE copy
+// serves the forward (inner-product form, k contiguous) and the input-gradient pass (outer-product form, the
+// output index contiguous).  LD = 56 (K <= 52) / 104 (decoder layer 1, K = 96): LD mod 32 in {8, 24} makes the
+// float4 accesses of 4 consecutive rows x 2 k-chunks hit 8 distinct 16-byte bank groups.
+// Decoder biases are folded in as column 50 of the weight rows against a constant-1 activation column 50
+// (row 50 of each hidden decoder layer is the unit vector e_50, which regenerates the constant).
+constexpr int LD = 56;
+constexpr int LD1 = 104;
+constexpr int ZCOL_F = 52;          // decoder input z = [s(0..49) | 1 | 0 | this_past(52..95)]
+constexpr int ONE_COL = 50;
+
+constexpr int SW_ENC_T = 0;                       // 28 x 56
+constexpr int SW_ENC_C = SW_ENC_T + 28 * LD;      // 28 x 56
+constexpr int SW_PAIR = SW_ENC_C + 28 * LD;       // 5 x (52 x 56)
+constexpr int SW_PAIR_SZ = 52 * LD;
+constexpr int SW_PAIR_TOTAL = SW_PAIR + NL * SW_PAIR_SZ;          // 17696 floats = 70784 B
+
+constexpr int SW_DEC1 = 0;                        // 52 x 104
+constexpr int SW_DEC2 = SW_DEC1 + 52 * LD1;       // 3 x (52 x 56)
+constexpr int SW_DEC5 = SW_DEC2 + 3 * SW_PAIR_SZ; // 24 x 56
+constexpr int SW_DEC_TOTAL = SW_DEC5 + 24 * LD;   // 15488 floats = 61952 B
+
+constexpr int TILE = 64;            // rows (foci or pairs) per shared-memory tile
+constexpr int NT = 256;             // threads per CTA
+constexpr int MAXOBJ = 64;          // objects per scene
+
+}  // namespace npe

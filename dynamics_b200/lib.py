@@ -1,0 +1,119 @@
+"""ctypes binding of libnpe_cuda.so (include/npe_cuda.h).  Mirrors what LuaJIT ``ffi.cdef`` binds in lua/npe_ffi.lua."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnpe_cuda.so")
+
+NPE_NUM_PARAMS = 28222
+OBJ_DIM = 22
+INPUT_DIM = 44
+
+
+class NPEError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libnpe_cuda error {code}: {msg}")
+        self.code = code
+
+
+class NPEConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("rnn_dim", C.c_int32), ("layers", C.c_int32),
+                ("num_past", C.c_int32), ("num_future", C.c_int32), ("object_dim", C.c_int32), ("nbrhd", C.c_int32),
+                ("nbrhdsize", C.c_float), ("max_ctx", C.c_int32), ("vlambda", C.c_float), ("lambda_", C.c_float),
+                ("ball_zero_mode", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+_H = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/npe_cuda.h declares
+SIGNATURES = {
+    "npe_abi_version": (C.c_int, []),
+    "npe_default_config": (None, [C.POINTER(NPEConfig)]),
+    "npe_create": (C.c_int, [C.POINTER(NPEConfig), C.POINTER(_H)]),
+    "npe_destroy": (C.c_int, [_H]),
+    "npe_last_error": (C.c_char_p, [_H]),
+    "npe_param_count": (C.c_int, [_H]),
+    "npe_params_set": (C.c_int, [_H, _fp, C.c_int32]),
+    "npe_params_get": (C.c_int, [_H, _fp, C.c_int32]),
+    "npe_grads_get": (C.c_int, [_H, _fp, C.c_int32]),
+    "npe_grads_set": (C.c_int, [_H, _fp, C.c_int32]),
+    "npe_batch_upload": (C.c_int, [_H, _fp, _fp, _fp, C.c_int32, C.c_int32]),
+    "npe_scenes_upload": (C.c_int, [_H, _fp, _ip, C.c_int32, C.c_int32, C.c_int32]),
+    "npe_windows_upload": (C.c_int, [_H, _ip, _ip, C.c_int32]),
+    "npe_select_windows": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "npe_num_foci": (C.c_int, [_H]),
+    "npe_ctx_slots": (C.c_int, [_H]),
+    "npe_batch_download": (C.c_int, [_H, _fp, _fp]),
+    "npe_build_pairs": (C.c_int, [_H, _ip, C.POINTER(C.c_uint8), _ip]),
+    "npe_forward": (C.c_int, [_H, _fp, _fp]),
+    "npe_forward_per_example": (C.c_int, [_H, _fp, _fp]),
+    "npe_backward": (C.c_int, [_H, C.c_int32]),
+    "npe_adam_step": (C.c_int, [_H, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "npe_rmsprop_step": (C.c_int, [_H, C.c_float, C.c_float, C.c_float]),
+    "npe_optim_reset": (C.c_int, [_H, C.c_float]),
+    "npe_train_step": (C.c_int, [_H, C.c_int32, C.c_float, C.c_int32, _fp]),
+    "npe_rollout": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),
+    "npe_rollout_resident": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "npe_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "npe_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
+    "npe_allreduce_grads": (C.c_int, [_H]),
+    "npe_sync": (C.c_int, [_H]),
+    "npe_event_record": (C.c_int, [_H, C.c_int32]),
+    "npe_event_elapsed_ms": (C.c_int, [_H, C.c_int32, C.c_int32, _fp]),
+    "npe_launch_count": (C.c_int64, [_H]),
+    "npe_batch_stats": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+}
+
+
+class NPELibrary:
+    """Loaded libnpe_cuda.so with typed entry points.  Raises if the library is missing: there is no fallback."""
+
+    def __init__(self, path=LIB_PATH):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it with `python -m dynamics_b200.build` (nvcc, sm_100a). "
+                "dynamics_b200 has no CPU or PyTorch fallback.")
+        self.path = path
+        self.dll = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.dll, name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+    def default_config(self, **over):
+        cfg = NPEConfig()
+        self.npe_default_config(C.byref(cfg))
+        for k, v in over.items():
+            setattr(cfg, "lambda_" if k == "lambda" else k, v)
+        return cfg
+
+
+_LIB = None
+
+
+def load_library(path=LIB_PATH):
+    global _LIB
+    if _LIB is None or _LIB.path != path:
+        _LIB = NPELibrary(path)
+    return _LIB
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def fptr(a):
+    return a.ctypes.data_as(_fp) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip) if a is not None else None

@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference's Lua ``model`` object (src/lua/npe.lua:69-526) over libnpe_cuda.so.
+
+Same method names, argument meaning and return values as the table returned by ``require 'npe'``:
+``create(mp, preload, model_path)``, ``fp``, ``fp_batch``, ``bp``, ``theta.params`` / ``theta.grad_params``.
+Tensors are numpy float32 arrays where the reference has torch.FloatTensors.  All arithmetic happens in the CUDA
+library; this file only marshals buffers (it is what lua/npe.lua does through LuaJIT FFI).
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import lib as L
+
+
+@dataclass
+class ModelParams:
+    """The ``mp`` fields npe.lua reads (main.lua:36-57,119-123)."""
+    batch_size: int = 50
+    rnn_dim: int = 50
+    layers: int = 5
+    num_past: int = 2
+    num_future: int = 1
+    object_dim: int = 22
+    nbrhd: bool = True
+    nbrhdsize: float = 3.5
+    vlambda: float = 1.0
+    lambda_: float = 1.0
+    max_ctx: int = 12
+    model: str = "npe"
+    device: int = 0
+    ball_zero_mode: int = 1
+
+    @property
+    def input_dim(self):
+        return self.object_dim * self.num_past
+
+    @property
+    def out_dim(self):
+        return self.object_dim * self.num_future
+
+
+class _Theta:
+    """model.theta: params / grad_params are host mirrors that read through to the device vectors."""
+
+    def __init__(self, model):
+        self._m = model
+
+    @property
+    def params(self):
+        return self._m.get_params()
+
+    @property
+    def grad_params(self):
+        return self._m.get_grads()
+
+
+class NPEModel:
+    def __init__(self, mp=None, library=None):
+        self.mp = mp or ModelParams()
+        self.lib = library or L.load_library()
+        if self.mp.model != "npe":
+            raise L.NPEError(-3, "only -model npe is built (np / lstm baselines are out of scope)")
+        cfg = self.lib.default_config(device=self.mp.device, rnn_dim=self.mp.rnn_dim, layers=self.mp.layers,
+                                      num_past=self.mp.num_past, num_future=self.mp.num_future,
+                                      object_dim=self.mp.object_dim, nbrhd=int(self.mp.nbrhd),
+                                      nbrhdsize=self.mp.nbrhdsize, max_ctx=self.mp.max_ctx, vlambda=self.mp.vlambda,
+                                      ball_zero_mode=self.mp.ball_zero_mode, **{"lambda": self.mp.lambda_})
+        h = C.c_void_p()
+        rc = self.lib.npe_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise L.NPEError(rc, self.lib.npe_last_error(None).decode())
+        self.h = h
+        self.theta = _Theta(self)
+        self.n_params = self.lib.npe_param_count(self.h)
+        self._batch_id = None
+
+    # model.create(mp_, preload, model_path)  (npe.lua:72-102)
+    @classmethod
+    def create(cls, mp=None, preload=False, model_path=None, params=None):
+        m = cls(mp)
+        if preload:
+            from .t7 import load_checkpoint_params
+            params = load_checkpoint_params(model_path)
+        if params is not None:
+            m.set_params(params)
+        return m
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.npe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise L.NPEError(rc, self.lib.npe_last_error(self.h).decode())
+
+    # ---- parameters -------------------------------------------------------------------------------------------
+    def set_params(self, flat):
+        flat = L.f32(flat).ravel()
+        self._ck(self.lib.npe_params_set(self.h, L.fptr(flat), flat.size))
+
+    def get_params(self):
+        out = np.empty(self.n_params, np.float32)
+        self._ck(self.lib.npe_params_get(self.h, L.fptr(out), out.size))
+        return out
+
+    def get_grads(self):
+        out = np.empty(self.n_params, np.float32)
+        self._ck(self.lib.npe_grads_get(self.h, L.fptr(out), out.size))
+        return out
+
+    def set_grads(self, flat):
+        flat = L.f32(flat).ravel()
+        self._ck(self.lib.npe_grads_set(self.h, L.fptr(flat), flat.size))
+
+    # ---- batch form (reference batch tuple) -------------------------------------------------------------------
+    def _upload(self, batch):
+        this, context, y = batch[0], batch[1], batch[2]
+        this = L.f32(this); context = L.f32(context)
+        B = this.shape[0]
+        Cn = context.shape[1] if context.ndim >= 2 else 0
+        yy = None if y is None else L.f32(np.asarray(y).reshape(B, -1))
+        self._ck(self.lib.npe_batch_upload(self.h, L.fptr(this), L.fptr(context), L.fptr(yy), B, Cn))
+        return B
+
+    def fp(self, params_, batch, sim=False):
+        """model:fp (npe.lua:225-247) -> loss, prediction (B,22), vel_loss, ang_vel_loss"""
+        if params_ is not None:
+            self.set_params(params_)
+        B = self._upload(batch)
+        pred = np.empty((B, L.OBJ_DIM), np.float32)
+        loss3 = np.empty(3, np.float32)
+        self._ck(self.lib.npe_forward(self.h, L.fptr(pred), L.fptr(loss3)))
+        return float(loss3[0]), pred, float(loss3[1]), float(loss3[2])
+
+    def fp_batch(self, params_, batch, sim=False):
+        """model:fp_batch (npe.lua:250-284) -> loss (B), prediction, vel_loss (B), ang_vel_loss (B)"""
+        if params_ is not None:
+            self.set_params(params_)
+        B = self._upload(batch)
+        pred = np.empty((B, L.OBJ_DIM), np.float32)
+        le = np.empty((B, 3), np.float32)
+        self._ck(self.lib.npe_forward_per_example(self.h, L.fptr(pred), L.fptr(le)))
+        return le[:, 0].copy(), pred, le[:, 1].copy(), le[:, 2].copy()
+
+    def bp(self, batch=None, prediction=None, sim=False, divisor_batch=0):
+        """model:bp (npe.lua:290-336) -> grad_params.  Like the reference it relies on the state of the immediately
+        preceding fp on the same batch (`batch`/`prediction` are accepted for signature compatibility)."""
+        self._ck(self.lib.npe_backward(self.h, divisor_batch))
+        return self.get_grads()
+
+    def pair_table(self):
+        """(closest_indices (F,K) int32, neighbour mask (F,K) uint8, kept count (F)) of the current batch."""
+        F, K = self.lib.npe_num_foci(self.h), self.lib.npe_ctx_slots(self.h)
+        idx = np.empty((F, K), np.int32); mask = np.empty((F, K), np.uint8); cnt = np.empty(F, np.int32)
+        self._ck(self.lib.npe_build_pairs(self.h, L.iptr(idx), mask.ctypes.data_as(C.POINTER(C.c_uint8)), L.iptr(cnt)))
+        return idx, mask, cnt
+
+    # ---- optimiser boundary (main.lua:135-144,301-302) ---------------------------------------------------------
+    def optim_reset(self, rmsprop_m_init=0.0):
+        self._ck(self.lib.npe_optim_reset(self.h, rmsprop_m_init))
+
+    def adam_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        self._ck(self.lib.npe_adam_step(self.h, lr, beta1, beta2, eps))
+
+    def rmsprop_step(self, lr, alpha=0.99, eps=1e-8):
+        self._ck(self.lib.npe_rmsprop_step(self.h, lr, alpha, eps))
+
+    def train_step(self, opt="adam", lr=3e-4, divisor_batch=0, want_loss=True):
+        loss3 = np.empty(3, np.float32) if want_loss else None
+        self._ck(self.lib.npe_train_step(self.h, 0 if opt == "adam" else 1, lr, divisor_batch, L.fptr(loss3)))
+        return loss3
+
+    # ---- scene form (device-resident trajectory batcher) -------------------------------------------------------
+    def upload_scenes(self, states, n_obj=None):
+        states = L.f32(states)
+        S, Nmax, T, D = states.shape
+        assert D == L.OBJ_DIM
+        n_obj = L.i32(np.full(S, Nmax) if n_obj is None else n_obj)
+        self._ck(self.lib.npe_scenes_upload(self.h, L.fptr(states), L.iptr(n_obj), S, Nmax, T))
+        self.scene_shape = (S, Nmax, T)
+
+    def upload_windows(self, scene_ids, t0):
+        scene_ids, t0 = L.i32(scene_ids), L.i32(t0)
+        self._ck(self.lib.npe_windows_upload(self.h, L.iptr(scene_ids), L.iptr(t0), scene_ids.size))
+
+    def select_windows(self, first, count):
+        self._ck(self.lib.npe_select_windows(self.h, first, count))
+        return self.lib.npe_num_foci(self.h)
+
+    def download_batch(self):
+        F = self.lib.npe_num_foci(self.h)
+        this = np.empty((F, L.INPUT_DIM), np.float32); y = np.empty((F, L.OBJ_DIM), np.float32)
+        self._ck(self.lib.npe_batch_download(self.h, L.fptr(this), L.fptr(y)))
+        return this, y
+
+    def forward_current(self, want_loss=True):
+        F = self.lib.npe_num_foci(self.h)
+        pred = np.empty((F, L.OBJ_DIM), np.float32)
+        loss3 = np.empty(3, np.float32) if want_loss else None
+        self._ck(self.lib.npe_forward(self.h, L.fptr(pred), L.fptr(loss3)))
+        return pred, loss3
+
+    def forward_per_example_current(self):
+        F = self.lib.npe_num_foci(self.h)
+        pred = np.empty((F, L.OBJ_DIM), np.float32); le = np.empty((F, 3), np.float32)
+        self._ck(self.lib.npe_forward_per_example(self.h, L.fptr(pred), L.fptr(le)))
+        return pred, le
+
+    def batch_stats(self):
+        f, p = C.c_int64(), C.c_int64()
+        self._ck(self.lib.npe_batch_stats(self.h, C.byref(f), C.byref(p)))
+        return f.value, p.value
+
+    # ---- rollout (eval.lua:237-454) ---------------------------------------------------------------------------
+    def rollout(self, t0, steps, use_gt=True, teacher=False, want_traj=True, want_metrics=True):
+        S, Nmax, T = self.scene_shape
+        traj = np.empty((S, Nmax, steps, L.OBJ_DIM), np.float32) if want_traj else None
+        met = np.zeros((steps, 7), np.float64) if want_metrics else None
+        mp = met.ctypes.data_as(C.POINTER(C.c_double)) if met is not None else None
+        self._ck(self.lib.npe_rollout(self.h, t0, steps, int(use_gt), int(teacher), L.fptr(traj), mp))
+        return traj, met
+
+    def rollout_resident(self, t0, steps):
+        n = C.c_int64()
+        self._ck(self.lib.npe_rollout_resident(self.h, t0, steps, C.byref(n)))
+        return n.value
+
+    # ---- misc -------------------------------------------------------------------------------------------------
+    def sync(self):
+        self._ck(self.lib.npe_sync(self.h))
+
+    def event_record(self, slot):
+        self._ck(self.lib.npe_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._ck(self.lib.npe_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.npe_launch_count(self.h))
+
+    def comm_init(self, rank, nranks, id_bytes):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(id_bytes))
+        self._ck(self.lib.npe_comm_init(self.h, rank, nranks, C.cast(buf, C.c_void_p)))
+
+    def unique_id(self):
+        buf = (C.c_char * 128)()
+        rc = self.lib.npe_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise L.NPEError(rc, self.lib.npe_last_error(None).decode())
+        return bytes(buf)
+
+    def allreduce_grads(self):
+        self._ck(self.lib.npe_allreduce_grads(self.h))
+
+
+def rollout_metrics_to_logs(met):
+    """(steps,7) sums -> the per-step columns of gt_divergence.log (eval.lua:437-452)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return {"loss": met[:, 0] / met[:, 3], "vel": met[:, 1] / met[:, 3], "angvel": met[:, 2] / met[:, 3],
+                "cos": met[:, 4] / met[:, 6], "mag": met[:, 5] / met[:, 6]}

@@ -1,0 +1,179 @@
+/*
+ * libnpe_cuda.so -- C ABI of the B200-native Neural Physics Engine hot path.
+ *
+ * This is the drop-in boundary for the NPE model that `th main.lua -model npe -nbrhd -rs` and
+ * `th eval.lua -mode sim` build in mbchang/dynamics.  Every entry point names the reference interface it replaces
+ * (file:line under /root/reference/src/lua).  Plain C: opaque handle, plain pointers and sizes; callable from LuaJIT
+ * `ffi.cdef`, Python `ctypes` and C.  See INTEGRATION.md for the Lua-side binding.
+ *
+ * Ownership: the caller owns every host buffer; the library owns all device memory behind the handle.
+ * Errors:    0 = NPE_OK, negative npe_status otherwise; message via npe_last_error().  Never aborts/throws.
+ * Threading: a handle is bound to one device and one CUDA stream and is not thread-safe; handles are independent.
+ * Async:     calls enqueue work on the handle's stream; any call that returns host data synchronises the stream.
+ *
+ * All tensors are float32, C-contiguous.  The object state vector has 22 floats (config.lua:25):
+ *   [px/800, py/800, vx/60, vy/60, a/pi, av/pi, mass1hot(4), oid1hot(3: ball,obstacle,block), size1hot(3), g(2), f(2), p(2)]
+ */
+#ifndef NPE_CUDA_H
+#define NPE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPE_ABI_VERSION 1
+
+typedef enum npe_status {
+    NPE_OK = 0,
+    NPE_ERR_INVALID = -1,     /* bad argument */
+    NPE_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    NPE_ERR_UNSUPPORTED = -3, /* configuration outside the north-star path (e.g. rnn_dim != 50) */
+    NPE_ERR_STATE = -4,       /* call order violated (e.g. backward before forward) */
+    NPE_ERR_NCCL = -5,        /* NCCL error or libnccl not loadable */
+    NPE_ERR_NOMEM = -6
+} npe_status;
+
+#define NPE_OBJ_DIM 22
+#define NPE_NUM_PAST 2
+#define NPE_INPUT_DIM 44
+#define NPE_RNN_DIM 50
+#define NPE_LAYERS 5
+#define NPE_NUM_PARAMS 28222 /* flattened getParameters() length, layout below */
+#define NPE_MAX_OBJECTS 64   /* objects per scene (contexts per focus <= 63) */
+
+/*
+ * Flat parameter layout == nn.Module:getParameters() of init_network (npe.lua:14-61, modules.lua:10-26,46-88) with
+ * -nbrhd (no bias on encoder / pairwise layers), weights (out,in) row-major, offsets in floats:
+ *       0 enc.this.W[25x44]   1100 enc.ctx.W[25x44]
+ *    2200 pair.L1.W[50x50]  4700 L2  7200 L3  9700 L4  12200 L5
+ *   14700 dec.L1.W[50x94] 19400 b[50]   (input = [pair_sum(50) | this_past(44)], modules.lua:55)
+ *   19450 dec.L2.W[50x50] 21950 b   22000 dec.L3.W 24500 b   24550 dec.L4.W 27050 b
+ *   27100 dec.L5.W[22x50] 28200 b[22]
+ */
+
+typedef struct npe_config {
+    int32_t struct_size; /* = sizeof(npe_config), ABI guard */
+    int32_t device;      /* CUDA device ordinal */
+    /* model hyper-parameters (mp.* in main.lua:36-44); only the north-star values are supported */
+    int32_t rnn_dim;    /* 50  (main.lua:37) */
+    int32_t layers;     /* 5   (main.lua:40) */
+    int32_t num_past;   /* 2   (main.lua:43) */
+    int32_t num_future; /* 1   (main.lua:44) */
+    int32_t object_dim; /* 22  (main.lua:120) */
+    int32_t nbrhd;      /* 1   (-nbrhd, main.lua:38) */
+    float nbrhdsize;    /* 3.5 (main.lua:39); threshold = nbrhdsize * 60 px (config.lua:34, npe.lua:180-186) */
+    int32_t max_ctx;    /* 12 nearest contexts kept (data_sampler.lua:168, data_process.lua:59); <= 0: no trim */
+    float vlambda;      /* 1 (main.lua:56) */
+    float lambda;       /* 1 (main.lua:57) */
+    int32_t ball_zero_mode; /* rollout: 1 = zero a/av of ball foci (eval.lua:176-178, per object), 0 = never */
+    int32_t reserved[4];
+} npe_config;
+
+typedef struct npe_handle npe_handle;
+
+/* Fills *cfg with the north-star defaults (main.lua:36-57). */
+void npe_default_config(npe_config* cfg);
+int npe_abi_version(void);
+
+/* model.create (npe.lua:72-102): allocates parameters (zero), gradient, optimiser state on cfg->device. */
+int npe_create(const npe_config* cfg, npe_handle** out);
+int npe_destroy(npe_handle* h);
+/* Last error message of this handle (or of npe_create when h == NULL). */
+const char* npe_last_error(const npe_handle* h);
+
+/* model.theta.params / grad_params (npe.lua:97-98): flat float32 vectors of npe_param_count() elements. */
+int npe_param_count(const npe_handle* h);
+int npe_params_set(npe_handle* h, const float* host, int32_t n);  /* fp's `params_` copy-in (npe.lua:226) */
+int npe_params_get(npe_handle* h, float* host, int32_t n);
+int npe_grads_get(npe_handle* h, float* host, int32_t n);         /* return value of model:bp (npe.lua:335) */
+int npe_grads_set(npe_handle* h, const float* host, int32_t n);   /* optimizer(feval, x, state) boundary: external grads */
+
+/*
+ * Batch form == the reference batch tuple {this, context, y, _, mask} (data_sampler.lua:190; npe.lua:120-132).
+ *   this_past (B,2,22), context (B,C,2,22), y (B,22) relative target or NULL (forward only).
+ * C may exceed max_ctx: the pair builder then trims to the max_ctx nearest (data_process.lua:51-70).
+ */
+int npe_batch_upload(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C);
+
+/*
+ * Scene form (the new trajectory batcher): padded device tensor states (S,Nmax,T,22), n_obj (S) objects per scene.
+ * Replaces the per-iteration torch.load of a batch file (data_sampler.lua:156-157).
+ */
+int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, int32_t S, int32_t Nmax, int32_t T);
+/*
+ * Window schedule: W (scene, t0) windows, uploaded once; past = frames t0,t0+1, target = frame t0+2
+ * (split_time, data_sampler.lua:83-101).  npe_select_windows makes windows [first, first+count) the current batch:
+ * every non-obstacle object of each window becomes a focus (expand_for_each_object, data_process.lua:254-295),
+ * in window-major, object-minor order; targets are made relative (relative_pair, data_process.lua:87-96).
+ */
+int npe_windows_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* t0, int32_t W);
+int npe_select_windows(npe_handle* h, int32_t first, int32_t count);
+/* Number of foci (examples) and context slots per focus of the current batch. */
+int npe_num_foci(const npe_handle* h);
+int npe_ctx_slots(const npe_handle* h);
+/* Copies the current batch's gathered focus rows (F,44) and relative targets (F,22) to the host (parity checks). */
+int npe_batch_download(npe_handle* h, float* this_past_out, float* y_out);
+
+/*
+ * Pair table + neighbourhood mask (k_nearest_context data_process.lua:51-70; select_neighbors npe.lua:170-206).
+ * Outputs (each may be NULL): ctx_idx (F,K) int32 kept context indices ascending, -1 padded (closest_indices);
+ * mask (F,K) uint8 neighbourhood mask of each kept slot; cnt (F) kept count.  K = npe_ctx_slots().
+ * Bit-exact with the reference (no FMA contraction; ties: smaller distance, then lower index).
+ */
+int npe_build_pairs(npe_handle* h, int32_t* ctx_idx_out, uint8_t* mask_out, int32_t* cnt_out);
+
+/*
+ * model:fp (npe.lua:225-247).  pred_out (F,22) or NULL; loss3_out = {loss, vel_loss, angvel_loss} or NULL.
+ * Builds the pair table if the batch changed.
+ */
+int npe_forward(npe_handle* h, float* pred_out, float* loss3_out);
+/* model:fp_batch (npe.lua:250-284): per-example losses loss_out (F,3) = {loss_i, vel_i, angvel_i}. */
+int npe_forward_per_example(npe_handle* h, float* pred_out, float* loss_out);
+/*
+ * model:bp (npe.lua:290-336): gradient of the reference-scaled objective into grad_params.  divisor_batch = the B of
+ * nElement() (npe.lua:307,315); 0 = this batch's F; data-parallel callers pass the GLOBAL batch.
+ * Must follow npe_forward on the same batch.
+ */
+int npe_backward(npe_handle* h, int32_t divisor_batch);
+
+/* optim.adam / optim.rmsprop on the flat vector (main.lua:135-144,301-302); state lives on the device. */
+int npe_adam_step(npe_handle* h, float lr, float beta1, float beta2, float eps);
+int npe_rmsprop_step(npe_handle* h, float lr, float alpha, float eps);
+/* Clears optimiser state; rmsprop_m_init: initial mean-square (0 = early optim rock, 1 = later versions). */
+int npe_optim_reset(npe_handle* h, float rmsprop_m_init);
+/* feval_train + optimizer in one call (main.lua:247-269,301-302) on the current batch: forward, backward,
+ * (all-reduce when a communicator is attached), Adam (opt=0) or RMSprop (opt=1).  loss3_out may be NULL (no sync). */
+int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out);
+
+/*
+ * simulate_all (eval.lua:237-454) in scene form on the uploaded scenes: past = frames t0,t0+1; `steps` autoregressive
+ * steps.  use_gt != 0: frames t0+2.. are ground truth (obstacles copied from it, metrics computed against it);
+ * otherwise obstacles stay static and metrics are zero.
+ *   traj_out (S,Nmax,steps,22) or NULL;  metrics_out (steps,7) or NULL:
+ *   {sum loss_i, sum vel_i, sum angvel_i, n_valid, sum cos, sum relmag, n_anglemask}  (eval.lua:337-356, infer.lua:32-74)
+ * teacher != 0: feed ground truth back instead of the predictions (teacher forcing; traj_out holds one-step preds).
+ */
+int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out,
+                double* metrics_out);
+/* Device-resident rollout for throughput runs: no host copies; object-steps advanced are returned. */
+int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out);
+
+/* Data-parallel: one handle per GPU/process.  id = 128-byte ncclUniqueId from npe_comm_unique_id on rank 0. */
+int npe_comm_unique_id(void* id128_out);
+int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128);
+int npe_allreduce_grads(npe_handle* h); /* sum of flat gradients (+3 loss sums) over ranks, in place */
+
+int npe_sync(npe_handle* h);
+/* CUDA-event timing on the handle's stream (bench/roofline): record marks, read elapsed ms between two marks. */
+int npe_event_record(npe_handle* h, int32_t slot);
+int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* ms_out);
+/* Counters: kernels launched by this handle since creation; active pairs / foci of the current batch. */
+int64_t npe_launch_count(const npe_handle* h);
+int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPE_CUDA_H */

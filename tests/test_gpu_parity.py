@@ -1,0 +1,303 @@
+"""-m gpu parity tests: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+
+Tolerances (north_star / SURVEY section 8d): pair indices, kept counts and neighbourhood masks bit-exact;
+pred, losses within 1e-4 relative (denominator max(|ref|, 1e-6)); gradients within 1e-4 of ||g_ref||_inf.
+"""
+import numpy as np
+import pytest
+
+from oracle import batcher, npe, optim, rollout, scenes
+from oracle import config as OC
+from tests.util import balls_batches, grad_err, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def oracle_pairs(batch_this, batch_ctx_untrimmed, k_max=12):
+    idx, d = batcher.k_nearest_indices(batch_this, batch_ctx_untrimmed, k_max)
+    tctx = np.take_along_axis(batch_ctx_untrimmed, idx[:, :, None, None], axis=1)
+    mask = npe.neighbor_mask(batch_this, tctx, check_focus=False)
+    return idx, mask, tctx
+
+
+@pytest.mark.parametrize("n_balls", [3, 4, 6, 8])
+def test_fp_fp_batch_balls(model, trained_like_params, n_balls):
+    _, batches = balls_batches(60, n_balls, seed=n_balls)
+    foc, ctx = batches[0]
+    batch = batcher.make_batch(foc, ctx, offset=5)
+    l, pred, lv, lw = npe.fp(trained_like_params, batch)
+    gl, gpred, glv, glw = model.fp(trained_like_params, batch)
+    assert rel_err(gpred[:, :6], pred[:, :6]) < TOL
+    assert np.max(np.abs(gpred[:, 6:] - pred[:, 6:])) < 1e-5      # sigmoid columns
+    assert rel_err([gl, glv, glw], [l, lv, lw]) < TOL
+    le, _, lve, lwe = npe.fp_batch(trained_like_params, batch)
+    gle, gp2, glve, glwe = model.fp_batch(None, batch)
+    assert np.array_equal(gp2, gpred)                               # deterministic
+    assert rel_err(gle, le, 1e-7) < 2e-3 and np.max(np.abs(gle - le)) < 1e-6
+    idx, mask, cnt = model.pair_table()
+    oidx, omask, _ = oracle_pairs(batch[0], batch[1])
+    assert np.array_equal(idx[:, :oidx.shape[1]], oidx.astype(np.int32))
+    assert np.array_equal(mask[:, :omask.shape[1]], omask.astype(np.uint8))
+    assert np.all(cnt == oidx.shape[1])
+
+
+def test_bp_matches_oracle(model, trained_like_params):
+    _, batches = balls_batches(60, 5, seed=11)
+    foc, ctx = batches[1]
+    batch = batcher.make_batch(foc, ctx, offset=0)
+    g_ref, _ = npe.bp(trained_like_params, batch)
+    model.fp(trained_like_params, batch)
+    g = model.bp(batch)
+    assert grad_err(g, g_ref) < TOL
+    # per-block check so that small blocks are not hidden by the largest one
+    ents, _ = npe.param_layout()
+    for name, off, shape in ents:
+        n = int(np.prod(shape))
+        ref = g_ref[off:off + n]
+        if np.max(np.abs(ref)) > 0:
+            assert grad_err(g[off:off + n], ref) < 5e-4, name
+    # run-to-run determinism
+    model.fp(None, batch)
+    assert np.array_equal(model.bp(batch), g)
+
+
+def test_bp_divisor_and_lambdas(trained_like_params):
+    from dynamics_b200 import ModelParams, NPEModel
+    _, batches = balls_batches(60, 4, seed=12)
+    batch = batcher.make_batch(*batches[0], offset=3)
+    m = NPEModel(ModelParams(vlambda=0.5, lambda_=2.0))
+    try:
+        m.fp(trained_like_params, batch)
+        g = m.bp(batch, divisor_batch=200)
+        g_ref, _ = npe.bp(trained_like_params, batch, vlambda=0.5, lam=2.0, divisor_batch=200)
+        assert grad_err(g, g_ref) < TOL
+    finally:
+        m.close()
+
+
+def test_trim_to_12_nearest_walls(model, trained_like_params):
+    """walls: 30+ static obstacles as contexts -> 12-NN trim on the GPU must pick the oracle's indices bit-exactly."""
+    st = scenes.raw_to_state(scenes.gen_walls(50, 8, seed=3, variant="U"))
+    N = st.shape[1]
+    j = N - 1
+    this = st[:, j, 2:4]
+    ctx = np.delete(st, j, axis=1)[:, :, 2:4]
+    y = batcher.relative_pair(this, st[:, j, 4:5])
+    oidx, omask, tctx = oracle_pairs(this, ctx)
+    pred_ref = npe.forward(trained_like_params, this.reshape(50, -1), tctx.reshape(50, 12, -1), omask)
+    gl, gpred, _, _ = model.fp(trained_like_params, (this, ctx, y))
+    idx, mask, cnt = model.pair_table()
+    assert idx.shape[1] == 12
+    assert np.array_equal(idx, oidx.astype(np.int32))
+    assert np.array_equal(mask, omask.astype(np.uint8))
+    assert omask.sum() > 0
+    assert rel_err(gpred[:, :6], pred_ref[:, :6]) < TOL
+    # backward through the trimmed table
+    g_ref, _ = npe.bp(trained_like_params, (this, tctx, y))
+    assert grad_err(model.bp(), g_ref) < TOL
+
+
+def test_equidistant_tie_rule(model, params):
+    """Contexts on a lattice, all at the same distance: ties resolve to the lower index (documented rule)."""
+    B, Cn = 50, 20
+    this = np.zeros((B, 2, 22), np.float32); this[:, :, 0:2] = 0.5; this[:, :, 10] = 1; this[:, :, 6] = 1
+    ctx = np.zeros((B, Cn, 2, 22), np.float32); ctx[..., 11] = 1; ctx[..., 9] = 1
+    ang = np.arange(Cn) * (2 * np.pi / Cn)
+    # eight directions with exactly representable equal distance 0.125, others farther
+    for c in range(Cn):
+        dx, dy = [(0.125, 0), (-0.125, 0), (0, 0.125), (0, -0.125)][c % 4]
+        scale = 1.0 if c < 16 else 2.0
+        ctx[:, c, :, 0] = 0.5 + dx * scale; ctx[:, c, :, 1] = 0.5 + dy * scale
+    y = np.zeros((B, 1, 22), np.float32)
+    model.fp(params, (this, ctx, y))
+    idx, mask, cnt = model.pair_table()
+    oidx, omask, _ = oracle_pairs(this, ctx)
+    assert np.array_equal(idx, oidx.astype(np.int32)) and np.array_equal(idx[0], np.arange(12))
+    assert np.array_equal(mask, omask.astype(np.uint8))
+
+
+def test_empty_neighbourhood_and_single_context(model, trained_like_params):
+    """No active pair at all (decoder still runs on [0 | focus]) and the C == 1 edge case."""
+    st = scenes.raw_to_state(scenes.gen_balls(50, 2, 8, seed=21))
+    this = st[:, 0, 0:2].copy(); ctx = st[:, 1:, 0:2].copy()
+    ctx[..., 0:2] += 5.0   # far away -> all masked
+    y = batcher.relative_pair(this, st[:, 0, 2:3])
+    l, pred, lv, lw = npe.fp(trained_like_params, (this, ctx, y))
+    gl, gpred, glv, glw = model.fp(trained_like_params, (this, ctx, y))
+    assert model.pair_table()[1].sum() == 0
+    assert rel_err(gpred[:, :6], pred[:, :6]) < TOL and rel_err(gl, l) < TOL
+    g_ref, _ = npe.bp(trained_like_params, (this, ctx, y))
+    g = model.bp()
+    assert np.all(g[:14700] == 0) and grad_err(g, g_ref) < TOL
+
+
+@pytest.mark.parametrize("opt", ["adam", "rmsprop"])
+def test_optimizer_100_steps(model, params, opt):
+    """Parameters after 100 optimiser steps on a fixed schedule of batches (1e-4 relative)."""
+    _, batches = balls_batches(60, 4, seed=31)
+    x = params.copy()
+    state = optim.adam_init(x.size) if opt == "adam" else optim.rmsprop_init(x.size)
+    model.set_params(params)
+    model.optim_reset(0.0)
+    lr = 3e-4
+    for it in range(100):
+        foc, ctx = batches[it % len(batches)]
+        batch = batcher.make_batch(foc, ctx, offset=it % 20)
+        g_ref, _ = npe.bp(x, batch)
+        if opt == "adam":
+            optim.adam_step(x, g_ref, state, lr)
+        else:
+            optim.rmsprop_step(x, g_ref, state, lr)
+        model._upload(batch)
+        model.train_step(opt, lr, want_loss=False)
+    got = model.get_params()
+    assert np.max(np.abs(got - x)) / np.max(np.abs(x)) < TOL
+    assert rel_err(got, x, 1e-3) < 5e-3
+
+
+def test_scene_form_matches_batch_form(model, trained_like_params):
+    """The device batcher (scenes + window schedule) must produce the examples the reference batcher produces."""
+    st = scenes.raw_to_state(scenes.gen_balls(40, 5, 12, seed=41))
+    model.set_params(trained_like_params)
+    model.upload_scenes(st)
+    sids = np.arange(40); t0 = (np.arange(40) * 3) % 10
+    model.upload_windows(sids, t0)
+    F = model.select_windows(0, 40)
+    assert F == 200
+    this_g, y_g = model.download_batch()
+    # oracle: window-major, object-minor
+    this_ref, ctx_ref, y_ref = [], [], []
+    for s, t in zip(sids, t0):
+        for o in range(5):
+            this_ref.append(st[s, o, t:t + 2]); ctx_ref.append(np.delete(st[s], o, axis=0)[:, t:t + 2])
+            y_ref.append(st[s, o, t + 2:t + 3])
+    this_ref = np.stack(this_ref); ctx_ref = np.stack(ctx_ref); y_ref = batcher.relative_pair(this_ref, np.stack(y_ref))
+    assert np.array_equal(this_g, this_ref.reshape(200, 44))
+    assert np.array_equal(y_g, y_ref.reshape(200, 22))
+    pred_g, loss_g = model.forward_current()
+    l, pred, lv, lw = npe.fp(trained_like_params, (this_ref, ctx_ref, y_ref))
+    assert rel_err(pred_g[:, :6], pred[:, :6]) < TOL
+    assert rel_err(loss_g, [l, lv, lw]) < TOL
+    g_ref, _ = npe.bp(trained_like_params, (this_ref, ctx_ref, y_ref))
+    assert grad_err(model.bp(), g_ref) < TOL
+    # a sub-range of windows is its own batch
+    F2 = model.select_windows(10, 7)
+    assert F2 == 35
+    pred2, _ = model.forward_current()
+    assert rel_err(pred2[:, :6], pred[50:85, :6]) < TOL
+
+
+def test_mixed_object_counts_and_obstacles(model, trained_like_params):
+    """Padded scene tensor with variable n_obj; obstacles are contexts but never foci."""
+    sw = scenes.raw_to_state(scenes.gen_walls(6, 6, seed=5, variant="O"))        # N = 30
+    sb = scenes.raw_to_state(scenes.gen_balls(6, 7, 6, seed=6))                   # N = 7
+    Nmax = 30
+    st = np.zeros((12, Nmax, 6, 22), np.float32)
+    st[:6] = sw; st[6:, :7] = sb
+    n_obj = np.array([30] * 6 + [7] * 6, np.int32)
+    model.set_params(trained_like_params)
+    model.upload_scenes(st, n_obj)
+    model.upload_windows(np.arange(12), np.ones(12, np.int32))
+    F = model.select_windows(0, 12)
+    assert F == 6 * 2 + 6 * 7
+    pred_g, _ = model.forward_current()
+    row = 0
+    for s in range(12):
+        N = n_obj[s]
+        for o in range(N):
+            if st[s, o, 0, 11] == 1:
+                continue
+            this = st[s:s + 1, o, 1:3]; ctx = np.delete(st[s:s + 1, :N], o, axis=1)[:, :, 1:3]
+            idx, mask, tctx = oracle_pairs(this, ctx)
+            pr = npe.forward(trained_like_params, this.reshape(1, -1), tctx.reshape(1, tctx.shape[1], -1), mask)
+            assert rel_err(pred_g[row, :6], pr[0, :6]) < TOL, (s, o)
+            row += 1
+    assert row == F
+
+
+def test_big_scene_no_trim(trained_like_params):
+    """S-64 stress shape (config 4): 64 balls, all-pairs with the 210-px mask, 12-NN trim off."""
+    from dynamics_b200 import ModelParams, NPEModel
+    st = scenes.raw_to_state(scenes.gen_big(8, 64, 3, seed=64))
+    m = NPEModel(ModelParams(max_ctx=0))
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(8), np.zeros(8, np.int32))
+        F = m.select_windows(0, 8)
+        assert F == 512
+        foc, ctx, si, oi = batcher.expand_for_each_object(st)
+        # expand_for_each_object is focus-major; device order is scene-major
+        order = np.lexsort((oi, si))
+        this = foc[order][:, 0:2]; cx = ctx[order][:, :, 0:2]; y = batcher.relative_pair(this, foc[order][:, 2:3])
+        mask = npe.neighbor_mask(this, cx)
+        pred = npe.forward(trained_like_params, this.reshape(512, -1), cx.reshape(512, 63, -1), mask)
+        pred_g, loss_g = m.forward_current()
+        idx, gmask, cnt = m.pair_table()
+        assert np.all(cnt == 63) and np.array_equal(gmask, mask.astype(np.uint8))
+        assert rel_err(pred_g[:, :6], pred[:, :6]) < TOL
+        g_ref, _ = npe.bp(trained_like_params, (this, cx, y))
+        assert grad_err(m.bp(), g_ref) < TOL
+        f, p = m.batch_stats()
+        assert f == 512 and p == int(mask.sum())
+    finally:
+        m.close()
+
+
+def test_rollout_balls(model, trained_like_params):
+    """58-step rollout on n6 scenes: teacher-forced one-step predictions within 1e-4; free-running positions within
+    1e-3 normalised units on scenes whose mask sequence is identical."""
+    st = scenes.raw_to_state(scenes.gen_balls(50, 6, 60, seed=6))
+    steps = 58
+    model.set_params(trained_like_params)
+    model.upload_scenes(st)
+    # teacher forcing
+    traj_t, met_t = model.rollout(0, steps, use_gt=True, teacher=True)
+    ref_t, mref_t = rollout.rollout_scenes(trained_like_params, st[:, :, 0:2], np.full(50, 6), steps, gt=st[:, :, 2:],
+                                           teacher=st[:, :, 2:])
+    assert rel_err(traj_t[..., 2:4], ref_t[..., 2:4], 1e-3) < 2e-3
+    assert np.max(np.abs(traj_t - ref_t)) < 1e-5
+    assert np.array_equal(traj_t[..., 0:2], ref_t[..., 0:2])       # positions integrate the previous velocity: exact
+    assert np.array_equal(traj_t[..., 6:], ref_t[..., 6:])         # properties restored
+    from dynamics_b200.model import rollout_metrics_to_logs
+    logs = rollout_metrics_to_logs(met_t)
+    for k in ("loss", "vel", "angvel", "cos", "mag"):
+        assert np.allclose(logs[k], mref_t[k], rtol=2e-3, atol=1e-7), k
+    # free running
+    traj, met = model.rollout(0, steps, use_gt=True, teacher=False)
+    ref, mref, masks = rollout.rollout_scenes(trained_like_params, st[:, :, 0:2], np.full(50, 6), steps, gt=st[:, :, 2:],
+                                              return_masks=True)
+    err = np.abs(traj[..., 0:2] - ref[..., 0:2]).max(axis=(1, 2, 3))
+    good = err <= 1e-3
+    assert good.mean() >= 0.9, f"{(~good).sum()} of 50 scenes diverged"
+    assert np.all(traj[..., 4:6] == 0)                             # balls: a = av = 0 (eval.lua:176-178)
+
+
+def test_rollout_walls_obstacles_static(model, trained_like_params):
+    st = scenes.raw_to_state(scenes.gen_walls(10, 14, seed=9, variant="I"))
+    N = st.shape[1]
+    steps = 12
+    model.set_params(trained_like_params)
+    model.upload_scenes(st)
+    traj, met = model.rollout(0, steps, use_gt=True, teacher=False)
+    ref, mref = rollout.rollout_scenes(trained_like_params, st[:, :, 0:2], np.full(10, N), steps, gt=st[:, :, 2:])
+    obst = st[0, :, 0, 11] == 1
+    assert np.array_equal(traj[:, obst], st[:, obst, 2:2 + steps])  # obstacles copied from ground truth
+    assert np.max(np.abs(traj[:, ~obst][..., 0:4] - ref[:, ~obst][..., 0:4])) < 1e-3
+    assert met[:, 3].min() == 10 * (~obst).sum()
+    # without ground truth obstacles stay where they are
+    traj2, _ = model.rollout(0, steps, use_gt=False, teacher=False, want_metrics=False)
+    assert np.array_equal(traj2[:, obst], np.repeat(st[:, obst, 1:2], steps, axis=2))
+
+
+def test_error_paths(model):
+    from dynamics_b200 import NPEError, ModelParams, NPEModel
+    with pytest.raises(NPEError):
+        model.bp()                                                  # backward before forward
+    with pytest.raises(NPEError):
+        model.set_params(np.zeros(10, np.float32))
+    with pytest.raises(NPEError):
+        NPEModel(ModelParams(rnn_dim=24, layers=2))                 # -debug shape is not built
+    with pytest.raises(NPEError):
+        model.select_windows(0, 1)                                  # no schedule
