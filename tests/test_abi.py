@@ -1,0 +1,63 @@
+"""CPU tests of the drop-in boundary: libnpe_cuda.so loads, exports every symbol include/npe_cuda.h declares, and
+fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "npe_cuda.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dynamics_b200.build import build
+    from dynamics_b200.lib import load_library
+    return load_library(build())
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(npe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from dynamics_b200.lib import SIGNATURES
+    syms = declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib.dll, s), f"{s} declared in npe_cuda.h but not exported"
+        assert s in SIGNATURES, f"{s} has no ctypes signature"
+    assert set(SIGNATURES) == set(syms)
+    assert lib.npe_abi_version() == 1
+
+
+def test_config_struct_matches_header(lib):
+    from dynamics_b200.lib import NPEConfig
+    cfg = lib.default_config()
+    assert cfg.struct_size == ctypes.sizeof(NPEConfig) == 17 * 4
+    assert (cfg.rnn_dim, cfg.layers, cfg.num_past, cfg.num_future, cfg.object_dim) == (50, 5, 2, 1, 22)
+    assert cfg.nbrhd == 1 and abs(cfg.nbrhdsize - 3.5) < 1e-7 and cfg.max_ctx == 12
+    assert cfg.vlambda == 1.0 and cfg.lambda_ == 1.0
+    assert lib.npe_param_count(None) == 28222
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_fails_loudly_without_gpu(lib):
+    from dynamics_b200 import NPEError, NPEModel
+    with pytest.raises(NPEError) as ei:
+        NPEModel()
+    assert "no CPU path" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under dynamics_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "dynamics_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".lua", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
