@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- NPE training throughput (samples/s) on N B200s, plus rollout object-steps/s, with roofline and CPU baseline.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line on rank 0.
+  step       = one feval_train + Adam update on one batch of 50 synthetic examples (main.lua:247-269,301-302)
+  workload   = BASELINE.json configs[1]: balls n3/n4/n5, variable mass, batch 50 (reference batch composition)
+  value      = samples/s with scenes and the example schedule resident in HBM (device batcher + fwd + bwd + Adam)
+  e2e        = the same metric through the reference-facing batch API with HOST buffers: per step H2D of
+               {this, context, y} from pinned memory, train step, D2H of the loss
+  roofline   = dominant kernel of the timed region, bracketed by CUDA events on its stream
+  extra      = the compute-bound shapes (configs[3] S-64 training, configs[4]-style rollout) with their own rooflines
+Multi-GPU (torchrun): weak scaling, one process per GPU, scenes sharded per rank, one NCCL all-reduce of the flat
+gradient per step (divisor = global batch); timing = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 50
+SETS = (3, 4, 5)             # training sets n3/n4/n5 (configs[1])
+SCENES_PER_SET = 4000        # x 60 frames: 317 MB of padded states > 126 MB L2
+T_FRAMES = 60
+LR = 3e-4
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: FFMA pipe at the 1965 MHz max clock
+FP32_PEAK_NOTE = ("148 SM x 128 FMA/clk x 2 x 1.965 GHz; tools/microbench/ffma measured 72.5 (FFMA) / 74.1 (FFMA2) "
+                  "TFLOP/s on this pool's B200")
+
+
+def fwd_flops(F, P):
+    return 28800.0 * F + 27200.0 * P
+
+
+KERNEL_FLOPS = {                       # algorithmic FLOPs: masked pairs and padding never count
+    "forward": lambda F, P: 28800.0 * F + 27200.0 * P,
+    "dec_backward": lambda F, P: 48800.0 * F,
+    "pair_backward": lambda F, P: 2200.0 * F + 52200.0 * P,
+}
+STEP_FLOPS = lambda F, P: 79800.0 * F + 79400.0 * P
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class Clocks:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for nme, v in zip(names, r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_training_data(rank):
+    from dynamics_b200 import synth
+    Nmax = max(SETS)
+    states = np.zeros((len(SETS) * SCENES_PER_SET, Nmax, T_FRAMES, 22), np.float32)
+    n_obj = np.zeros(len(SETS) * SCENES_PER_SET, np.int32)
+    offs = []
+    for i, n in enumerate(SETS):
+        a = i * SCENES_PER_SET
+        states[a:a + SCENES_PER_SET, :n] = synth.ball_scenes(SCENES_PER_SET, n, T_FRAMES, seed=n + 100 * rank)
+        n_obj[a:a + SCENES_PER_SET] = n
+        offs.append(a)
+    return states, n_obj, offs
+
+
+def host_batches(states, sc, ob, tt, nsteps):
+    """Reference batch tuples {this, context, y} for the e2e / CPU legs (host-side gather, untimed)."""
+    out = []
+    for s in range(nsteps):
+        sl = slice(s * BATCH, (s + 1) * BATCH)
+        scn, o, t0 = sc[sl], int(ob[sl][0]), int(tt[sl][0])
+        n = 3 + int(scn[0] // SCENES_PER_SET)
+        blk = states[scn, :n]
+        this = blk[:, o, t0:t0 + 2]
+        ctx = np.delete(blk, o, axis=1)[:, :, t0:t0 + 2]
+        y = blk[:, o, t0 + 2].copy()
+        y[:, :6] -= this[:, 1, :6]
+        out.append((np.ascontiguousarray(this), np.ascontiguousarray(ctx), np.ascontiguousarray(y)))
+    return out
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (torch-CPU port of `th main.lua`, all host threads) on the same config."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from dynamics_b200 import synth
+    from dynamics_b200.model import init_params
+    from oracle.npe_torch import TorchNPE
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    states = np.zeros((len(SETS) * 200, max(SETS), T_FRAMES, 22), np.float32)
+    for i, n in enumerate(SETS):
+        states[i * 200:(i + 1) * 200, :n] = synth.ball_scenes(200, n, T_FRAMES, seed=n)
+    offs = [i * 200 for i in range(len(SETS))]
+    total = args.warmup + args.steps
+    sc, ob, tt = synth.reference_batch_schedule(200, SETS, total, BATCH, 11, offs)
+    # scene ids are relative to blocks of 200 here
+    batches = []
+    for s in range(total):
+        sl = slice(s * BATCH, (s + 1) * BATCH)
+        scn, o, t0 = sc[sl], int(ob[sl][0]), int(tt[sl][0])
+        n = 3 + int(scn[0] // 200)
+        blk = states[scn, :n]
+        this = blk[:, o, t0:t0 + 2]; ctx = np.delete(blk, o, axis=1)[:, :, t0:t0 + 2]
+        y = blk[:, o, t0 + 2].copy(); y[:, :6] -= this[:, 1, :6]
+        batches.append((np.ascontiguousarray(this), np.ascontiguousarray(ctx), np.ascontiguousarray(y)))
+    m = TorchNPE(init_params(1234), threads=cores)
+    for s in range(args.warmup):
+        m.train_step(*batches[s], lr=LR)
+    t0 = time.perf_counter()
+    for s in range(args.warmup, total):
+        m.train_step(*batches[s], lr=LR)
+    dt = time.perf_counter() - t0
+    val = BATCH * args.steps / dt
+    line = {"impl": "reference", "metric": "NPE train samples/sec", "value": val, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: NPE train, balls n3/n4/n5 variable mass, batch 50", "global_batch": BATCH,
+                       "optimizer": "adam"},
+            "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of batch 50 (torch-CPU float32 port of th main.lua; the "
+                                       "Lua/Torch7 reference cannot run: no th/LuaJIT in the image)"},
+            "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(batches, seconds=12.0):
+    import torch
+    from dynamics_b200.model import init_params
+    from oracle.npe_torch import TorchNPE
+    cores = os.cpu_count() or 1
+    m = TorchNPE(init_params(1234), threads=cores)
+    for b in batches[:5]:
+        m.train_step(*b, lr=LR)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        m.train_step(*batches[n % len(batches)], lr=LR)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": BATCH * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of batch 50 in {dt:.1f}s (torch-CPU float32 port of feval_train+adam, {cores} threads)"}
+
+
+def timed_loop(model, step_fn, warmup, steps, barrier):
+    for s in range(warmup):
+        step_fn(s)
+    model.sync()
+    barrier()
+    model.event_record(0)
+    for s in range(warmup, warmup + steps):
+        step_fn(s)
+    model.event_record(1)
+    model.sync()
+    barrier()
+    return model.event_elapsed_ms(0, 1)
+
+
+def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_step=1024):
+    """configs[3]: 64-ball scenes, all-pairs with the 210-px mask (12-NN trim off), 1024 scenes per GPU per step."""
+    from dynamics_b200 import synth
+    from dynamics_b200.model import init_params
+    st = synth.ball_scenes(scenes_per_step * 2, 64, 3, seed=64, world=(3200, 2400), collide=False)
+    m = model_cls(mp_cls(max_ctx=0, device=device))
+    try:
+        m.set_params(init_params(1234)); m.optim_reset(0.0)
+        m.upload_scenes(st)
+        W = scenes_per_step * 2
+        m.upload_windows(np.arange(W), np.zeros(W, np.int32))
+        stats = []
+        for k in range(2):
+            m.select_windows(k * scenes_per_step, scenes_per_step)
+            stats.append(m.batch_stats())
+        F = stats[0][0]; P = float(np.mean([s[1] for s in stats]))
+
+        def step(s):
+            m.select_windows((s % 2) * scenes_per_step, scenes_per_step)
+            m.train_step("adam", LR, want_loss=False)
+        out = {}
+        ms = timed_loop(m, step, warmup, steps, lambda: None)
+        out.update({"value": F * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps,
+                    "config": {"workload": "configs[3]: 64-ball scenes, 12-NN trim off, 1024 scenes/step",
+                               "foci_per_step": F, "active_pairs_per_step": P},
+                    "step_tflops": STEP_FLOPS(F, P) * steps / (ms * 1e-3) / 1e12})
+        kern = {}
+        for k in ("forward", "dec_backward", "pair_backward"):
+            m.profile_select(k)
+            for s in range(4):
+                step(s)
+            n, tot = m.profile_read()
+            kern[k] = tot / max(n, 1)
+        m.profile_select(None)
+        dom = max(kern, key=kern.get)
+        ach = KERNEL_FLOPS[dom](F, P) / (kern[dom] * 1e-3) / 1e12
+        out["kernel_ms"] = kern
+        out["roofline"] = {"kernel": "k_" + dom, "bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS,
+                           "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": None}
+        return out
+    finally:
+        m.close()
+
+
+def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
+    """configs[4]-style rollout: `scenes` 8-ball scenes advanced `steps` steps, state resident on chip."""
+    from dynamics_b200 import synth
+    from dynamics_b200.model import init_params
+    st = synth.ball_scenes(scenes, balls, 2, seed=5)
+    m = model_cls(mp_cls(device=device))
+    try:
+        m.set_params(init_params(1234))
+        m.upload_scenes(st)
+        m.rollout_resident(0, 5); m.sync()
+        m.event_record(0)
+        n = m.rollout_resident(0, steps)
+        m.event_record(1); m.sync()
+        ms = m.event_elapsed_ms(0, 1)
+        return {"value": n / (ms * 1e-3), "unit": "object-steps/s", "ms": ms,
+                "config": {"workload": f"configs[4]-style: {scenes} x {balls}-ball scenes x {steps} steps, no ground truth",
+                           "object_steps": n}}
+    finally:
+        m.close()
+
+
+def run_ours(args):
+    rank, local_rank, world = dist_env()
+    from dynamics_b200 import ModelParams, NPEModel, synth
+    from dynamics_b200 import lib as L
+    from dynamics_b200.model import init_params
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    barrier = (lambda: dist.barrier()) if dist else (lambda: None)
+
+    states, n_obj, offs = make_training_data(rank)
+    total = args.warmup + args.steps
+    sc, ob, tt = synth.reference_batch_schedule(SCENES_PER_SET, SETS, total, BATCH, 11 + rank, offs)
+    m = NPEModel(ModelParams(device=local_rank))
+    m.set_params(init_params(1234)); m.optim_reset(0.0)
+    if world > 1:
+        import torch
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, 0)
+        m.comm_init(rank, world, bytes(idt.tolist()))
+    m.upload_scenes(states, n_obj)
+    m.upload_foci(sc, ob, tt)
+    gB = BATCH * world
+
+    # active pairs per scheduled batch (untimed): algorithmic FLOPs
+    pairs = []
+    for s in range(total):
+        m.select_foci(s * BATCH, BATCH)
+        pairs.append(m.batch_stats()[1])
+    P_mean = float(np.mean(pairs[args.warmup:]))
+
+    def step(s):
+        m.select_foci(s * BATCH, BATCH)
+        m.train_step("adam", LR, divisor_batch=gB, want_loss=False)
+
+    # untimed pre-pass: which kernel dominates the step?
+    kern = {}
+    for k in ("build_pairs", "forward", "dec_backward", "pair_backward", "reduce", "optim"):
+        m.profile_select(k)
+        for s in range(min(8, total)):
+            step(s)
+        n, tot = m.profile_read()
+        kern[k] = tot / max(n, 1)
+    dom = max(("forward", "dec_backward", "pair_backward"), key=lambda k: kern[k])
+    m.set_params(init_params(1234)); m.optim_reset(0.0)
+
+    # ---- timed region: device-resident path ----
+    m.profile_select(dom)
+    launches0 = m.launch_count()
+    clocks = Clocks(local_rank)
+    clocks.start()
+    ms = timed_loop(m, step, args.warmup, args.steps, barrier)
+    clk = clocks.stop()
+    nprof, prof_ms = m.profile_read()
+    m.profile_select(None)
+    launches = (m.launch_count() - launches0) * args.steps // total
+    if dist:
+        import torch
+        tmax = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax[0])
+    value = gB * args.steps / (ms * 1e-3)
+    k_ms = prof_ms / max(nprof, 1)
+    ach = KERNEL_FLOPS[dom](BATCH, P_mean) / (k_ms * 1e-3) / 1e12
+
+    # ---- e2e: reference-facing batch API, host buffers ----
+    ring = min(total, 64)
+    hb = host_batches(states, sc, ob, tt, ring)
+    pinned = []
+    for this, ctx, y in hb:
+        bufs = []
+        for a in (this, ctx, y):
+            arr, ptr = L.pinned_array(m.lib, a.shape)
+            arr[...] = a
+            bufs.append(arr)
+        pinned.append(bufs)
+    h2d = int(np.mean([sum(a.nbytes for a in b) for b in pinned]))
+    m.set_params(init_params(1234)); m.optim_reset(0.0)
+    loss3 = np.zeros(3, np.float32)
+
+    def e2e_step(s):
+        this, ctx, y = pinned[s % ring]
+        m._ck(m.lib.npe_batch_upload(m.h, L.fptr(this), L.fptr(ctx), L.fptr(y), BATCH, ctx.shape[1]))
+        m._ck(m.lib.npe_train_step(m.h, 0, LR, gB, L.fptr(loss3)))
+    barrier()
+    t_wall = time.perf_counter()
+    ms_e2e = timed_loop(m, e2e_step, args.warmup, args.steps, barrier)
+    if dist:
+        import torch
+        tmax = torch.tensor([ms_e2e], dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tmax[0])
+    e2e_val = gB * args.steps / (ms_e2e * 1e-3)
+
+    line = {"metric": "NPE train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: NPE train, balls n3/n4/n5 variable mass, batch 50 per GPU, adam",
+                       "global_batch": gB, "parallelism": f"dp{world}", "scenes_per_gpu": int(states.shape[0]),
+                       "resident_state_bytes": int(states.nbytes), "l2": "inputs (317 MB/GPU) larger than L2; random batches",
+                       "active_pairs_per_step": P_mean, "optimizer": "adam", "lr": LR},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_" + dom, "bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": None,
+                         "kernel_ms": k_ms, "launches_timed": nprof, "peak_source": FP32_PEAK_NOTE,
+                         "note": "batch 50 -> one 64-row tile on one SM: latency-bound by construction; see extra.stress64"},
+            "kernel_ms_prepass": kern,
+            "step_tflops": STEP_FLOPS(BATCH, P_mean) * world * args.steps / (ms * 1e-3) / 1e12}
+    m.close()
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            line["extra"] = {"stress64": bench_stress64(NPEModel, ModelParams, local_rank),
+                             "rollout": bench_rollout(NPEModel, ModelParams, local_rank)}
+        except Exception as e:  # the headline must still print
+            line["extra"] = {"error": repr(e)}
+        line["cpu_baseline"] = cpu_baseline_leg(hb, seconds=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads and the CPU baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps > 3000:
+            args.steps = 3000
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,11 @@ struct npe_handle {
     DevBuf<float> traj;
     DevBuf<double> metrics;
 
+    // kernel-class profiling (roofline): event pairs around launches of one selected kernel class
+    int prof_kernel = -1;
+    std::vector<cudaEvent_t> prof_events;   // pairs
+    size_t prof_used = 0;
+
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -149,6 +154,22 @@ int fail(npe_handle* h, int code, const char* fmt, ...) {
         if (e__ != cudaSuccess)                                                                           \
             return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
+// Brackets one launch with events when its class is selected.
+struct ProfScope {
+    npe_handle* h; bool on;
+    ProfScope(npe_handle* hh, int kid) : h(hh), on(hh->prof_kernel == kid) {
+        if (!on) return;
+        if (h->prof_used + 2 > h->prof_events.size()) {
+            for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_events.push_back(e); }
+        }
+        cudaEventRecord(h->prof_events[h->prof_used], h->stream);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(h->prof_events[h->prof_used + 1], h->stream);
+        h->prof_used += 2;
+    }
+};
 #define NEED(h)                                      \
     do {                                             \
         if (!(h)) return NPE_ERR_INVALID;            \
@@ -178,9 +199,10 @@ int build_pairs(npe_handle* h) {
     CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));
     const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
     const int kmax = h->cfg.nbrhd ? h->cfg.max_ctx : h->cfg.max_ctx;
-    k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), kmax, h->cfg.nbrhd ? thr : INFINITY, h->keep.p,
+    { ProfScope ps__(h, NPE_K_BUILD_PAIRS); k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), kmax, h->cfg.nbrhd ? thr : INFINITY, h->keep.p,
                                                         h->nbr.p, h->active_total);
-    CKL();
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     h->pairs_valid = true;
     return NPE_OK;
 }
@@ -190,10 +212,11 @@ int run_forward(npe_handle* h, bool training) {
     if (rc) return rc;
     const int ntiles = (h->F + TILE - 1) / TILE;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
-    k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->have_y ? h->y.p : nullptr,
+    { ProfScope ps__(h, NPE_K_FORWARD); k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->have_y ? h->y.p : nullptr,
                                                         h->pred.p, h->have_y ? h->loss_ex.p : nullptr,
                                                         training ? h->s_sum.p : nullptr);
-    CKL();
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     h->fwd_valid = training;
     return NPE_OK;
 }
@@ -214,13 +237,16 @@ int run_backward(npe_handle* h, int divisor_batch) {
     const int nt_d = (h->F + TILE - 1) / TILE, nt_p = (h->F + FT_B - 1) / FT_B;
     const int gd = nt_d < h->num_sms ? nt_d : h->num_sms;
     const int gp = nt_p < h->num_sms ? nt_p : h->num_sms;
-    k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->params, h->y.p, h->s_sum.p, h->ds.p,
+    { ProfScope ps__(h, NPE_K_DEC_BACKWARD); k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->params, h->y.p, h->s_sum.p, h->ds.p,
                                                               h->partial, sv, sw);
-    CKL();
-    k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->ds.p, h->partial);
-    CKL();
-    k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
-    CKL();
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
+    { ProfScope ps__(h, NPE_K_PAIR_BACKWARD); k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->ds.p, h->partial);
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
+    { ProfScope ps__(h, NPE_K_REDUCE); k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
 }
 
@@ -228,14 +254,16 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
-    k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, NPARAM, b1, b2, eps, step);
-    CKL();
+    { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, NPARAM, b1, b2, eps, step);
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
 }
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
-    k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, NPARAM, alpha, eps, lr);
-    CKL();
+    { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, NPARAM, alpha, eps, lr);
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
 }
 
@@ -333,6 +361,7 @@ int npe_destroy(npe_handle* h) {
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NPE_OK;
@@ -467,6 +496,27 @@ int npe_select_windows(npe_handle* h, int32_t first, int32_t count) {
     h->pairs_valid = false; h->fwd_valid = false;
     return NPE_OK;
 }
+
+int npe_foci_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* obj_ids, const int32_t* t0, int32_t n) {
+    NEED(h);
+    if (h->batch_form || h->S == 0) return fail(h, NPE_ERR_STATE, "foci_upload: upload scenes first");
+    if (!scene_ids || !obj_ids || !t0 || n <= 0) return fail(h, NPE_ERR_INVALID, "foci_upload: bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (scene_ids[i] < 0 || scene_ids[i] >= h->S || obj_ids[i] < 0 || obj_ids[i] >= h->Nmax || t0[i] < 0 || t0[i] + 3 > h->T)
+            return fail(h, NPE_ERR_INVALID, "foci_upload: example %d out of range", i);
+    CK(h->foc_scene.ensure(n)); CK(h->foc_obj.ensure(n)); CK(h->foc_t0.ensure(n));
+    CK(cudaMemcpyAsync(h->foc_scene.p, scene_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->foc_obj.p, obj_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->foc_t0.p, t0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->win_start.resize((size_t)n + 1);
+    for (int i = 0; i <= n; ++i) h->win_start[i] = i;   // one-example "windows": select_foci == select_windows
+    h->F = 0;
+    h->pairs_valid = false; h->fwd_valid = false;
+    return NPE_OK;
+}
+
+int npe_select_foci(npe_handle* h, int32_t first, int32_t count) { return npe_select_windows(h, first, count); }
 
 int npe_num_foci(const npe_handle* h) { return h ? h->F : 0; }
 int npe_ctx_slots(const npe_handle* h) {
@@ -609,8 +659,9 @@ static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teache
     const int G = TILE / h->Nmax;
     const int ngroups = (h->S + G - 1) / G;
     const int grid = ngroups < h->num_sms ? ngroups : h->num_sms;
-    k_rollout<<<grid, NT, sizeof(RollSmem), h->stream>>>(A);
-    CKL();
+    { ProfScope ps__(h, NPE_K_ROLLOUT); k_rollout<<<grid, NT, sizeof(RollSmem), h->stream>>>(A);
+    h->launches++; }
+    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
 }
 
@@ -664,6 +715,35 @@ int npe_allreduce_grads(npe_handle* h) {
 int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+void* npe_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void npe_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int npe_profile_select(npe_handle* h, int32_t kernel_id) {
+    NEED(h);
+    if (kernel_id < -1 || kernel_id >= NPE_K_COUNT) return fail(h, NPE_ERR_INVALID, "profile_select: bad kernel id");
+    CK(cudaStreamSynchronize(h->stream));
+    h->prof_kernel = kernel_id;
+    h->prof_used = 0;
+    return NPE_OK;
+}
+int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out) {
+    NEED(h);
+    CK(cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+        tot += ms;
+    }
+    if (launches_out) *launches_out = (int32_t)(h->prof_used / 2);
+    if (total_ms_out) *total_ms_out = tot;
     return NPE_OK;
 }
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "npe_scenes_upload": (C.c_int, [_H, _fp, _ip, C.c_int32, C.c_int32, C.c_int32]),
     "npe_windows_upload": (C.c_int, [_H, _ip, _ip, C.c_int32]),
     "npe_select_windows": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "npe_foci_upload": (C.c_int, [_H, _ip, _ip, _ip, C.c_int32]),
+    "npe_select_foci": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "npe_num_foci": (C.c_int, [_H]),
     "npe_ctx_slots": (C.c_int, [_H]),
     "npe_batch_download": (C.c_int, [_H, _fp, _fp]),
@@ -62,6 +64,10 @@ SIGNATURES = {
     "npe_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "npe_allreduce_grads": (C.c_int, [_H]),
     "npe_sync": (C.c_int, [_H]),
+    "npe_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "npe_host_free": (None, [C.c_void_p]),
+    "npe_profile_select": (C.c_int, [_H, C.c_int32]),
+    "npe_profile_read": (C.c_int, [_H, _ip, C.POINTER(C.c_double)]),
     "npe_event_record": (C.c_int, [_H, C.c_int32]),
     "npe_event_elapsed_ms": (C.c_int, [_H, C.c_int32, C.c_int32, _fp]),
     "npe_launch_count": (C.c_int64, [_H]),
@@ -101,6 +107,21 @@ def load_library(path=LIB_PATH):
     if _LIB is None or _LIB.path != path:
         _LIB = NPELibrary(path)
     return _LIB
+
+
+KERNEL_IDS = {"build_pairs": 0, "forward": 1, "dec_backward": 2, "pair_backward": 3, "reduce": 4, "optim": 5,
+              "rollout": 6, "targets": 7}
+
+
+def pinned_array(lib, shape, dtype=np.float32):
+    """numpy view over page-locked host memory owned by the library (npe_host_alloc)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.npe_host_alloc(max(n, 16))
+    if not ptr:
+        raise MemoryError("npe_host_alloc failed")
+    buf = (C.c_char * max(n, 16)).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr, ptr
 
 
 def f32(a):

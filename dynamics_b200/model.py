@@ -40,6 +40,41 @@ class ModelParams:
         return self.object_dim * self.num_future
 
 
+# Flat getParameters() layout of init_network with -nbrhd (npe.lua:14-61, modules.lua:10-26,46-88): (name, shape)
+PARAM_LAYOUT = ([("enc.this.W", (25, 44)), ("enc.ctx.W", (25, 44))] + [(f"pair.L{l}.W", (50, 50)) for l in range(1, 6)] +
+                [("dec.L1.W", (50, 94)), ("dec.L1.b", (50,))] +
+                [x for i in range(2, 5) for x in ((f"dec.L{i}.W", (50, 50)), (f"dec.L{i}.b", (50,)))] +
+                [("dec.L5.W", (22, 50)), ("dec.L5.b", (22,))])
+
+
+def param_offsets():
+    off, out = 0, {}
+    for name, shape in PARAM_LAYOUT:
+        n = int(np.prod(shape))
+        out[name] = (off, shape)
+        off += n
+    assert off == L.NPE_NUM_PARAMS
+    return out
+
+
+def init_params(seed=1234):
+    """model.create without preload: nn.Linear:reset() draws weight and bias from U(-1/sqrt(in), 1/sqrt(in)); the five
+    pairwise Linears are layer:clone() of one Linear, i.e. start identical (npe.lua:21,39)."""
+    rng = np.random.default_rng(seed)
+    flat = np.zeros(L.NPE_NUM_PARAMS, np.float32)
+    first_pair, fan_in = None, None
+    for name, (off, shape) in param_offsets().items():
+        if len(shape) == 2:
+            fan_in = shape[1]
+        vals = rng.uniform(-1.0 / np.sqrt(fan_in), 1.0 / np.sqrt(fan_in), size=shape).astype(np.float32)
+        if name.startswith("pair."):
+            if first_pair is None:
+                first_pair = vals
+            vals = first_pair
+        flat[off:off + vals.size] = vals.ravel()
+    return flat
+
+
 class _Theta:
     """model.theta: params / grad_params are host mirrors that read through to the device vectors."""
 
@@ -191,6 +226,14 @@ class NPEModel:
         scene_ids, t0 = L.i32(scene_ids), L.i32(t0)
         self._ck(self.lib.npe_windows_upload(self.h, L.iptr(scene_ids), L.iptr(t0), scene_ids.size))
 
+    def upload_foci(self, scene_ids, obj_ids, t0):
+        scene_ids, obj_ids, t0 = L.i32(scene_ids), L.i32(obj_ids), L.i32(t0)
+        self._ck(self.lib.npe_foci_upload(self.h, L.iptr(scene_ids), L.iptr(obj_ids), L.iptr(t0), scene_ids.size))
+
+    def select_foci(self, first, count):
+        self._ck(self.lib.npe_select_foci(self.h, first, count))
+        return self.lib.npe_num_foci(self.h)
+
     def select_windows(self, first, count):
         self._ck(self.lib.npe_select_windows(self.h, first, count))
         return self.lib.npe_num_foci(self.h)
@@ -244,6 +287,14 @@ class NPEModel:
         ms = C.c_float()
         self._ck(self.lib.npe_event_elapsed_ms(self.h, a, b, C.byref(ms)))
         return ms.value
+
+    def profile_select(self, kernel):
+        self._ck(self.lib.npe_profile_select(self.h, -1 if kernel is None else L.KERNEL_IDS[kernel]))
+
+    def profile_read(self):
+        n, ms = C.c_int32(), C.c_double()
+        self._ck(self.lib.npe_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
 
     def launch_count(self):
         return int(self.lib.npe_launch_count(self.h))

@@ -17,6 +17,7 @@
 #ifndef NPE_CUDA_H
 #define NPE_CUDA_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -110,6 +111,13 @@ int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, 
  */
 int npe_windows_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* t0, int32_t W);
 int npe_select_windows(npe_handle* h, int32_t first, int32_t count);
+/*
+ * Explicit focus schedule: n (scene, object, t0) examples uploaded once; npe_select_foci makes examples
+ * [first, first+count) the current batch.  This reproduces the reference's batch composition exactly (50 scenes, the
+ * same focus slot and window offset: data_process.lua:254-295, data_sampler.lua:198-203) with device-resident data.
+ */
+int npe_foci_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* obj_ids, const int32_t* t0, int32_t n);
+int npe_select_foci(npe_handle* h, int32_t first, int32_t count);
 /* Number of foci (examples) and context slots per focus of the current batch. */
 int npe_num_foci(const npe_handle* h);
 int npe_ctx_slots(const npe_handle* h);
@@ -166,6 +174,25 @@ int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128
 int npe_allreduce_grads(npe_handle* h); /* sum of flat gradients (+3 loss sums) over ranks, in place */
 
 int npe_sync(npe_handle* h);
+/* Page-locked host buffers for callers that stream batches (cudaHostAlloc / cudaFreeHost). */
+void* npe_host_alloc(size_t bytes);
+void npe_host_free(void* p);
+/*
+ * Kernel-level timing for roofline reports: kernel_id selects one kernel class (NPE_K_*) whose launches are
+ * bracketed with CUDA events on the handle's stream (-1 = off).  npe_profile_read returns the number of bracketed
+ * launches and their summed duration since the last npe_profile_select.
+ */
+#define NPE_K_BUILD_PAIRS 0
+#define NPE_K_FORWARD 1
+#define NPE_K_DEC_BACKWARD 2
+#define NPE_K_PAIR_BACKWARD 3
+#define NPE_K_REDUCE 4
+#define NPE_K_OPTIM 5
+#define NPE_K_ROLLOUT 6
+#define NPE_K_TARGETS 7
+#define NPE_K_COUNT 8
+int npe_profile_select(npe_handle* h, int32_t kernel_id);
+int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out);
 /* CUDA-event timing on the handle's stream (bench/roofline): record marks, read elapsed ms between two marks. */
 int npe_event_record(npe_handle* h, int32_t slot);
 int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* ms_out);
