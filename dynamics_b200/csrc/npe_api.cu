@@ -84,6 +84,7 @@ struct npe_handle {
     int adam_t = 0;
     float rms_m_init = 0.f;
     float* partial = nullptr;         // [num_sms][NPARAM]
+    float* wpack = nullptr;           // packed (shared-memory layout) weight image, kept in sync with params
     float* loss3_dev = nullptr;
     double* loss_sums_dev = nullptr;
 
@@ -212,7 +213,7 @@ int run_forward(npe_handle* h, bool training) {
     if (rc) return rc;
     const int ntiles = (h->F + TILE - 1) / TILE;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
-    { ProfScope ps__(h, NPE_K_FORWARD); k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->have_y ? h->y.p : nullptr,
+    { ProfScope ps__(h, NPE_K_FORWARD); k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->wpack, h->have_y ? h->y.p : nullptr,
                                                         h->pred.p, h->have_y ? h->loss_ex.p : nullptr,
                                                         training ? h->s_sum.p : nullptr);
     h->launches++; }
@@ -237,11 +238,11 @@ int run_backward(npe_handle* h, int divisor_batch) {
     const int nt_d = (h->F + TILE - 1) / TILE, nt_p = (h->F + FT_B - 1) / FT_B;
     const int gd = nt_d < h->num_sms ? nt_d : h->num_sms;
     const int gp = nt_p < h->num_sms ? nt_p : h->num_sms;
-    { ProfScope ps__(h, NPE_K_DEC_BACKWARD); k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->params, h->y.p, h->s_sum.p, h->ds.p,
+    { ProfScope ps__(h, NPE_K_DEC_BACKWARD); k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->wpack, h->y.p, h->s_sum.p, h->ds.p,
                                                               h->partial, sv, sw);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
-    { ProfScope ps__(h, NPE_K_PAIR_BACKWARD); k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->params, h->ds.p, h->partial);
+    { ProfScope ps__(h, NPE_K_PAIR_BACKWARD); k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->wpack, h->ds.p, h->partial);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     { ProfScope ps__(h, NPE_K_REDUCE); k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
@@ -254,14 +255,14 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
-    { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, NPARAM, b1, b2, eps, step);
+    { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, h->wpack, NPARAM, b1, (float)(1.0 - (double)b1), b2, (float)(1.0 - (double)b2), eps, step);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
 }
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
-    { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, NPARAM, alpha, eps, lr);
+    { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, h->wpack, NPARAM, alpha, (float)(1.0 - (double)alpha), eps, lr);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
     return NPE_OK;
@@ -334,6 +335,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         cudaMemset(*b, 0, NPARAM * sizeof(float));
     }
     if ((e = cudaMalloc((void**)&h->partial, (size_t)h->num_sms * NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->wpack, WPACK_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    k_pack_zero<<<(WPACK_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wpack);
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -352,7 +355,7 @@ int npe_destroy(npe_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf};
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
@@ -373,6 +376,8 @@ int npe_params_set(npe_handle* h, const float* host, int32_t n) {
     NEED(h);
     if (!host || n != NPARAM) return fail(h, NPE_ERR_INVALID, "params_set: expected %d floats", NPARAM);
     CK(cudaMemcpyAsync(h->params, host, NPARAM * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    k_pack_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wpack);
+    CKL();
     CK(cudaStreamSynchronize(h->stream));
     h->fwd_valid = false;
     return NPE_OK;
@@ -644,7 +649,7 @@ static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teache
     A.t0 = t0; A.steps = steps; A.use_gt = use_gt; A.teacher = teacher;
     A.kmax = h->cfg.max_ctx; A.ball_zero = h->cfg.ball_zero_mode;
     A.thr_px = h->cfg.nbrhdsize * 60.f;
-    A.params = h->params;
+    A.wpack = h->wpack;
     A.traj = nullptr; A.metrics = nullptr;
     if (want_traj) {
         CK(h->traj.ensure((size_t)h->S * h->Nmax * steps * D));

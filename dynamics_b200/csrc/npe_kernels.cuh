@@ -37,54 +37,67 @@ __device__ __forceinline__ size_t row_off(const FocusSrc& s, int scene, int obj,
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// weights: flat (reference layout) -> padded shared memory
+// weights: the flat (reference layout) vector is mirrored in a PACKED image = the exact shared-memory layout
+// [pair image (SW_PAIR_TOTAL) | decoder image (SW_DEC_TOTAL)], maintained by k_pack_weights and written through by
+// the optimiser kernels.  Kernels stage it with one TMA bulk copy per image (cp.async.bulk + mbarrier).
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_pair_weights(float* sW, const float* __restrict__ P) {
-    for (int idx = threadIdx.x; idx < SW_PAIR_TOTAL; idx += NT) {
-        float v = 0.f;
-        if (idx < SW_PAIR) {
-            const int m = idx / (28 * LD), rem = idx - m * 28 * LD;
-            const int n = rem / LD, k = rem - n * LD;
-            if (n < H2 && k < IN) v = P[(m ? OFF_ENC_C : OFF_ENC_T) + n * IN + k];
-        } else {
-            const int rem0 = idx - SW_PAIR;
-            const int l = rem0 / SW_PAIR_SZ, rem = rem0 - l * SW_PAIR_SZ;
-            const int n = rem / LD, k = rem - n * LD;
-            if (n < H && k < H) v = P[OFF_PAIR + l * 2500 + n * H + k];
-        }
-        sW[idx] = v;
+constexpr int WPACK_TOTAL = SW_PAIR_TOTAL + SW_DEC_TOTAL;
+
+__host__ __device__ __forceinline__ int pack_index(int i) {
+    if (i < OFF_ENC_C) { const int n = i / IN, k = i - n * IN; return SW_ENC_T + n * LD + k; }
+    if (i < OFF_PAIR) { const int r = i - OFF_ENC_C, n = r / IN, k = r - n * IN; return SW_ENC_C + n * LD + k; }
+    if (i < OFF_DEC1_W) {
+        const int r0 = i - OFF_PAIR, l = r0 / 2500, r = r0 - l * 2500, n = r / H, k = r - n * H;
+        return SW_PAIR + l * SW_PAIR_SZ + n * LD + k;
     }
+    const int base = SW_PAIR_TOTAL;
+    if (i < OFF_DEC1_B) {
+        const int r = i - OFF_DEC1_W, n = r / DEC_IN, k = r - n * DEC_IN;
+        return base + SW_DEC1 + n * LD1 + (k < H ? k : k + 2);
+    }
+    if (i < OFF_DEC2_W) return base + SW_DEC1 + (i - OFF_DEC1_B) * LD1 + ONE_COL;
+    if (i < OFF_DEC5_W) {
+        const int j = i - OFF_DEC2_W, li = j / 2550, r = j - li * 2550;
+        if (r < 2500) { const int n = r / H, k = r - n * H; return base + SW_DEC2 + li * SW_PAIR_SZ + n * LD + k; }
+        return base + SW_DEC2 + li * SW_PAIR_SZ + (r - 2500) * LD + ONE_COL;
+    }
+    if (i < OFF_DEC5_B) { const int r = i - OFF_DEC5_W, n = r / H, k = r - n * H; return base + SW_DEC5 + n * LD + k; }
+    return base + SW_DEC5 + (i - OFF_DEC5_B) * LD + ONE_COL;
 }
 
-__device__ __forceinline__ void load_dec_weights(float* sW, const float* __restrict__ P) {
-    for (int idx = threadIdx.x; idx < SW_DEC_TOTAL; idx += NT) {
-        float v = 0.f;
-        if (idx < SW_DEC2) {
-            const int n = idx / LD1, k = idx - n * LD1;
-            if (n < H) {
-                if (k < H) v = P[OFF_DEC1_W + n * DEC_IN + k];
-                else if (k == ONE_COL) v = P[OFF_DEC1_B + n];
-                else if (k >= ZCOL_F && k < ZCOL_F + IN) v = P[OFF_DEC1_W + n * DEC_IN + (k - 2)];
-            } else if (n == ONE_COL && k == ONE_COL) v = 1.f;
-        } else if (idx < SW_DEC5) {
-            const int rem0 = idx - SW_DEC2;
-            const int i = rem0 / SW_PAIR_SZ, rem = rem0 - i * SW_PAIR_SZ;
-            const int n = rem / LD, k = rem - n * LD;
-            if (n < H) {
-                if (k < H) v = P[off_dec_w(i + 2) + n * H + k];
-                else if (k == ONE_COL) v = P[off_dec_b(i + 2) + n];
-            } else if (n == ONE_COL && k == ONE_COL) v = 1.f;
-        } else {
-            const int rem = idx - SW_DEC5;
-            const int n = rem / LD, k = rem - n * LD;
-            if (n < OUT) {
-                if (k < H) v = P[OFF_DEC5_W + n * H + k];
-                else if (k == ONE_COL) v = P[OFF_DEC5_B + n];
-            }
-        }
-        sW[idx] = v;
+// Rebuilds the whole packed image: zeros, the unit entries that regenerate the constant-1 column, then the scatter.
+__global__ void k_pack_zero(float* __restrict__ wpack) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= WPACK_TOTAL) return;
+    float v = 0.f;
+    const int d = i - SW_PAIR_TOTAL;
+    if (d == SW_DEC1 + ONE_COL * LD1 + ONE_COL) v = 1.f;
+    for (int li = 0; li < 3; ++li)
+        if (d == SW_DEC2 + li * SW_PAIR_SZ + ONE_COL * LD + ONE_COL) v = 1.f;
+    wpack[i] = v;
+}
+__global__ void k_pack_scatter(const float* __restrict__ params, float* __restrict__ wpack) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < NPARAM) wpack[pack_index(i)] = params[i];
+}
+
+struct WeightStage {
+    unsigned long long bar;
+};
+// Thread 0 arms the barrier and issues the bulk copies; everyone waits with stage_wait() before the first use.
+__device__ __forceinline__ void stage_issue(WeightStage& st, float* sWp, float* sWd, const float* __restrict__ wpack) {
+    if (threadIdx.x == 0) mbar_init(&st.bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bytes = 0;
+        if (sWp) bytes += SW_PAIR_TOTAL * 4;
+        if (sWd) bytes += SW_DEC_TOTAL * 4;
+        mbar_expect_tx(&st.bar, bytes);
+        if (sWp) bulk_g2s(sWp, wpack, SW_PAIR_TOTAL * 4, &st.bar);
+        if (sWd) bulk_g2s(sWd, wpack + SW_PAIR_TOTAL, SW_DEC_TOTAL * 4, &st.bar);
     }
 }
+__device__ __forceinline__ void stage_wait(WeightStage& st) { mbar_wait(&st.bar, 0); }
 
 // ----------------------------------------------------------------------------------------------------------------
 // K1: pair table.  One warp per focus.  Context index c in [0, N-1) enumerates the other objects in original order
@@ -236,7 +249,7 @@ __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 // h0 .. h5 of one pair sub-tile.  X rows are already gathered.  bufs[l] receives h_l (l = 0..5); bufs may alias in
 // ping-pong fashion for the forward pass (bufs[l] != bufs[l-1]).
 __device__ __forceinline__ void pair_chain_forward(const float* sWp, const float* sX, const float* sEf, int ldef,
-                                                   const int* pf, int nrows, float* const (&bufs)[NL + 1]) {
+                                                   const int* pf, int nrows, float* const* bufs) {
     float* h0 = bufs[0];
     // focus half of the encoder output is shared by every pair of the focus; pad columns 50..55 are zero
     for (int idx = threadIdx.x; idx < TILE * 32; idx += NT) {
@@ -244,31 +257,25 @@ __device__ __forceinline__ void pair_chain_forward(const float* sWp, const float
         if (n < H2) h0[r * LD + n] = (r < nrows) ? sEf[pf[r] * ldef + n] : 0.f;
         else if (n >= 26) h0[r * LD + (n - 26) + H] = 0.f;   // n = 26..31 -> cols 50..55
     }
-    gemm_nt<11, 7, LD, LD, 2>(sX, sWp + SW_ENC_C, [&](int row, int n, float v) {
-        if (n < H2) h0[row * LD + H2 + n] = relu(v);
-    });
+    gemm_nt<7, LD, LD, 2>(sX, sWp + SW_ENC_C, 11, EpiNT{h0 + H2, LD, H2, 1});
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < NL; ++l) {
-        float* out = bufs[l + 1];
-        gemm_nt<13, 13, LD, LD, 2>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ,
-                                   [&](int row, int n, float v) { out[row * LD + n] = relu(v); });
+        gemm_nt<13, LD, LD, 2>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, EpiNT{bufs[l + 1], LD, 52, 1});
         __syncthreads();
     }
 }
 
-// u1..u4 and raw output o of the decoder on a 64-row focus tile; z = sZ [64][104].
-__device__ __forceinline__ void decoder_forward(const float* sWd, const float* sZ, float* u1, float* u2, float* u3,
-                                                float* u4, float* o) {
-    gemm_nt<24, 13, LD1, LD1, 2>(sZ, sWd + SW_DEC1, [&](int row, int n, float v) { u1[row * LD + n] = relu(v); });
+// u1..u4 and raw output o of the decoder on a 64-row focus tile; z = sZ [64][104].  u[i] receives u_{i+1}.
+__device__ __forceinline__ void decoder_forward(const float* sWd, const float* sZ, float* const* u, float* o) {
+    gemm_nt<13, LD1, LD1, 2>(sZ, sWd + SW_DEC1, 24, EpiNT{u[0], LD, 52, 1});
     __syncthreads();
-    gemm_nt<13, 13, LD, LD, 2>(u1, sWd + SW_DEC2, [&](int row, int n, float v) { u2[row * LD + n] = relu(v); });
-    __syncthreads();
-    gemm_nt<13, 13, LD, LD, 2>(u2, sWd + SW_DEC2 + SW_PAIR_SZ, [&](int row, int n, float v) { u3[row * LD + n] = relu(v); });
-    __syncthreads();
-    gemm_nt<13, 13, LD, LD, 2>(u3, sWd + SW_DEC2 + 2 * SW_PAIR_SZ, [&](int row, int n, float v) { u4[row * LD + n] = relu(v); });
-    __syncthreads();
-    gemm_nt<13, 6, LD, LD, 2>(u4, sWd + SW_DEC5, [&](int row, int n, float v) { o[row * LD + n] = v; });
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        gemm_nt<13, LD, LD, 2>(u[i], sWd + SW_DEC2 + i * SW_PAIR_SZ, 13, EpiNT{u[i + 1], LD, 52, 1});
+        __syncthreads();
+    }
+    gemm_nt<6, LD, LD, 2>(u[3], sWd + SW_DEC5, 13, EpiNT{o, LD, 24, 0});
     __syncthreads();
 }
 
@@ -325,15 +332,16 @@ struct FwdSmem {
     float P0[TILE * LD];
     float P1[TILE * LD];
     TileMeta M;
+    WeightStage W;
 };
 
 __global__ void __launch_bounds__(NT, 1)
-k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ params, const float* __restrict__ y,
+k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ wpack, const float* __restrict__ y,
           float* __restrict__ pred, float* __restrict__ loss_ex, float* __restrict__ s_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
-    load_pair_weights(S.Wp, params);
-    load_dec_weights(S.Wd, params);
+    stage_issue(S.W, S.Wp, S.Wd, wpack);
+    bool staged = false;
     const int ntiles = (src.F + TILE - 1) / TILE;
     const int objstride = src.T * D;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -356,17 +364,17 @@ k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ p
         load_focus_tile(S.Z, src.states, S.M.foff, nf);
         scan_counts(S.M, nf);
         __syncthreads();
-        gemm_nt<11, 7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T,
-                                   [&](int row, int n, float v) { S.Ef[row * 28 + n] = relu(v); });
+        if (!staged) { stage_wait(S.W); staged = true; }
+        gemm_nt<7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
         __syncthreads();
         const int P = S.M.start[TILE];
+        float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
         for (int lo = 0; lo < P; lo += TILE) {
             const int nrows = min(TILE, P - lo);
             fill_pair_meta(S.M, nf, lo, objstride);
             __syncthreads();
             gather_rows<LD>(S.X, src.states, S.M.px, nrows, TILE);
             __syncthreads();
-            float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
             pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
             segmented_add<LD1>(S.Z, S.P1, S.M, nf, lo);
             __syncthreads();
@@ -378,7 +386,8 @@ k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ p
             }
         }
         // decoder: u1 -> P0, u2 -> P1, u3 -> P0, u4 -> P1, o -> X
-        decoder_forward(S.Wd, S.Z, S.P0, S.P1, S.P0, S.P1, S.X);
+        float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
+        decoder_forward(S.Wd, S.Z, ubufs, S.X);
         for (int idx = threadIdx.x; idx < nf * OUT; idx += NT) {
             const int r = idx / OUT, n = idx - r * OUT;
             float v = S.X[r * LD + n];
@@ -433,6 +442,7 @@ struct DecBwdSmem {
     float Da[TILE * LD];
     float Db[TILE * LD];
     long long foff[TILE];
+    WeightStage W;
 };
 
 __device__ __forceinline__ float4 relu_mask4(float4 v, const float* h) {
@@ -441,12 +451,14 @@ __device__ __forceinline__ float4 relu_mask4(float4 v, const float* h) {
 }
 
 __global__ void __launch_bounds__(NT, 1)
-k_dec_backward(FocusSrc src, const float* __restrict__ params, const float* __restrict__ y,
+k_dec_backward(FocusSrc src, const float* __restrict__ wpack, const float* __restrict__ y,
                const float* __restrict__ s_in, float* __restrict__ ds_out, float* __restrict__ partial,
                float scale_v, float scale_w) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     DecBwdSmem& S = *reinterpret_cast<DecBwdSmem*>(smem_raw);
-    load_dec_weights(S.Wd, params);
+    stage_issue(S.W, nullptr, S.Wd, wpack);
+    bool staged = false;
+    float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
     float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
@@ -466,7 +478,8 @@ k_dec_backward(FocusSrc src, const float* __restrict__ params, const float* __re
         }
         for (int idx = t; idx < TILE * LD; idx += NT) S.Da[idx] = 0.f;
         __syncthreads();
-        decoder_forward(S.Wd, S.Z, S.U[0], S.U[1], S.U[2], S.U[3], S.O);
+        if (!staged) { stage_wait(S.W); staged = true; }
+        decoder_forward(S.Wd, S.Z, ubufs, S.O);
         if (t < nf) {
             const float* yy = y + (size_t)(f0 + t) * OUT;
             S.Da[t * LD + 2] = (S.O[t * LD + 2] - yy[2]) * scale_v;
@@ -476,34 +489,24 @@ k_dec_backward(FocusSrc src, const float* __restrict__ params, const float* __re
         __syncthreads();
         // layer 5 (22 x 50): dz = Da (24 cols), input u4
         if (t >= 169 && t < 169 + 78) wgrad<13, LD, LD, true>(a5, S.Da, S.U[3], t - 169, nf);
-        gemm_nn<6, 13, LD, LD>(S.Da, S.Wd + SW_DEC5, [&](int row, int kc, float4 v) {
-            st4(S.Db + row * LD + 4 * kc, relu_mask4(v, S.U[3] + row * LD + 4 * kc));
-        });
+        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC5, 6, EpiNN{S.Db, LD, S.U[3], TILE});
         __syncthreads();
         // layer 4: dz = Db, input u3
         if (t < 169) wgrad<13, LD, LD, true>(a4, S.Db, S.U[2], t, nf);
-        gemm_nn<13, 13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, [&](int row, int kc, float4 v) {
-            st4(S.Da + row * LD + 4 * kc, relu_mask4(v, S.U[2] + row * LD + 4 * kc));
-        });
+        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, EpiNN{S.Da, LD, S.U[2], TILE});
         __syncthreads();
         // layer 3: dz = Da, input u2
         if (t < 169) wgrad<13, LD, LD, true>(a3, S.Da, S.U[1], t, nf);
-        gemm_nn<13, 13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, [&](int row, int kc, float4 v) {
-            st4(S.Db + row * LD + 4 * kc, relu_mask4(v, S.U[1] + row * LD + 4 * kc));
-        });
+        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, EpiNN{S.Db, LD, S.U[1], TILE});
         __syncthreads();
         // layer 2: dz = Db, input u1
         if (t < 169) wgrad<13, LD, LD, true>(a2, S.Db, S.U[0], t, nf);
-        gemm_nn<13, 13, LD, LD>(S.Db, S.Wd + SW_DEC2, [&](int row, int kc, float4 v) {
-            st4(S.Da + row * LD + 4 * kc, relu_mask4(v, S.U[0] + row * LD + 4 * kc));
-        });
+        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2, 13, EpiNN{S.Da, LD, S.U[0], TILE});
         __syncthreads();
         // layer 1 (50 x 94 (+bias)): dz = Da, input z (24 k-chunks); input grad only for the pair-sum columns
         wgrad<24, LD, LD1, true>(a1a, S.Da, S.Z, t, nf);
         if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Da, S.Z, t + NT, nf);
-        gemm_nn<13, 13, LD, LD1>(S.Da, S.Wd + SW_DEC1, [&](int row, int kc, float4 v) {
-            if (row < nf) st4(ds_out + (size_t)(f0 + row) * 52 + 4 * kc, v);
-        });
+        gemm_nn<13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
     }
     // write the register tiles into this CTA's partial (reference flat layout)
     float* out = partial + (size_t)blockIdx.x * NPARAM;
@@ -569,14 +572,17 @@ struct PairBwdSmem {
     float Ef[FT_B * 28];     // focus half of the encoder output
     float De[FT_B * 28];     // gradient into it (summed over the focus's pairs)
     TileMeta M;
+    WeightStage W;
 };
 
 __global__ void __launch_bounds__(NT, 1)
-k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ params,
+k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ wpack,
                 const float* __restrict__ ds_in, float* __restrict__ partial) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     PairBwdSmem& S = *reinterpret_cast<PairBwdSmem*>(smem_raw);
-    load_pair_weights(S.Wp, params);
+    stage_issue(S.W, S.Wp, nullptr, wpack);
+    bool staged = false;
+    float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
     float acc[NL][16];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
@@ -610,7 +616,8 @@ k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restri
         for (int idx = t; idx < FT_B * 28; idx += NT) S.De[idx] = 0.f;
         scan_counts(S.M, nf);
         __syncthreads();
-        gemm_nt<11, 7, LD, LD, 1>(S.Fr, S.Wp + SW_ENC_T, [&](int row, int n, float v) { S.Ef[row * 28 + n] = relu(v); });
+        if (!staged) { stage_wait(S.W); staged = true; }
+        gemm_nt<7, LD, LD, 1>(S.Fr, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
         __syncthreads();
         const int P = S.M.start[TILE];
         for (int lo = 0; lo < P; lo += TILE) {
@@ -619,7 +626,6 @@ k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restri
             __syncthreads();
             gather_rows<LD>(S.X, src.states, S.M.px, nrows, TILE);
             __syncthreads();
-            float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
             pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
             // dz5 = ds[focus] * (h5 > 0); rows >= nrows zero
             for (int idx = t; idx < TILE * (LD / 4); idx += NT) {
@@ -635,9 +641,7 @@ k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restri
             for (int l = NL - 1; l >= 0; --l) {
                 const float* hin = S.Hh[l];
                 if (t < 169) wgrad<13, LD, LD, true>(acc[l], da, hin, t, nrows);
-                gemm_nn<13, 13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, [&](int row, int kc, float4 v) {
-                    st4(db + row * LD + 4 * kc, relu_mask4(v, hin + row * LD + 4 * kc));
-                });
+                gemm_nn<13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, EpiNN{db, LD, hin, TILE});
                 __syncthreads();
                 float* tmp = da; da = db; db = tmp;
             }
@@ -697,24 +701,28 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
 // K5: optimisers (upstream optim rock semantics; call sites main.lua:135-144,301-302)
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                       int n, float b1, float b2, float eps, float step) {
+                       float* __restrict__ wpack, int n, float b1, float omb1, float b2, float omb2, float eps, float step) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float gi = g[i];
-    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(1.f - b1, gi));
-    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(1.f - b2, __fmul_rn(gi, gi)));
+    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(omb1, gi));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(omb2, __fmul_rn(gi, gi)));
     m[i] = mi; v[i] = vi;
-    x[i] = __fsub_rn(x[i], __fdiv_rn(__fmul_rn(step, mi), __fadd_rn(__fsqrt_rn(vi), eps)));
+    const float xn = __fsub_rn(x[i], __fdiv_rn(__fmul_rn(step, mi), __fadd_rn(__fsqrt_rn(vi), eps)));
+    x[i] = xn;
+    wpack[pack_index(i)] = xn;
 }
 
-__global__ void k_rmsprop(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, int n, float alpha,
-                          float eps, float lr) {
+__global__ void k_rmsprop(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m,
+                          float* __restrict__ wpack, int n, float alpha, float oma, float eps, float lr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float gi = g[i];
-    const float mi = __fadd_rn(__fmul_rn(alpha, m[i]), __fmul_rn(1.f - alpha, __fmul_rn(gi, gi)));
+    const float mi = __fadd_rn(__fmul_rn(alpha, m[i]), __fmul_rn(oma, __fmul_rn(gi, gi)));
     m[i] = mi;
-    x[i] = __fsub_rn(x[i], __fdiv_rn(__fmul_rn(lr, gi), __fadd_rn(__fsqrt_rn(mi), eps)));
+    const float xn = __fsub_rn(x[i], __fdiv_rn(__fmul_rn(lr, gi), __fadd_rn(__fsqrt_rn(mi), eps)));
+    x[i] = xn;
+    wpack[pack_index(i)] = xn;
 }
 
 __global__ void k_fill(float* p, int n, float v) {

@@ -27,6 +27,7 @@ struct RollSmem {
     TileMeta M;
     int kind[TILE];           // 0 = empty slot, 1 = predicted focus, 2 = obstacle
     double red[7][NT / 32];
+    WeightStage W;
 };
 
 struct RollArgs {
@@ -35,16 +36,18 @@ struct RollArgs {
     int S, Nmax, T;
     int t0, steps, use_gt, teacher, kmax, ball_zero;
     float thr_px;
-    const float* params;
+    const float* wpack;       // packed weight image
     float* traj;              // (S, Nmax, steps, 22) or null
     double* metrics;          // (steps, 7) or null
 };
 
 __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     RollSmem& S = *reinterpret_cast<RollSmem*>(smem_raw);
-    load_pair_weights(S.Wp, A.params);
-    load_dec_weights(S.Wd, A.params);
+    stage_issue(S.W, S.Wp, S.Wd, A.wpack);
+    bool staged = false;
+    float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
+    float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int G = TILE / A.Nmax;
     const int ngroups = (A.S + G - 1) / G;
@@ -95,8 +98,8 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
             }
             __syncthreads();
             scan_counts(S.M, TILE);
-            gemm_nt<11, 7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T,
-                                       [&](int row, int n, float v) { S.Ef[row * 28 + n] = relu(v); });
+            if (!staged) { stage_wait(S.W); staged = true; }
+            gemm_nt<7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
             __syncthreads();
             const int P = S.M.start[TILE];
             for (int lo = 0; lo < P; lo += TILE) {
@@ -123,12 +126,11 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                     st4(S.X + r * LD + 4 * c4, v);
                 }
                 __syncthreads();
-                float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
                 pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
                 segmented_add<LD1>(S.Z, S.P1, S.M, TILE, lo);
                 __syncthreads();
             }
-            decoder_forward(S.Wd, S.Z, S.P0, S.P1, S.P0, S.P1, S.X);
+            decoder_forward(S.Wd, S.Z, ubufs, S.X);
             // ---- post-process, metrics ----
             double mt[7] = {0, 0, 0, 0, 0, 0, 0};
             if (t < TILE && S.kind[t]) {

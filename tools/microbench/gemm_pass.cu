@@ -1,0 +1,67 @@
+// Cycle cost of one CTA-cooperative tile pass (the building blocks of the fused NPE kernels), one CTA per SM.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include "../../dynamics_b200/csrc/npe_tile.cuh"
+using namespace npe;
+
+struct Smem {
+    float W[52 * LD];
+    float A[TILE * LD];
+    float B[TILE * LD];
+    float C[TILE * LD];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1) k(long long* out, int iters) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    Smem& S = *reinterpret_cast<Smem*>(raw);
+    for (int i = threadIdx.x; i < 52 * LD; i += NT) S.W[i] = 0.001f * (i % 97);
+    for (int i = threadIdx.x; i < TILE * LD; i += NT) { S.A[i] = 0.01f * (i % 13); S.B[i] = 0.f; S.C[i] = 0.02f; }
+    __syncthreads();
+    float acc[16];
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0) {
+            gemm_nt<13, LD, LD, 2>(S.A, S.W, 13, EpiNT{S.B, LD, 52, 1});
+            __syncthreads();
+            gemm_nt<13, LD, LD, 2>(S.B, S.W, 13, EpiNT{S.A, LD, 52, 1});
+            __syncthreads();
+        } else if (MODE == 1) {
+            gemm_nn<13, LD, LD>(S.A, S.W, 13, EpiNN{S.B, LD, S.C, TILE});
+            __syncthreads();
+            gemm_nn<13, LD, LD>(S.B, S.W, 13, EpiNN{S.A, LD, S.C, TILE});
+            __syncthreads();
+        } else {
+            if (threadIdx.x < 169) wgrad<13, LD, LD, true>(acc, S.A, S.C, threadIdx.x, TILE);
+            __syncthreads();
+            if (threadIdx.x < 169) wgrad<13, LD, LD, true>(acc, S.C, S.A, threadIdx.x, TILE);
+            __syncthreads();
+        }
+    }
+    long long t1 = clock64();
+    float s = 0;
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (threadIdx.x == 0) out[blockIdx.x] = (t1 - t0) / (2 * iters);
+    if (s == 12345.f) out[0] = 0;
+}
+
+int main() {
+    long long* out;
+    cudaMalloc(&out, 148 * sizeof(long long));
+    const char* names[] = {"gemm_nt 64x52x52", "gemm_nn 64x52x52", "wgrad   52x52 over 64 rows"};
+    for (int mode = 0; mode < 3; ++mode) {
+        for (int grid : {1, 148}) {
+            auto fn = mode == 0 ? k<0> : mode == 1 ? k<1> : k<2>;
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+            fn<<<grid, NT, sizeof(Smem)>>>(out, 200);
+            cudaDeviceSynchronize();
+            long long h[148];
+            cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+            double fma = 64.0 * 52 * 52;
+            printf("%-28s grid %3d: %6lld cycles/pass  -> %.1f FMA/clk/SM (ideal 128)  [%s]\n", names[mode], grid, h[0],
+                   fma / h[0], cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    return 0;
+}
