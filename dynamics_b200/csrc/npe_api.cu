@@ -101,8 +101,12 @@ struct npe_handle {
     bool have_y = false;
 
     // per-batch buffers
-    DevBuf<float> y, pred, loss_ex, s_sum, ds, this_rows;
+    DevBuf<float> y, pred, loss_ex, ds, this_rows, Hp;
     DevBuf<u64> keep, nbr;
+    DevBuf<int> cnt, pair_start, pair_foc;
+    DevBuf<long long> foc_row, pair_crow;
+    int pair_cap = 0;
+    int* info_dev = nullptr;          // {P, overflow}
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
     DevBuf<int> ctx_idx_out, cnt_out;
@@ -183,14 +187,31 @@ __global__ void k_batch_foci(int* scene, int* obj, int* t0, int* n_obj, int B, i
     if (i < B) { scene[i] = i; obj[i] = 0; t0[i] = 0; n_obj[i] = N; }
 }
 
+int ctx_slots(const npe_handle* h) {
+    const int cn = h->Nmax - 1;
+    return (h->cfg.max_ctx > 0 && h->cfg.max_ctx < cn) ? h->cfg.max_ctx : cn;
+}
+
 int ensure_batch_buffers(npe_handle* h, int F) {
     CK(h->y.ensure((size_t)F * OUT));
     CK(h->pred.ensure((size_t)F * OUT));
     CK(h->loss_ex.ensure((size_t)F * 3));
-    CK(h->s_sum.ensure((size_t)F * 52));
     CK(h->ds.ensure((size_t)F * 52));
     CK(h->keep.ensure(F));
     CK(h->nbr.ensure(F));
+    CK(h->cnt.ensure(F));
+    CK(h->foc_row.ensure(F));
+    CK(h->pair_start.ensure((size_t)F + 1));
+    // dense active-pair list: capacity = F * min(context slots, 16).  Non-overlapping radius-60 discs cannot have more
+    // than ~15 centres within 210 px, so 16 per focus is a physical bound for ball scenes; overflow is flagged.
+    int per = ctx_slots(h);
+    if (per > 16) per = 16;
+    if (per < 1) per = 1;
+    const size_t cap = (size_t)F * per;
+    CK(h->pair_foc.ensure(cap));
+    CK(h->pair_crow.ensure(cap));
+    CK(h->Hp.ensure(cap * 52 + 4));
+    h->pair_cap = (int)cap;
     return NPE_OK;
 }
 
@@ -199,13 +220,32 @@ int build_pairs(npe_handle* h) {
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
     CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));
     const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
-    const int kmax = h->cfg.nbrhd ? h->cfg.max_ctx : h->cfg.max_ctx;
-    { ProfScope ps__(h, NPE_K_BUILD_PAIRS); k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), kmax, h->cfg.nbrhd ? thr : INFINITY, h->keep.p,
-                                                        h->nbr.p, h->active_total);
-    h->launches++; }
-    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
+    {
+        ProfScope ps__(h, NPE_K_BUILD_PAIRS);
+        k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
+                                                            h->foc_row.p, h->batch_form ? nullptr : h->y.p, h->active_total);
+        h->launches++;
+        k_scan_expand<<<1, 1024, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->pair_start.p, h->pair_foc.p,
+                                                 h->pair_crow.p, h->pair_cap, h->info_dev);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
     h->pairs_valid = true;
     return NPE_OK;
+}
+
+// Called at points that synchronise anyway: surfaces a dropped-pair condition instead of returning wrong sums.
+int check_pair_overflow(npe_handle* h) {
+    int info[2] = {0, 0};
+    CK(cudaMemcpyAsync(info, h->info_dev, sizeof info, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (info[1]) return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
+    return NPE_OK;
+}
+
+int pair_grid(const npe_handle* h) {
+    const long long tiles = ((long long)h->pair_cap + TILE - 1) / TILE;
+    return (int)(tiles < h->num_sms ? (tiles > 0 ? tiles : 1) : h->num_sms);
 }
 
 int run_forward(npe_handle* h, bool training) {
@@ -213,12 +253,19 @@ int run_forward(npe_handle* h, bool training) {
     if (rc) return rc;
     const int ntiles = (h->F + TILE - 1) / TILE;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
-    { ProfScope ps__(h, NPE_K_FORWARD); k_forward<<<grid, NT, sizeof(FwdSmem), h->stream>>>(h->src(), h->nbr.p, h->wpack, h->have_y ? h->y.p : nullptr,
-                                                        h->pred.p, h->have_y ? h->loss_ex.p : nullptr,
-                                                        training ? h->s_sum.p : nullptr);
-    h->launches++; }
-    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
-    h->fwd_valid = training;
+    {
+        ProfScope ps__(h, NPE_K_FORWARD);
+        k_pair_forward<<<pair_grid(h), NT, sizeof(PairFwdSmem), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
+                                                                          h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
+        h->launches++;
+        k_dec_forward<<<grid, NT, sizeof(DecFwdSmem), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p, h->Hp.p,
+                                                                   h->wpack, h->have_y ? h->y.p : nullptr, h->pred.p,
+                                                                   h->have_y ? h->loss_ex.p : nullptr);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    h->fwd_valid = true;
+    (void)training;
     return NPE_OK;
 }
 
@@ -235,16 +282,22 @@ int run_backward(npe_handle* h, int divisor_batch) {
     // d_vel = 2 (p - y) * vlambda / (2B); d_ang_vel = 2 (p - y) * lambda / B   (npe.lua:304-315)
     const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
     const float sw = 2.f * h->cfg.lambda / (float)B;
-    const int nt_d = (h->F + TILE - 1) / TILE, nt_p = (h->F + FT_B - 1) / FT_B;
+    const int nt_d = (h->F + TILE - 1) / TILE;
     const int gd = nt_d < h->num_sms ? nt_d : h->num_sms;
-    const int gp = nt_p < h->num_sms ? nt_p : h->num_sms;
-    { ProfScope ps__(h, NPE_K_DEC_BACKWARD); k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->src(), h->wpack, h->y.p, h->s_sum.p, h->ds.p,
-                                                              h->partial, sv, sw);
-    h->launches++; }
-    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
-    { ProfScope ps__(h, NPE_K_PAIR_BACKWARD); k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->src(), h->nbr.p, h->wpack, h->ds.p, h->partial);
-    h->launches++; }
-    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
+    const int gp = pair_grid(h);
+    {
+        ProfScope ps__(h, NPE_K_DEC_BACKWARD);
+        k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p, h->Hp.p,
+                                                                  h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
+        h->launches++;
+    }
+    {
+        ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
+        k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                    h->info_dev, h->wpack, h->ds.p, h->partial);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
     { ProfScope ps__(h, NPE_K_REDUCE); k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
@@ -340,8 +393,11 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(h->info_dev, 0, 4 * sizeof(int));
     cudaMemset(h->active_total, 0, sizeof(u64));
-    if ((e = cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem))) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(k_pair_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairFwdSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess)
@@ -359,8 +415,10 @@ int npe_destroy(npe_handle* h) {
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
+    if (h->info_dev) cudaFree(h->info_dev);
+    h->cnt.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
-    h->y.release(); h->pred.release(); h->loss_ex.release(); h->s_sum.release(); h->ds.release(); h->this_rows.release();
+    h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->this_rows.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
@@ -412,6 +470,7 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     CK(h->states.ensure((size_t)B * N * IN));
     CK(h->n_obj.ensure(B));
     CK(h->foc_scene.ensure(B)); CK(h->foc_obj.ensure(B)); CK(h->foc_t0.ensure(B));
+    h->S = B; h->Nmax = N; h->T = 2;
     int rc = ensure_batch_buffers(h, B);
     if (rc) return rc;
     // scene b = [this_b | context_b,0 | ... | context_b,C-1], T = 2  (== `past` of eval.lua:283)
@@ -495,9 +554,7 @@ int npe_select_windows(npe_handle* h, int32_t first, int32_t count) {
     if (h->F <= 0) return fail(h, NPE_ERR_INVALID, "select_windows: empty batch");
     int rc = ensure_batch_buffers(h, h->F);
     if (rc) return rc;
-    k_window_targets<<<((size_t)h->F * IN + 255) / 256, 256, 0, h->stream>>>(h->src(), h->y.p, nullptr);
-    CKL();
-    h->have_y = true;
+    h->have_y = true;   // relative targets are written by the pair builder (K1 + K7)
     h->pairs_valid = false; h->fwd_valid = false;
     return NPE_OK;
 }
@@ -524,23 +581,20 @@ int npe_foci_upload(npe_handle* h, const int32_t* scene_ids, const int32_t* obj_
 int npe_select_foci(npe_handle* h, int32_t first, int32_t count) { return npe_select_windows(h, first, count); }
 
 int npe_num_foci(const npe_handle* h) { return h ? h->F : 0; }
-int npe_ctx_slots(const npe_handle* h) {
-    if (!h) return 0;
-    const int cn = h->Nmax - 1;
-    return (h->cfg.max_ctx > 0 && h->cfg.max_ctx < cn) ? h->cfg.max_ctx : cn;
-}
+int npe_ctx_slots(const npe_handle* h) { return h ? ctx_slots(h) : 0; }
 
 int npe_batch_download(npe_handle* h, float* this_past_out, float* y_out) {
     NEED(h);
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
     if (this_past_out) {
         CK(h->this_rows.ensure((size_t)h->F * IN));
-        k_window_targets<<<((size_t)h->F * IN + 255) / 256, 256, 0, h->stream>>>(h->src(), nullptr, h->this_rows.p);
+        k_gather_this<<<((size_t)h->F * IN + 255) / 256, 256, 0, h->stream>>>(h->src(), h->this_rows.p);
         CKL();
         CK(cudaMemcpyAsync(this_past_out, h->this_rows.p, (size_t)h->F * IN * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     if (y_out) {
         if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+        { int rc = build_pairs(h); if (rc) return rc; }
         CK(cudaMemcpyAsync(y_out, h->y.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -577,7 +631,7 @@ int npe_forward(npe_handle* h, float* pred_out, float* loss3_out) {
         CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     if (pred_out) CK(cudaMemcpyAsync(pred_out, h->pred.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (pred_out || loss3_out) CK(cudaStreamSynchronize(h->stream));
+    if (pred_out || loss3_out) return check_pair_overflow(h);
     return NPE_OK;
 }
 
@@ -591,7 +645,7 @@ int npe_forward_per_example(npe_handle* h, float* pred_out, float* loss_out) {
         CK(cudaMemcpyAsync(loss_out, h->loss_ex.p, (size_t)h->F * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     if (pred_out) CK(cudaMemcpyAsync(pred_out, h->pred.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (pred_out || loss_out) CK(cudaStreamSynchronize(h->stream));
+    if (pred_out || loss_out) return check_pair_overflow(h);
     return NPE_OK;
 }
 
@@ -634,7 +688,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     h->fwd_valid = false;   // parameters changed
     if (loss3_out) {
         CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        return check_pair_overflow(h);
     }
     return NPE_OK;
 }
@@ -775,6 +829,9 @@ int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out)
     u64 tot = 0;
     CK(cudaMemcpyAsync(&tot, h->active_total, sizeof tot, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    int info[2] = {0, 0};
+    CK(cudaMemcpy(info, h->info_dev, sizeof info, cudaMemcpyDeviceToHost));
+    if (info[1]) return fail(h, NPE_ERR_NOMEM, "active-pair list overflow: %llu pairs > capacity %d", (unsigned long long)tot, h->pair_cap);
     if (foci_out) *foci_out = h->F;
     if (active_pairs_out) *active_pairs_out = (int64_t)tot;
     return NPE_OK;

@@ -146,17 +146,84 @@ __device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, 
     nbr = (u64)m0 | ((u64)m1 << 32);
 }
 
+// K1 (+K7): one warp per focus: pair bits, active count, focus row offset, and the relative target
+// y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96).
 __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
-                                                    u64* __restrict__ nbr_out, u64* __restrict__ active_total) {
+                                                    u64* __restrict__ nbr_out, int* __restrict__ cnt_out,
+                                                    long long* __restrict__ foc_row, float* __restrict__ y,
+                                                    u64* __restrict__ active_total) {
     const int f = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (f >= src.F) return;
+    const int lane = threadIdx.x & 31;
     const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
     u64 keep, nbr;
     warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
-    if ((threadIdx.x & 31) == 0) {
+    const size_t ro = row_off(src, s, n, t0);
+    if (y && lane < D) {
+        const float* p = src.states + ro;
+        float v = p[2 * D + lane];
+        if (lane < 6) v = __fsub_rn(v, p[D + lane]);
+        y[(size_t)f * D + lane] = v;
+    }
+    if (lane == 0) {
         keep_out[f] = keep;
         nbr_out[f] = nbr;
+        cnt_out[f] = __popcll(nbr);
+        foc_row[f] = (long long)ro;
         atomicAdd(active_total, (u64)__popcll(nbr));
+    }
+}
+
+// K1b: exclusive scan of the active counts -> pair_start[F+1], then the dense pair list: for pair p of focus f
+// (contexts in ascending index order) pair_foc[p] = f and pair_crow[p] = float offset of the context's window.
+// One CTA; each thread owns a contiguous chunk of foci.  Pairs beyond `cap` are dropped and flagged.
+__global__ void __launch_bounds__(1024) k_scan_expand(FocusSrc src, const u64* __restrict__ nbr, const int* __restrict__ cnt,
+                                                      int* __restrict__ pair_start, int* __restrict__ pair_foc,
+                                                      long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
+    __shared__ int warp_sums[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int chunk = (src.F + 1023) / 1024;
+    const int f0 = min(t * chunk, src.F), f1 = min(f0 + chunk, src.F);
+    int local = 0;
+    for (int f = f0; f < f1; ++f) local += cnt[f];
+    int incl = local;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int v = warp_sums[lane];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += u;
+        }
+        warp_sums[lane] = v;
+    }
+    __syncthreads();
+    int base = incl - local + (w ? warp_sums[w - 1] : 0);
+    const int objstride = src.T * D;
+    for (int f = f0; f < f1; ++f) {
+        pair_start[f] = min(base, cap);
+        u64 bits = nbr[f];
+        const int fo = src.foc_obj[f];
+        const long long sbase = (long long)row_off(src, src.foc_scene[f], 0, src.foc_t0[f]);
+        while (bits) {
+            const int c = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (base < cap) {
+                pair_foc[base] = f;
+                pair_crow[base] = sbase + (long long)(c + (c >= fo)) * objstride;
+            }
+            ++base;
+        }
+    }
+    if (t == 1023) {
+        const int total = warp_sums[31];
+        pair_start[src.F] = min(total, cap);
+        info[0] = min(total, cap);     // P
+        info[1] = total > cap;         // overflow flag
     }
 }
 
@@ -184,59 +251,22 @@ __global__ void k_expand_pairs(const u64* __restrict__ keep, const u64* __restri
     }
 }
 
-// K7: relative targets y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96),
-// plus the gathered focus rows for parity checks.
-__global__ void k_window_targets(FocusSrc src, float* __restrict__ y, float* __restrict__ this_out) {
+// Gathered focus rows (F,44) for parity checks.
+__global__ void k_gather_this(FocusSrc src, float* __restrict__ this_out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = idx / IN, c = idx - f * IN;
     if (f >= src.F) return;
-    const float* p = src.states + row_off(src, src.foc_scene[f], src.foc_obj[f], src.foc_t0[f]);
-    if (this_out) this_out[(size_t)f * IN + c] = p[c];
-    if (y && c < D) {
-        float v = p[2 * D + c];
-        if (c < 6) v = __fsub_rn(v, p[D + c]);
-        y[(size_t)f * D + c] = v;
-    }
+    this_out[(size_t)f * IN + c] = src.states[row_off(src, src.foc_scene[f], src.foc_obj[f], src.foc_t0[f]) + c];
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// shared helpers for the fused kernels
+// shared helpers
 // ----------------------------------------------------------------------------------------------------------------
-struct TileMeta {           // lives in shared memory
-    long long foff[TILE];   // float offset of each focus row (frame t0) in `states`
-    long long sbase[TILE];  // float offset of object 0, frame t0, of the focus's scene
-    u64 nbr[TILE];          // active-context bits
-    int fobj[TILE];         // focus object index within its scene
-    int start[TILE + 1];    // exclusive scan of active-pair counts
-    long long px[TILE];     // per pair row: float offset of the context row
-    int pf[TILE];           // per pair row: local focus index
-};
-
-// Fill per-row metadata of pair sub-tile [lo, lo + 64).
-__device__ __forceinline__ void fill_pair_meta(TileMeta& M, int nf, int lo, int objstride) {
-    const int f = threadIdx.x;
-    if (f < nf) {
-        u64 bits = M.nbr[f];
-        int pos = M.start[f] - lo;
-        while (bits) {
-            const int c = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (pos >= 0 && pos < TILE) {
-                const int j = c + (c >= M.fobj[f]);
-                M.pf[pos] = f;
-                M.px[pos] = M.sbase[f] + (long long)j * objstride;
-            }
-            ++pos;
-        }
-    }
-}
-
 // Gather rows of 44 floats (two frames) into dst[r][LDD]; rows >= nrows are zero-filled.  Row offsets are multiples
 // of 22 floats (8-byte aligned): float2 loads.
 template <int LDD>
-__device__ __forceinline__ void gather_rows(float* dst, const float* __restrict__ base, const long long* offs, int nrows,
-                                            int nrows_total) {
-    for (int idx = threadIdx.x; idx < nrows_total * (IN / 2); idx += NT) {
+__device__ __forceinline__ void gather_rows(float* dst, const float* __restrict__ base, const long long* offs, int nrows) {
+    for (int idx = threadIdx.x; idx < TILE * (IN / 2); idx += NT) {
         const int r = idx / (IN / 2), c2 = idx - r * (IN / 2);
         float2 v = make_float2(0.f, 0.f);
         if (r < nrows) v = *reinterpret_cast<const float2*>(base + offs[r] + 2 * c2);
@@ -246,40 +276,20 @@ __device__ __forceinline__ void gather_rows(float* dst, const float* __restrict_
 
 __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 
-// h0 .. h5 of one pair sub-tile.  X rows are already gathered.  bufs[l] receives h_l (l = 0..5); bufs may alias in
-// ping-pong fashion for the forward pass (bufs[l] != bufs[l-1]).
-__device__ __forceinline__ void pair_chain_forward(const float* sWp, const float* sX, const float* sEf, int ldef,
-                                                   const int* pf, int nrows, float* const* bufs) {
-    float* h0 = bufs[0];
-    // focus half of the encoder output is shared by every pair of the focus; pad columns 50..55 are zero
-    for (int idx = threadIdx.x; idx < TILE * 32; idx += NT) {
-        const int r = idx >> 5, n = idx & 31;
-        if (n < H2) h0[r * LD + n] = (r < nrows) ? sEf[pf[r] * ldef + n] : 0.f;
-        else if (n >= 26) h0[r * LD + (n - 26) + H] = 0.f;   // n = 26..31 -> cols 50..55
-    }
-    gemm_nt<7, LD, LD, 2>(sX, sWp + SW_ENC_C, 11, EpiNT{h0 + H2, LD, H2, 1});
-    __syncthreads();
-#pragma unroll 1
-    for (int l = 0; l < NL; ++l) {
-        gemm_nt<13, LD, LD, 2>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, EpiNT{bufs[l + 1], LD, 52, 1});
-        __syncthreads();
-    }
-}
-
 // u1..u4 and raw output o of the decoder on a 64-row focus tile; z = sZ [64][104].  u[i] receives u_{i+1}.
-__device__ __forceinline__ void decoder_forward(const float* sWd, const float* sZ, float* const* u, float* o) {
-    gemm_nt<13, LD1, LD1, 2>(sZ, sWd + SW_DEC1, 24, EpiNT{u[0], LD, 52, 1});
+__device__ __forceinline__ void decoder_forward(const float* sWd, const float* sZ, float* const* u, float* o, int nrows) {
+    gemm_nt<7, LD1, LD1>(sZ, sWd + SW_DEC1, 24, nrows, EpiNT{u[0], LD, 52, 1});
     __syncthreads();
 #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
-        gemm_nt<13, LD, LD, 2>(u[i], sWd + SW_DEC2 + i * SW_PAIR_SZ, 13, EpiNT{u[i + 1], LD, 52, 1});
+        gemm_nt<7, LD, LD>(u[i], sWd + SW_DEC2 + i * SW_PAIR_SZ, 13, nrows, EpiNT{u[i + 1], LD, 52, 1});
         __syncthreads();
     }
-    gemm_nt<6, LD, LD, 2>(u[3], sWd + SW_DEC5, 13, EpiNT{o, LD, 24, 0});
+    gemm_nt<3, LD, LD>(u[3], sWd + SW_DEC5, 13, nrows, EpiNT{o, LD, 24, 0});
     __syncthreads();
 }
 
-// Load a focus tile: z[r] = [0 x 50 | 1 | 0 | this_past(44) | 0 x 8]; rows >= nf are all zero.
+// Load a focus tile: z[r] = [s x 50 (zero here) | 1 | 0 | this_past(44) | 0 x 8]; rows >= nf are all zero.
 __device__ __forceinline__ void load_focus_tile(float* sZ, const float* __restrict__ states, const long long* foff, int nf) {
     for (int idx = threadIdx.x; idx < TILE * (ZCOL_F / 2); idx += NT) {
         const int r = idx / (ZCOL_F / 2), c2 = idx - r * (ZCOL_F / 2);
@@ -295,109 +305,141 @@ __device__ __forceinline__ void load_focus_tile(float* sZ, const float* __restri
     }
 }
 
-__device__ __forceinline__ void scan_counts(TileMeta& M, int nf) {
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int f = 0; f < TILE; ++f) {
-            M.start[f] = acc;
-            acc += (f < nf) ? __popcll(M.nbr[f]) : 0;
-        }
-        M.start[TILE] = acc;
-    }
-}
-
-// s[f][0..49] += sum of h5 rows of focus f inside sub-tile [lo, lo+64): fixed order -> deterministic.
-template <int LDS_>
-__device__ __forceinline__ void segmented_add(float* sS, const float* h5, const TileMeta& M, int nfoc, int lo) {
-    for (int idx = threadIdx.x; idx < nfoc * H; idx += NT) {
-        const int f = idx / H, n = idx - f * H;
-        const int r0 = max(M.start[f], lo) - lo, r1 = min(M.start[f + 1], lo + TILE) - lo;
-        if (r1 > r0) {
-            float acc = sS[f * LDS_ + n];
-            for (int r = r0; r < r1; ++r) acc += h5[r * LD + n];
-            sS[f * LDS_ + n] = acc;
-        }
-    }
-}
-
 // ----------------------------------------------------------------------------------------------------------------
-// K2 + K3: fused forward
+// K2a: pair-MLP forward on DENSE tiles of 64 active pairs (independent of focus tiles): both encoder halves per pair
+// (like the reference, which re-encodes the focus for every pair), 5 pairwise layers, h5 rows to Hp (P,52).
 // ----------------------------------------------------------------------------------------------------------------
-struct FwdSmem {
+struct PairMeta {
+    long long frow[TILE];
+    long long crow[TILE];
+    int pf[TILE];
+};
+
+struct PairFwdSmem {
     float Wp[SW_PAIR_TOTAL];
-    float Wd[SW_DEC_TOTAL];
-    float Z[TILE * LD1];
-    float Ef[TILE * 28];
-    float X[TILE * LD];
+    float Xf[TILE * LD];
+    float Xc[TILE * LD];
     float P0[TILE * LD];
     float P1[TILE * LD];
-    TileMeta M;
+    PairMeta M;
     WeightStage W;
 };
 
+// h0 = [relu(Wt f) | relu(Wc c)] into h0buf (cols 50..55 zeroed), then h_l = relu(L_l h_{l-1}) into bufs[l].
+__device__ __forceinline__ void pair_chain_dense(const float* sWp, const float* sXf, const float* sXc, int nrows,
+                                                 float* const* bufs) {
+    float* h0 = bufs[0];
+    for (int idx = threadIdx.x; idx < TILE * 6; idx += NT) h0[(idx / 6) * LD + H + (idx % 6)] = 0.f;
+    gemm_nt<4, LD, LD>(sXf, sWp + SW_ENC_T, 11, nrows, EpiNT{h0, LD, H2, 1});
+    gemm_nt<4, LD, LD>(sXc, sWp + SW_ENC_C, 11, nrows, EpiNT{h0 + H2, LD, H2, 1});
+    __syncthreads();
+#pragma unroll 1
+    for (int l = 0; l < NL; ++l) {
+        gemm_nt<7, LD, LD>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{bufs[l + 1], LD, 52, 1});
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void load_pair_meta(PairMeta& M, const int* __restrict__ pair_foc,
+                                               const long long* __restrict__ pair_crow,
+                                               const long long* __restrict__ foc_row, int lo, int nrows) {
+    if (threadIdx.x < nrows) {
+        const int pf = pair_foc[lo + threadIdx.x];
+        M.pf[threadIdx.x] = pf;
+        M.crow[threadIdx.x] = pair_crow[lo + threadIdx.x];
+        M.frow[threadIdx.x] = foc_row[pf];
+    }
+}
+
 __global__ void __launch_bounds__(NT, 1)
-k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ wpack, const float* __restrict__ y,
-          float* __restrict__ pred, float* __restrict__ loss_ex, float* __restrict__ s_out) {
+k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
+               const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
+               float* __restrict__ Hp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
-    stage_issue(S.W, S.Wp, S.Wd, wpack);
+    PairFwdSmem& S = *reinterpret_cast<PairFwdSmem*>(smem_raw);
+    const int P = info[0];
+    if ((int)blockIdx.x * TILE >= P) return;
+    stage_issue(S.W, S.Wp, nullptr, wpack);
     bool staged = false;
-    const int ntiles = (src.F + TILE - 1) / TILE;
-    const int objstride = src.T * D;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int f0 = tile * TILE;
-        const int nf = min(TILE, src.F - f0);
+    float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
+    for (int lo = blockIdx.x * TILE; lo < P; lo += gridDim.x * TILE) {
+        const int nrows = min(TILE, P - lo);
         __syncthreads();
-        if (threadIdx.x < TILE) {
-            const int r = threadIdx.x;
-            if (r < nf) {
-                const int s = src.foc_scene[f0 + r], o = src.foc_obj[f0 + r], t0 = src.foc_t0[f0 + r];
-                S.M.foff[r] = (long long)row_off(src, s, o, t0);
-                S.M.sbase[r] = (long long)row_off(src, s, 0, t0);
-                S.M.fobj[r] = o;
-                S.M.nbr[r] = nbr[f0 + r];
-            } else {
-                S.M.nbr[r] = 0;
-            }
-        }
+        load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
         __syncthreads();
-        load_focus_tile(S.Z, src.states, S.M.foff, nf);
-        scan_counts(S.M, nf);
+        gather_rows<LD>(S.Xf, states, S.M.frow, nrows);
+        gather_rows<LD>(S.Xc, states, S.M.crow, nrows);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        gemm_nt<7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
+        pair_chain_dense(S.Wp, S.Xf, S.Xc, nrows, bufs);
+        for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
+            const int r = idx / 13, c4 = idx - r * 13;
+            st4(Hp + (size_t)(lo + r) * 52 + 4 * c4, ld4(S.P1 + r * LD + 4 * c4));
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// K2b + K3: per-focus segmented sum of the pair outputs (fixed order -> deterministic), decoder, sigmoid split,
+// per-example losses.
+// ----------------------------------------------------------------------------------------------------------------
+struct DecFwdSmem {
+    float Wd[SW_DEC_TOTAL];
+    float Z[TILE * LD1];
+    float P0[TILE * LD];
+    float P1[TILE * LD];
+    float O[TILE * LD];
+    long long foff[TILE];
+    int pstart[TILE + 1];
+    WeightStage W;
+};
+
+__device__ __forceinline__ void focus_sums(float* sZ, const int* pstart, const float* __restrict__ Hp, int nf) {
+    for (int idx = threadIdx.x; idx < nf * 13; idx += NT) {
+        const int f = idx / 13, c4 = idx - f * 13;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = pstart[f]; p < pstart[f + 1]; ++p) {
+            const float4 v = ld4(Hp + (size_t)p * 52 + 4 * c4);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (c4 == 12) { a.z = 1.f; a.w = 0.f; }   // columns 50, 51: constant-1 column, pad
+        st4(sZ + f * LD1 + 4 * c4, a);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+k_dec_forward(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
+              const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wpack,
+              const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DecFwdSmem& S = *reinterpret_cast<DecFwdSmem*>(smem_raw);
+    stage_issue(S.W, nullptr, S.Wd, wpack);
+    bool staged = false;
+    float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
+    const int ntiles = (F + TILE - 1) / TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int f0 = tile * TILE;
+        const int nf = min(TILE, F - f0);
         __syncthreads();
-        const int P = S.M.start[TILE];
-        float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
-        for (int lo = 0; lo < P; lo += TILE) {
-            const int nrows = min(TILE, P - lo);
-            fill_pair_meta(S.M, nf, lo, objstride);
-            __syncthreads();
-            gather_rows<LD>(S.X, src.states, S.M.px, nrows, TILE);
-            __syncthreads();
-            pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
-            segmented_add<LD1>(S.Z, S.P1, S.M, nf, lo);
-            __syncthreads();
-        }
-        if (s_out) {
-            for (int idx = threadIdx.x; idx < nf * 52; idx += NT) {
-                const int r = idx / 52, n = idx - r * 52;
-                s_out[(size_t)(f0 + r) * 52 + n] = (n < H) ? S.Z[r * LD1 + n] : 0.f;
-            }
-        }
-        // decoder: u1 -> P0, u2 -> P1, u3 -> P0, u4 -> P1, o -> X
-        float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
-        decoder_forward(S.Wd, S.Z, ubufs, S.X);
+        if (threadIdx.x < nf) S.foff[threadIdx.x] = foc_row[f0 + threadIdx.x];
+        if (threadIdx.x <= nf) S.pstart[threadIdx.x] = pair_start[f0 + threadIdx.x];
+        __syncthreads();
+        load_focus_tile(S.Z, states, S.foff, nf);
+        __syncthreads();
+        focus_sums(S.Z, S.pstart, Hp, nf);
+        __syncthreads();
+        if (!staged) { stage_wait(S.W); staged = true; }
+        decoder_forward(S.Wd, S.Z, ubufs, S.O, nf);
         for (int idx = threadIdx.x; idx < nf * OUT; idx += NT) {
             const int r = idx / OUT, n = idx - r * OUT;
-            float v = S.X[r * LD + n];
+            float v = S.O[r * LD + n];
             if (n >= 6) v = 1.f / (1.f + expf(-v));   // Sigmoid on the property columns (modules.lua:80-86)
             pred[(size_t)(f0 + r) * OUT + n] = v;
         }
         if (loss_ex && y && threadIdx.x < nf) {
             const int r = threadIdx.x;
             const float* yy = y + (size_t)(f0 + r) * OUT;
-            const float e2 = S.X[r * LD + 2] - yy[2], e3 = S.X[r * LD + 3] - yy[3], e5 = S.X[r * LD + 5] - yy[5];
+            const float e2 = S.O[r * LD + 2] - yy[2], e3 = S.O[r * LD + 3] - yy[3], e5 = S.O[r * LD + 5] - yy[5];
             const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
             loss_ex[(size_t)(f0 + r) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);   // npe.lua:271-272
             loss_ex[(size_t)(f0 + r) * 3 + 1] = __fdiv_rn(lv, 2.f);                  // npe.lua:273
@@ -407,7 +449,7 @@ k_forward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ w
 }
 
 // Batch losses from the per-example ones (npe.lua:238-246): {sum/(3B), vel/(2B), angvel/B}; double accumulation like
-// THNN's accreal.  Also leaves the three raw sums in sums_out (for the data-parallel all-reduce).
+// THNN's accreal.
 __global__ void k_loss_reduce(const float* __restrict__ loss_ex, int F, float* __restrict__ loss3, double* __restrict__ sums_out) {
     __shared__ double sv[256], sw[256];
     double av = 0.0, aw = 0.0;
@@ -442,17 +484,14 @@ struct DecBwdSmem {
     float Da[TILE * LD];
     float Db[TILE * LD];
     long long foff[TILE];
+    int pstart[TILE + 1];
     WeightStage W;
 };
 
-__device__ __forceinline__ float4 relu_mask4(float4 v, const float* h) {
-    const float4 hv = ld4(h);
-    return make_float4(hv.x > 0.f ? v.x : 0.f, hv.y > 0.f ? v.y : 0.f, hv.z > 0.f ? v.z : 0.f, hv.w > 0.f ? v.w : 0.f);
-}
-
 __global__ void __launch_bounds__(NT, 1)
-k_dec_backward(FocusSrc src, const float* __restrict__ wpack, const float* __restrict__ y,
-               const float* __restrict__ s_in, float* __restrict__ ds_out, float* __restrict__ partial,
+k_dec_backward(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
+               const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wpack,
+               const float* __restrict__ y, float* __restrict__ ds_out, float* __restrict__ partial,
                float scale_v, float scale_w) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecBwdSmem& S = *reinterpret_cast<DecBwdSmem*>(smem_raw);
@@ -463,23 +502,21 @@ k_dec_backward(FocusSrc src, const float* __restrict__ wpack, const float* __res
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
     const int t = threadIdx.x;
-    const int ntiles = (src.F + TILE - 1) / TILE;
+    const int ntiles = (F + TILE - 1) / TILE;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int f0 = tile * TILE;
-        const int nf = min(TILE, src.F - f0);
+        const int nf = min(TILE, F - f0);
         __syncthreads();
-        if (t < nf) S.foff[t] = (long long)row_off(src, src.foc_scene[f0 + t], src.foc_obj[f0 + t], src.foc_t0[f0 + t]);
+        if (t < nf) S.foff[t] = foc_row[f0 + t];
+        if (t <= nf) S.pstart[t] = pair_start[f0 + t];
         __syncthreads();
-        load_focus_tile(S.Z, src.states, S.foff, nf);
-        __syncthreads();
-        for (int idx = t; idx < nf * H; idx += NT) {
-            const int r = idx / H, n = idx - r * H;
-            S.Z[r * LD1 + n] = s_in[(size_t)(f0 + r) * 52 + n];
-        }
+        load_focus_tile(S.Z, states, S.foff, nf);
         for (int idx = t; idx < TILE * LD; idx += NT) S.Da[idx] = 0.f;
         __syncthreads();
+        focus_sums(S.Z, S.pstart, Hp, nf);
+        __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        decoder_forward(S.Wd, S.Z, ubufs, S.O);
+        decoder_forward(S.Wd, S.Z, ubufs, S.O, nf);
         if (t < nf) {
             const float* yy = y + (size_t)(f0 + t) * OUT;
             S.Da[t * LD + 2] = (S.O[t * LD + 2] - yy[2]) * scale_v;
@@ -489,24 +526,24 @@ k_dec_backward(FocusSrc src, const float* __restrict__ wpack, const float* __res
         __syncthreads();
         // layer 5 (22 x 50): dz = Da (24 cols), input u4
         if (t >= 169 && t < 169 + 78) wgrad<13, LD, LD, true>(a5, S.Da, S.U[3], t - 169, nf);
-        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC5, 6, EpiNN{S.Db, LD, S.U[3], TILE});
+        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC5, 6, nf, EpiNN{S.Db, LD, S.U[3], TILE});
         __syncthreads();
         // layer 4: dz = Db, input u3
         if (t < 169) wgrad<13, LD, LD, true>(a4, S.Db, S.U[2], t, nf);
-        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, EpiNN{S.Da, LD, S.U[2], TILE});
+        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, nf, EpiNN{S.Da, LD, S.U[2], TILE});
         __syncthreads();
         // layer 3: dz = Da, input u2
         if (t < 169) wgrad<13, LD, LD, true>(a3, S.Da, S.U[1], t, nf);
-        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, EpiNN{S.Db, LD, S.U[1], TILE});
+        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, nf, EpiNN{S.Db, LD, S.U[1], TILE});
         __syncthreads();
         // layer 2: dz = Db, input u1
         if (t < 169) wgrad<13, LD, LD, true>(a2, S.Db, S.U[0], t, nf);
-        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2, 13, EpiNN{S.Da, LD, S.U[0], TILE});
+        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2, 13, nf, EpiNN{S.Da, LD, S.U[0], TILE});
         __syncthreads();
         // layer 1 (50 x 94 (+bias)): dz = Da, input z (24 k-chunks); input grad only for the pair-sum columns
         wgrad<24, LD, LD1, true>(a1a, S.Da, S.Z, t, nf);
         if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Da, S.Z, t + NT, nf);
-        gemm_nn<13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
+        gemm_nn<13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, nf, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
     }
     // write the register tiles into this CTA's partial (reference flat layout)
     float* out = partial + (size_t)blockIdx.x * NPARAM;
@@ -556,82 +593,59 @@ k_dec_backward(FocusSrc src, const float* __restrict__ wpack, const float* __res
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// K4b: pair-MLP backward (encoders + 5 pairwise layers).  32 foci per tile, 64 pair rows per sub-tile; forward is
-// recomputed in the tile (no activation round trip through HBM); masked pairs never enter (apply_mask on the
-// CAddTable gradient, npe.lua:326-328, is the identity on the active list).
+// K4b: pair-MLP backward on dense 64-pair tiles.  The forward chain is recomputed in the tile (no activation round
+// trip through HBM); dz5 = ds[focus(p)] * (h5 > 0) (CAddTable backward = copy; apply_mask is the identity on the
+// active list, npe.lua:326-328); weight-gradient tiles stay in registers for the whole kernel.
 // ----------------------------------------------------------------------------------------------------------------
-constexpr int FT_B = 32;
 struct PairBwdSmem {
     float Wp[SW_PAIR_TOTAL];
-    float X[TILE * LD];
+    float Xf[TILE * LD];
+    float Xc[TILE * LD];
     float Hh[NL + 1][TILE * LD];
     float Da[TILE * LD];
     float Db[TILE * LD];
-    float Fr[FT_B * LD];     // focus rows (44 valid)
-    float Ds[FT_B * LD];     // gradient into the pair sum
-    float Ef[FT_B * 28];     // focus half of the encoder output
-    float De[FT_B * 28];     // gradient into it (summed over the focus's pairs)
-    TileMeta M;
+    PairMeta M;
     WeightStage W;
 };
 
 __global__ void __launch_bounds__(NT, 1)
-k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restrict__ wpack,
+k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
+                const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
                 const float* __restrict__ ds_in, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairBwdSmem& S = *reinterpret_cast<PairBwdSmem*>(smem_raw);
-    stage_issue(S.W, S.Wp, nullptr, wpack);
-    bool staged = false;
-    float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
+    const int P = info[0];
+    const int t = threadIdx.x;
     float acc[NL][16];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
 #pragma unroll
         for (int i = 0; i < 16; ++i) acc[l][i] = 0.f;
-    const int t = threadIdx.x;
     const bool enc_thread = (t >= 169 && t < 169 + 77);
-    const int ntiles = (src.F + FT_B - 1) / FT_B;
-    const int objstride = src.T * D;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int f0 = tile * FT_B;
-        const int nf = min(FT_B, src.F - f0);
-        __syncthreads();
-        if (t < TILE) {
-            if (t < nf) {
-                const int s = src.foc_scene[f0 + t], o = src.foc_obj[f0 + t], t0 = src.foc_t0[f0 + t];
-                S.M.foff[t] = (long long)row_off(src, s, o, t0);
-                S.M.sbase[t] = (long long)row_off(src, s, 0, t0);
-                S.M.fobj[t] = o;
-                S.M.nbr[t] = nbr[f0 + t];
-            } else {
-                S.M.nbr[t] = 0;
-            }
-        }
-        __syncthreads();
-        gather_rows<LD>(S.Fr, src.states, S.M.foff, nf, FT_B);
-        for (int idx = t; idx < FT_B * LD; idx += NT) {
-            const int r = idx / LD, n = idx - r * LD;
-            S.Ds[idx] = (r < nf && n < H) ? ds_in[(size_t)(f0 + r) * 52 + n] : 0.f;
-        }
-        for (int idx = t; idx < FT_B * 28; idx += NT) S.De[idx] = 0.f;
-        scan_counts(S.M, nf);
-        __syncthreads();
-        if (!staged) { stage_wait(S.W); staged = true; }
-        gemm_nt<7, LD, LD, 1>(S.Fr, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
-        __syncthreads();
-        const int P = S.M.start[TILE];
-        for (int lo = 0; lo < P; lo += TILE) {
+    float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
+    if ((int)blockIdx.x * TILE < P) {
+        stage_issue(S.W, S.Wp, nullptr, wpack);
+        bool staged = false;
+        for (int lo = blockIdx.x * TILE; lo < P; lo += gridDim.x * TILE) {
             const int nrows = min(TILE, P - lo);
-            fill_pair_meta(S.M, nf, lo, objstride);
             __syncthreads();
-            gather_rows<LD>(S.X, src.states, S.M.px, nrows, TILE);
+            load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
             __syncthreads();
-            pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
+            gather_rows<LD>(S.Xf, states, S.M.frow, nrows);
+            gather_rows<LD>(S.Xc, states, S.M.crow, nrows);
+            __syncthreads();
+            if (!staged) { stage_wait(S.W); staged = true; }
+            pair_chain_dense(S.Wp, S.Xf, S.Xc, nrows, bufs);
             // dz5 = ds[focus] * (h5 > 0); rows >= nrows zero
             for (int idx = t; idx < TILE * (LD / 4); idx += NT) {
                 const int r = idx / (LD / 4), c4 = idx - r * (LD / 4);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < nrows && c4 < 13) v = relu_mask4(ld4(S.Ds + S.M.pf[r] * LD + 4 * c4), S.Hh[NL] + r * LD + 4 * c4);
+                if (r < nrows && c4 < 13) {
+                    v = ld4(ds_in + (size_t)S.M.pf[r] * 52 + 4 * c4);
+                    const float4 hv = ld4(S.Hh[NL] + r * LD + 4 * c4);
+                    v.x = hv.x > 0.f ? v.x : 0.f; v.y = hv.y > 0.f ? v.y : 0.f;
+                    v.z = hv.z > 0.f ? v.z : 0.f; v.w = hv.w > 0.f ? v.w : 0.f;
+                }
                 st4(S.Da + r * LD + 4 * c4, v);
             }
             __syncthreads();
@@ -641,24 +655,16 @@ k_pair_backward(FocusSrc src, const u64* __restrict__ nbr, const float* __restri
             for (int l = NL - 1; l >= 0; --l) {
                 const float* hin = S.Hh[l];
                 if (t < 169) wgrad<13, LD, LD, true>(acc[l], da, hin, t, nrows);
-                gemm_nn<13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, EpiNN{db, LD, hin, TILE});
+                gemm_nn<13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNN{db, LD, hin, TILE});
                 __syncthreads();
                 float* tmp = da; da = db; db = tmp;
             }
-            // da = dz0: cols 0..24 focus-encoder part, 25..49 context-encoder part
-            if (enc_thread) wgrad<11, LD, LD, false>(acc[0], da, S.X, t - 169, nrows, H2);
-            for (int idx = t; idx < nf * H2; idx += NT) {
-                const int f = idx / H2, n = idx - f * H2;
-                const int r0 = max(S.M.start[f], lo) - lo, r1 = min(S.M.start[f + 1], lo + TILE) - lo;
-                if (r1 > r0) {
-                    float a = S.De[f * 28 + n];
-                    for (int r = r0; r < r1; ++r) a += da[r * LD + n];
-                    S.De[f * 28 + n] = a;
-                }
+            // da = dz0: cols 0..24 -> focus encoder (input Xf), cols 25..49 -> context encoder (input Xc)
+            if (enc_thread) {
+                wgrad<11, LD, LD, false>(acc[0], da, S.Xc, t - 169, nrows, H2);
+                wgrad<11, LD, LD, true>(acc[1], da, S.Xf, t - 169, nrows, 0);
             }
-            __syncthreads();
         }
-        if (enc_thread) wgrad<11, 28, LD, true>(acc[1], S.De, S.Fr, t - 169, nf);
     }
     float* out = partial + (size_t)blockIdx.x * NPARAM;
     if (t < 169) {

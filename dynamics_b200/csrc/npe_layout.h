@@ -41,16 +41,18 @@ constexpr int LD1 = 104;
 constexpr int ZCOL_F = 52;          // decoder input z = [s(0..49) | 1 | 0 | this_past(52..95)]
 constexpr int ONE_COL = 50;
 
-constexpr int SW_ENC_T = 0;                       // 28 x 56
-constexpr int SW_ENC_C = SW_ENC_T + 28 * LD;      // 28 x 56
-constexpr int SW_PAIR = SW_ENC_C + 28 * LD;       // 5 x (52 x 56)
-constexpr int SW_PAIR_SZ = 52 * LD;
-constexpr int SW_PAIR_TOTAL = SW_PAIR + NL * SW_PAIR_SZ;          // 17696 floats = 70784 B
+// Weight tiles are padded to the row counts the thread mapping touches (output column n = cg + 8 i, cg < 8):
+// hidden layers 56 rows, encoders 32 rows, decoder output layer 24 rows; pad rows/columns are zero.
+constexpr int SW_ENC_T = 0;                       // 32 x 56
+constexpr int SW_ENC_C = SW_ENC_T + 32 * LD;      // 32 x 56
+constexpr int SW_PAIR = SW_ENC_C + 32 * LD;       // 5 x (56 x 56)
+constexpr int SW_PAIR_SZ = 56 * LD;
+constexpr int SW_PAIR_TOTAL = SW_PAIR + NL * SW_PAIR_SZ;          // 19264 floats = 77056 B
 
-constexpr int SW_DEC1 = 0;                        // 52 x 104
-constexpr int SW_DEC2 = SW_DEC1 + 52 * LD1;       // 3 x (52 x 56)
+constexpr int SW_DEC1 = 0;                        // 56 x 104
+constexpr int SW_DEC2 = SW_DEC1 + 56 * LD1;       // 3 x (56 x 56)
 constexpr int SW_DEC5 = SW_DEC2 + 3 * SW_PAIR_SZ; // 24 x 56
-constexpr int SW_DEC_TOTAL = SW_DEC5 + 24 * LD;   // 15488 floats = 61952 B
+constexpr int SW_DEC_TOTAL = SW_DEC5 + 24 * LD;   // 16576 floats = 66304 B
 
 constexpr int TILE = 64;            // rows (foci or pairs) per shared-memory tile
 constexpr int NT = 256;             // threads per CTA

@@ -15,16 +15,24 @@
 
 namespace npe {
 
+struct RollMeta {
+    u64 nbr[TILE];            // active-context bits per slot
+    int start[TILE + 1];      // exclusive scan of active-pair counts
+    int pf[TILE];             // per pair row: focus slot
+    int px[TILE];             // per pair row: context slot
+};
+
 struct RollSmem {
     float Wp[SW_PAIR_TOTAL];
     float Wd[SW_DEC_TOTAL];
     float Z[TILE * LD1];      // cols 52..95 hold the window [frame0 | frame1] of every object slot
     float Ef[TILE * 28];
-    float X[TILE * LD];
     float P0[TILE * LD];
-    float P1[TILE * LD];
+    float P1[TILE * LD];      // also the gathered context rows X (dead once h0 is built)
+    float O[TILE * LD];
     float New[TILE * 24];
-    TileMeta M;
+    RollMeta M;
+    long long foff[TILE];
     int kind[TILE];           // 0 = empty slot, 1 = predicted focus, 2 = obstacle
     double red[7][NT / 32];
     WeightStage W;
@@ -46,7 +54,6 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
     RollSmem& S = *reinterpret_cast<RollSmem*>(smem_raw);
     stage_issue(S.W, S.Wp, S.Wd, A.wpack);
     bool staged = false;
-    float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
     float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int G = TILE / A.Nmax;
@@ -64,14 +71,14 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
             int kind = 0;
             if (t < nslots && o < A.n_obj[s0 + g]) kind = 1;
             S.kind[t] = kind;
-            S.M.foff[t] = (((long long)(s0 + min(g, ns - 1)) * A.Nmax + o) * A.T + A.t0) * D;
+            S.foff[t] = (((long long)(s0 + min(g, ns - 1)) * A.Nmax + o) * A.T + A.t0) * D;
         }
         __syncthreads();
         for (int idx = t; idx < TILE * LD1; idx += NT) S.Z[idx] = 0.f;
         __syncthreads();
         for (int idx = t; idx < TILE * IN; idx += NT) {
             const int r = idx / IN, c = idx - r * IN;
-            if (S.kind[r]) S.Z[r * LD1 + ZCOL_F + c] = A.states[S.M.foff[r] + c];
+            if (S.kind[r]) S.Z[r * LD1 + ZCOL_F + c] = A.states[S.foff[r] + c];
         }
         __syncthreads();
         if (t < TILE && S.kind[t] && S.Z[t * LD1 + ZCOL_F + D + 11] == 1.f) S.kind[t] = 2;   // oid one-hot: obstacle
@@ -84,11 +91,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                     const int g = r / A.Nmax, o = r - g * A.Nmax;
                     warp_pairs(S.Z + (g * A.Nmax) * LD1 + ZCOL_F + D, LD1, A.n_obj[s0 + g], o, A.kmax, A.thr_px, keep, nbr);
                 }
-                if (lane == 0) {
-                    S.M.nbr[r] = nbr;
-                    S.M.fobj[r] = r % A.Nmax;
-                    S.M.sbase[r] = (long long)(r / A.Nmax) * A.Nmax;   // slot of object 0 of the scene
-                }
+                if (lane == 0) S.M.nbr[r] = nbr;
             }
             for (int idx = t; idx < TILE * 26; idx += NT) {
                 const int r = idx / 26, c2 = idx - r * 26;
@@ -97,45 +100,71 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                 *reinterpret_cast<float2*>(S.Z + r * LD1 + 2 * c2) = v;
             }
             __syncthreads();
-            scan_counts(S.M, TILE);
+            if (t == 0) {
+                int acc = 0;
+                for (int f = 0; f < TILE; ++f) { S.M.start[f] = acc; acc += __popcll(S.M.nbr[f]); }
+                S.M.start[TILE] = acc;
+            }
             if (!staged) { stage_wait(S.W); staged = true; }
-            gemm_nt<7, LD1, LD, 2>(S.Z + ZCOL_F, S.Wp + SW_ENC_T, 11, EpiNT{S.Ef, 28, 28, 1});
+            // focus half of the encoder once per focus
+            gemm_nt<4, LD1, LD>(S.Z + ZCOL_F, S.Wp + SW_ENC_T, 11, TILE, EpiNT{S.Ef, 28, 28, 1});
             __syncthreads();
             const int P = S.M.start[TILE];
             for (int lo = 0; lo < P; lo += TILE) {
                 const int nrows = min(TILE, P - lo);
-                // pair metadata: px = slot index of the context object
                 if (t < TILE) {
                     u64 bits = S.M.nbr[t];
                     int pos = S.M.start[t] - lo;
+                    const int fo = t % A.Nmax, sb = (t / A.Nmax) * A.Nmax;
                     while (bits) {
                         const int c = __ffsll((long long)bits) - 1;
                         bits &= bits - 1;
-                        if (pos >= 0 && pos < TILE) {
-                            S.M.pf[pos] = t;
-                            S.M.px[pos] = S.M.sbase[t] + c + (c >= S.M.fobj[t]);
-                        }
+                        if (pos >= 0 && pos < TILE) { S.M.pf[pos] = t; S.M.px[pos] = sb + c + (c >= fo); }
                         ++pos;
                     }
                 }
                 __syncthreads();
+                // X (context rows) -> P1; h0 -> P0 = [Ef[focus] | relu(Wc x) | 0]
                 for (int idx = t; idx < TILE * (IN / 4); idx += NT) {
                     const int r = idx / (IN / 4), c4 = idx - r * (IN / 4);
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nrows) v = ld4(S.Z + (int)S.M.px[r] * LD1 + ZCOL_F + 4 * c4);
-                    st4(S.X + r * LD + 4 * c4, v);
+                    if (r < nrows) v = ld4(S.Z + S.M.px[r] * LD1 + ZCOL_F + 4 * c4);
+                    st4(S.P1 + r * LD + 4 * c4, v);
+                }
+                for (int idx = t; idx < TILE * 32; idx += NT) {
+                    const int r = idx >> 5, n = idx & 31;
+                    if (n < H2) S.P0[r * LD + n] = (r < nrows) ? S.Ef[S.M.pf[r] * 28 + n] : 0.f;
+                    else if (n >= 26) S.P0[r * LD + (n - 26) + H] = 0.f;
                 }
                 __syncthreads();
-                pair_chain_forward(S.Wp, S.X, S.Ef, 28, S.M.pf, nrows, bufs);
-                segmented_add<LD1>(S.Z, S.P1, S.M, TILE, lo);
+                gemm_nt<4, LD, LD>(S.P1, S.Wp + SW_ENC_C, 11, nrows, EpiNT{S.P0 + H2, LD, H2, 1});
+                __syncthreads();
+                float* hin = S.P0;
+                float* hout = S.P1;
+#pragma unroll 1
+                for (int l = 0; l < NL; ++l) {
+                    gemm_nt<7, LD, LD>(hin, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{hout, LD, 52, 1});
+                    __syncthreads();
+                    float* tmp = hin; hin = hout; hout = tmp;
+                }
+                // h5 is in `hin` (= P1 after five swaps); fixed-order segmented add into the pair-sum columns
+                for (int idx = t; idx < TILE * H; idx += NT) {
+                    const int f = idx / H, n = idx - f * H;
+                    const int r0 = max(S.M.start[f], lo) - lo, r1 = min(S.M.start[f + 1], lo + TILE) - lo;
+                    if (r1 > r0) {
+                        float a = S.Z[f * LD1 + n];
+                        for (int r = r0; r < r1; ++r) a += hin[r * LD + n];
+                        S.Z[f * LD1 + n] = a;
+                    }
+                }
                 __syncthreads();
             }
-            decoder_forward(S.Wd, S.Z, ubufs, S.X);
+            decoder_forward(S.Wd, S.Z, ubufs, S.O, TILE);
             // ---- post-process, metrics ----
             double mt[7] = {0, 0, 0, 0, 0, 0, 0};
             if (t < TILE && S.kind[t]) {
                 const float* last = S.Z + t * LD1 + ZCOL_F + D;
-                const float* o = S.X + t * LD;
+                const float* o = S.O + t * LD;
                 const int g = t / A.Nmax, ob = t - g * A.Nmax;
                 const float* gt = A.use_gt ? A.states + ((((size_t)(s0 + g) * A.Nmax + ob) * A.T) + A.t0 + 2 + step) * D : nullptr;
                 float q[D];

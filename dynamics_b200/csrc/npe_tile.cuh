@@ -1,29 +1,28 @@
-// CTA-cooperative FP32 tile micro-kernels over shared memory (256 threads, 64- or 32-row tiles).
+// CTA-cooperative FP32 tile micro-kernels over shared memory (256 threads, 64-row tiles).
 //
 //   gemm_nt : C[r][n]  = act(sum_k A[r][k] * W[n][k])        (forward;    both operands k-contiguous)
 //   gemm_nn : dA[r][k] = mask(sum_n dZ[r][n] * W[n][k])      (input grad; W rows contiguous in the OUTPUT index)
 //   wgrad   : dW[n][k] += sum_r dZ[r][n] * Hm[r][k]          (weight grad; per-thread 4x4 register tile, persistent)
 //
-// Thread mapping for the two GEMMs (tid = threadIdx.x):  ks = tid & 1 (split of the reduction index),
-// cg = (tid >> 1) & 3 (output-column group), rg = tid >> 3 (row group, 0..31).  A thread owns rows {rg, rg + 32}
-// (RPT = 2) or {rg} (RPT = 1) and output columns {cg + 4 i}; the two ks lanes are adjacent and exchange partial
-// sums with one shuffle per output, after which lane ks finalises row rg + 32 * ks (RPT = 2) / both hold row rg.
+// Thread mapping of the two GEMMs (tid = threadIdx.x):  ks = tid & 1 (2-way split of the reduction index, adjacent
+// lanes), cg = (tid >> 1) & 7 (output-column group), rg = tid >> 4 (row group, 0..15).  A thread owns the FOUR rows
+// {rg + 16 j} and output columns {cg + 8 i}; the two ks lanes exchange partial sums with one shuffle per output and
+// lane ks finalises rows j in {2 ks, 2 ks + 1}.
 //
-// Code size matters more than unrolling here: the first version inlined one fully unrolled GEMM per layer (190-220 KB
-// of SASS per kernel) and ncu showed "no instruction" (instruction-cache miss) as the top stall with 2 warps per
-// scheduler.  The GEMMs are therefore __noinline__, shared by all layers (runtime pointers + a runtime epilogue
-// descriptor), and the reduction loop is unrolled only twice (~4 KB bodies, inside the 32 KB L1.5 I-cache).
+// Why 4 rows per thread: the shared-memory crossbar delivers 128 B/clk/SM to lanes and an LDS.128 costs 4 wavefronts
+// per warp whether or not lanes broadcast (measured: 3.4 wavefronts per LDS.128, tools/microbench/gemm_pass), so the
+// loaded bytes per FMA decide the speed: 64x52x52 costs 5408 * (1/RT + 1/CT) LDS cycles for an RT x CT register tile
+// (2x13: 3120, measured 3881 cycles/pass; 4x7: 2124) against 1352 FMA cycles.
+// Why __noinline__ + runtime epilogue: one fully unrolled GEMM per layer made 190-220 KB of SASS per kernel and the
+// top stall was instruction fetch (ncu: no_instruction 3.3 per issue at 2 warps/scheduler).
 #pragma once
 #include "npe_layout.h"
 
 namespace npe {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float dot4(float4 a, float4 b, float c) {
-    c = fmaf(a.x, b.x, c); c = fmaf(a.y, b.y, c); c = fmaf(a.z, b.z, c); c = fmaf(a.w, b.w, c);
-    return c;
-}
 __device__ __forceinline__ void axpy4(float4& acc, float a, float4 w) {
     acc.x = fmaf(a, w.x, acc.x); acc.y = fmaf(a, w.y, acc.y); acc.z = fmaf(a, w.z, acc.z); acc.w = fmaf(a, w.w, acc.w);
 }
@@ -36,55 +35,56 @@ struct EpiNT {
     int relu;
 };
 
-// C[r][cg + 4 i] for i < NI; reduction over kc chunks of 4.
-template <int NI, int LDA, int LDW, int RPT>
-__device__ __noinline__ void gemm_nt(const float* __restrict__ A, const float* __restrict__ W, int kc, EpiNT e) {
+// C[rg + 16 j][cg + 8 i] for j < 4, i < NI; reduction over kc chunks of 4.  Rows >= 16 * jmax are skipped.
+template <int NI, int LDA, int LDW>
+__device__ __noinline__ void gemm_nt(const float* __restrict__ A, const float* __restrict__ W, int kc, int nrows, EpiNT e) {
     const int tid = threadIdx.x;
-    const int ks = tid & 1, cg = (tid >> 1) & 3, rg = tid >> 3;
-    float acc0[NI], acc1[NI];
+    const int ks = tid & 1, cg = (tid >> 1) & 7, rg = tid >> 4;
+    const int jmax = (nrows + 15) >> 4;
+    float acc[4][NI];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
-    const float* a0 = A + rg * LDA + 4 * ks;
-    const float* a1 = a0 + 32 * LDA;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[j][i] = 0.f;
+    const float* a = A + rg * LDA + 4 * ks;
     const float* w = W + cg * LDW + 4 * ks;
 #pragma unroll 1
     for (int c = ks; c < kc; c += 2) {
-        const float4 x0 = ld4(a0);
-        float4 x1 = x0;
-        if (RPT == 2) x1 = ld4(a1);
-        float4 wv[NI];
+        float4 x[4], wv[NI];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) wv[i] = ld4(w + 4 * i * LDW);
-        // component-major order: consecutive FMAs hit different accumulators (dependency distance 2 NI), which is
-        // what hides the 4-cycle FMA latency with only two warps per scheduler
+        for (int j = 0; j < 4; ++j) x[j] = (j < jmax) ? ld4(a + 16 * j * LDA) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) { acc0[i] = fmaf(x0.x, wv[i].x, acc0[i]); if (RPT == 2) acc1[i] = fmaf(x1.x, wv[i].x, acc1[i]); }
+        for (int i = 0; i < NI; ++i) wv[i] = ld4(w + 8 * i * LDW);
+        // component-major: consecutive FMAs hit different accumulators (dependency distance 4 NI)
 #pragma unroll
-        for (int i = 0; i < NI; ++i) { acc0[i] = fmaf(x0.y, wv[i].y, acc0[i]); if (RPT == 2) acc1[i] = fmaf(x1.y, wv[i].y, acc1[i]); }
+        for (int i = 0; i < NI; ++i)
 #pragma unroll
-        for (int i = 0; i < NI; ++i) { acc0[i] = fmaf(x0.z, wv[i].z, acc0[i]); if (RPT == 2) acc1[i] = fmaf(x1.z, wv[i].z, acc1[i]); }
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].x, wv[i].x, acc[j][i]);
 #pragma unroll
-        for (int i = 0; i < NI; ++i) { acc0[i] = fmaf(x0.w, wv[i].w, acc0[i]); if (RPT == 2) acc1[i] = fmaf(x1.w, wv[i].w, acc1[i]); }
-        a0 += 8; a1 += 8; w += 8;
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].y, wv[i].y, acc[j][i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].z, wv[i].z, acc[j][i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].w, wv[i].w, acc[j][i]);
+        a += 8; w += 8;
     }
     __syncwarp();
-    if (RPT == 2) {
-        float* o = e.out + (rg + 32 * ks) * e.ldo + cg;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+        float* o = e.out + (rg + 16 * (2 * ks + jj)) * e.ldo + cg;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-            const float send = ks ? acc0[i] : acc1[i];
+            const float send = ks ? acc[jj][i] : acc[2 + jj][i];
             const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            float mine = (ks ? acc1[i] : acc0[i]) + recv;
+            float mine = (ks ? acc[2 + jj][i] : acc[jj][i]) + recv;
             if (e.relu) mine = fmaxf(mine, 0.f);
-            if (cg + 4 * i < e.nmax) o[4 * i] = mine;
-        }
-    } else {
-        float* o = e.out + rg * e.ldo + cg;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            float tot = acc0[i] + __shfl_xor_sync(0xffffffffu, acc0[i], 1);
-            if (e.relu) tot = fmaxf(tot, 0.f);
-            if ((i & 1) == ks && cg + 4 * i < e.nmax) o[4 * i] = tot;
+            if (cg + 8 * i < e.nmax) o[8 * i] = mine;
         }
     }
 }
@@ -98,51 +98,63 @@ struct EpiNN {
     int nrows;
 };
 
-// dA[r][4 kc .. 4 kc + 3] for kc = cg + 4 m < KCO; reduction over nc chunks of 4 n (ks lane takes n = 4 q + 2 ks + {0,1}).
+// dA[rg + 16 j][4 kc .. 4 kc + 3] for kc = cg + 8 m < KCO; reduction over nc chunks of 4 n (ks lane takes
+// n = 4 q + 2 ks + {0, 1}).
 template <int KCO, int LDZ, int LDW>
-__device__ __noinline__ void gemm_nn(const float* __restrict__ dZ, const float* __restrict__ W, int nc, EpiNN e) {
-    constexpr int MI = (KCO + 3) / 4;
+__device__ __noinline__ void gemm_nn(const float* __restrict__ dZ, const float* __restrict__ W, int nc, int nrows, EpiNN e) {
+    constexpr int MI = (KCO + 7) / 8;
     const int tid = threadIdx.x;
-    const int ks = tid & 1, cg = (tid >> 1) & 3, rg = tid >> 3;
-    float4 acc0[MI], acc1[MI];
+    const int ks = tid & 1, cg = (tid >> 1) & 7, rg = tid >> 4;
+    const int jmax = (nrows + 15) >> 4;
+    float4 acc[4][MI];
 #pragma unroll
-    for (int m = 0; m < MI; ++m) { acc0[m] = make_float4(0.f, 0.f, 0.f, 0.f); acc1[m] = acc0[m]; }
-    const float* z0p = dZ + rg * LDZ + 2 * ks;
-    const float* z1p = z0p + 32 * LDZ;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < MI; ++m) acc[j][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* zp = dZ + rg * LDZ + 2 * ks;
     const float* wa = W + (2 * ks) * LDW + 4 * cg;
 #pragma unroll 1
     for (int q = 0; q < nc; ++q) {
-        const float2 z0 = *reinterpret_cast<const float2*>(z0p), z1 = *reinterpret_cast<const float2*>(z1p);
+        float2 z[4];
         float4 w0[MI], w1[MI];
 #pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = (j < jmax) ? ld2(zp + 16 * j * LDZ) : make_float2(0.f, 0.f);
+#pragma unroll
         for (int m = 0; m < MI; ++m) {
-            if (cg + 4 * m < KCO) { w0[m] = ld4(wa + 16 * m); w1[m] = ld4(wa + LDW + 16 * m); }
+            if (cg + 8 * m < KCO) { w0[m] = ld4(wa + 32 * m); w1[m] = ld4(wa + LDW + 32 * m); }
             else { w0[m] = make_float4(0.f, 0.f, 0.f, 0.f); w1[m] = w0[m]; }
         }
 #pragma unroll
-        for (int m = 0; m < MI; ++m) { axpy4(acc0[m], z0.x, w0[m]); axpy4(acc1[m], z1.x, w0[m]); }
+        for (int m = 0; m < MI; ++m)
 #pragma unroll
-        for (int m = 0; m < MI; ++m) { axpy4(acc0[m], z0.y, w1[m]); axpy4(acc1[m], z1.y, w1[m]); }
-        z0p += 4; z1p += 4; wa += 4 * LDW;
+            for (int j = 0; j < 4; ++j) axpy4(acc[j][m], z[j].x, w0[m]);
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) axpy4(acc[j][m], z[j].y, w1[m]);
+        zp += 4; wa += 4 * LDW;
     }
     __syncwarp();
-    const int row = rg + 32 * ks;
 #pragma unroll
-    for (int m = 0; m < MI; ++m) {
-        const float4 s = ks ? acc0[m] : acc1[m];
-        float4 r;
-        r.x = __shfl_xor_sync(0xffffffffu, s.x, 1); r.y = __shfl_xor_sync(0xffffffffu, s.y, 1);
-        r.z = __shfl_xor_sync(0xffffffffu, s.z, 1); r.w = __shfl_xor_sync(0xffffffffu, s.w, 1);
-        const float4 o = ks ? acc1[m] : acc0[m];
-        const int kc = cg + 4 * m;
-        if (kc < KCO && row < e.nrows) {
-            float4 v = make_float4(o.x + r.x, o.y + r.y, o.z + r.z, o.w + r.w);
-            if (e.hmask) {
-                const float4 hv = ld4(e.hmask + row * LD + 4 * kc);
-                v.x = hv.x > 0.f ? v.x : 0.f; v.y = hv.y > 0.f ? v.y : 0.f;
-                v.z = hv.z > 0.f ? v.z : 0.f; v.w = hv.w > 0.f ? v.w : 0.f;
+    for (int jj = 0; jj < 2; ++jj) {
+        const int row = rg + 16 * (2 * ks + jj);
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const float4 s = ks ? acc[jj][m] : acc[2 + jj][m];
+            float4 r;
+            r.x = __shfl_xor_sync(0xffffffffu, s.x, 1); r.y = __shfl_xor_sync(0xffffffffu, s.y, 1);
+            r.z = __shfl_xor_sync(0xffffffffu, s.z, 1); r.w = __shfl_xor_sync(0xffffffffu, s.w, 1);
+            const float4 o = ks ? acc[2 + jj][m] : acc[jj][m];
+            const int kc = cg + 8 * m;
+            if (kc < KCO && row < e.nrows) {
+                float4 v = make_float4(o.x + r.x, o.y + r.y, o.z + r.z, o.w + r.w);
+                if (e.hmask) {
+                    const float4 hv = ld4(e.hmask + row * LD + 4 * kc);
+                    v.x = hv.x > 0.f ? v.x : 0.f; v.y = hv.y > 0.f ? v.y : 0.f;
+                    v.z = hv.z > 0.f ? v.z : 0.f; v.w = hv.w > 0.f ? v.w : 0.f;
+                }
+                st4(e.out + (size_t)row * e.ldo + 4 * kc, v);
             }
-            st4(e.out + (size_t)row * e.ldo + 4 * kc, v);
         }
     }
 }

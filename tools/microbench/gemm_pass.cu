@@ -5,7 +5,7 @@
 using namespace npe;
 
 struct Smem {
-    float W[52 * LD];
+    float W[56 * LD];
     float A[TILE * LD];
     float B[TILE * LD];
     float C[TILE * LD];
@@ -15,7 +15,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NT, 1) k(long long* out, int iters) {
     extern __shared__ __align__(16) unsigned char raw[];
     Smem& S = *reinterpret_cast<Smem*>(raw);
-    for (int i = threadIdx.x; i < 52 * LD; i += NT) S.W[i] = 0.001f * (i % 97);
+    for (int i = threadIdx.x; i < 56 * LD; i += NT) S.W[i] = 0.001f * (i % 97);
     for (int i = threadIdx.x; i < TILE * LD; i += NT) { S.A[i] = 0.01f * (i % 13); S.B[i] = 0.f; S.C[i] = 0.02f; }
     __syncthreads();
     float acc[16];
@@ -23,14 +23,14 @@ __global__ void __launch_bounds__(NT, 1) k(long long* out, int iters) {
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         if (MODE == 0) {
-            gemm_nt<13, LD, LD, 2>(S.A, S.W, 13, EpiNT{S.B, LD, 52, 1});
+            gemm_nt<7, LD, LD>(S.A, S.W, 13, TILE, EpiNT{S.B, LD, 52, 1});
             __syncthreads();
-            gemm_nt<13, LD, LD, 2>(S.B, S.W, 13, EpiNT{S.A, LD, 52, 1});
+            gemm_nt<7, LD, LD>(S.B, S.W, 13, TILE, EpiNT{S.A, LD, 52, 1});
             __syncthreads();
         } else if (MODE == 1) {
-            gemm_nn<13, LD, LD>(S.A, S.W, 13, EpiNN{S.B, LD, S.C, TILE});
+            gemm_nn<13, LD, LD>(S.A, S.W, 13, TILE, EpiNN{S.B, LD, S.C, TILE});
             __syncthreads();
-            gemm_nn<13, LD, LD>(S.B, S.W, 13, EpiNN{S.A, LD, S.C, TILE});
+            gemm_nn<13, LD, LD>(S.B, S.W, 13, TILE, EpiNN{S.A, LD, S.C, TILE});
             __syncthreads();
         } else {
             if (threadIdx.x < 169) wgrad<13, LD, LD, true>(acc, S.A, S.C, threadIdx.x, TILE);
