@@ -231,14 +231,14 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
                                "foci_per_step": F, "active_pairs_per_step": P},
                     "step_tflops": STEP_FLOPS(F, P) * steps / (ms * 1e-3) / 1e12})
         kern = {}
-        for k in ("forward", "dec_backward", "pair_backward"):
+        for k in ("build_pairs", "forward", "dec_backward", "pair_backward", "reduce", "optim"):
             m.profile_select(k)
             for s in range(4):
                 step(s)
             n, tot = m.profile_read()
             kern[k] = tot / max(n, 1)
         m.profile_select(None)
-        dom = max(kern, key=kern.get)
+        dom = max(("forward", "dec_backward", "pair_backward"), key=lambda k: kern[k])
         ach = KERNEL_FLOPS[dom](F, P) / (kern[dom] * 1e-3) / 1e12
         out["kernel_ms"] = kern
         out["roofline"] = {"kernel": "k_" + dom, "bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS,

@@ -14,6 +14,7 @@
 #include "../../include/npe_cuda.h"
 #include "npe_kernels.cuh"
 #include "npe_rollout.cuh"
+#include "npe_tc.cuh"
 
 using namespace npe;
 
@@ -85,6 +86,12 @@ struct npe_handle {
     float rms_m_init = 0.f;
     float* partial = nullptr;         // [num_sms][NPARAM]
     float* wpack = nullptr;           // packed (shared-memory layout) weight image, kept in sync with params
+    float* wtc = nullptr;             // tensor-core (K-major canonical layout, TF32-rounded) weight image
+    bool wtc_dirty = true;
+    int precision = 0, rollout_mode = 0;
+    DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
+    DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
+    int roll_F = 0;
     float* loss3_dev = nullptr;
     double* loss_sums_dev = nullptr;
 
@@ -103,7 +110,7 @@ struct npe_handle {
     // per-batch buffers
     DevBuf<float> y, pred, loss_ex, ds, this_rows, Hp;
     DevBuf<u64> keep, nbr;
-    DevBuf<int> cnt, pair_start, pair_foc;
+    DevBuf<int> cnt, block_sums, pair_start, pair_foc;   // cnt = CTA-local exclusive prefix of active counts
     DevBuf<long long> foc_row, pair_crow;
     int pair_cap = 0;
     int* info_dev = nullptr;          // {P, overflow}
@@ -200,6 +207,7 @@ int ensure_batch_buffers(npe_handle* h, int F) {
     CK(h->keep.ensure(F));
     CK(h->nbr.ensure(F));
     CK(h->cnt.ensure(F));
+    CK(h->block_sums.ensure((size_t)(F + FPB - 1) / FPB));
     CK(h->foc_row.ensure(F));
     CK(h->pair_start.ensure((size_t)F + 1));
     // dense active-pair list: capacity = F * min(context slots, 16).  Non-overlapping radius-60 discs cannot have more
@@ -222,11 +230,13 @@ int build_pairs(npe_handle* h) {
     const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
-        k_build_pairs<<<(h->F + 7) / 8, NT, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
-                                                            h->foc_row.p, h->batch_form ? nullptr : h->y.p, h->active_total);
+        const int nblk = (h->F + FPB - 1) / FPB;
+        k_build_pairs<<<nblk, NT, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
+                                                  h->block_sums.p, h->foc_row.p, h->batch_form ? nullptr : h->y.p,
+                                                  h->active_total);
         h->launches++;
-        k_scan_expand<<<1, 1024, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->pair_start.p, h->pair_foc.p,
-                                                 h->pair_crow.p, h->pair_cap, h->info_dev);
+        k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
+                                                          h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -248,24 +258,51 @@ int pair_grid(const npe_handle* h) {
     return (int)(tiles < h->num_sms ? (tiles > 0 ? tiles : 1) : h->num_sms);
 }
 
-int run_forward(npe_handle* h, bool training) {
-    int rc = build_pairs(h);
-    if (rc) return rc;
-    const int ntiles = (h->F + TILE - 1) / TILE;
+int refresh_wtc(npe_handle* h) {
+    if (!h->wtc_dirty) return NPE_OK;
+    k_pack_tc_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc);
+    CKL();
+    h->wtc_dirty = false;
+    return NPE_OK;
+}
+
+// pair MLP + decoder forward on the current pair list; `st` = scene tensor the row offsets point into
+int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, bool tc) {
+    const int ntiles = (F + TILE - 1) / TILE;
     const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
-    {
-        ProfScope ps__(h, NPE_K_FORWARD);
-        k_pair_forward<<<pair_grid(h), NT, sizeof(PairFwdSmem), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
-                                                                          h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
+    ProfScope ps__(h, NPE_K_FORWARD);
+    if (tc) {
+        int rc = refresh_wtc(h);
+        if (rc) return rc;
+        const long long ptiles = ((long long)h->pair_cap + 127) / 128;
+        const int pg = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
+        const int ft = (F + 127) / 128;
+        k_pair_forward_tc<<<pg, NT, sizeof(PairTcSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                   h->info_dev, h->wtc, h->Hp.p);
         h->launches++;
-        k_dec_forward<<<grid, NT, sizeof(DecFwdSmem), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p, h->Hp.p,
-                                                                   h->wpack, h->have_y ? h->y.p : nullptr, h->pred.p,
-                                                                   h->have_y ? h->loss_ex.p : nullptr);
+        k_dec_forward_tc<<<ft < h->num_sms ? ft : h->num_sms, NT, sizeof(DecTcSmem), h->stream>>>(
+            st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y, h->pred.p, loss_ex);
+        h->launches++;
+    } else {
+        k_pair_forward<<<pair_grid(h), NT, sizeof(PairFwdSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                          h->info_dev, h->wpack, h->Hp.p);
+        h->launches++;
+        k_dec_forward<<<grid, NT, sizeof(DecFwdSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y,
+                                                                   h->pred.p, loss_ex);
         h->launches++;
     }
     CK(cudaGetLastError());
-    h->fwd_valid = true;
-    (void)training;
+    return NPE_OK;
+}
+
+// training == true: the FP32 kernels always (backward recomputes from the FP32 pair outputs)
+int run_forward(npe_handle* h, bool training) {
+    int rc = build_pairs(h);
+    if (rc) return rc;
+    const bool tc = !training && h->precision == NPE_PRECISION_TF32_TC;
+    rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc);
+    if (rc) return rc;
+    h->fwd_valid = !tc;
     return NPE_OK;
 }
 
@@ -306,6 +343,7 @@ int run_backward(npe_handle* h, int divisor_batch) {
 
 int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
+    h->wtc_dirty = true;
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
     { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, h->wpack, NPARAM, b1, (float)(1.0 - (double)b1), b2, (float)(1.0 - (double)b2), eps, step);
@@ -315,6 +353,7 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
 }
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
+    h->wtc_dirty = true;
     { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, h->wpack, NPARAM, alpha, (float)(1.0 - (double)alpha), eps, lr);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
@@ -390,6 +429,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->partial, (size_t)h->num_sms * NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->wpack, WPACK_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     k_pack_zero<<<(WPACK_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wpack);
+    if ((e = cudaMalloc((void**)&h->wtc, TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    k_pack_tc_zero<<<(TC_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wtc);
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -400,7 +441,9 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_dec_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess)
         return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
     *out = h;
     return NPE_OK;
@@ -411,16 +454,17 @@ int npe_destroy(npe_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack};
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
     if (h->info_dev) cudaFree(h->info_dev);
-    h->cnt.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
+    h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->this_rows.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release();
+    h->roll.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -438,6 +482,7 @@ int npe_params_set(npe_handle* h, const float* host, int32_t n) {
     CKL();
     CK(cudaStreamSynchronize(h->stream));
     h->fwd_valid = false;
+    h->wtc_dirty = true;
     return NPE_OK;
 }
 int npe_params_get(npe_handle* h, float* host, int32_t n) {
@@ -623,7 +668,7 @@ int npe_build_pairs(npe_handle* h, int32_t* ctx_idx_out, uint8_t* mask_out, int3
 int npe_forward(npe_handle* h, float* pred_out, float* loss3_out) {
     NEED(h);
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
-    int rc = run_forward(h, true);
+    int rc = run_forward(h, h->precision != NPE_PRECISION_TF32_TC);
     if (rc) return rc;
     if (loss3_out) {
         if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
@@ -724,9 +769,83 @@ static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teache
     return NPE_OK;
 }
 
+// Rollout as a host loop of kernels over a window tensor in HBM (large scene counts; the tcgen05 variant).
+static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int teacher, bool want_traj, bool want_metrics) {
+    if (h->batch_form || h->S == 0) return fail(h, NPE_ERR_STATE, "rollout: upload scenes first");
+    if (steps <= 0 || t0 < 0 || t0 + 2 > h->T) return fail(h, NPE_ERR_INVALID, "rollout: bad t0/steps");
+    if (use_gt && t0 + 2 + steps > h->T)
+        return fail(h, NPE_ERR_INVALID, "rollout: %d steps need %d frames of ground truth, scenes have %d", steps, t0 + 2 + steps, h->T);
+    const int SN = h->S * h->Nmax;
+    // foci = every non-obstacle object, window at t0 = 0 of the roll tensor
+    std::vector<int> fs, fo, fmap((size_t)SN, -1);
+    for (int s = 0; s < h->S; ++s)
+        for (int o : h->scene_foci[s]) { fmap[(size_t)s * h->Nmax + o] = (int)fs.size(); fs.push_back(s); fo.push_back(o); }
+    const int F = (int)fs.size();
+    if (F == 0) return fail(h, NPE_ERR_INVALID, "rollout: no predictable objects");
+    std::vector<int> zeros((size_t)F, 0);
+    CK(h->roll.ensure((size_t)SN * 2 * D));
+    CK(h->roll_scene.ensure(F)); CK(h->roll_obj.ensure(F)); CK(h->roll_t0.ensure(F)); CK(h->foc_of_obj.ensure(SN));
+    CK(cudaMemcpyAsync(h->roll_scene.p, fs.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->roll_obj.p, fo.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->roll_t0.p, zeros.data(), (size_t)F * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->foc_of_obj.p, fmap.data(), (size_t)SN * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // host vectors go out of scope
+    int rc = ensure_batch_buffers(h, F);
+    if (rc) return rc;
+    RollPostArgs A;
+    A.roll = h->roll.p; A.states = h->states.p; A.n_obj = h->n_obj.p; A.foc_of_obj = h->foc_of_obj.p; A.pred = h->pred.p;
+    A.S = h->S; A.Nmax = h->Nmax; A.T = h->T; A.t0 = t0; A.steps = steps; A.use_gt = use_gt; A.teacher = teacher;
+    A.ball_zero = h->cfg.ball_zero_mode; A.traj = nullptr; A.metrics = nullptr; A.step = 0;
+    if (want_traj) {
+        CK(h->traj.ensure((size_t)SN * steps * D));
+        CK(cudaMemsetAsync(h->traj.p, 0, (size_t)SN * steps * D * sizeof(float), h->stream));
+        A.traj = h->traj.p;
+    }
+    if (want_metrics) {
+        CK(h->metrics.ensure((size_t)steps * 7));
+        CK(cudaMemsetAsync(h->metrics.p, 0, (size_t)steps * 7 * sizeof(double), h->stream));
+        A.metrics = h->metrics.p;
+    }
+    k_rollout_init<<<(SN * 2 * D + 255) / 256, 256, 0, h->stream>>>(h->roll.p, h->states.p, SN, h->T, t0);
+    CKL();
+    FocusSrc src;
+    src.states = h->roll.p; src.n_obj = h->n_obj.p; src.Nmax = h->Nmax; src.T = 2;
+    src.foc_scene = h->roll_scene.p; src.foc_obj = h->roll_obj.p; src.foc_t0 = h->roll_t0.p; src.F = F;
+    const float thr = h->cfg.nbrhdsize * 60.f;
+    const int nblk = (F + FPB - 1) / FPB;
+    const bool tc = h->precision == NPE_PRECISION_TF32_TC;
+    for (int step = 0; step < steps; ++step) {
+        {
+            ProfScope ps__(h, NPE_K_BUILD_PAIRS);
+            k_build_pairs<<<nblk, NT, 0, h->stream>>>(src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
+                                                      h->foc_row.p, nullptr, h->active_total);
+            k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(src, h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
+                                                              h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
+            h->launches += 2;
+        }
+        if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc))) return rc;
+        A.step = step;
+        {
+            ProfScope ps__(h, NPE_K_ROLLOUT);
+            k_rollout_post<<<(SN + 255) / 256, 256, 0, h->stream>>>(A);
+            h->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    h->F = 0; h->pairs_valid = false; h->fwd_valid = false;   // the batch buffers were reused
+    h->roll_F = F;
+    return NPE_OK;
+}
+
+static int rollout_dispatch(npe_handle* h, int t0, int steps, int use_gt, int teacher, bool want_traj, bool want_metrics) {
+    if (h->precision == NPE_PRECISION_TF32_TC || h->rollout_mode == NPE_ROLLOUT_BY_KERNELS)
+        return rollout_by_kernels(h, t0, steps, use_gt, teacher, want_traj, want_metrics);
+    return rollout_impl(h, t0, steps, use_gt, teacher, want_traj, want_metrics);
+}
+
 int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* metrics_out) {
     NEED(h);
-    int rc = rollout_impl(h, t0, steps, use_gt, teacher, traj_out != nullptr, metrics_out != nullptr);
+    int rc = rollout_dispatch(h, t0, steps, use_gt, teacher, traj_out != nullptr, metrics_out != nullptr);
     if (rc) return rc;
     if (traj_out) CK(cudaMemcpyAsync(traj_out, h->traj.p, (size_t)h->S * h->Nmax * steps * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (metrics_out) CK(cudaMemcpyAsync(metrics_out, h->metrics.p, (size_t)steps * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -736,9 +855,24 @@ int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_
 
 int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out) {
     NEED(h);
-    int rc = rollout_impl(h, t0, steps, 0, 0, false, false);
+    int rc = rollout_dispatch(h, t0, steps, 0, 0, false, false);
     if (rc) return rc;
     if (object_steps_out) *object_steps_out = h->scene_pred_objects * (int64_t)steps;
+    return NPE_OK;
+}
+
+int npe_set_precision(npe_handle* h, int32_t mode) {
+    NEED(h);
+    if (mode != NPE_PRECISION_FP32 && mode != NPE_PRECISION_TF32_TC) return fail(h, NPE_ERR_INVALID, "set_precision: unknown mode %d", mode);
+    h->precision = mode;
+    h->fwd_valid = false;
+    return NPE_OK;
+}
+
+int npe_set_rollout_mode(npe_handle* h, int32_t mode) {
+    NEED(h);
+    if (mode != NPE_ROLLOUT_PERSISTENT && mode != NPE_ROLLOUT_BY_KERNELS) return fail(h, NPE_ERR_INVALID, "set_rollout_mode: unknown mode %d", mode);
+    h->rollout_mode = mode;
     return NPE_OK;
 }
 

@@ -146,69 +146,79 @@ __device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, 
     nbr = (u64)m0 | ((u64)m1 << 32);
 }
 
-// K1 (+K7): one warp per focus: pair bits, active count, focus row offset, and the relative target
-// y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96).
+// K1 (+K7): one warp per focus (8 foci per warp, 64 per CTA): pair bits, focus row offset, the relative target
+// y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96), and the first level of
+// the active-pair scan: exclusive prefix of the counts inside the CTA + the CTA total.
+constexpr int FPB = 64;   // foci per CTA of the pair builder
 __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
-                                                    u64* __restrict__ nbr_out, int* __restrict__ cnt_out,
-                                                    long long* __restrict__ foc_row, float* __restrict__ y,
-                                                    u64* __restrict__ active_total) {
-    const int f = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    if (f >= src.F) return;
-    const int lane = threadIdx.x & 31;
-    const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
-    u64 keep, nbr;
-    warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
-    const size_t ro = row_off(src, s, n, t0);
-    if (y && lane < D) {
-        const float* p = src.states + ro;
-        float v = p[2 * D + lane];
-        if (lane < 6) v = __fsub_rn(v, p[D + lane]);
-        y[(size_t)f * D + lane] = v;
+                                                    u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
+                                                    int* __restrict__ block_sums, long long* __restrict__ foc_row,
+                                                    float* __restrict__ y, u64* __restrict__ active_total) {
+    __shared__ int s_cnt[FPB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = 0; i < FPB / (NT / 32); ++i) {
+        const int fl = warp * (FPB / (NT / 32)) + i;
+        const int f = blockIdx.x * FPB + fl;
+        int c = 0;
+        if (f < src.F) {
+            const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
+            u64 keep, nbr;
+            warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
+            const size_t ro = row_off(src, s, n, t0);
+            if (y && lane < D) {
+                const float* p = src.states + ro;
+                float v = p[2 * D + lane];
+                if (lane < 6) v = __fsub_rn(v, p[D + lane]);
+                y[(size_t)f * D + lane] = v;
+            }
+            c = __popcll(nbr);
+            if (lane == 0) { keep_out[f] = keep; nbr_out[f] = nbr; foc_row[f] = (long long)ro; }
+        }
+        if (lane == 0) s_cnt[fl] = c;
     }
-    if (lane == 0) {
-        keep_out[f] = keep;
-        nbr_out[f] = nbr;
-        cnt_out[f] = __popcll(nbr);
-        foc_row[f] = (long long)ro;
-        atomicAdd(active_total, (u64)__popcll(nbr));
+    __syncthreads();
+    if (warp == 0) {
+        const int c0 = s_cnt[lane], c1 = s_cnt[lane + 32];
+        int i0 = c0, i1 = c1;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v0 = __shfl_up_sync(0xffffffffu, i0, off), v1 = __shfl_up_sync(0xffffffffu, i1, off);
+            if (lane >= off) { i0 += v0; i1 += v1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        const int f = blockIdx.x * FPB + lane;
+        if (f < src.F) local_prefix[f] = i0 - c0;
+        if (f + 32 < src.F) local_prefix[f + 32] = tot0 + i1 - c1;
+        if (lane == 0) {
+            block_sums[blockIdx.x] = tot0 + tot1;
+            atomicAdd(active_total, (u64)(tot0 + tot1));
+        }
     }
 }
 
-// K1b: exclusive scan of the active counts -> pair_start[F+1], then the dense pair list: for pair p of focus f
-// (contexts in ascending index order) pair_foc[p] = f and pair_crow[p] = float offset of the context's window.
-// One CTA; each thread owns a contiguous chunk of foci.  Pairs beyond `cap` are dropped and flagged.
-__global__ void __launch_bounds__(1024) k_scan_expand(FocusSrc src, const u64* __restrict__ nbr, const int* __restrict__ cnt,
-                                                      int* __restrict__ pair_start, int* __restrict__ pair_foc,
-                                                      long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
-    __shared__ int warp_sums[32];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int chunk = (src.F + 1023) / 1024;
-    const int f0 = min(t * chunk, src.F), f1 = min(f0 + chunk, src.F);
-    int local = 0;
-    for (int f = f0; f < f1; ++f) local += cnt[f];
-    int incl = local;
-    for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += v;
-    }
-    if (lane == 31) warp_sums[w] = incl;
+// K1b: second level of the scan + the dense pair list: for pair p of focus f (contexts in ascending index order)
+// pair_foc[p] = f and pair_crow[p] = float offset of the context's window.  One CTA per 64 foci; each CTA sums the
+// totals of the CTAs before it.  Pairs beyond `cap` are dropped and flagged.
+__global__ void __launch_bounds__(FPB) k_expand_pairs_dense(FocusSrc src, const u64* __restrict__ nbr,
+                                                           const int* __restrict__ local_prefix,
+                                                           const int* __restrict__ block_sums, int* __restrict__ pair_start,
+                                                           int* __restrict__ pair_foc, long long* __restrict__ pair_crow,
+                                                           int cap, int* __restrict__ info) {
+    __shared__ int s_part[2];
+    const int t = threadIdx.x, lane = t & 31;
+    int part = 0;
+    for (int b = t; b < (int)blockIdx.x; b += FPB) part += block_sums[b];
+    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if (lane == 0) s_part[t >> 5] = part;
     __syncthreads();
-    if (w == 0) {
-        int v = warp_sums[lane];
-        for (int off = 1; off < 32; off <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, v, off);
-            if (lane >= off) v += u;
-        }
-        warp_sums[lane] = v;
-    }
-    __syncthreads();
-    int base = incl - local + (w ? warp_sums[w - 1] : 0);
-    const int objstride = src.T * D;
-    for (int f = f0; f < f1; ++f) {
+    const int blk_base = s_part[0] + s_part[1];
+    const int f = blockIdx.x * FPB + t;
+    if (f < src.F) {
+        int base = blk_base + local_prefix[f];
         pair_start[f] = min(base, cap);
         u64 bits = nbr[f];
         const int fo = src.foc_obj[f];
         const long long sbase = (long long)row_off(src, src.foc_scene[f], 0, src.foc_t0[f]);
+        const int objstride = src.T * D;
         while (bits) {
             const int c = __ffsll((long long)bits) - 1;
             bits &= bits - 1;
@@ -218,12 +228,11 @@ __global__ void __launch_bounds__(1024) k_scan_expand(FocusSrc src, const u64* _
             }
             ++base;
         }
-    }
-    if (t == 1023) {
-        const int total = warp_sums[31];
-        pair_start[src.F] = min(total, cap);
-        info[0] = min(total, cap);     // P
-        info[1] = total > cap;         // overflow flag
+        if (f == src.F - 1) {
+            pair_start[src.F] = min(base, cap);
+            info[0] = min(base, cap);      // P
+            info[1] = base > cap;          // overflow flag
+        }
     }
 }
 

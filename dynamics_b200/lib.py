@@ -60,6 +60,8 @@ SIGNATURES = {
     "npe_train_step": (C.c_int, [_H, C.c_int32, C.c_float, C.c_int32, _fp]),
     "npe_rollout": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),
     "npe_rollout_resident": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
+    "npe_set_precision": (C.c_int, [_H, C.c_int32]),
+    "npe_set_rollout_mode": (C.c_int, [_H, C.c_int32]),
     "npe_comm_unique_id": (C.c_int, [C.c_void_p]),
     "npe_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "npe_allreduce_grads": (C.c_int, [_H]),

@@ -39,6 +39,8 @@ int npe_optim_reset(npe_handle* h, float rmsprop_m_init);
 int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out);
 int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* metrics_out);
 int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out);
+int npe_set_precision(npe_handle* h, int32_t mode);
+int npe_set_rollout_mode(npe_handle* h, int32_t mode);
 int npe_comm_unique_id(void* id128_out);
 int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128);
 int npe_allreduce_grads(npe_handle* h);

@@ -276,6 +276,14 @@ class NPEModel:
         self._ck(self.lib.npe_rollout_resident(self.h, t0, steps, C.byref(n)))
         return n.value
 
+    def set_precision(self, mode):
+        """'fp32' (FFMA kernels, default) or 'tf32' (tcgen05 forward / rollout kernels)."""
+        self._ck(self.lib.npe_set_precision(self.h, {"fp32": 0, "tf32": 1}[mode]))
+
+    def set_rollout_mode(self, mode):
+        """'persistent' (one kernel, window on chip) or 'kernels' (window in HBM, 5 launches per step)."""
+        self._ck(self.lib.npe_set_rollout_mode(self.h, {"persistent": 0, "kernels": 1}[mode]))
+
     # ---- misc -------------------------------------------------------------------------------------------------
     def sync(self):
         self._ck(self.lib.npe_sync(self.h))

@@ -168,6 +168,21 @@ int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_
 /* Device-resident rollout for throughput runs: no host copies; object-steps advanced are returned. */
 int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out);
 
+/*
+ * Arithmetic variant of the forward path (north star: FP32 FFMA variant and tf32 tcgen05 variant):
+ *   NPE_PRECISION_FP32 (default): FP32 FFMA kernels everywhere (the parity path, 1e-4).
+ *   NPE_PRECISION_TF32_TC: npe_forward / npe_forward_per_example / npe_rollout run the tcgen05 kernels (TF32 inputs,
+ *   FP32 accumulation in TMEM; ~1e-3 relative).  Backward, optimiser, pair table and masks are unaffected.
+ * Rollout mode: NPE_ROLLOUT_PERSISTENT (default for FP32: one persistent kernel, window on chip) or
+ * NPE_ROLLOUT_BY_KERNELS (window in HBM, 5 launches per step; always used by the tcgen05 variant).
+ */
+#define NPE_PRECISION_FP32 0
+#define NPE_PRECISION_TF32_TC 1
+#define NPE_ROLLOUT_PERSISTENT 0
+#define NPE_ROLLOUT_BY_KERNELS 1
+int npe_set_precision(npe_handle* h, int32_t mode);
+int npe_set_rollout_mode(npe_handle* h, int32_t mode);
+
 /* Data-parallel: one handle per GPU/process.  id = 128-byte ncclUniqueId from npe_comm_unique_id on rank 0. */
 int npe_comm_unique_id(void* id128_out);
 int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128);

@@ -301,3 +301,72 @@ def test_error_paths(model):
         NPEModel(ModelParams(rnn_dim=24, layers=2))                 # -debug shape is not built
     with pytest.raises(NPEError):
         model.select_windows(0, 1)                                  # no schedule
+
+
+# ---- tcgen05 (TF32) variant and rollout-by-kernels ---------------------------------------------------------------
+TOL_TF32 = 2e-3   # TF32 inputs (10-bit mantissa), FP32 accumulation: SURVEY 8d states 1e-3; 2e-3 leaves margin for 11 layers
+
+
+def test_tf32_forward_matches_oracle(model, trained_like_params):
+    _, batches = balls_batches(60, 7, seed=17)
+    batch = batcher.make_batch(*batches[0], offset=4)
+    le, pred, lve, lwe = npe.fp_batch(trained_like_params, batch)
+    model.set_precision("tf32")
+    gle, gpred, _, _ = model.fp_batch(trained_like_params, batch)
+    idx, mask, cnt = model.pair_table()
+    oidx, omask, _ = oracle_pairs(batch[0], batch[1])
+    assert np.array_equal(mask[:, :omask.shape[1]], omask.astype(np.uint8))     # masks never touch the tensor path
+    scale = np.abs(pred[:, :6]).max()
+    err = np.abs(gpred[:, :6] - pred[:, :6]).max() / scale
+    assert 1e-7 < err < TOL_TF32, err                                           # really TF32, and within tolerance
+    assert np.max(np.abs(gpred[:, 6:] - pred[:, 6:])) < 1e-3
+    with pytest.raises(Exception):
+        model.fp(None, batch); model.bp()                                       # backward needs the FP32 forward
+    model.set_precision("fp32")
+    gl2, gpred2, _, _ = model.fp(None, batch)
+    assert rel_err(gpred2[:, :6], pred[:, :6]) < TOL
+
+
+def test_tf32_forward_big_scene(trained_like_params):
+    from dynamics_b200 import ModelParams, NPEModel
+    st = scenes.raw_to_state(scenes.gen_big(6, 64, 3, seed=65))
+    m = NPEModel(ModelParams(max_ctx=0))
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(6), np.zeros(6, np.int32))
+        m.select_windows(0, 6)
+        p32, l32 = m.forward_current()
+        m.set_precision("tf32")
+        ptc, ltc = m.forward_current()
+        scale = np.abs(p32[:, :6]).max()
+        assert np.abs(ptc[:, :6] - p32[:, :6]).max() / scale < TOL_TF32
+        assert np.allclose(ltc, l32, rtol=2e-2)
+    finally:
+        m.close()
+
+
+def test_rollout_by_kernels_fp32_and_tf32(model, trained_like_params):
+    st = scenes.raw_to_state(scenes.gen_balls(40, 6, 14, seed=19))
+    sw = scenes.raw_to_state(scenes.gen_walls(8, 14, seed=9, variant="U"))
+    for states in (st, sw):
+        steps = 12
+        S, N = states.shape[:2]
+        model.set_params(trained_like_params)
+        model.upload_scenes(states)
+        model.set_precision("fp32"); model.set_rollout_mode("persistent")
+        traj_p, met_p = model.rollout(0, steps, use_gt=True, teacher=True)
+        model.set_rollout_mode("kernels")
+        traj_k, met_k = model.rollout(0, steps, use_gt=True, teacher=True)
+        assert np.max(np.abs(traj_k - traj_p)) < 1e-6
+        assert np.array_equal(traj_k[..., 0:2], traj_p[..., 0:2]) and np.array_equal(traj_k[..., 6:], traj_p[..., 6:])
+        assert np.allclose(met_k, met_p, rtol=1e-4, atol=1e-9)
+        model.set_precision("tf32")
+        traj_t, met_t = model.rollout(0, steps, use_gt=True, teacher=True)
+        ref, _ = rollout.rollout_scenes(trained_like_params, states[:, :, 0:2], np.full(S, N), steps, gt=states[:, :, 2:],
+                                        teacher=states[:, :, 2:])
+        scale = np.abs(ref[..., 2:4]).max()
+        assert np.max(np.abs(traj_t[..., 2:4] - ref[..., 2:4])) / scale < TOL_TF32
+        assert np.array_equal(traj_t[..., 0:2], ref[..., 0:2])     # positions: previous velocity -> exact under teacher forcing
+        assert met_t[:, 3].min() == met_p[:, 3].min()
+        model.set_precision("fp32"); model.set_rollout_mode("persistent")

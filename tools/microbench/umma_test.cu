@@ -1,0 +1,123 @@
+// Stand-alone validation of the tcgen05 building block used by the tensor-core NPE path:
+//   D[128 x 64] (fp32, TMEM) = A[128 x 56] (tf32, smem, K-major, no swizzle) * W[64 x 56]^T (tf32, smem, K-major)
+// Operand layout ("interleaved" canonical layout): element (row, k) at byte (k / 4) * ROWS * 16 + row * 16 + (k % 4) * 4,
+// i.e. 8-row x 16-byte core matrices are contiguous 128-byte blocks; SBO = 128 B (next 8 rows), LBO = ROWS * 16 B
+// (next 16-byte k-chunk).  One thread issues 7 MMAs (K = 8 each); 4 warps read the accumulator with tcgen05.ld.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+
+constexpr int M = 128, N = 64, K = 56, KC = K / 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version 1 (sm_100)
+    return d;                 // layout_type = 0 (SWIZZLE_NONE), base_offset 0
+}
+
+__global__ void __launch_bounds__(128, 1) k(const float* A, const float* W, float* D, long long* cycles) {
+    __shared__ __align__(1024) float sA[KC * M * 4];
+    __shared__ __align__(1024) float sB[KC * N * 4];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int c = 0; c < KC; ++c) {
+        float4 v = *reinterpret_cast<const float4*>(A + t * K + 4 * c);
+        *reinterpret_cast<float4*>(sA + (c * M + t) * 4) = v;
+        if (t < N) {
+            float4 w = *reinterpret_cast<const float4*>(W + t * K + 4 * c);
+            *reinterpret_cast<float4*>(sB + (c * N + t) * 4) = w;
+        }
+    }
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the MMA
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    long long t0 = clock64();
+    if (t == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        for (int s = 0; s < K / 8; ++s) {
+            const uint64_t da = make_desc(smem_u32(sA) + 2 * s * M * 16, M * 16, 128);
+            const uint64_t db = make_desc(smem_u32(sB) + 2 * s * N * 16, N * 16, 128);
+            const uint32_t acc = s > 0;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    // wait for the accumulator
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[64];
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]),
+              "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]), "=r"(r[c + 12]),
+              "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+            : "r"(taddr + c));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    long long t1 = clock64();
+    for (int c = 0; c < 64; ++c) D[t * N + c] = __uint_as_float(r[c]);
+    if (t == 0) cycles[0] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem));
+}
+
+static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
+
+int main() {
+    std::vector<float> A(M * K), W(N * K), D(M * N), ref(M * N), reft(M * N);
+    srand(1);
+    for (auto& v : A) v = (rand() % 2001 - 1000) / 1000.f;
+    for (auto& v : W) v = (rand() % 2001 - 1000) / 1000.f;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            double s = 0, st = 0;
+            for (int k = 0; k < K; ++k) { s += (double)A[m * K + k] * W[n * K + k]; st += (double)tf32_trunc(A[m * K + k]) * tf32_trunc(W[n * K + k]); }
+            ref[m * N + n] = (float)s; reft[m * N + n] = (float)st;
+        }
+    float *dA, *dW, *dD; long long* dc;
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dW, W.size() * 4); cudaMalloc(&dD, D.size() * 4); cudaMalloc(&dc, 8);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dW, W.data(), W.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dD, 0, D.size() * 4);
+    k<<<1, 128>>>(dA, dW, dD, dc);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("kernel: %s\n", cudaGetErrorString(e));
+    if (e != cudaSuccess) return 1;
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    long long cyc; cudaMemcpy(&cyc, dc, 8, cudaMemcpyDeviceToHost);
+    double e_full = 0, e_trunc = 0, mx = 0;
+    for (int i = 0; i < M * N; ++i) { e_full = fmax(e_full, fabs(D[i] - ref[i])); e_trunc = fmax(e_trunc, fabs(D[i] - reft[i])); mx = fmax(mx, fabs(ref[i])); }
+    printf("max|ref| %.3f  max err vs fp64(fp32 inputs) %.3e  vs fp64(tf32-truncated inputs) %.3e  cycles (7 MMA + commit + ld) %lld\n", mx, e_full, e_trunc, cyc);
+    printf("D[0][0..3] = %f %f %f %f   ref %f %f %f %f\n", D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    printf("D[77][60..63] = %f %f %f %f   ref %f %f %f %f\n", D[77 * N + 60], D[77 * N + 61], D[77 * N + 62], D[77 * N + 63], ref[77 * N + 60], ref[77 * N + 61], ref[77 * N + 62], ref[77 * N + 63]);
+    return 0;
+}
