@@ -31,6 +31,7 @@ SCENES_PER_SET = 4000        # x 60 frames: 317 MB of padded states > 126 MB L2
 T_FRAMES = 60
 LR = 3e-4
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.4: FFMA pipe at the 1965 MHz max clock
+TF32_PEAK_TFLOPS = None   # filled from MEASURED_PEAKS.json (bf16 burst / 2: TF32 runs at half the bf16 rate)
 FP32_PEAK_NOTE = ("148 SM x 128 FMA/clk x 2 x 1.965 GHz; tools/microbench/ffma measured 72.5 (FFMA) / 74.1 (FFMA2) "
                   "TFLOP/s on this pool's B200")
 
@@ -45,6 +46,18 @@ KERNEL_FLOPS = {                       # algorithmic FLOPs: maske
     "pair_backward": lambda F, P: 2200.0 * F + 52200.0 * P,
 }
 STEP_FLOPS = lambda F, P: 79800.0 * F + 79400.0 * P
+
+
+def _load_peaks():
+    global TF32_PEAK_TFLOPS
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        TF32_PEAK_TFLOPS = pk["bf16_tflops"] / 2.0
+    except Exception:
+        TF32_PEAK_TFLOPS = 1590.0 / 2.0      # B200_PROFILING.md fallback (of fallback)
+
+
+_load_peaks()
 
 
 def dist_env():
@@ -249,22 +262,69 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
 
 
 def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
-    """configs[4]-style rollout: `scenes` 8-ball scenes advanced `steps` steps, state resident on chip."""
+    """configs[4]-style rollout: `scenes` 8-ball scenes advanced `steps` steps, three variants:
+    fp32 persistent kernel (window on chip), fp32 by kernels (window in HBM), tf32 tcgen05 by kernels."""
     from dynamics_b200 import synth
     from dynamics_b200.model import init_params
     st = synth.ball_scenes(scenes, balls, 2, seed=5)
     m = model_cls(mp_cls(device=device))
+    out = {"config": {"workload": f"configs[4]-style: {scenes} x {balls}-ball scenes x {steps} steps, no ground truth"}}
     try:
         m.set_params(init_params(1234))
         m.upload_scenes(st)
-        m.rollout_resident(0, 5); m.sync()
-        m.event_record(0)
-        n = m.rollout_resident(0, steps)
-        m.event_record(1); m.sync()
-        ms = m.event_elapsed_ms(0, 1)
-        return {"value": n / (ms * 1e-3), "unit": "object-steps/s", "ms": ms,
-                "config": {"workload": f"configs[4]-style: {scenes} x {balls}-ball scenes x {steps} steps, no ground truth",
-                           "object_steps": n}}
+        for name, prec, mode, nsteps in (("fp32_persistent", "fp32", "persistent", steps), ("fp32_kernels", "fp32", "kernels", steps // 4),
+                                         ("tf32_tcgen05", "tf32", "kernels", steps)):
+            m.set_precision(prec); m.set_rollout_mode(mode)
+            m.rollout_resident(0, 3); m.sync()
+            m.event_record(0)
+            n = m.rollout_resident(0, nsteps)
+            m.event_record(1); m.sync()
+            ms = m.event_elapsed_ms(0, 1)
+            out[name] = {"value": n / (ms * 1e-3), "unit": "object-steps/s", "ms": ms, "steps": nsteps, "object_steps": n}
+        # kernel-level view of the tcgen05 pair kernel: active pairs per step from one build
+        m.set_precision("tf32"); m.set_rollout_mode("kernels")
+        m.profile_select("forward")
+        m.rollout_resident(0, 8)
+        nk, tot = m.profile_read()
+        m.profile_select(None)
+        out["tf32_tcgen05"]["forward_ms_per_step"] = tot / max(nk, 1)
+        best = max(("fp32_persistent", "fp32_kernels", "tf32_tcgen05"), key=lambda k: out[k]["value"])
+        out["value"] = out[best]["value"]; out["unit"] = "object-steps/s"; out["best"] = best
+        return out
+    finally:
+        m.close()
+
+
+def bench_forward_stress(model_cls, mp_cls, device, scenes=1024):
+    """Forward-only (fp_batch) throughput on the S-64 shape for both arithmetic variants, with kernel rooflines."""
+    from dynamics_b200 import synth
+    from dynamics_b200.model import init_params
+    st = synth.ball_scenes(scenes, 64, 3, seed=64, world=(3200, 2400), collide=False)
+    m = model_cls(mp_cls(max_ctx=0, device=device))
+    out = {}
+    try:
+        m.set_params(init_params(1234))
+        m.upload_scenes(st); m.upload_windows(np.arange(scenes), np.zeros(scenes, np.int32))
+        m.select_windows(0, scenes)
+        F, P = m.batch_stats()
+        for prec in ("fp32", "tf32"):
+            m.set_precision(prec)
+            for _ in range(3):
+                m._ck(m.lib.npe_forward_per_example(m.h, None, None))
+            m.profile_select("forward")
+            for _ in range(10):
+                m._ck(m.lib.npe_forward_per_example(m.h, None, None))
+            n, tot = m.profile_read()
+            m.profile_select(None)
+            ms = tot / max(n, 1)
+            ach = KERNEL_FLOPS["forward"](F, P) / (ms * 1e-3) / 1e12
+            peak = FP32_PEAK_TFLOPS if prec == "fp32" else TF32_PEAK_TFLOPS
+            out[prec] = {"forward_ms": ms, "samples_per_s": F / (ms * 1e-3),
+                         "roofline": {"kernel": "k_pair_forward%s + k_dec_forward%s" % (("", "") if prec == "fp32" else ("_tc", "_tc")),
+                                      "bound": "fp32" if prec == "fp32" else "tensor", "achieved": ach, "peak": peak,
+                                      "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}}
+        out["config"] = {"workload": "configs[3] forward only", "foci": F, "active_pairs": P}
+        return out
     finally:
         m.close()
 
@@ -387,6 +447,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_extra:
         try:
             line["extra"] = {"stress64": bench_stress64(NPEModel, ModelParams, local_rank),
+                             "forward_stress64": bench_forward_stress(NPEModel, ModelParams, local_rank),
                              "rollout": bench_rollout(NPEModel, ModelParams, local_rank)}
         except Exception as e:  # the headline must still print
             line["extra"] = {"error": repr(e)}

@@ -233,11 +233,14 @@ int build_pairs(npe_handle* h) {
         const int nblk = (h->F + FPB - 1) / FPB;
         k_build_pairs<<<nblk, NT, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
                                                   h->block_sums.p, h->foc_row.p, h->batch_form ? nullptr : h->y.p,
-                                                  h->active_total);
+                                                  h->active_total, h->pair_start.p, h->pair_foc.p, h->pair_crow.p,
+                                                  h->pair_cap, h->info_dev);
         h->launches++;
-        k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
-                                                          h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
-        h->launches++;
+        if (nblk > 1) {
+            k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
+                                                              h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
+            h->launches++;
+        }
     }
     CK(cudaGetLastError());
     h->pairs_valid = true;
@@ -253,9 +256,16 @@ int check_pair_overflow(npe_handle* h) {
     return NPE_OK;
 }
 
-int pair_grid(const npe_handle* h) {
-    const long long tiles = ((long long)h->pair_cap + TILE - 1) / TILE;
+// Small batches take the 16-row (latency) mapping: more CTAs, each pass ~3x shorter; large ones the 64-row mapping.
+bool small_batch(const npe_handle* h, int F) { return F <= 16 * h->num_sms / 4; }
+
+int pair_grid(const npe_handle* h, int rows) {
+    const long long tiles = ((long long)h->pair_cap + rows - 1) / rows;
     return (int)(tiles < h->num_sms ? (tiles > 0 ? tiles : 1) : h->num_sms);
+}
+int focus_grid(const npe_handle* h, int F, int rows) {
+    const int tiles = (F + rows - 1) / rows;
+    return tiles < h->num_sms ? tiles : h->num_sms;
 }
 
 int refresh_wtc(npe_handle* h) {
@@ -268,8 +278,6 @@ int refresh_wtc(npe_handle* h) {
 
 // pair MLP + decoder forward on the current pair list; `st` = scene tensor the row offsets point into
 int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, bool tc) {
-    const int ntiles = (F + TILE - 1) / TILE;
-    const int grid = ntiles < h->num_sms ? ntiles : h->num_sms;
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
         int rc = refresh_wtc(h);
@@ -284,12 +292,18 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
             st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y, h->pred.p, loss_ex);
         h->launches++;
     } else {
-        k_pair_forward<<<pair_grid(h), NT, sizeof(PairFwdSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                          h->info_dev, h->wpack, h->Hp.p);
-        h->launches++;
-        k_dec_forward<<<grid, NT, sizeof(DecFwdSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y,
-                                                                   h->pred.p, loss_ex);
-        h->launches++;
+        if (small_batch(h, F)) {
+            k_pair_forward<16><<<pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream>>>(
+                st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
+            k_dec_forward<16><<<focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream>>>(
+                st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex);
+        } else {
+            k_pair_forward<64><<<pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>), h->stream>>>(
+                st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
+            k_dec_forward<64><<<focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream>>>(
+                st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex);
+        }
+        h->launches += 2;
     }
     CK(cudaGetLastError());
     return NPE_OK;
@@ -312,32 +326,61 @@ int run_loss_reduce(npe_handle* h) {
     return NPE_OK;
 }
 
-int run_backward(npe_handle* h, int divisor_batch) {
+// fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
+int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f) {
     if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
     if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
     const int B = divisor_batch > 0 ? divisor_batch : h->F;
     // d_vel = 2 (p - y) * vlambda / (2B); d_ang_vel = 2 (p - y) * lambda / B   (npe.lua:304-315)
     const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
     const float sw = 2.f * h->cfg.lambda / (float)B;
-    const int nt_d = (h->F + TILE - 1) / TILE;
-    const int gd = nt_d < h->num_sms ? nt_d : h->num_sms;
-    const int gp = pair_grid(h);
+    const bool small = small_batch(h, h->F);
+    const int rows = small ? 16 : 64;
+    const int gd = focus_grid(h, h->F, rows);
+    const int gp = pair_grid(h, rows);
     {
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
-        k_dec_backward<<<gd, NT, sizeof(DecBwdSmem), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p, h->Hp.p,
-                                                                  h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
+        if (small)
+            k_dec_backward<16><<<gd, NT, sizeof(DecBwdSmem<16>), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p,
+                                                                              h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
+        else
+            k_dec_backward<64><<<gd, NT, sizeof(DecBwdSmem<64>), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p,
+                                                                              h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
-        k_pair_backward<<<gp, NT, sizeof(PairBwdSmem), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                    h->info_dev, h->wpack, h->ds.p, h->partial);
+        if (small)
+            k_pair_backward<16><<<gp, NT, sizeof(PairBwdSmem<16>), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
+                                                                                h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial);
+        else
+            k_pair_backward<64><<<gp, NT, sizeof(PairBwdSmem<64>), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
+                                                                                h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial);
         h->launches++;
     }
     CK(cudaGetLastError());
-    { ProfScope ps__(h, NPE_K_REDUCE); k_reduce_grads<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads);
-    h->launches++; }
-    { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
+    {
+        ProfScope ps__(h, NPE_K_REDUCE);
+        OptArgs o;
+        o.x = h->params; o.m = h->adam_m; o.v = h->adam_v; o.wpack = h->wpack;
+        o.b1 = 0.9f; o.omb1 = (float)(1.0 - 0.9); o.b2 = 0.999f; o.omb2 = (float)(1.0 - 0.999); o.eps = 1e-8f; o.step = lr;
+        const int nb = (NPARAM + 255) / 256;
+        if (fuse_opt == 1) {
+            h->adam_t += 1;
+            const double t = (double)h->adam_t;
+            o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
+            k_reduce_grads<1><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+            h->wtc_dirty = true;
+        } else if (fuse_opt == 2) {
+            o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
+            k_reduce_grads<2><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+            h->wtc_dirty = true;
+        } else {
+            k_reduce_grads<0><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+        }
+        h->launches++;
+    }
+    CK(cudaGetLastError());
     return NPE_OK;
 }
 
@@ -413,7 +456,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
     h->num_sms = prop.multiProcessorCount;
-    if ((size_t)prop.sharedMemPerBlockOptin < sizeof(PairBwdSmem)) {
+    if ((size_t)prop.sharedMemPerBlockOptin < sizeof(PairBwdSmem<64>)) {
         g_create_error = "device shared memory per block too small (needs an sm_100-class GPU)";
         delete hh;
         return NPE_ERR_UNSUPPORTED;
@@ -437,10 +480,14 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(h->info_dev, 0, 4 * sizeof(int));
     cudaMemset(h->active_total, 0, sizeof(u64));
-    if ((e = cudaFuncSetAttribute(k_pair_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairFwdSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pair_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem))) != cudaSuccess ||
+    if ((e = cudaFuncSetAttribute(k_pair_forward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairFwdSmem<64>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem<64>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_backward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem<64>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_backward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem<64>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_forward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairFwdSmem<16>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem<16>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem<16>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem<16>))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess)
@@ -724,12 +771,16 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     int rc;
     if ((rc = run_forward(h, true))) return rc;
     if (loss3_out && (rc = run_loss_reduce(h))) return rc;
-    if ((rc = run_backward(h, divisor_batch))) return rc;
-    if ((rc = run_allreduce(h))) return rc;
-    if (opt == 0) rc = run_adam(h, lr, 0.9f, 0.999f, 1e-8f);
-    else if (opt == 1) rc = run_rmsprop(h, lr, 0.99f, 1e-8f);
-    else return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
-    if (rc) return rc;
+    if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
+    if (!h->comm) {
+        // single GPU: reduction of the CTA partials, optimiser step and weight-image write-through in ONE kernel
+        if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr))) return rc;
+    } else {
+        if ((rc = run_backward(h, divisor_batch))) return rc;
+        if ((rc = run_allreduce(h))) return rc;
+        rc = (opt == 0) ? run_adam(h, lr, 0.9f, 0.999f, 1e-8f) : run_rmsprop(h, lr, 0.99f, 1e-8f);
+        if (rc) return rc;
+    }
     h->fwd_valid = false;   // parameters changed
     if (loss3_out) {
         CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -818,10 +869,14 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
             k_build_pairs<<<nblk, NT, 0, h->stream>>>(src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
-                                                      h->foc_row.p, nullptr, h->active_total);
-            k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(src, h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
-                                                              h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
-            h->launches += 2;
+                                                      h->foc_row.p, nullptr, h->active_total, h->pair_start.p, h->pair_foc.p,
+                                                      h->pair_crow.p, h->pair_cap, h->info_dev);
+            h->launches++;
+            if (nblk > 1) {
+                k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(src, h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
+                                                                  h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
+                h->launches++;
+            }
         }
         if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc))) return rc;
         A.step = step;

@@ -153,8 +153,12 @@ constexpr int FPB = 64;   // foci per CTA of the pair builder
 __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
                                                     u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
                                                     int* __restrict__ block_sums, long long* __restrict__ foc_row,
-                                                    float* __restrict__ y, u64* __restrict__ active_total) {
+                                                    float* __restrict__ y, u64* __restrict__ active_total,
+                                                    int* __restrict__ pair_start, int* __restrict__ pair_foc,
+                                                    long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
     __shared__ int s_cnt[FPB];
+    __shared__ int s_pre[FPB];
+    __shared__ u64 s_nbr[FPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = 0; i < FPB / (NT / 32); ++i) {
         const int fl = warp * (FPB / (NT / 32)) + i;
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, floa
                 y[(size_t)f * D + lane] = v;
             }
             c = __popcll(nbr);
-            if (lane == 0) { keep_out[f] = keep; nbr_out[f] = nbr; foc_row[f] = (long long)ro; }
+            if (lane == 0) { keep_out[f] = keep; nbr_out[f] = nbr; foc_row[f] = (long long)ro; s_nbr[fl] = nbr; }
         }
         if (lane == 0) s_cnt[fl] = c;
     }
@@ -188,10 +192,30 @@ __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, floa
         const int f = blockIdx.x * FPB + lane;
         if (f < src.F) local_prefix[f] = i0 - c0;
         if (f + 32 < src.F) local_prefix[f + 32] = tot0 + i1 - c1;
+        s_pre[lane] = i0 - c0; s_pre[lane + 32] = tot0 + i1 - c1;
         if (lane == 0) {
             block_sums[blockIdx.x] = tot0 + tot1;
             atomicAdd(active_total, (u64)(tot0 + tot1));
         }
+    }
+    if (gridDim.x > 1) return;
+    // single-CTA batch (F <= 64, e.g. the reference's batch of 50): build the dense pair list here and save a launch
+    __syncthreads();
+    if (threadIdx.x < FPB && (int)threadIdx.x < src.F) {
+        const int f = threadIdx.x;
+        int base = s_pre[f];
+        pair_start[f] = min(base, cap);
+        u64 bits = s_nbr[f];
+        const int fo = src.foc_obj[f];
+        const long long sbase = (long long)row_off(src, src.foc_scene[f], 0, src.foc_t0[f]);
+        const int objstride = src.T * D;
+        while (bits) {
+            const int c = __ffsll((long long)bits) - 1;
+            bits &= bits - 1;
+            if (base < cap) { pair_foc[base] = f; pair_crow[base] = sbase + (long long)(c + (c >= fo)) * objstride; }
+            ++base;
+        }
+        if (f == src.F - 1) { pair_start[src.F] = min(base, cap); info[0] = min(base, cap); info[1] = base > cap; }
     }
 }
 
@@ -273,9 +297,9 @@ __global__ void k_gather_this(FocusSrc src, float* __restrict__ this_out) {
 // ----------------------------------------------------------------------------------------------------------------
 // Gather rows of 44 floats (two frames) into dst[r][LDD]; rows >= nrows are zero-filled.  Row offsets are multiples
 // of 22 floats (8-byte aligned): float2 loads.
-template <int LDD>
+template <int ROWS, int LDD>
 __device__ __forceinline__ void gather_rows(float* dst, const float* __restrict__ base, const long long* offs, int nrows) {
-    for (int idx = threadIdx.x; idx < TILE * (IN / 2); idx += NT) {
+    for (int idx = threadIdx.x; idx < ROWS * (IN / 2); idx += NT) {
         const int r = idx / (IN / 2), c2 = idx - r * (IN / 2);
         float2 v = make_float2(0.f, 0.f);
         if (r < nrows) v = *reinterpret_cast<const float2*>(base + offs[r] + 2 * c2);
@@ -286,27 +310,29 @@ __device__ __forceinline__ void gather_rows(float* dst, const float* __restrict_
 __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 
 // u1..u4 and raw output o of the decoder on a 64-row focus tile; z = sZ [64][104].  u[i] receives u_{i+1}.
+template <int ROWS>
 __device__ __forceinline__ void decoder_forward(const float* sWd, const float* sZ, float* const* u, float* o, int nrows) {
-    gemm_nt<7, LD1, LD1>(sZ, sWd + SW_DEC1, 24, nrows, EpiNT{u[0], LD, 52, 1});
+    gemm_nt_r<ROWS, 7, LD1, LD1>(sZ, sWd + SW_DEC1, 24, nrows, EpiNT{u[0], LD, 52, 1});
     __syncthreads();
 #pragma unroll 1
     for (int i = 0; i < 3; ++i) {
-        gemm_nt<7, LD, LD>(u[i], sWd + SW_DEC2 + i * SW_PAIR_SZ, 13, nrows, EpiNT{u[i + 1], LD, 52, 1});
+        gemm_nt_r<ROWS, 7, LD, LD>(u[i], sWd + SW_DEC2 + i * SW_PAIR_SZ, 13, nrows, EpiNT{u[i + 1], LD, 52, 1});
         __syncthreads();
     }
-    gemm_nt<3, LD, LD>(u[3], sWd + SW_DEC5, 13, nrows, EpiNT{o, LD, 24, 0});
+    gemm_nt_r<ROWS, 3, LD, LD>(u[3], sWd + SW_DEC5, 13, nrows, EpiNT{o, LD, 24, 0});
     __syncthreads();
 }
 
 // Load a focus tile: z[r] = [s x 50 (zero here) | 1 | 0 | this_past(44) | 0 x 8]; rows >= nf are all zero.
+template <int ROWS>
 __device__ __forceinline__ void load_focus_tile(float* sZ, const float* __restrict__ states, const long long* foff, int nf) {
-    for (int idx = threadIdx.x; idx < TILE * (ZCOL_F / 2); idx += NT) {
+    for (int idx = threadIdx.x; idx < ROWS * (ZCOL_F / 2); idx += NT) {
         const int r = idx / (ZCOL_F / 2), c2 = idx - r * (ZCOL_F / 2);
         float2 v = make_float2(0.f, 0.f);
         if (c2 == ONE_COL / 2 && r < nf) v.x = 1.f;
         *reinterpret_cast<float2*>(sZ + r * LD1 + 2 * c2) = v;
     }
-    for (int idx = threadIdx.x; idx < TILE * (LD1 - ZCOL_F) / 2; idx += NT) {
+    for (int idx = threadIdx.x; idx < ROWS * (LD1 - ZCOL_F) / 2; idx += NT) {
         const int r = idx / ((LD1 - ZCOL_F) / 2), c2 = idx - r * ((LD1 - ZCOL_F) / 2);
         float2 v = make_float2(0.f, 0.f);
         if (r < nf && c2 < IN / 2) v = *reinterpret_cast<const float2*>(states + foff[r] + 2 * c2);
@@ -318,38 +344,42 @@ __device__ __forceinline__ void load_focus_tile(float* sZ, const float* __restri
 // K2a: pair-MLP forward on DENSE tiles of 64 active pairs (independent of focus tiles): both encoder halves per pair
 // (like the reference, which re-encodes the focus for every pair), 5 pairwise layers, h5 rows to Hp (P,52).
 // ----------------------------------------------------------------------------------------------------------------
+template <int ROWS>
 struct PairMeta {
-    long long frow[TILE];
-    long long crow[TILE];
-    int pf[TILE];
+    long long frow[ROWS];
+    long long crow[ROWS];
+    int pf[ROWS];
 };
 
+template <int ROWS>
 struct PairFwdSmem {
     float Wp[SW_PAIR_TOTAL];
-    float Xf[TILE * LD];
-    float Xc[TILE * LD];
-    float P0[TILE * LD];
-    float P1[TILE * LD];
-    PairMeta M;
+    float Xf[ROWS * LD];
+    float Xc[ROWS * LD];
+    float P0[ROWS * LD];
+    float P1[ROWS * LD];
+    PairMeta<ROWS> M;
     WeightStage W;
 };
 
 // h0 = [relu(Wt f) | relu(Wc c)] into h0buf (cols 50..55 zeroed), then h_l = relu(L_l h_{l-1}) into bufs[l].
+template <int ROWS>
 __device__ __forceinline__ void pair_chain_dense(const float* sWp, const float* sXf, const float* sXc, int nrows,
                                                  float* const* bufs) {
     float* h0 = bufs[0];
-    for (int idx = threadIdx.x; idx < TILE * 6; idx += NT) h0[(idx / 6) * LD + H + (idx % 6)] = 0.f;
-    gemm_nt<4, LD, LD>(sXf, sWp + SW_ENC_T, 11, nrows, EpiNT{h0, LD, H2, 1});
-    gemm_nt<4, LD, LD>(sXc, sWp + SW_ENC_C, 11, nrows, EpiNT{h0 + H2, LD, H2, 1});
+    for (int idx = threadIdx.x; idx < ROWS * 6; idx += NT) h0[(idx / 6) * LD + H + (idx % 6)] = 0.f;
+    gemm_nt_r<ROWS, 4, LD, LD>(sXf, sWp + SW_ENC_T, 11, nrows, EpiNT{h0, LD, H2, 1});
+    gemm_nt_r<ROWS, 4, LD, LD>(sXc, sWp + SW_ENC_C, 11, nrows, EpiNT{h0 + H2, LD, H2, 1});
     __syncthreads();
 #pragma unroll 1
     for (int l = 0; l < NL; ++l) {
-        gemm_nt<7, LD, LD>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{bufs[l + 1], LD, 52, 1});
+        gemm_nt_r<ROWS, 7, LD, LD>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{bufs[l + 1], LD, 52, 1});
         __syncthreads();
     }
 }
 
-__device__ __forceinline__ void load_pair_meta(PairMeta& M, const int* __restrict__ pair_foc,
+template <int ROWS>
+__device__ __forceinline__ void load_pair_meta(PairMeta<ROWS>& M, const int* __restrict__ pair_foc,
                                                const long long* __restrict__ pair_crow,
                                                const long long* __restrict__ foc_row, int lo, int nrows) {
     if (threadIdx.x < nrows) {
@@ -360,27 +390,28 @@ __device__ __forceinline__ void load_pair_meta(PairMeta& M, const int* __restric
     }
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
                float* __restrict__ Hp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    PairFwdSmem& S = *reinterpret_cast<PairFwdSmem*>(smem_raw);
+    PairFwdSmem<ROWS>& S = *reinterpret_cast<PairFwdSmem<ROWS>*>(smem_raw);
     const int P = info[0];
-    if ((int)blockIdx.x * TILE >= P) return;
+    if ((int)blockIdx.x * ROWS >= P) return;
     stage_issue(S.W, S.Wp, nullptr, wpack);
     bool staged = false;
     float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
-    for (int lo = blockIdx.x * TILE; lo < P; lo += gridDim.x * TILE) {
-        const int nrows = min(TILE, P - lo);
+    for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
+        const int nrows = min(ROWS, P - lo);
         __syncthreads();
         load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
         __syncthreads();
-        gather_rows<LD>(S.Xf, states, S.M.frow, nrows);
-        gather_rows<LD>(S.Xc, states, S.M.crow, nrows);
+        gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
+        gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        pair_chain_dense(S.Wp, S.Xf, S.Xc, nrows, bufs);
+        pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs);
         for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
             const int r = idx / 13, c4 = idx - r * 13;
             st4(Hp + (size_t)(lo + r) * 52 + 4 * c4, ld4(S.P1 + r * LD + 4 * c4));
@@ -392,14 +423,15 @@ k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_fo
 // K2b + K3: per-focus segmented sum of the pair outputs (fixed order -> deterministic), decoder, sigmoid split,
 // per-example losses.
 // ----------------------------------------------------------------------------------------------------------------
+template <int ROWS>
 struct DecFwdSmem {
     float Wd[SW_DEC_TOTAL];
-    float Z[TILE * LD1];
-    float P0[TILE * LD];
-    float P1[TILE * LD];
-    float O[TILE * LD];
-    long long foff[TILE];
-    int pstart[TILE + 1];
+    float Z[ROWS * LD1];
+    float P0[ROWS * LD];
+    float P1[ROWS * LD];
+    float O[ROWS * LD];
+    long long foff[ROWS];
+    int pstart[ROWS + 1];
     WeightStage W;
 };
 
@@ -416,29 +448,30 @@ __device__ __forceinline__ void focus_sums(float* sZ, const int* pstart, const f
     }
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_dec_forward(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
               const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wpack,
               const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    DecFwdSmem& S = *reinterpret_cast<DecFwdSmem*>(smem_raw);
+    DecFwdSmem<ROWS>& S = *reinterpret_cast<DecFwdSmem<ROWS>*>(smem_raw);
     stage_issue(S.W, nullptr, S.Wd, wpack);
     bool staged = false;
     float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
-    const int ntiles = (F + TILE - 1) / TILE;
+    const int ntiles = (F + ROWS - 1) / ROWS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int f0 = tile * TILE;
-        const int nf = min(TILE, F - f0);
+        const int f0 = tile * ROWS;
+        const int nf = min(ROWS, F - f0);
         __syncthreads();
         if (threadIdx.x < nf) S.foff[threadIdx.x] = foc_row[f0 + threadIdx.x];
         if (threadIdx.x <= nf) S.pstart[threadIdx.x] = pair_start[f0 + threadIdx.x];
         __syncthreads();
-        load_focus_tile(S.Z, states, S.foff, nf);
+        load_focus_tile<ROWS>(S.Z, states, S.foff, nf);
         __syncthreads();
         focus_sums(S.Z, S.pstart, Hp, nf);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        decoder_forward(S.Wd, S.Z, ubufs, S.O, nf);
+        decoder_forward<ROWS>(S.Wd, S.Z, ubufs, S.O, nf);
         for (int idx = threadIdx.x; idx < nf * OUT; idx += NT) {
             const int r = idx / OUT, n = idx - r * OUT;
             float v = S.O[r * LD + n];
@@ -485,25 +518,28 @@ __global__ void k_loss_reduce(const float* __restrict__ loss_ex, int F, float* _
 // K4a: decoder backward.  d_pred = 2 (p - y) vlambda / (2B) on cols 2,3; 2 (p - y) lambda / B on col 5; zero
 // elsewhere (npe.lua:301-320).  Weight-gradient tiles live in registers for the whole kernel.
 // ----------------------------------------------------------------------------------------------------------------
+template <int ROWS>
 struct DecBwdSmem {
     float Wd[SW_DEC_TOTAL];
-    float Z[TILE * LD1];
-    float U[4][TILE * LD];
-    float O[TILE * LD];
-    float Da[TILE * LD];
-    float Db[TILE * LD];
-    long long foff[TILE];
-    int pstart[TILE + 1];
+    float Z[ROWS * LD1];
+    float U[4][ROWS * LD];
+    float O[ROWS * LD];
+    float Da[ROWS * LD];
+    float Db[ROWS * LD];
+    long long foff[ROWS];
+    int pstart[ROWS + 1];
     WeightStage W;
 };
 
+template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_dec_backward(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
                const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wpack,
                const float* __restrict__ y, float* __restrict__ ds_out, float* __restrict__ partial,
                float scale_v, float scale_w) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    DecBwdSmem& S = *reinterpret_cast<DecBwdSmem*>(smem_raw);
+    DecBwdSmem<ROWS>& S = *reinterpret_cast<DecBwdSmem<ROWS>*>(smem_raw);
+    for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) S.Db[idx] = 0.f;   // pad columns 52..55 are read by the 16-row mapping
     stage_issue(S.W, nullptr, S.Wd, wpack);
     bool staged = false;
     float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
@@ -511,21 +547,21 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
 #pragma unroll
     for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
     const int t = threadIdx.x;
-    const int ntiles = (F + TILE - 1) / TILE;
+    const int ntiles = (F + ROWS - 1) / ROWS;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int f0 = tile * TILE;
-        const int nf = min(TILE, F - f0);
+        const int f0 = tile * ROWS;
+        const int nf = min(ROWS, F - f0);
         __syncthreads();
         if (t < nf) S.foff[t] = foc_row[f0 + t];
         if (t <= nf) S.pstart[t] = pair_start[f0 + t];
         __syncthreads();
-        load_focus_tile(S.Z, states, S.foff, nf);
-        for (int idx = t; idx < TILE * LD; idx += NT) S.Da[idx] = 0.f;
+        load_focus_tile<ROWS>(S.Z, states, S.foff, nf);
+        for (int idx = t; idx < ROWS * LD; idx += NT) S.Da[idx] = 0.f;
         __syncthreads();
         focus_sums(S.Z, S.pstart, Hp, nf);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        decoder_forward(S.Wd, S.Z, ubufs, S.O, nf);
+        decoder_forward<ROWS>(S.Wd, S.Z, ubufs, S.O, nf);
         if (t < nf) {
             const float* yy = y + (size_t)(f0 + t) * OUT;
             S.Da[t * LD + 2] = (S.O[t * LD + 2] - yy[2]) * scale_v;
@@ -535,24 +571,24 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
         __syncthreads();
         // layer 5 (22 x 50): dz = Da (24 cols), input u4
         if (t >= 169 && t < 169 + 78) wgrad<13, LD, LD, true>(a5, S.Da, S.U[3], t - 169, nf);
-        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC5, 6, nf, EpiNN{S.Db, LD, S.U[3], TILE});
+        gemm_nn_r<ROWS, 13, LD, LD>(S.Da, S.Wd + SW_DEC5, 6, nf, EpiNN{S.Db, LD, S.U[3], ROWS});
         __syncthreads();
         // layer 4: dz = Db, input u3
         if (t < 169) wgrad<13, LD, LD, true>(a4, S.Db, S.U[2], t, nf);
-        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, nf, EpiNN{S.Da, LD, S.U[2], TILE});
+        gemm_nn_r<ROWS, 13, LD, LD>(S.Db, S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, nf, EpiNN{S.Da, LD, S.U[2], ROWS});
         __syncthreads();
         // layer 3: dz = Da, input u2
         if (t < 169) wgrad<13, LD, LD, true>(a3, S.Da, S.U[1], t, nf);
-        gemm_nn<13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, nf, EpiNN{S.Db, LD, S.U[1], TILE});
+        gemm_nn_r<ROWS, 13, LD, LD>(S.Da, S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, nf, EpiNN{S.Db, LD, S.U[1], ROWS});
         __syncthreads();
         // layer 2: dz = Db, input u1
         if (t < 169) wgrad<13, LD, LD, true>(a2, S.Db, S.U[0], t, nf);
-        gemm_nn<13, LD, LD>(S.Db, S.Wd + SW_DEC2, 13, nf, EpiNN{S.Da, LD, S.U[0], TILE});
+        gemm_nn_r<ROWS, 13, LD, LD>(S.Db, S.Wd + SW_DEC2, 13, nf, EpiNN{S.Da, LD, S.U[0], ROWS});
         __syncthreads();
         // layer 1 (50 x 94 (+bias)): dz = Da, input z (24 k-chunks); input grad only for the pair-sum columns
         wgrad<24, LD, LD1, true>(a1a, S.Da, S.Z, t, nf);
         if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Da, S.Z, t + NT, nf);
-        gemm_nn<13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, nf, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
+        gemm_nn_r<ROWS, 13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, nf, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
     }
     // write the register tiles into this CTA's partial (reference flat layout)
     float* out = partial + (size_t)blockIdx.x * NPARAM;
@@ -606,23 +642,26 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
 // trip through HBM); dz5 = ds[focus(p)] * (h5 > 0) (CAddTable backward = copy; apply_mask is the identity on the
 // active list, npe.lua:326-328); weight-gradient tiles stay in registers for the whole kernel.
 // ----------------------------------------------------------------------------------------------------------------
+template <int ROWS>
 struct PairBwdSmem {
     float Wp[SW_PAIR_TOTAL];
-    float Xf[TILE * LD];
-    float Xc[TILE * LD];
-    float Hh[NL + 1][TILE * LD];
-    float Da[TILE * LD];
-    float Db[TILE * LD];
-    PairMeta M;
+    float Xf[ROWS * LD];
+    float Xc[ROWS * LD];
+    float Hh[NL + 1][ROWS * LD];
+    float Da[ROWS * LD];
+    float Db[ROWS * LD];
+    PairMeta<ROWS> M;
     WeightStage W;
 };
 
+template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                 const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
                 const float* __restrict__ ds_in, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    PairBwdSmem& S = *reinterpret_cast<PairBwdSmem*>(smem_raw);
+    PairBwdSmem<ROWS>& S = *reinterpret_cast<PairBwdSmem<ROWS>*>(smem_raw);
+    for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) { S.Da[idx] = 0.f; S.Db[idx] = 0.f; }   // pad columns stay zero
     const int P = info[0];
     const int t = threadIdx.x;
     float acc[NL][16];
@@ -632,21 +671,21 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
         for (int i = 0; i < 16; ++i) acc[l][i] = 0.f;
     const bool enc_thread = (t >= 169 && t < 169 + 77);
     float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
-    if ((int)blockIdx.x * TILE < P) {
+    if ((int)blockIdx.x * ROWS < P) {
         stage_issue(S.W, S.Wp, nullptr, wpack);
         bool staged = false;
-        for (int lo = blockIdx.x * TILE; lo < P; lo += gridDim.x * TILE) {
-            const int nrows = min(TILE, P - lo);
+        for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
+            const int nrows = min(ROWS, P - lo);
             __syncthreads();
             load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
             __syncthreads();
-            gather_rows<LD>(S.Xf, states, S.M.frow, nrows);
-            gather_rows<LD>(S.Xc, states, S.M.crow, nrows);
+            gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
+            gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
             __syncthreads();
             if (!staged) { stage_wait(S.W); staged = true; }
-            pair_chain_dense(S.Wp, S.Xf, S.Xc, nrows, bufs);
+            pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs);
             // dz5 = ds[focus] * (h5 > 0); rows >= nrows zero
-            for (int idx = t; idx < TILE * (LD / 4); idx += NT) {
+            for (int idx = t; idx < ROWS * (LD / 4); idx += NT) {
                 const int r = idx / (LD / 4), c4 = idx - r * (LD / 4);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < nrows && c4 < 13) {
@@ -664,7 +703,7 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
             for (int l = NL - 1; l >= 0; --l) {
                 const float* hin = S.Hh[l];
                 if (t < 169) wgrad<13, LD, LD, true>(acc[l], da, hin, t, nrows);
-                gemm_nn<13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNN{db, LD, hin, TILE});
+                gemm_nn_r<ROWS, 13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNN{db, LD, hin, ROWS});
                 __syncthreads();
                 float* tmp = da; da = db; db = tmp;
             }
@@ -703,13 +742,34 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
 }
 
 // grad[i] = sum over CTA partials in CTA order (deterministic); pair part and decoder part have their own grids.
-__global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad) {
+// OPT = 1 / 2 fuses the Adam / RMSprop update (and the write-through to the packed weight image) into the same
+// kernel: used whenever no all-reduce sits between the reduction and the optimiser (single GPU).
+struct OptArgs {
+    float* x; float* m; float* v; float* wpack;
+    float b1, omb1, b2, omb2, eps, step;   // adam: step = lr * sqrt(1 - b2^t) / (1 - b1^t); rmsprop: b1 = alpha, step = lr
+};
+template <int OPT>
+__global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     float a = 0.f;
     for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
     grad[i] = a;
+    if (OPT == 1) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
+        const float vi = __fadd_rn(__fmul_rn(o.b2, o.v[i]), __fmul_rn(o.omb2, __fmul_rn(a, a)));
+        o.m[i] = mi; o.v[i] = vi;
+        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    } else if (OPT == 2) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, __fmul_rn(a, a)));
+        o.m[i] = mi;
+        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------------

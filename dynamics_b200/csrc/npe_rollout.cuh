@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                 }
                 __syncthreads();
             }
-            decoder_forward(S.Wd, S.Z, ubufs, S.O, TILE);
+            decoder_forward<TILE>(S.Wd, S.Z, ubufs, S.O, TILE);
             // ---- post-process, metrics ----
             double mt[7] = {0, 0, 0, 0, 0, 0, 0};
             if (t < TILE && S.kind[t]) {

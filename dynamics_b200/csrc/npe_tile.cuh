@@ -159,6 +159,156 @@ __device__ __noinline__ void gemm_nn(const float* __restrict__ dZ, const float* 
     }
 }
 
+// ---- 16-row variants (latency path: small batches are split over many CTAs) ------------------------------------
+// rg = tid >> 6 (0..3) owns rows {rg + 4 j}; cg = (tid >> 3) & 7; the reduction index is split EIGHT ways over
+// adjacent lanes (ks = tid & 7) so that a 16-row pass still occupies all 256 threads with the same loaded-bytes-per-FMA
+// ratio as the 64-row mapping; the eight partial sums are combined with a 3-round butterfly that also scatters
+// ownership (rows, then columns), ~25 shuffles per thread.
+template <int NI, int LDA, int LDW>
+__device__ __noinline__ void gemm_nt16(const float* __restrict__ A, const float* __restrict__ W, int kc, int nrows, EpiNT e) {
+    const int tid = threadIdx.x;
+    const int ks = tid & 7, cg = (tid >> 3) & 7, rg = tid >> 6;
+    float acc[4][NI];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) acc[j][i] = 0.f;
+    const float* a = A + rg * LDA + 4 * ks;
+    const float* w = W + cg * LDW + 4 * ks;
+#pragma unroll 1
+    for (int c = ks; c < kc; c += 8) {
+        float4 x[4], wv[NI];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ld4(a + 4 * j * LDA);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) wv[i] = ld4(w + 8 * i * LDW);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].x, wv[i].x, acc[j][i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].y, wv[i].y, acc[j][i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].z, wv[i].z, acc[j][i]);
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][i] = fmaf(x[j].w, wv[i].w, acc[j][i]);
+        a += 32; w += 32;
+    }
+    __syncwarp();
+    // round 1 (lane ^ 4): keep rows {0,1} (bit clear) or {2,3} (bit set)
+    const int b2 = (ks >> 2) & 1, b1 = (ks >> 1) & 1, b0 = ks & 1;
+    float r1[2][NI];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const float send = b2 ? acc[jj][i] : acc[2 + jj][i];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            r1[jj][i] = (b2 ? acc[2 + jj][i] : acc[jj][i]) + recv;
+        }
+    // round 2 (lane ^ 2): keep one of the two rows
+    float r2[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const float send = b1 ? r1[0][i] : r1[1][i];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        r2[i] = (b1 ? r1[1][i] : r1[0][i]) + recv;
+    }
+    // round 3 (lane ^ 1): keep columns i with (i & 1) == b0
+    const int row = rg + 4 * (2 * b2 + b1);
+    float* o = e.out + row * e.ldo + cg;
+#pragma unroll
+    for (int i2 = 0; i2 < (NI + 1) / 2; ++i2) {
+        const int ie = 2 * i2, io = 2 * i2 + 1;           // even / odd column slots of this pair
+        const float even = r2[ie], odd = (io < NI) ? r2[io] : 0.f;
+        const float send = b0 ? even : odd;
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        float mine = (b0 ? odd : even) + recv;
+        const int i = b0 ? io : ie;
+        if (e.relu) mine = fmaxf(mine, 0.f);
+        if (i < NI && row < 16 && cg + 8 * i < e.nmax) o[8 * i] = mine;
+    }
+    (void)nrows;
+}
+
+// dA[rg + 4 j][4 kc..] for kc = cg + 8 m < KCO (m < 2); lane ks takes n = 8 q + ks.
+template <int KCO, int LDZ, int LDW>
+__device__ __noinline__ void gemm_nn16(const float* __restrict__ dZ, const float* __restrict__ W, int nq, int nrows, EpiNN e) {
+    constexpr int MI = (KCO + 7) / 8;
+    static_assert(MI == 2, "gemm_nn16 assumes two output chunks per thread");
+    const int tid = threadIdx.x;
+    const int ks = tid & 7, cg = (tid >> 3) & 7, rg = tid >> 6;
+    float4 acc[4][MI];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < MI; ++m) acc[j][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* zp = dZ + rg * LDZ + ks;
+    const float* wa = W + ks * LDW + 4 * cg;
+#pragma unroll 1
+    for (int q = 0; q < nq; ++q) {
+        float z[4];
+        float4 w0[MI];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = zp[4 * j * LDZ];
+#pragma unroll
+        for (int m = 0; m < MI; ++m) w0[m] = (cg + 8 * m < KCO) ? ld4(wa + 32 * m) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) axpy4(acc[j][m], z[j], w0[m]);
+        zp += 8; wa += 8 * LDW;
+    }
+    __syncwarp();
+    const int b2 = (ks >> 2) & 1, b1 = (ks >> 1) & 1, b0 = ks & 1;
+    auto xchg = [](float4 send, int lane_mask) {
+        float4 r;
+        r.x = __shfl_xor_sync(0xffffffffu, send.x, lane_mask); r.y = __shfl_xor_sync(0xffffffffu, send.y, lane_mask);
+        r.z = __shfl_xor_sync(0xffffffffu, send.z, lane_mask); r.w = __shfl_xor_sync(0xffffffffu, send.w, lane_mask);
+        return r;
+    };
+    auto add4 = [](float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); };
+    float4 r1[2][MI];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+        for (int m = 0; m < MI; ++m)
+            r1[jj][m] = add4(b2 ? acc[2 + jj][m] : acc[jj][m], xchg(b2 ? acc[jj][m] : acc[2 + jj][m], 4));
+    float4 r2[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) r2[m] = add4(b1 ? r1[1][m] : r1[0][m], xchg(b1 ? r1[0][m] : r1[1][m], 2));
+    float4 v = add4(b0 ? r2[1] : r2[0], xchg(b0 ? r2[0] : r2[1], 1));
+    const int row = rg + 4 * (2 * b2 + b1), kc = cg + 8 * b0;
+    if (kc < KCO && row < e.nrows) {
+        if (e.hmask) {
+            const float4 hv = ld4(e.hmask + row * LD + 4 * kc);
+            v.x = hv.x > 0.f ? v.x : 0.f; v.y = hv.y > 0.f ? v.y : 0.f;
+            v.z = hv.z > 0.f ? v.z : 0.f; v.w = hv.w > 0.f ? v.w : 0.f;
+        }
+        st4(e.out + (size_t)row * e.ldo + 4 * kc, v);
+    }
+    (void)nrows;
+}
+
+// ROWS-dispatching wrappers used by the kernels (ROWS = 64: throughput mapping, ROWS = 16: latency mapping).
+template <int ROWS, int NI, int LDA, int LDW>
+__device__ __forceinline__ void gemm_nt_r(const float* A, const float* W, int kc, int nrows, EpiNT e) {
+    if (ROWS == 64) gemm_nt<NI, LDA, LDW>(A, W, kc, nrows, e);
+    else gemm_nt16<NI, LDA, LDW>(A, W, kc, nrows, e);
+}
+// nc = reduction length in chunks of 4 n (64-row mapping); the 16-row mapping walks it in steps of 8 n.
+template <int ROWS, int KCO, int LDZ, int LDW>
+__device__ __forceinline__ void gemm_nn_r(const float* dZ, const float* W, int nc, int nrows, EpiNN e) {
+    if (ROWS == 64) gemm_nn<KCO, LDZ, LDW>(dZ, W, nc, nrows, e);
+    else gemm_nn16<KCO, LDZ, LDW>(dZ, W, (nc + 1) / 2, nrows, e);
+}
+
 // acc[4 i + j] += sum_{r < nrows} dZ[r][zoff + 4 a + i] * Hm[r][4 b + j];  (a, b) = (tile / KCH, tile % KCH).
 // ZALIGNED: zoff + 4 a is 16-byte aligned (one LDS.128), else four scalar loads.
 template <int KCH, int LDZ, int LDH, bool ZALIGNED>
