@@ -114,6 +114,15 @@ struct npe_handle {
     DevBuf<long long> foc_row, pair_crow;
     int pair_cap = 0;
     int* info_dev = nullptr;          // {P, overflow}
+    // batch-form staging: the three host arrays are packed into the scene layout in page-locked memory and shipped
+    // with ONE async copy (two buffers alternate; an event guards reuse)
+    float* stage[2] = {nullptr, nullptr};
+    size_t stage_cap = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    int stage_idx = 0;
+    int foci_B = -1, foci_N = -1;     // shape the iota focus arrays / n_obj were last built for
+    float* loss4_host = nullptr;      // host-mapped {loss, vel, angvel, overflow}
+    float* loss4_devptr = nullptr;
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
     DevBuf<int> ctx_idx_out, cnt_out;
@@ -194,6 +203,19 @@ __global__ void k_batch_foci(int* scene, int* obj, int* t0, int* n_obj, int B, i
     if (i < B) { scene[i] = i; obj[i] = 0; t0[i] = 0; n_obj[i] = N; }
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; it calls
+// griddepcontrol.wait before touching predecessor outputs.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int ctx_slots(const npe_handle* h) {
     const int cn = h->Nmax - 1;
     return (h->cfg.max_ctx > 0 && h->cfg.max_ctx < cn) ? h->cfg.max_ctx : cn;
@@ -231,7 +253,7 @@ int build_pairs(npe_handle* h) {
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
         const int nblk = (h->F + FPB - 1) / FPB;
-        k_build_pairs<<<nblk, NT, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
+        k_build_pairs<<<nblk, NT_PAIRS, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
                                                   h->block_sums.p, h->foc_row.p, h->batch_form ? nullptr : h->y.p,
                                                   h->active_total, h->pair_start.p, h->pair_foc.p, h->pair_crow.p,
                                                   h->pair_cap, h->info_dev);
@@ -293,15 +315,15 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
         h->launches++;
     } else {
         if (small_batch(h, F)) {
-            k_pair_forward<16><<<pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream>>>(
-                st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
-            k_dec_forward<16><<<focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream>>>(
-                st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex);
+            CK(launch_pdl(k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream,
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p));
+            CK(launch_pdl(k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream,
+                          st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         } else {
-            k_pair_forward<64><<<pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>), h->stream>>>(
-                st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p);
-            k_dec_forward<64><<<focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream>>>(
-                st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex);
+            CK(launch_pdl(k_pair_forward<64>, pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>), h->stream,
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p));
+            CK(launch_pdl(k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream,
+                          st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         }
         h->launches += 2;
     }
@@ -327,7 +349,7 @@ int run_loss_reduce(npe_handle* h) {
 }
 
 // fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
-int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f) {
+int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false) {
     if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
     if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
     const int B = divisor_batch > 0 ? divisor_batch : h->F;
@@ -341,21 +363,21 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
     {
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
         if (small)
-            k_dec_backward<16><<<gd, NT, sizeof(DecBwdSmem<16>), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p,
-                                                                              h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
+            CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw));
         else
-            k_dec_backward<64><<<gd, NT, sizeof(DecBwdSmem<64>), h->stream>>>(h->states.p, h->foc_row.p, h->F, h->pair_start.p,
-                                                                              h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw);
+            CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw));
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
         if (small)
-            k_pair_backward<16><<<gp, NT, sizeof(PairBwdSmem<16>), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
-                                                                                h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial);
+            CK(launch_pdl(k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->stream, h->states.p, h->pair_foc.p,
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial));
         else
-            k_pair_backward<64><<<gp, NT, sizeof(PairBwdSmem<64>), h->stream>>>(h->states.p, h->pair_foc.p, h->pair_crow.p,
-                                                                                h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial);
+            CK(launch_pdl(k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->stream, h->states.p, h->pair_foc.p,
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -364,19 +386,21 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         OptArgs o;
         o.x = h->params; o.m = h->adam_m; o.v = h->adam_v; o.wpack = h->wpack;
         o.b1 = 0.9f; o.omb1 = (float)(1.0 - 0.9); o.b2 = 0.999f; o.omb2 = (float)(1.0 - 0.999); o.eps = 1e-8f; o.step = lr;
-        const int nb = (NPARAM + 255) / 256;
+        LossArgs L;
+        L.loss_ex = h->loss_ex.p; L.F = h->F; L.loss4_out = want_loss ? h->loss4_devptr : nullptr; L.info = h->info_dev;
+        const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
         if (fuse_opt == 1) {
             h->adam_t += 1;
             const double t = (double)h->adam_t;
             o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
-            k_reduce_grads<1><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+            CK(launch_pdl(k_reduce_grads<1>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
             h->wtc_dirty = true;
         } else if (fuse_opt == 2) {
             o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
-            k_reduce_grads<2><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+            CK(launch_pdl(k_reduce_grads<2>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
             h->wtc_dirty = true;
         } else {
-            k_reduce_grads<0><<<nb, 256, 0, h->stream>>>(h->partial, gp, gd, h->grads, o);
+            CK(launch_pdl(k_reduce_grads<0>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
         }
         h->launches++;
     }
@@ -478,6 +502,10 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaHostAlloc((void**)&h->loss4_host, 16 * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer((void**)&h->loss4_devptr, h->loss4_host, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaMemset(h->info_dev, 0, 4 * sizeof(int));
     cudaMemset(h->active_total, 0, sizeof(u64));
     if ((e = cudaFuncSetAttribute(k_pair_forward<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairFwdSmem<64>))) != cudaSuccess ||
@@ -506,6 +534,8 @@ int npe_destroy(npe_handle* h) {
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
     if (h->info_dev) cudaFree(h->info_dev);
+    if (h->loss4_host) cudaFreeHost(h->loss4_host);
+    for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->this_rows.release();
@@ -559,22 +589,39 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     if (!this_past || B <= 0 || C < 0 || (C > 0 && !context)) return fail(h, NPE_ERR_INVALID, "batch_upload: bad arguments");
     if (C + 1 > MAXOBJ) return fail(h, NPE_ERR_INVALID, "batch_upload: at most %d contexts", MAXOBJ - 1);
     const int N = C + 1;
-    CK(h->states.ensure((size_t)B * N * IN));
     CK(h->n_obj.ensure(B));
     CK(h->foc_scene.ensure(B)); CK(h->foc_obj.ensure(B)); CK(h->foc_t0.ensure(B));
     h->S = B; h->Nmax = N; h->T = 2;
     int rc = ensure_batch_buffers(h, B);
     if (rc) return rc;
-    // scene b = [this_b | context_b,0 | ... | context_b,C-1], T = 2  (== `past` of eval.lua:283)
-    CK(cudaMemcpy2DAsync(h->states.p, (size_t)N * IN * sizeof(float), this_past, IN * sizeof(float), IN * sizeof(float), B,
-                         cudaMemcpyHostToDevice, h->stream));
-    if (C > 0)
-        CK(cudaMemcpy2DAsync(h->states.p + IN, (size_t)N * IN * sizeof(float), context, (size_t)C * IN * sizeof(float),
-                             (size_t)C * IN * sizeof(float), B, cudaMemcpyHostToDevice, h->stream));
-    if (y) CK(cudaMemcpyAsync(h->y.p, y, (size_t)B * OUT * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    k_batch_foci<<<(B + 255) / 256, 256, 0, h->stream>>>(h->foc_scene.p, h->foc_obj.p, h->foc_t0.p, h->n_obj.p, B, N);
-    CKL();
-    h->S = B; h->Nmax = N; h->T = 2;
+    // scene b = [this_b | context_b,0 | ... | context_b,C-1], T = 2  (== `past` of eval.lua:283), followed by y (B,22):
+    // packed on the host into page-locked staging, ONE H2D copy
+    const size_t n_state = (size_t)B * N * IN, n_y = y ? (size_t)B * OUT : 0;
+    if (n_state + n_y > h->stage_cap) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage[i]) { cudaEventSynchronize(h->stage_ev[i]); cudaFreeHost(h->stage[i]); h->stage[i] = nullptr; }
+            CK(cudaHostAlloc((void**)&h->stage[i], (n_state + (size_t)B * OUT) * 2 * sizeof(float), cudaHostAllocDefault));
+        }
+        h->stage_cap = (n_state + (size_t)B * OUT) * 2;
+    }
+    const int si = h->stage_idx;
+    h->stage_idx ^= 1;
+    CK(cudaEventSynchronize(h->stage_ev[si]));
+    float* sg = h->stage[si];
+    for (int b = 0; b < B; ++b) {
+        memcpy(sg + (size_t)b * N * IN, this_past + (size_t)b * IN, IN * sizeof(float));
+        if (C > 0) memcpy(sg + (size_t)b * N * IN + IN, context + (size_t)b * C * IN, (size_t)C * IN * sizeof(float));
+    }
+    CK(h->states.ensure(n_state + (size_t)B * OUT));
+    if (y) memcpy(sg + n_state, y, n_y * sizeof(float));
+    CK(cudaMemcpyAsync(h->states.p, sg, (n_state + n_y) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->stage_ev[si], h->stream));
+    if (y) CK(cudaMemcpyAsync(h->y.p, h->states.p + n_state, n_y * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    if (h->foci_B != B || h->foci_N != N) {
+        k_batch_foci<<<(B + 255) / 256, 256, 0, h->stream>>>(h->foc_scene.p, h->foc_obj.p, h->foc_t0.p, h->n_obj.p, B, N);
+        CKL();
+        h->foci_B = B; h->foci_N = N;
+    }
     h->foc_first = 0; h->F = B;
     h->batch_form = true; h->have_y = (y != nullptr);
     h->pairs_valid = false; h->fwd_valid = false;
@@ -592,6 +639,7 @@ int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, 
     CK(h->n_obj.ensure(S));
     CK(cudaMemcpyAsync(h->states.p, states, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->n_obj.p, n_obj, (size_t)S * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->foci_B = h->foci_N = -1;
     h->scene_foci.assign(S, {});
     h->scene_pred_objects = 0;
     for (int s = 0; s < S; ++s) {
@@ -770,21 +818,24 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
     int rc;
     if ((rc = run_forward(h, true))) return rc;
-    if (loss3_out && (rc = run_loss_reduce(h))) return rc;
     if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
+    const bool want_loss = loss3_out != nullptr;
     if (!h->comm) {
-        // single GPU: reduction of the CTA partials, optimiser step and weight-image write-through in ONE kernel
-        if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr))) return rc;
+        // single GPU: reduction of the CTA partials, optimiser step, weight-image write-through and the batch loss in ONE kernel
+        if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr, want_loss))) return rc;
     } else {
-        if ((rc = run_backward(h, divisor_batch))) return rc;
+        if ((rc = run_backward(h, divisor_batch, 0, 0.f, want_loss))) return rc;
         if ((rc = run_allreduce(h))) return rc;
         rc = (opt == 0) ? run_adam(h, lr, 0.9f, 0.999f, 1e-8f) : run_rmsprop(h, lr, 0.99f, 1e-8f);
         if (rc) return rc;
     }
     h->fwd_valid = false;   // parameters changed
-    if (loss3_out) {
-        CK(cudaMemcpyAsync(loss3_out, h->loss3_dev, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-        return check_pair_overflow(h);
+    if (want_loss) {
+        // the loss kernel wrote {loss, vel, angvel, overflow} straight into host-mapped memory: one sync, no copy
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->loss4_host[3] != 0.f)
+            return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
+        loss3_out[0] = h->loss4_host[0]; loss3_out[1] = h->loss4_host[1]; loss3_out[2] = h->loss4_host[2];
     }
     return NPE_OK;
 }
@@ -868,7 +919,7 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
-            k_build_pairs<<<nblk, NT, 0, h->stream>>>(src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
+            k_build_pairs<<<nblk, NT_PAIRS, 0, h->stream>>>(src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
                                                       h->foc_row.p, nullptr, h->active_total, h->pair_start.p, h->pair_foc.p,
                                                       h->pair_crow.p, h->pair_cap, h->info_dev);
             h->launches++;

@@ -81,6 +81,14 @@ __global__ void k_pack_scatter(const float* __restrict__ params, float* __restri
     if (i < NPARAM) wpack[pack_index(i)] = params[i];
 }
 
+// Programmatic dependent launch (PDL): the forward/backward kernels of one step are launched with the
+// programmatic-stream-serialization attribute, so a kernel's prologue (mbarrier init, TMA weight staging, shared-memory
+// clears -- nothing that depends on the previous kernel) overlaps the tail of its predecessor.  pdl_wait() must be
+// executed by EVERY CTA before it touches predecessor outputs or exits (grid completion is what successors wait on).
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct WeightStage {
     unsigned long long bar;
 };
@@ -150,7 +158,8 @@ __device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, 
 // y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96), and the first level of
 // the active-pair scan: exclusive prefix of the counts inside the CTA + the CTA total.
 constexpr int FPB = 64;   // foci per CTA of the pair builder
-__global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
+constexpr int NT_PAIRS = 1024;   // 32 warps: two foci per warp, so the dependent global loads of the 64 foci overlap
+__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
                                                     u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
                                                     int* __restrict__ block_sums, long long* __restrict__ foc_row,
                                                     float* __restrict__ y, u64* __restrict__ active_total,
@@ -160,8 +169,8 @@ __global__ void __launch_bounds__(NT) k_build_pairs(FocusSrc src, int kmax, floa
     __shared__ int s_pre[FPB];
     __shared__ u64 s_nbr[FPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = 0; i < FPB / (NT / 32); ++i) {
-        const int fl = warp * (FPB / (NT / 32)) + i;
+    for (int i = 0; i < FPB / (NT_PAIRS / 32); ++i) {
+        const int fl = warp * (FPB / (NT_PAIRS / 32)) + i;
         const int f = blockIdx.x * FPB + fl;
         int c = 0;
         if (f < src.F) {
@@ -397,9 +406,11 @@ k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_fo
                float* __restrict__ Hp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairFwdSmem<ROWS>& S = *reinterpret_cast<PairFwdSmem<ROWS>*>(smem_raw);
-    const int P = info[0];
-    if ((int)blockIdx.x * ROWS >= P) return;
+    pdl_launch_dependents();
     stage_issue(S.W, S.Wp, nullptr, wpack);
+    pdl_wait();
+    const int P = info[0];
+    if ((int)blockIdx.x * ROWS >= P) { stage_wait(S.W); return; }   // never exit with a bulk copy in flight
     bool staged = false;
     float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
     for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
@@ -455,7 +466,9 @@ k_dec_forward(const float* __restrict__ states, const long long* __restrict__ fo
               const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecFwdSmem<ROWS>& S = *reinterpret_cast<DecFwdSmem<ROWS>*>(smem_raw);
+    pdl_launch_dependents();
     stage_issue(S.W, nullptr, S.Wd, wpack);
+    pdl_wait();
     bool staged = false;
     float* const ubufs[4] = {S.P0, S.P1, S.P0, S.P1};
     const int ntiles = (F + ROWS - 1) / ROWS;
@@ -539,8 +552,10 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
                float scale_v, float scale_w) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecBwdSmem<ROWS>& S = *reinterpret_cast<DecBwdSmem<ROWS>*>(smem_raw);
+    pdl_launch_dependents();
     for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) S.Db[idx] = 0.f;   // pad columns 52..55 are read by the 16-row mapping
     stage_issue(S.W, nullptr, S.Wd, wpack);
+    pdl_wait();
     bool staged = false;
     float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
     float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
@@ -661,7 +676,10 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
                 const float* __restrict__ ds_in, float* __restrict__ partial) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairBwdSmem<ROWS>& S = *reinterpret_cast<PairBwdSmem<ROWS>*>(smem_raw);
+    pdl_launch_dependents();
     for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) { S.Da[idx] = 0.f; S.Db[idx] = 0.f; }   // pad columns stay zero
+    stage_issue(S.W, S.Wp, nullptr, wpack);
+    pdl_wait();
     const int P = info[0];
     const int t = threadIdx.x;
     float acc[NL][16];
@@ -671,8 +689,8 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
         for (int i = 0; i < 16; ++i) acc[l][i] = 0.f;
     const bool enc_thread = (t >= 169 && t < 169 + 77);
     float* const bufs[NL + 1] = {S.Hh[0], S.Hh[1], S.Hh[2], S.Hh[3], S.Hh[4], S.Hh[5]};
+    if ((int)blockIdx.x * ROWS >= P) stage_wait(S.W);   // never exit with a bulk copy in flight
     if ((int)blockIdx.x * ROWS < P) {
-        stage_issue(S.W, S.Wp, nullptr, wpack);
         bool staged = false;
         for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
             const int nrows = min(ROWS, P - lo);
@@ -748,8 +766,39 @@ struct OptArgs {
     float* x; float* m; float* v; float* wpack;
     float b1, omb1, b2, omb2, eps, step;   // adam: step = lr * sqrt(1 - b2^t) / (1 - b1^t); rmsprop: b1 = alpha, step = lr
 };
+// Last block (index gridDim.x - 1, launched as an extra block) optionally reduces the per-example losses and publishes
+// {loss, vel, angvel, overflow flag} to `loss4_out` (device or host-mapped memory): saves a launch and a copy per step.
+struct LossArgs {
+    const float* loss_ex; int F; float* loss4_out; const int* info;
+};
+__device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
+    __shared__ double sv[256], sw[256];
+    double av = 0.0, aw = 0.0;
+    for (int f = threadIdx.x; f < L.F; f += 256) {
+        av += 2.0 * (double)L.loss_ex[(size_t)f * 3 + 1];
+        aw += (double)L.loss_ex[(size_t)f * 3 + 2];
+    }
+    sv[threadIdx.x] = av; sw[threadIdx.x] = aw;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sv[threadIdx.x] += sv[threadIdx.x + s]; sw[threadIdx.x] += sw[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double B = (double)L.F;
+        L.loss4_out[0] = (float)((sv[0] + sw[0]) / (3.0 * B));
+        L.loss4_out[1] = (float)(sv[0] / (2.0 * B));
+        L.loss4_out[2] = (float)(sw[0] / B);
+        L.loss4_out[3] = L.info ? (float)L.info[1] : 0.f;
+        __threadfence_system();
+    }
+}
+
 template <int OPT>
-__global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o) {
+__global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o,
+                               LossArgs L) {
+    pdl_wait();
+    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
