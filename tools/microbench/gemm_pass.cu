@@ -32,6 +32,16 @@ __global__ void __launch_bounds__(NT, 1) k(long long* out, int iters) {
             __syncthreads();
             gemm_nn<13, LD, LD>(S.B, S.W, 13, TILE, EpiNN{S.A, LD, S.C, TILE});
             __syncthreads();
+        } else if (MODE == 3) {
+            gemm_nt16<7, LD, LD>(S.A, S.W, 13, 16, EpiNT{S.B, LD, 52, 1});
+            __syncthreads();
+            gemm_nt16<7, LD, LD>(S.B, S.W, 13, 16, EpiNT{S.A, LD, 52, 1});
+            __syncthreads();
+        } else if (MODE == 4) {
+            gemm_nn16<13, LD, LD>(S.A, S.W, 7, 16, EpiNN{S.B, LD, S.C, 16});
+            __syncthreads();
+            gemm_nn16<13, LD, LD>(S.B, S.W, 7, 16, EpiNN{S.A, LD, S.C, 16});
+            __syncthreads();
         } else {
             if (threadIdx.x < 169) wgrad<13, LD, LD, true>(acc, S.A, S.C, threadIdx.x, TILE);
             __syncthreads();
@@ -49,16 +59,16 @@ __global__ void __launch_bounds__(NT, 1) k(long long* out, int iters) {
 int main() {
     long long* out;
     cudaMalloc(&out, 148 * sizeof(long long));
-    const char* names[] = {"gemm_nt 64x52x52", "gemm_nn 64x52x52", "wgrad   52x52 over 64 rows"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[] = {"gemm_nt 64x52x52", "gemm_nn 64x52x52", "wgrad   52x52 over 64 rows", "gemm_nt16 16x52x52", "gemm_nn16 16x52x52"};
+    for (int mode = 0; mode < 5; ++mode) {
         for (int grid : {1, 148}) {
-            auto fn = mode == 0 ? k<0> : mode == 1 ? k<1> : k<2>;
+            auto fn = mode == 0 ? k<0> : mode == 1 ? k<1> : mode == 2 ? k<2> : mode == 3 ? k<3> : k<4>;
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
             fn<<<grid, NT, sizeof(Smem)>>>(out, 200);
             cudaDeviceSynchronize();
             long long h[148];
             cudaMemcpy(h, out, grid * sizeof(long long), cudaMemcpyDeviceToHost);
-            double fma = 64.0 * 52 * 52;
+            double fma = (mode >= 3 ? 16.0 : 64.0) * 52 * 52;
             printf("%-28s grid %3d: %6lld cycles/pass  -> %.1f FMA/clk/SM (ideal 128)  [%s]\n", names[mode], grid, h[0],
                    fma / h[0], cudaGetErrorString(cudaGetLastError()));
         }
