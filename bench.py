@@ -347,11 +347,17 @@ def run_ours(args):
     m.set_params(init_params(1234)); m.optim_reset(0.0)
     if world > 1:
         import torch
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
-        dist.broadcast(idt, 0)
-        m.comm_init(rank, world, bytes(idt.tolist()))
+        if args.dp == "nccl":
+            idt = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
+            dist.broadcast(idt, 0)
+            m.comm_init(rank, world, bytes(idt.tolist()))
+        else:   # fused all-reduce + optimiser over NVLink peer memory (CUDA IPC handles exchanged by the launcher)
+            mine = torch.tensor(list(m.peer_export()), dtype=torch.uint8)
+            allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            m.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
     m.upload_scenes(states, n_obj)
     m.upload_foci(sc, ob, tt)
     gB = BATCH * world
@@ -430,7 +436,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: NPE train, balls n3/n4/n5 variable mass, batch 50 per GPU, adam",
-                       "global_batch": gB, "parallelism": f"dp{world}", "scenes_per_gpu": int(states.shape[0]),
+                       "global_batch": gB, "parallelism": f"dp{world}", "grad_exchange": (args.dp if world > 1 else None), "scenes_per_gpu": int(states.shape[0]),
                        "resident_state_bytes": int(states.nbytes), "l2": "inputs (317 MB/GPU) larger than L2; random batches",
                        "active_pairs_per_step": P_mean, "optimizer": "adam", "lr": LR},
             "clocks": clk,
@@ -467,6 +473,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads and the CPU baseline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--dp", default="p2p", choices=["p2p", "nccl"],
+                    help="gradient exchange at N > 1: fused NVLink peer-memory all-reduce (default) or ncclAllReduce")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps > 3000:

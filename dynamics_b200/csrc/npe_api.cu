@@ -140,6 +140,13 @@ struct npe_handle {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // NVLink peer exchange (fused DP step)
+    float* xregion = nullptr;         // xgrad[2][NPARAM] + 2 ready counters (+ pad)
+    unsigned* xcounter = nullptr;     // block counter of k_reduce_publish
+    void* peer_ptr[MAX_PEERS] = {};
+    bool peer_opened[MAX_PEERS] = {};
+    bool peer_ready = false;
+    unsigned peer_step = 0;
 
     FocusSrc src() const {
         FocusSrc s;
@@ -349,7 +356,8 @@ int run_loss_reduce(npe_handle* h) {
 }
 
 // fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
-int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false) {
+// peer_opt: 1 / 2 = fused NVLink all-reduce + Adam / RMSprop (requires npe_peer_attach)
+int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0) {
     if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
     if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
     const int B = divisor_batch > 0 ? divisor_batch : h->F;
@@ -389,7 +397,29 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         LossArgs L;
         L.loss_ex = h->loss_ex.p; L.F = h->F; L.loss4_out = want_loss ? h->loss4_devptr : nullptr; L.info = h->info_dev;
         const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
-        if (fuse_opt == 1) {
+        if (peer_opt) {
+            const int buf = (int)(h->peer_step & 1u);
+            const unsigned stamp = h->peer_step + 1u;
+            h->peer_step += 1u;
+            unsigned* flags = reinterpret_cast<unsigned*>(h->xregion + 2 * NPARAM);
+            CK(launch_pdl(k_reduce_publish, nb, 256, 0, h->stream, h->partial, gp, gd, h->xregion + (size_t)buf * NPARAM,
+                          flags + buf, stamp, h->xcounter, L));
+            PeerPtrs P;
+            P.nranks = h->nranks; P.rank = h->rank;
+            for (int r = 0; r < MAX_PEERS; ++r) P.x[r] = r < h->nranks ? (const float*)h->peer_ptr[r] : nullptr;
+            const int nb2 = (NPARAM + 255) / 256;
+            if (peer_opt == 1) {
+                h->adam_t += 1;
+                const double t = (double)h->adam_t;
+                o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
+                k_peer_allreduce_opt<1><<<nb2, 256, 0, h->stream>>>(P, buf, stamp, h->grads, o);
+            } else {
+                o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
+                k_peer_allreduce_opt<2><<<nb2, 256, 0, h->stream>>>(P, buf, stamp, h->grads, o);
+            }
+            h->wtc_dirty = true;
+            h->launches++;
+        } else if (fuse_opt == 1) {
             h->adam_t += 1;
             const double t = (double)h->adam_t;
             o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
@@ -529,6 +559,9 @@ int npe_destroy(npe_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int r = 0; r < MAX_PEERS; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
+    if (h->xregion) cudaFree(h->xregion);
+    if (h->xcounter) cudaFree(h->xcounter);
     float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
@@ -820,7 +853,10 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     if ((rc = run_forward(h, true))) return rc;
     if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
     const bool want_loss = loss3_out != nullptr;
-    if (!h->comm) {
+    if (h->peer_ready) {
+        // data parallel over NVLink peer memory: local reduce + publish, then all-reduce fused with the optimiser
+        if ((rc = run_backward(h, divisor_batch, 0, lr, want_loss, opt == 0 ? 1 : 2))) return rc;
+    } else if (!h->comm) {
         // single GPU: reduction of the CTA partials, optimiser step, weight-image write-through and the batch loss in ONE kernel
         if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr, want_loss))) return rc;
     } else {
@@ -1002,6 +1038,40 @@ int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128
     ncclResult_t r = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
     if (r != 0) return fail(h, NPE_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     h->rank = rank; h->nranks = nranks;
+    return NPE_OK;
+}
+
+int npe_peer_export(npe_handle* h, void* handle64_out) {
+    NEED(h);
+    if (!handle64_out) return fail(h, NPE_ERR_INVALID, "peer_export: null output");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NPE_PEER_HANDLE_BYTES, "IPC handle size");
+    if (!h->xregion) {
+        CK(cudaMalloc((void**)&h->xregion, (2 * (size_t)NPARAM + 64) * sizeof(float)));
+        CK(cudaMemset(h->xregion, 0, (2 * (size_t)NPARAM + 64) * sizeof(float)));
+        CK(cudaMalloc((void**)&h->xcounter, 64));
+        CK(cudaMemset(h->xcounter, 0, 64));
+    }
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, h->xregion));
+    memcpy(handle64_out, &hd, sizeof hd);
+    return NPE_OK;
+}
+
+int npe_peer_attach(npe_handle* h, int32_t rank, int32_t nranks, const void* all_handles) {
+    NEED(h);
+    if (!all_handles || nranks < 1 || nranks > MAX_PEERS || rank < 0 || rank >= nranks)
+        return fail(h, NPE_ERR_INVALID, "peer_attach: bad arguments (at most %d ranks)", MAX_PEERS);
+    if (!h->xregion) return fail(h, NPE_ERR_STATE, "peer_attach: call npe_peer_export first");
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { h->peer_ptr[r] = h->xregion; continue; }
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, (const char*)all_handles + (size_t)r * NPE_PEER_HANDLE_BYTES, sizeof hd);
+        CK(cudaIpcOpenMemHandle(&h->peer_ptr[r], hd, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_opened[r] = true;
+    }
+    h->rank = rank; h->nranks = nranks;
+    h->peer_ready = true;
+    h->peer_step = 0;
     return NPE_OK;
 }
 

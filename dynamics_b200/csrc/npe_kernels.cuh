@@ -822,6 +822,85 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
 }
 
 // ----------------------------------------------------------------------------------------------------------------
+// Data-parallel exchange over NVLink peer memory.  Region layout per rank: xgrad[2][NPARAM] floats (double-buffered by
+// step parity) followed by one 32-bit ready counter per buffer.  k_reduce_publish reduces this rank's CTA partials into
+// its own buffer and, when the last block has finished, publishes `stamp` with a system-scope release.
+// k_peer_allreduce_opt waits (system-scope acquire over NVLink) until every peer has published the same stamp, sums
+// the peers' vectors in rank order and applies the optimiser.  Double buffering makes a "done" handshake unnecessary:
+// a rank can only overwrite buffer b two steps later, after every peer has passed the next step's ready barrier.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int MAX_PEERS = 8;
+struct PeerPtrs {
+    const float* x[MAX_PEERS];            // peer exchange regions (own region at index `rank`)
+    int nranks, rank;
+};
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void k_reduce_publish(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ xbuf,
+                                 unsigned* __restrict__ ready_flag, unsigned stamp, unsigned* __restrict__ block_counter,
+                                 LossArgs L) {
+    pdl_wait();
+    if (L.loss4_out && blockIdx.x == gridDim.x - 1) {
+        block_loss_reduce(L);
+    } else {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < NPARAM) {
+            const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
+            float a = 0.f;
+            for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
+            xbuf[i] = a;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(block_counter, 1u) + 1u;
+        if (done == gridDim.x) {
+            *block_counter = 0u;
+            __threadfence_system();
+            st_release_sys(ready_flag, stamp);
+        }
+    }
+}
+
+template <int OPT>
+__global__ void k_peer_allreduce_opt(PeerPtrs P, int buf, unsigned stamp, float* __restrict__ grad, OptArgs o) {
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < P.nranks; ++r) {
+            const unsigned* flag = reinterpret_cast<const unsigned*>(P.x[r] + 2 * NPARAM) + buf;
+            while (ld_acquire_sys(flag) != stamp) { __nanosleep(40); }
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NPARAM) return;
+    float a = 0.f;
+    for (int r = 0; r < P.nranks; ++r) a += __ldcv(P.x[r] + (size_t)buf * NPARAM + i);   // rank order: same sum everywhere
+    grad[i] = a;
+    if (OPT == 1) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
+        const float vi = __fadd_rn(__fmul_rn(o.b2, o.v[i]), __fmul_rn(o.omb2, __fmul_rn(a, a)));
+        o.m[i] = mi; o.v[i] = vi;
+        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    } else if (OPT == 2) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, __fmul_rn(a, a)));
+        o.m[i] = mi;
+        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
 // K5: optimisers (upstream optim rock semantics; call sites main.lua:135-144,301-302)
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void k_adam(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,

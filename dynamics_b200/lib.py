@@ -65,6 +65,8 @@ SIGNATURES = {
     "npe_comm_unique_id": (C.c_int, [C.c_void_p]),
     "npe_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "npe_allreduce_grads": (C.c_int, [_H]),
+    "npe_peer_export": (C.c_int, [_H, C.c_void_p]),
+    "npe_peer_attach": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "npe_sync": (C.c_int, [_H]),
     "npe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "npe_host_free": (None, [C.c_void_p]),

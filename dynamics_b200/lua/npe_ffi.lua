@@ -44,6 +44,8 @@ int npe_set_rollout_mode(npe_handle* h, int32_t mode);
 int npe_comm_unique_id(void* id128_out);
 int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128);
 int npe_allreduce_grads(npe_handle* h);
+int npe_peer_export(npe_handle* h, void* handle64_out);
+int npe_peer_attach(npe_handle* h, int32_t rank, int32_t nranks, const void* all_handles);
 int npe_sync(npe_handle* h);
 void* npe_host_alloc(size_t bytes);
 void npe_host_free(void* p);

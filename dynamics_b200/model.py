@@ -318,6 +318,17 @@ class NPEModel:
             raise L.NPEError(rc, self.lib.npe_last_error(None).decode())
         return bytes(buf)
 
+    def peer_export(self):
+        buf = (C.c_char * 64)()
+        self._ck(self.lib.npe_peer_export(self.h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def peer_attach(self, rank, nranks, all_handles):
+        blob = bytes(all_handles)
+        assert len(blob) == 64 * nranks
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        self._ck(self.lib.npe_peer_attach(self.h, rank, nranks, C.cast(buf, C.c_void_p)))
+
     def allreduce_grads(self):
         self._ck(self.lib.npe_allreduce_grads(self.h))
 

@@ -17,15 +17,23 @@ from oracle import batcher, npe, optim  # noqa: E402
 from tests.util import balls_batches  # noqa: E402
 
 
-def main():
-    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    m = NPEModel(ModelParams(device=local))
+def attach(m, rank, world, mode):
     idt = torch.zeros(128, dtype=torch.uint8)
-    if rank == 0:
-        idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
-    dist.broadcast(idt, 0)
-    m.comm_init(rank, world, bytes(idt.tolist()))
+    if mode == "nccl":
+        if rank == 0:
+            idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, 0)
+        m.comm_init(rank, world, bytes(idt.tolist()))
+    else:
+        mine = torch.tensor(list(m.peer_export()), dtype=torch.uint8)
+        allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        m.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
+
+
+def run(mode, rank, local, world):
+    m = NPEModel(ModelParams(device=local))
+    attach(m, rank, world, mode)
     _, batches = balls_batches(60, 5, seed=91)
     params = npe.init_params(1234)
     cuts = np.linspace(0, 50, world + 1).astype(int)
@@ -33,12 +41,11 @@ def main():
     lo, hi = cuts[rank], cuts[rank + 1]
     x = params.copy(); st = optim.adam_init(x.size)
     m.set_params(params); m.optim_reset(0.0)
-    worst = 0.0
     for it in range(20):
         this, ctx, y, *_ = batcher.make_batch(*batches[it % len(batches)], offset=it % 20)
         g_ref, _ = npe.bp(x, (this, ctx, y))
         m._upload((this[lo:hi], ctx[lo:hi], y[lo:hi]))
-        if it == 0:
+        if it == 0 and mode == "nccl":
             m.fp(None, (this[lo:hi], ctx[lo:hi], y[lo:hi]))
             m.bp(divisor_batch=50)
             m.allreduce_grads()
@@ -46,18 +53,29 @@ def main():
             err = float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)))
             assert err < 1e-4, f"rank {rank}: all-reduced gradient error {err}"
             m._upload((this[lo:hi], ctx[lo:hi], y[lo:hi]))
-        m.train_step("adam", 3e-4, divisor_batch=50, want_loss=False)
+        m.train_step("adam", 3e-4, divisor_batch=50, want_loss=(it % 3 == 0))
+        if mode == "p2p" and it == 0:
+            g = m.get_grads()            # the fused kernel leaves the all-reduced gradient in grad_params
+            err = float(np.max(np.abs(g - g_ref)) / np.max(np.abs(g_ref)))
+            assert err < 1e-4, f"rank {rank}: peer all-reduced gradient error {err}"
         optim.adam_step(x, g_ref, st, 3e-4)
     got = m.get_params()
     worst = float(np.max(np.abs(got - x)) / np.max(np.abs(x)))
-    assert worst < 1e-4, f"rank {rank}: parameters after 20 DP steps differ by {worst}"
+    assert worst < 1e-4, f"rank {rank} [{mode}]: parameters after 20 DP steps differ by {worst}"
     allp = [torch.zeros(got.size) for _ in range(world)]
     dist.all_gather(allp, torch.from_numpy(got))
-    assert all(torch.equal(allp[0], p) for p in allp), "replicas diverged"
+    assert all(torch.equal(allp[0], p) for p in allp), f"[{mode}] replicas diverged"
     if rank == 0:
-        print(f"dp_gpu_check ok: world={world} grad/param error {worst:.2e}, replicas bit-identical")
+        print(f"dp_gpu_check ok [{mode}]: world={world} param error after 20 steps {worst:.2e}, replicas bit-identical")
     dist.barrier()
     m.close()
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for mode in ("nccl", "p2p"):
+        run(mode, rank, local, world)
     dist.destroy_process_group()
 
 
