@@ -121,6 +121,8 @@ struct npe_handle {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     int stage_idx = 0;
     int foci_B = -1, foci_N = -1;     // shape the iota focus arrays / n_obj were last built for
+    DevBuf<float> loss_hist;          // per-step {loss, vel, angvel, overflow} of npe_train_steps
+    float* loss4_override = nullptr;  // when set, the fused loss reduction writes here instead of the mapped buffer
     float* loss4_host = nullptr;      // host-mapped {loss, vel, angvel, overflow}
     float* loss4_devptr = nullptr;
     u64* active_total = nullptr;
@@ -395,7 +397,7 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         o.x = h->params; o.m = h->adam_m; o.v = h->adam_v; o.wpack = h->wpack;
         o.b1 = 0.9f; o.omb1 = (float)(1.0 - 0.9); o.b2 = 0.999f; o.omb2 = (float)(1.0 - 0.999); o.eps = 1e-8f; o.step = lr;
         LossArgs L;
-        L.loss_ex = h->loss_ex.p; L.F = h->F; L.loss4_out = want_loss ? h->loss4_devptr : nullptr; L.info = h->info_dev;
+        L.loss_ex = h->loss_ex.p; L.F = h->F; L.loss4_out = want_loss ? (h->loss4_override ? h->loss4_override : h->loss4_devptr) : nullptr; L.info = h->info_dev;
         const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
         if (peer_opt) {
             const int buf = (int)(h->peer_step & 1u);
@@ -852,7 +854,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     int rc;
     if ((rc = run_forward(h, true))) return rc;
     if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
-    const bool want_loss = loss3_out != nullptr;
+    const bool want_loss = loss3_out != nullptr || h->loss4_override != nullptr;
     if (h->peer_ready) {
         // data parallel over NVLink peer memory: local reduce + publish, then all-reduce fused with the optimiser
         if ((rc = run_backward(h, divisor_batch, 0, lr, want_loss, opt == 0 ? 1 : 2))) return rc;
@@ -866,12 +868,37 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
         if (rc) return rc;
     }
     h->fwd_valid = false;   // parameters changed
-    if (want_loss) {
+    if (want_loss && !h->loss4_override) {
         // the loss kernel wrote {loss, vel, angvel, overflow} straight into host-mapped memory: one sync, no copy
         CK(cudaStreamSynchronize(h->stream));
         if (h->loss4_host[3] != 0.f)
             return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
         loss3_out[0] = h->loss4_host[0]; loss3_out[1] = h->loss4_host[1]; loss3_out[2] = h->loss4_host[2];
+    }
+    return NPE_OK;
+}
+
+int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr,
+                    int32_t divisor_batch, float* losses_out) {
+    NEED(h);
+    if (batch <= 0 || nsteps <= 0 || first < 0) return fail(h, NPE_ERR_INVALID, "train_steps: bad arguments");
+    if (losses_out) CK(h->loss_hist.ensure((size_t)nsteps * 4));
+    int rc = NPE_OK;
+    for (int s = 0; s < nsteps && rc == NPE_OK; ++s) {
+        if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
+        h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
+        rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
+    }
+    h->loss4_override = nullptr;
+    if (rc) return rc;
+    if (losses_out) {
+        std::vector<float> tmp((size_t)nsteps * 4);
+        CK(cudaMemcpyAsync(tmp.data(), h->loss_hist.p, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int s = 0; s < nsteps; ++s) {
+            if (tmp[(size_t)s * 4 + 3] != 0.f) return fail(h, NPE_ERR_NOMEM, "active-pair list overflow in step %d", s);
+            for (int k = 0; k < 3; ++k) losses_out[(size_t)s * 3 + k] = tmp[(size_t)s * 4 + k];
+        }
     }
     return NPE_OK;
 }

@@ -213,6 +213,13 @@ class NPEModel:
         self._ck(self.lib.npe_train_step(self.h, 0 if opt == "adam" else 1, lr, divisor_batch, L.fptr(loss3)))
         return loss3
 
+    def train_steps(self, first, batch, nsteps, opt="adam", lr=3e-4, divisor_batch=0, want_losses=False):
+        """The inner loop of train() (main.lua:299-304) over the uploaded schedule, one host call for all steps."""
+        losses = np.empty((nsteps, 3), np.float32) if want_losses else None
+        self._ck(self.lib.npe_train_steps(self.h, first, batch, nsteps, 0 if opt == "adam" else 1, lr, divisor_batch,
+                                          L.fptr(losses)))
+        return losses
+
     # ---- scene form (device-resident trajectory batcher) -------------------------------------------------------
     def upload_scenes(self, states, n_obj=None):
         states = L.f32(states)

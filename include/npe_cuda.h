@@ -156,6 +156,15 @@ int npe_optim_reset(npe_handle* h, float rmsprop_m_init);
 int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out);
 
 /*
+ * The inner loop of train() (main.lua:299-304) over a device-resident schedule: step s trains on examples
+ * [first + s*batch, first + (s+1)*batch) of the uploaded focus/window schedule.  One host call enqueues all `nsteps`
+ * steps (no host round trip between steps).  losses_out (nsteps,3) or NULL: per-step {loss, vel_loss, angvel_loss},
+ * copied back once at the end.
+ */
+int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr,
+                    int32_t divisor_batch, float* losses_out);
+
+/*
  * simulate_all (eval.lua:237-454) in scene form on the uploaded scenes: past = frames t0,t0+1; `steps` autoregressive
  * steps.  use_gt != 0: frames t0+2.. are ground truth (obstacles copied from it, metrics computed against it);
  * otherwise obstacles stay static and metrics are zero.

@@ -370,3 +370,27 @@ def test_rollout_by_kernels_fp32_and_tf32(model, trained_like_params):
         assert np.array_equal(traj_t[..., 0:2], ref[..., 0:2])     # positions: previous velocity -> exact under teacher forcing
         assert met_t[:, 3].min() == met_p[:, 3].min()
         model.set_precision("fp32"); model.set_rollout_mode("persistent")
+
+
+def test_train_steps_equals_step_by_step(model, params):
+    """npe_train_steps (C-side inner loop of train()) == the same steps issued one by one, bit for bit; per-step losses
+    match the oracle's fp loss on the same examples."""
+    st = scenes.raw_to_state(scenes.gen_balls(100, 4, 12, seed=51))
+    sc = np.repeat(np.arange(100), 1); ob = np.tile(np.arange(4), 25); t0 = (np.arange(100) * 7) % 9
+    model.upload_scenes(st)
+    model.upload_foci(sc, ob, t0)
+    model.set_params(params); model.optim_reset(0.0)
+    losses = model.train_steps(0, 50, 2, "adam", 3e-4, want_losses=True)
+    p_multi = model.get_params()
+    model.set_params(params); model.optim_reset(0.0)
+    l_single = []
+    for s in range(2):
+        model.select_foci(s * 50, 50)
+        l_single.append(model.train_step("adam", 3e-4))
+    assert np.array_equal(model.get_params(), p_multi)
+    assert np.allclose(losses, np.stack(l_single), rtol=1e-6)
+    this = np.stack([st[sc[i], ob[i], t0[i]:t0[i] + 2] for i in range(50)])
+    ctx = np.stack([np.delete(st[sc[i]], ob[i], axis=0)[:, t0[i]:t0[i] + 2] for i in range(50)])
+    y = batcher.relative_pair(this, np.stack([st[sc[i], ob[i], t0[i] + 2:t0[i] + 3] for i in range(50)]))
+    l, _, lv, lw = npe.fp(params, (this, ctx, y))
+    assert rel_err(losses[0], [l, lv, lw], 1e-6) < 1e-4
