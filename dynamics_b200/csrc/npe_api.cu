@@ -414,10 +414,10 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
                 h->adam_t += 1;
                 const double t = (double)h->adam_t;
                 o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
-                k_peer_allreduce_opt<1><<<nb2, 256, 0, h->stream>>>(P, buf, stamp, h->grads, o);
+                CK(launch_pdl(k_peer_allreduce_opt<1>, nb2, 256, 0, h->stream, P, buf, stamp, h->grads, o));
             } else {
                 o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
-                k_peer_allreduce_opt<2><<<nb2, 256, 0, h->stream>>>(P, buf, stamp, h->grads, o);
+                CK(launch_pdl(k_peer_allreduce_opt<2>, nb2, 256, 0, h->stream, P, buf, stamp, h->grads, o));
             }
             h->wtc_dirty = true;
             h->launches++;

@@ -846,6 +846,7 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 __global__ void k_reduce_publish(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ xbuf,
                                  unsigned* __restrict__ ready_flag, unsigned stamp, unsigned* __restrict__ block_counter,
                                  LossArgs L) {
+    pdl_launch_dependents();   // the all-reduce kernel may start spinning on the ready flags right away
     pdl_wait();
     if (L.loss4_out && blockIdx.x == gridDim.x - 1) {
         block_loss_reduce(L);
