@@ -108,7 +108,8 @@ struct npe_handle {
     bool have_y = false;
 
     // per-batch buffers
-    DevBuf<float> y, pred, loss_ex, ds, this_rows, Hp;
+    DevBuf<float> y, pred, loss_ex, ds, this_rows, Hp, hact;
+    bool hact_valid = false;          // the activation stash holds the current batch's pair activations
     DevBuf<u64> keep, nbr;
     DevBuf<int> cnt, block_sums, pair_start, pair_foc;   // cnt = CTA-local exclusive prefix of active counts
     DevBuf<long long> foc_row, pair_crow;
@@ -275,6 +276,7 @@ int build_pairs(npe_handle* h) {
     }
     CK(cudaGetLastError());
     h->pairs_valid = true;
+    h->hact_valid = false;
     return NPE_OK;
 }
 
@@ -307,8 +309,19 @@ int refresh_wtc(npe_handle* h) {
     return NPE_OK;
 }
 
-// pair MLP + decoder forward on the current pair list; `st` = scene tensor the row offsets point into
-int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, bool tc) {
+// Activation stash for training (h0..h5 per active pair); skipped (recompute instead) when it would exceed 2 GB.
+float* training_stash(npe_handle* h) {
+    const size_t need = (size_t)h->pair_cap * HACT_STRIDE;
+    if (need * sizeof(float) > (size_t)2 << 30) return nullptr;
+    if (h->hact.ensure(need) != cudaSuccess) return nullptr;
+    return h->hact.p;
+}
+
+// pair MLP + decoder forward on the current pair list; `st` = scene tensor the row offsets point into.
+// stash: activation stash for a following backward (training) or nullptr; skip_decoder: the fused training step lets
+// k_dec_backward produce pred / losses.
+int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, bool tc,
+                           float* stash = nullptr, bool skip_decoder = false) {
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
         int rc = refresh_wtc(h);
@@ -325,29 +338,35 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
     } else {
         if (small_batch(h, F)) {
             CK(launch_pdl(k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream,
-                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p));
-            CK(launch_pdl(k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream,
-                          st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
+            if (!skip_decoder)
+                CK(launch_pdl(k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream,
+                              st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         } else {
             CK(launch_pdl(k_pair_forward<64>, pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>), h->stream,
-                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p));
-            CK(launch_pdl(k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream,
-                          st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
+            if (!skip_decoder)
+                CK(launch_pdl(k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream,
+                              st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         }
-        h->launches += 2;
+        h->launches += skip_decoder ? 1 : 2;
     }
     CK(cudaGetLastError());
     return NPE_OK;
 }
 
-// training == true: the FP32 kernels always (backward recomputes from the FP32 pair outputs)
-int run_forward(npe_handle* h, bool training) {
+// training == true: the FP32 kernels always, with the activation stash for the backward kernels; fused == true
+// (npe_train_step): the decoder forward is left to k_dec_backward, which recomputes it anyway.
+int run_forward(npe_handle* h, bool training, bool fused = false) {
     int rc = build_pairs(h);
     if (rc) return rc;
     const bool tc = !training && h->precision == NPE_PRECISION_TF32_TC;
-    rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc);
+    float* stash = (training && h->have_y) ? training_stash(h) : nullptr;
+    rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
+                                stash, fused);
     if (rc) return rc;
     h->fwd_valid = !tc;
+    h->hact_valid = stash != nullptr;
     return NPE_OK;
 }
 
@@ -359,7 +378,8 @@ int run_loss_reduce(npe_handle* h) {
 
 // fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
 // peer_opt: 1 / 2 = fused NVLink all-reduce + Adam / RMSprop (requires npe_peer_attach)
-int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0) {
+int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0,
+                 bool fused_fwd = false) {
     if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
     if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
     const int B = divisor_batch > 0 ? divisor_batch : h->F;
@@ -374,20 +394,24 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
         if (small)
             CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw));
+                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw,
+                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         else
             CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw));
+                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw,
+                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
         if (small)
             CK(launch_pdl(k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->stream, h->states.p, h->pair_foc.p,
-                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial));
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
+                          h->hact_valid ? h->hact.p : nullptr));
         else
             CK(launch_pdl(k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->stream, h->states.p, h->pair_foc.p,
-                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial));
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
+                          h->hact_valid ? h->hact.p : nullptr));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -443,6 +467,7 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
 int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
     h->wtc_dirty = true;
+    h->fwd_valid = false; h->hact_valid = false;   // parameters change: forward state is stale
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
     { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, h->wpack, NPARAM, b1, (float)(1.0 - (double)b1), b2, (float)(1.0 - (double)b2), eps, step);
@@ -453,6 +478,7 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
     h->wtc_dirty = true;
+    h->fwd_valid = false; h->hact_valid = false;
     { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, h->wpack, NPARAM, alpha, (float)(1.0 - (double)alpha), eps, lr);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
@@ -573,7 +599,7 @@ int npe_destroy(npe_handle* h) {
     for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
-    h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->this_rows.release();
+    h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release();
     h->roll.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
@@ -593,7 +619,7 @@ int npe_params_set(npe_handle* h, const float* host, int32_t n) {
     k_pack_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wpack);
     CKL();
     CK(cudaStreamSynchronize(h->stream));
-    h->fwd_valid = false;
+    h->fwd_valid = false; h->hact_valid = false;
     h->wtc_dirty = true;
     return NPE_OK;
 }
@@ -852,17 +878,18 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     NEED(h);
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
     int rc;
-    if ((rc = run_forward(h, true))) return rc;
+    if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+    if ((rc = run_forward(h, true, /*fused=*/true))) return rc;
     if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
     const bool want_loss = loss3_out != nullptr || h->loss4_override != nullptr;
     if (h->peer_ready) {
         // data parallel over NVLink peer memory: local reduce + publish, then all-reduce fused with the optimiser
-        if ((rc = run_backward(h, divisor_batch, 0, lr, want_loss, opt == 0 ? 1 : 2))) return rc;
+        if ((rc = run_backward(h, divisor_batch, 0, lr, want_loss, opt == 0 ? 1 : 2, true))) return rc;
     } else if (!h->comm) {
         // single GPU: reduction of the CTA partials, optimiser step, weight-image write-through and the batch loss in ONE kernel
-        if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr, want_loss))) return rc;
+        if ((rc = run_backward(h, divisor_batch, opt == 0 ? 1 : 2, lr, want_loss, 0, true))) return rc;
     } else {
-        if ((rc = run_backward(h, divisor_batch, 0, 0.f, want_loss))) return rc;
+        if ((rc = run_backward(h, divisor_batch, 0, 0.f, want_loss, 0, true))) return rc;
         if ((rc = run_allreduce(h))) return rc;
         rc = (opt == 0) ? run_adam(h, lr, 0.9f, 0.999f, 1e-8f) : run_rmsprop(h, lr, 0.99f, 1e-8f);
         if (rc) return rc;

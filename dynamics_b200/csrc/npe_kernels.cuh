@@ -372,18 +372,33 @@ struct PairFwdSmem {
 };
 
 // h0 = [relu(Wt f) | relu(Wc c)] into h0buf (cols 50..55 zeroed), then h_l = relu(L_l h_{l-1}) into bufs[l].
+constexpr int HACT_STRIDE = (NL + 1) * 52;   // floats per pair in the activation stash: h0..h5, 52 columns each
+
+// Copies rows [0, nrows) x 52 columns of a shared tile to the stash slot `l` of pairs [lo, lo + nrows).
+__device__ __forceinline__ void stash_store(float* __restrict__ hact, int lo, int l, const float* tile, int nrows) {
+    for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
+        const int r = idx / 13, c4 = idx - r * 13;
+        st4(hact + (size_t)(lo + r) * HACT_STRIDE + l * 52 + 4 * c4, ld4(tile + r * LD + 4 * c4));
+    }
+}
+
+// hact != nullptr (training): every h_l is also written to the global activation stash so that the backward kernel
+// loads it instead of recomputing the chain -- with the LDS-bound FP32 tiles a pass costs ~3.5 k cycles per 64 rows,
+// the 2.5 KB/pair round trip (mostly L2) about a quarter of the seven passes it replaces.
 template <int ROWS>
 __device__ __forceinline__ void pair_chain_dense(const float* sWp, const float* sXf, const float* sXc, int nrows,
-                                                 float* const* bufs) {
+                                                 float* const* bufs, float* __restrict__ hact = nullptr, int lo = 0) {
     float* h0 = bufs[0];
     for (int idx = threadIdx.x; idx < ROWS * 6; idx += NT) h0[(idx / 6) * LD + H + (idx % 6)] = 0.f;
     gemm_nt_r<ROWS, 4, LD, LD>(sXf, sWp + SW_ENC_T, 11, nrows, EpiNT{h0, LD, H2, 1});
     gemm_nt_r<ROWS, 4, LD, LD>(sXc, sWp + SW_ENC_C, 11, nrows, EpiNT{h0 + H2, LD, H2, 1});
     __syncthreads();
+    if (hact) stash_store(hact, lo, 0, h0, nrows);
 #pragma unroll 1
     for (int l = 0; l < NL; ++l) {
         gemm_nt_r<ROWS, 7, LD, LD>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{bufs[l + 1], LD, 52, 1});
         __syncthreads();
+        if (hact) stash_store(hact, lo, l + 1, bufs[l + 1], nrows);
     }
 }
 
@@ -403,7 +418,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
-               float* __restrict__ Hp) {
+               float* __restrict__ Hp, float* __restrict__ hact) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairFwdSmem<ROWS>& S = *reinterpret_cast<PairFwdSmem<ROWS>*>(smem_raw);
     pdl_launch_dependents();
@@ -422,7 +437,7 @@ k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_fo
         gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
-        pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs);
+        pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs, hact, lo);
         for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
             const int r = idx / 13, c4 = idx - r * 13;
             st4(Hp + (size_t)(lo + r) * 52 + 4 * c4, ld4(S.P1 + r * LD + 4 * c4));
@@ -549,7 +564,7 @@ __global__ void __launch_bounds__(NT, 1)
 k_dec_backward(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
                const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wpack,
                const float* __restrict__ y, float* __restrict__ ds_out, float* __restrict__ partial,
-               float scale_v, float scale_w) {
+               float scale_v, float scale_w, float* __restrict__ pred, float* __restrict__ loss_ex) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecBwdSmem<ROWS>& S = *reinterpret_cast<DecBwdSmem<ROWS>*>(smem_raw);
     pdl_launch_dependents();
@@ -577,6 +592,22 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
         decoder_forward<ROWS>(S.Wd, S.Z, ubufs, S.O, nf);
+        if (pred) {   // fused training step: this kernel IS the decoder forward (model:fp outputs) as well
+            for (int idx = t; idx < nf * OUT; idx += NT) {
+                const int r = idx / OUT, n = idx - r * OUT;
+                float v = S.O[r * LD + n];
+                if (n >= 6) v = 1.f / (1.f + expf(-v));
+                pred[(size_t)(f0 + r) * OUT + n] = v;
+            }
+            if (loss_ex && t < nf) {
+                const float* yy = y + (size_t)(f0 + t) * OUT;
+                const float e2 = S.O[t * LD + 2] - yy[2], e3 = S.O[t * LD + 3] - yy[3], e5 = S.O[t * LD + 5] - yy[5];
+                const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
+                loss_ex[(size_t)(f0 + t) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
+                loss_ex[(size_t)(f0 + t) * 3 + 1] = __fdiv_rn(lv, 2.f);
+                loss_ex[(size_t)(f0 + t) * 3 + 2] = lw;
+            }
+        }
         if (t < nf) {
             const float* yy = y + (size_t)(f0 + t) * OUT;
             S.Da[t * LD + 2] = (S.O[t * LD + 2] - yy[2]) * scale_v;
@@ -673,7 +704,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                 const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
-                const float* __restrict__ ds_in, float* __restrict__ partial) {
+                const float* __restrict__ ds_in, float* __restrict__ partial, const float* __restrict__ hact) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairBwdSmem<ROWS>& S = *reinterpret_cast<PairBwdSmem<ROWS>*>(smem_raw);
     pdl_launch_dependents();
@@ -701,7 +732,19 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
             gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
             __syncthreads();
             if (!staged) { stage_wait(S.W); staged = true; }
-            pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs);
+            if (hact) {
+                // activations of this tile from the forward kernel's stash (rows >= nrows and pad columns zero)
+                for (int idx = t; idx < (NL + 1) * ROWS * (LD / 4); idx += NT) {
+                    const int l = idx / (ROWS * (LD / 4)), rem = idx - l * (ROWS * (LD / 4));
+                    const int r = rem / (LD / 4), c4 = rem - r * (LD / 4);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < nrows && c4 < 13) v = ld4(hact + (size_t)(lo + r) * HACT_STRIDE + l * 52 + 4 * c4);
+                    st4(S.Hh[l] + r * LD + 4 * c4, v);
+                }
+                __syncthreads();
+            } else {
+                pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs);
+            }
             // dz5 = ds[focus] * (h5 > 0); rows >= nrows zero
             for (int idx = t; idx < ROWS * (LD / 4); idx += NT) {
                 const int r = idx / (LD / 4), c4 = idx - r * (LD / 4);
