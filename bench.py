@@ -273,7 +273,7 @@ def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
         m.set_params(init_params(1234))
         m.upload_scenes(st)
         for name, prec, mode, nsteps in (("fp32_persistent", "fp32", "persistent", steps), ("fp32_kernels", "fp32", "kernels", steps // 4),
-                                         ("tf32_tcgen05", "tf32", "kernels", steps)):
+                                         ("tf32x3_tcgen05", "tf32x3", "kernels", steps), ("tf32_tcgen05", "tf32", "kernels", steps)):
             m.set_precision(prec); m.set_rollout_mode(mode)
             m.rollout_resident(0, 3); m.sync()
             m.event_record(0)
@@ -288,7 +288,8 @@ def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
         nk, tot = m.profile_read()
         m.profile_select(None)
         out["tf32_tcgen05"]["forward_ms_per_step"] = tot / max(nk, 1)
-        best = max(("fp32_persistent", "fp32_kernels", "tf32_tcgen05"), key=lambda k: out[k]["value"])
+        # headline rollout number: the fastest FP32-grade variant (tf32 single pass is reported beside it)
+        best = max(("fp32_persistent", "fp32_kernels", "tf32x3_tcgen05"), key=lambda k: out[k]["value"])
         out["value"] = out[best]["value"]; out["unit"] = "object-steps/s"; out["best"] = best
         return out
     finally:
@@ -307,7 +308,7 @@ def bench_forward_stress(model_cls, mp_cls, device, scenes=1024):
         m.upload_scenes(st); m.upload_windows(np.arange(scenes), np.zeros(scenes, np.int32))
         m.select_windows(0, scenes)
         F, P = m.batch_stats()
-        for prec in ("fp32", "tf32"):
+        for prec in ("fp32", "tf32x3", "tf32"):
             m.set_precision(prec)
             for _ in range(3):
                 m._ck(m.lib.npe_forward_per_example(m.h, None, None))
@@ -319,8 +320,9 @@ def bench_forward_stress(model_cls, mp_cls, device, scenes=1024):
             ms = tot / max(n, 1)
             ach = KERNEL_FLOPS["forward"](F, P) / (ms * 1e-3) / 1e12
             peak = FP32_PEAK_TFLOPS if prec == "fp32" else TF32_PEAK_TFLOPS
+            sfx = {"fp32": "", "tf32": "_tc", "tf32x3": "_tc3"}[prec]
             out[prec] = {"forward_ms": ms, "samples_per_s": F / (ms * 1e-3),
-                         "roofline": {"kernel": "k_pair_forward%s + k_dec_forward%s" % (("", "") if prec == "fp32" else ("_tc", "_tc")),
+                         "roofline": {"kernel": "k_pair_forward%s + k_dec_forward%s" % (sfx, sfx),
                                       "bound": "fp32" if prec == "fp32" else "tensor", "achieved": ach, "peak": peak,
                                       "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}}
         out["config"] = {"workload": "configs[3] forward only", "foci": F, "active_pairs": P}

@@ -88,6 +88,8 @@ struct npe_handle {
     float* wpack = nullptr;           // packed (shared-memory layout) weight image, kept in sync with params
     float* wtc = nullptr;             // tensor-core (K-major canonical layout, TF32-rounded) weight image
     bool wtc_dirty = true;
+    float* wtc3 = nullptr;            // hi | lo images for the 3xTF32 variant (2 * TC_TOTAL floats)
+    bool wtc3_dirty = true;
     int precision = 0, rollout_mode = 0;
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
@@ -301,11 +303,16 @@ int focus_grid(const npe_handle* h, int F, int rows) {
     return tiles < h->num_sms ? tiles : h->num_sms;
 }
 
-int refresh_wtc(npe_handle* h) {
-    if (!h->wtc_dirty) return NPE_OK;
-    k_pack_tc_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc);
-    CKL();
-    h->wtc_dirty = false;
+int refresh_wtc(npe_handle* h, int mode) {
+    if (mode == NPE_PRECISION_TF32_TC && h->wtc_dirty) {
+        k_pack_tc_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc);
+        CKL();
+        h->wtc_dirty = false;
+    } else if (mode == NPE_PRECISION_TF32X3_TC && h->wtc3_dirty) {
+        k_pack_tc3_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc3, h->wtc3 + TC_TOTAL);
+        CKL();
+        h->wtc3_dirty = false;
+    }
     return NPE_OK;
 }
 
@@ -320,21 +327,28 @@ float* training_stash(npe_handle* h) {
 // pair MLP + decoder forward on the current pair list; `st` = scene tensor the row offsets point into.
 // stash: activation stash for a following backward (training) or nullptr; skip_decoder: the fused training step lets
 // k_dec_backward produce pred / losses.
-int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, bool tc,
+int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, int tc,
                            float* stash = nullptr, bool skip_decoder = false) {
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
-        int rc = refresh_wtc(h);
+        int rc = refresh_wtc(h, tc);
         if (rc) return rc;
         const long long ptiles = ((long long)h->pair_cap + 127) / 128;
         const int pg = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
         const int ft = (F + 127) / 128;
-        k_pair_forward_tc<<<pg, NT, sizeof(PairTcSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                   h->info_dev, h->wtc, h->Hp.p);
-        h->launches++;
-        k_dec_forward_tc<<<ft < h->num_sms ? ft : h->num_sms, NT, sizeof(DecTcSmem), h->stream>>>(
-            st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y, h->pred.p, loss_ex);
-        h->launches++;
+        const int fg = ft < h->num_sms ? ft : h->num_sms;
+        if (tc == NPE_PRECISION_TF32_TC) {
+            k_pair_forward_tc<<<pg, NT, sizeof(PairTcSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                       h->info_dev, h->wtc, h->Hp.p);
+            k_dec_forward_tc<<<fg, NT, sizeof(DecTcSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y,
+                                                                       h->pred.p, loss_ex);
+        } else {
+            k_pair_forward_tc3<<<pg, NT, sizeof(PairTc3Smem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                         h->info_dev, h->wtc3, h->Hp.p);
+            k_dec_forward_tc3<<<fg, NT, sizeof(DecTc3Smem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc3, y,
+                                                                         h->pred.p, loss_ex);
+        }
+        h->launches += 2;
     } else {
         if (small_batch(h, F)) {
             CK(launch_pdl(k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream,
@@ -360,7 +374,7 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
 int run_forward(npe_handle* h, bool training, bool fused = false) {
     int rc = build_pairs(h);
     if (rc) return rc;
-    const bool tc = !training && h->precision == NPE_PRECISION_TF32_TC;
+    const int tc = training ? 0 : h->precision;
     float* stash = (training && h->have_y) ? training_stash(h) : nullptr;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused);
@@ -443,18 +457,18 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
                 o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
                 CK(launch_pdl(k_peer_allreduce_opt<2>, nb2, 256, 0, h->stream, P, buf, stamp, h->grads, o));
             }
-            h->wtc_dirty = true;
+            h->wtc_dirty = true; h->wtc3_dirty = true;
             h->launches++;
         } else if (fuse_opt == 1) {
             h->adam_t += 1;
             const double t = (double)h->adam_t;
             o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
             CK(launch_pdl(k_reduce_grads<1>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
-            h->wtc_dirty = true;
+            h->wtc_dirty = true; h->wtc3_dirty = true;
         } else if (fuse_opt == 2) {
             o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
             CK(launch_pdl(k_reduce_grads<2>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
-            h->wtc_dirty = true;
+            h->wtc_dirty = true; h->wtc3_dirty = true;
         } else {
             CK(launch_pdl(k_reduce_grads<0>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
         }
@@ -466,7 +480,7 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
 
 int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
-    h->wtc_dirty = true;
+    h->wtc_dirty = true; h->wtc3_dirty = true;
     h->fwd_valid = false; h->hact_valid = false;   // parameters change: forward state is stale
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
@@ -477,7 +491,7 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
 }
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
-    h->wtc_dirty = true;
+    h->wtc_dirty = true; h->wtc3_dirty = true;
     h->fwd_valid = false; h->hact_valid = false;
     { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, h->wpack, NPARAM, alpha, (float)(1.0 - (double)alpha), eps, lr);
     h->launches++; }
@@ -556,6 +570,9 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     k_pack_zero<<<(WPACK_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wpack);
     if ((e = cudaMalloc((void**)&h->wtc, TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     k_pack_tc_zero<<<(TC_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wtc);
+    if ((e = cudaMalloc((void**)&h->wtc3, 2 * (size_t)TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    k_pack_tc_zero<<<(TC_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wtc3);                 // hi image: unit entries
+    cudaMemsetAsync(h->wtc3 + TC_TOTAL, 0, (size_t)TC_TOTAL * sizeof(float), h->stream);   // lo image: zero
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -576,7 +593,9 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_pair_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem<16>))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTc3Smem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTc3Smem))) != cudaSuccess)
         return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
     *out = h;
     return NPE_OK;
@@ -590,7 +609,7 @@ int npe_destroy(npe_handle* h) {
     for (int r = 0; r < MAX_PEERS; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
     if (h->xregion) cudaFree(h->xregion);
     if (h->xcounter) cudaFree(h->xcounter);
-    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc};
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
@@ -620,7 +639,7 @@ int npe_params_set(npe_handle* h, const float* host, int32_t n) {
     CKL();
     CK(cudaStreamSynchronize(h->stream));
     h->fwd_valid = false; h->hact_valid = false;
-    h->wtc_dirty = true;
+    h->wtc_dirty = true; h->wtc3_dirty = true;
     return NPE_OK;
 }
 int npe_params_get(npe_handle* h, float* host, int32_t n) {
@@ -824,7 +843,7 @@ int npe_build_pairs(npe_handle* h, int32_t* ctx_idx_out, uint8_t* mask_out, int3
 int npe_forward(npe_handle* h, float* pred_out, float* loss3_out) {
     NEED(h);
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
-    int rc = run_forward(h, h->precision != NPE_PRECISION_TF32_TC);
+    int rc = run_forward(h, h->precision == NPE_PRECISION_FP32);
     if (rc) return rc;
     if (loss3_out) {
         if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
@@ -1005,7 +1024,7 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     src.foc_scene = h->roll_scene.p; src.foc_obj = h->roll_obj.p; src.foc_t0 = h->roll_t0.p; src.F = F;
     const float thr = h->cfg.nbrhdsize * 60.f;
     const int nblk = (F + FPB - 1) / FPB;
-    const bool tc = h->precision == NPE_PRECISION_TF32_TC;
+    const int tc = h->precision;
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
@@ -1034,7 +1053,7 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
 }
 
 static int rollout_dispatch(npe_handle* h, int t0, int steps, int use_gt, int teacher, bool want_traj, bool want_metrics) {
-    if (h->precision == NPE_PRECISION_TF32_TC || h->rollout_mode == NPE_ROLLOUT_BY_KERNELS)
+    if (h->precision != NPE_PRECISION_FP32 || h->rollout_mode == NPE_ROLLOUT_BY_KERNELS)
         return rollout_by_kernels(h, t0, steps, use_gt, teacher, want_traj, want_metrics);
     return rollout_impl(h, t0, steps, use_gt, teacher, want_traj, want_metrics);
 }
@@ -1059,7 +1078,7 @@ int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* obje
 
 int npe_set_precision(npe_handle* h, int32_t mode) {
     NEED(h);
-    if (mode != NPE_PRECISION_FP32 && mode != NPE_PRECISION_TF32_TC) return fail(h, NPE_ERR_INVALID, "set_precision: unknown mode %d", mode);
+    if (mode != NPE_PRECISION_FP32 && mode != NPE_PRECISION_TF32_TC && mode != NPE_PRECISION_TF32X3_TC) return fail(h, NPE_ERR_INVALID, "set_precision: unknown mode %d", mode);
     h->precision = mode;
     h->fwd_valid = false;
     return NPE_OK;

@@ -49,6 +49,53 @@ __device__ __forceinline__ void umma_gemm_tf32(uint32_t tmem_d, const float* sA,
     }
 }
 
+// A operand in TENSOR MEMORY (lane = row, column = k; validated in tools/microbench/umma_test.cu, kernel k2).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// 3xTF32: D (+)= Ahi*Bhi + Ahi*Blo + Alo*Bhi with A (hi at tmem_ahi, lo at tmem_alo) in tensor memory and the two
+// images of B in shared memory.  K = 8 * ksteps.  FP32-grade (1.5e-6 relative in the stand-alone test).  One thread.
+__device__ __forceinline__ void umma_gemm_tf32x3_ts(uint32_t tmem_d, uint32_t tmem_ahi, uint32_t tmem_alo, const float* sBhi,
+                                                    const float* sBlo, int rows_b, int n, int ksteps) {
+    const uint32_t idesc = umma_idesc_tf32(n);
+    const uint32_t bh = smem_u32(sBhi), bl = smem_u32(sBlo);
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a0 = pass == 2 ? tmem_alo : tmem_ahi;
+        const uint32_t b0 = pass == 1 ? bl : bh;
+        for (int s = 0; s < ksteps; ++s)
+            umma_tf32_ts(tmem_d, a0 + 8 * s, umma_desc(b0 + 2 * s * rows_b * 16, rows_b * 16, 128), idesc, (pass | s) ? 1u : 0u);
+    }
+}
+
+// This thread's row: 8 consecutive 32-bit columns starting at `col` of tensor memory.
+__device__ __forceinline__ void tmem_st8(uint32_t tmem_base, int col, const float* v) {
+    const uint32_t taddr = tmem_base + ((uint32_t)((threadIdx.x >> 5) & 3) * 32u << 16) + (uint32_t)col;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// hi = x with the low 13 mantissa bits cleared (what the tensor core keeps), lo = x - hi (exact in fp32)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Writes NCH chunks of 8 values of this thread's row, split into hi / lo, at tensor-memory columns col_hi / col_lo.
+template <int NCH>
+__device__ __forceinline__ void tmem_store_split(uint32_t tmem_base, int col_hi, int col_lo, const float* v) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        float h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { h[i] = tf32_hi(v[8 * c + i]); l[i] = v[8 * c + i] - h[i]; }
+        tmem_st8(tmem_base, col_hi + 8 * c, h);
+        tmem_st8(tmem_base, col_lo + 8 * c, l);
+    }
+}
+
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -284,8 +284,8 @@ class NPEModel:
         return n.value
 
     def set_precision(self, mode):
-        """'fp32' (FFMA kernels, default) or 'tf32' (tcgen05 forward / rollout kernels)."""
-        self._ck(self.lib.npe_set_precision(self.h, {"fp32": 0, "tf32": 1}[mode]))
+        """'fp32' (FFMA kernels, default), 'tf32' (tcgen05, single pass) or 'tf32x3' (tcgen05, FP32-grade split)."""
+        self._ck(self.lib.npe_set_precision(self.h, {"fp32": 0, "tf32": 1, "tf32x3": 2}[mode]))
 
     def set_rollout_mode(self, mode):
         """'persistent' (one kernel, window on chip) or 'kernels' (window in HBM, 5 launches per step)."""

@@ -187,6 +187,7 @@ int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* obje
  */
 #define NPE_PRECISION_FP32 0
 #define NPE_PRECISION_TF32_TC 1
+#define NPE_PRECISION_TF32X3_TC 2 /* tcgen05 with the 3xTF32 split, activations in tensor memory: FP32-grade (~1e-6) */
 #define NPE_ROLLOUT_PERSISTENT 0
 #define NPE_ROLLOUT_BY_KERNELS 1
 int npe_set_precision(npe_handle* h, int32_t mode);

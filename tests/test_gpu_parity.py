@@ -394,3 +394,26 @@ def test_train_steps_equals_step_by_step(model, params):
     y = batcher.relative_pair(this, np.stack([st[sc[i], ob[i], t0[i] + 2:t0[i] + 3] for i in range(50)]))
     l, _, lv, lw = npe.fp(params, (this, ctx, y))
     assert rel_err(losses[0], [l, lv, lw], 1e-6) < 1e-4
+
+
+def test_tf32x3_forward_is_fp32_grade(model, trained_like_params):
+    """tcgen05 with the 3xTF32 split (activations in tensor memory): within the FP32 tolerance of the oracle."""
+    for n in (4, 8):
+        _, batches = balls_batches(60, n, seed=20 + n)
+        batch = batcher.make_batch(*batches[0], offset=6)
+        le, pred, lve, lwe = npe.fp_batch(trained_like_params, batch)
+        model.set_precision("tf32x3")
+        gle, gpred, glve, glwe = model.fp_batch(trained_like_params, batch)
+        assert rel_err(gpred[:, :6], pred[:, :6]) < TOL
+        assert np.max(np.abs(gle - le)) < 1e-6
+        model.set_precision("fp32")
+    # walls: 12 contexts per focus, rollout by kernels (FP32-grade: free-running positions stay together)
+    sw = scenes.raw_to_state(scenes.gen_walls(8, 14, seed=9, variant="U"))
+    model.set_params(trained_like_params)
+    model.upload_scenes(sw)
+    model.set_precision("tf32x3")
+    traj, met = model.rollout(0, 12, use_gt=True, teacher=False)
+    model.set_precision("fp32"); model.set_rollout_mode("persistent")
+    ref, mref = model.rollout(0, 12, use_gt=True, teacher=False)
+    assert np.max(np.abs(traj - ref)) < 1e-4
+    assert np.allclose(met, mref, rtol=1e-3, atol=1e-9)

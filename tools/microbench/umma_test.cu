@@ -90,6 +90,92 @@ __global__ void __launch_bounds__(128, 1) k(const float* A, const float* W, floa
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem));
 }
 
+// ---- variant 2: A operand in TENSOR MEMORY (lane = row, column = k), 3xTF32 split: D = Ahi*Whi + Ahi*Wlo + Alo*Whi ----
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+__global__ void __launch_bounds__(128, 1) k2(const float* A, const float* W, float* D, long long* cycles) {
+    __shared__ __align__(1024) float sBh[KC * N * 4];
+    __shared__ __align__(1024) float sBl[KC * N * 4];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int c = 0; c < KC; ++c) {
+        if (t < N) {
+            float4 w = *reinterpret_cast<const float4*>(W + t * K + 4 * c);
+            float4 h = make_float4(tf32_hi(w.x), tf32_hi(w.y), tf32_hi(w.z), tf32_hi(w.w));
+            float4 l = make_float4(w.x - h.x, w.y - h.y, w.z - h.z, w.w - h.w);
+            *reinterpret_cast<float4*>(sBh + (c * N + t) * 4) = h;
+            *reinterpret_cast<float4*>(sBl + (c * N + t) * 4) = l;
+        }
+    }
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // each thread writes its row of A (hi at columns 64.., lo at columns 128..) into tensor memory, 8 columns per st
+    long long t0 = clock64();
+    for (int c = 0; c < K; c += 8) {
+        uint32_t h[8], l[8];
+        for (int i = 0; i < 8; ++i) { float x = A[t * K + c + i]; float hh = tf32_hi(x); h[i] = __float_as_uint(hh); l[i] = __float_as_uint(x - hh); }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(lane_base + 64 + c),
+                     "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(lane_base + 128 + c),
+                     "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (t == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        for (int pass = 0; pass < 3; ++pass) {
+            const float* sB = pass == 1 ? sBl : sBh;
+            const uint32_t acol = pass == 2 ? 128 : 64;
+            for (int s = 0; s < K / 8; ++s) {
+                const uint64_t db = make_desc(smem_u32(sB) + 2 * s * N * 16, N * 16, 128);
+                const uint32_t acc = (pass > 0 || s > 0);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                    ::"r"(tmem), "r"(tmem + acol + 8 * s), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[64];
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]),
+              "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]), "=r"(r[c + 12]),
+              "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+            : "r"(lane_base + c));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    long long t1 = clock64();
+    for (int c = 0; c < 64; ++c) D[t * N + c] = __uint_as_float(r[c]);
+    if (t == 0) cycles[0] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
 static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
 int main() {
@@ -118,6 +204,21 @@ int main() {
     for (int i = 0; i < M * N; ++i) { e_full = fmax(e_full, fabs(D[i] - ref[i])); e_trunc = fmax(e_trunc, fabs(D[i] - reft[i])); mx = fmax(mx, fabs(ref[i])); }
     printf("max|ref| %.3f  max err vs fp64(fp32 inputs) %.3e  vs fp64(tf32-truncated inputs) %.3e  cycles (7 MMA + commit + ld) %lld\n", mx, e_full, e_trunc, cyc);
     printf("D[0][0..3] = %f %f %f %f   ref %f %f %f %f\n", D[0], D[1], D[2], D[3], ref[0], ref[1], ref[2], ref[3]);
+    {
+        cudaMemset(dD, 0, D.size() * 4);
+        k2<<<1, 128>>>(dA, dW, dD, dc);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        printf("k2 (A in TMEM, 3xTF32): %s\n", cudaGetErrorString(e2));
+        if (e2 == cudaSuccess) {
+            std::vector<float> D2(M * N);
+            cudaMemcpy(D2.data(), dD, D2.size() * 4, cudaMemcpyDeviceToHost);
+            long long c2; cudaMemcpy(&c2, dc, 8, cudaMemcpyDeviceToHost);
+            double e3 = 0;
+            for (int i = 0; i < M * N; ++i) e3 = fmax(e3, fabs(D2[i] - ref[i]));
+            printf("k2 max err vs fp64(fp32 inputs) %.3e (rel %.2e)  cycles (st A + 21 MMA + commit + ld) %lld\n", e3, e3 / mx, c2);
+            printf("k2 D[5][0..3] = %f %f %f %f   ref %f %f %f %f\n", D2[5 * N], D2[5 * N + 1], D2[5 * N + 2], D2[5 * N + 3], ref[5 * N], ref[5 * N + 1], ref[5 * N + 2], ref[5 * N + 3]);
+        }
+    }
     printf("D[77][60..63] = %f %f %f %f   ref %f %f %f %f\n", D[77 * N + 60], D[77 * N + 61], D[77 * N + 62], D[77 * N + 63], ref[77 * N + 60], ref[77 * N + 61], ref[77 * N + 62], ref[77 * N + 63]);
     return 0;
 }
