@@ -20,6 +20,16 @@ if which == "stress64":
         m.select_windows(0, 1024)
         m.train_step("adam", 3e-4, want_loss=False)
     m.sync()
+elif which in ("fwd_tf32", "fwd_tf32x3", "fwd_fp32"):
+    m = NPEModel(ModelParams(max_ctx=0))
+    st = synth.ball_scenes(1024, 64, 3, seed=64, world=(3200, 2400), collide=False)
+    m.set_params(init_params())
+    m.upload_scenes(st); m.upload_windows(np.arange(1024), np.zeros(1024, np.int32))
+    m.select_windows(0, 1024)
+    m.set_precision(which.split("_")[1])
+    for s in range(steps):
+        m._ck(m.lib.npe_forward_per_example(m.h, None, None))
+    m.sync()
 elif which == "b50":
     m = NPEModel()
     st = synth.ball_scenes(200, 4, 10, seed=4)
