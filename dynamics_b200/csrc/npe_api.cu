@@ -91,6 +91,7 @@ struct npe_handle {
     float* wtc3 = nullptr;            // hi | lo images for the 3xTF32 variant (2 * TC_TOTAL floats)
     bool wtc3_dirty = true;
     int precision = 0, rollout_mode = 0;
+    int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
     int roll_F = 0;
@@ -344,11 +345,12 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
                                                                        h->pred.p, loss_ex);
         } else {
             k_pair_forward_tc3<<<pg, NT, sizeof(PairTc3Smem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                         h->info_dev, h->wtc3, h->Hp.p);
-            k_dec_forward_tc3<<<fg, NT, sizeof(DecTc3Smem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc3, y,
-                                                                         h->pred.p, loss_ex);
+                                                                         h->info_dev, h->wtc3, h->Hp.p, stash);
+            if (!skip_decoder)
+                k_dec_forward_tc3<<<fg, NT, sizeof(DecTc3Smem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc3,
+                                                                             y, h->pred.p, loss_ex);
         }
-        h->launches += 2;
+        h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
         if (small_batch(h, F)) {
             CK(launch_pdl(k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream,
@@ -374,12 +376,13 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
 int run_forward(npe_handle* h, bool training, bool fused = false) {
     int rc = build_pairs(h);
     if (rc) return rc;
-    const int tc = training ? 0 : h->precision;
+    // training forward: FP32 FFMA kernels, or (train_fwd_tc) the FP32-grade tcgen05 pair kernel; never single-pass TF32
+    const int tc = training ? (h->train_fwd_tc && !small_batch(h, h->F) ? NPE_PRECISION_TF32X3_TC : 0) : h->precision;
     float* stash = (training && h->have_y) ? training_stash(h) : nullptr;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused);
     if (rc) return rc;
-    h->fwd_valid = !tc;
+    h->fwd_valid = (tc != NPE_PRECISION_TF32_TC);
     h->hact_valid = stash != nullptr;
     return NPE_OK;
 }

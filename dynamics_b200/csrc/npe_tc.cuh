@@ -332,7 +332,7 @@ struct PairTc3Smem {
 __global__ void __launch_bounds__(NT, 1)
 k_pair_forward_tc3(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                    const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wtc3,
-                   float* __restrict__ Hp) {
+                   float* __restrict__ Hp, float* __restrict__ hact) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairTc3Smem& S = *reinterpret_cast<PairTc3Smem*>(smem_raw);
     const int P = info[0];
@@ -395,6 +395,11 @@ k_pair_forward_tc3(const float* __restrict__ states, const int* __restrict__ pai
 #pragma unroll
             for (int k = 0; k < 56; ++k) act[k] = k < H2 ? relu(d[k]) : (k < H ? relu(d[32 + k - H2]) : 0.f);
             tmem_store_split<7>(tmem, TM_AHI, TM_ALO, act);
+            if (hact && t < nrows) {   // training: activation stash for the backward kernel
+                float* o = hact + (size_t)(lo + t) * HACT_STRIDE;
+#pragma unroll
+                for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(act[4 * c], act[4 * c + 1], act[4 * c + 2], act[4 * c + 3]));
+            }
             tmem_st_wait();
         }
         phase ^= 1;
@@ -415,6 +420,11 @@ k_pair_forward_tc3(const float* __restrict__ states, const int* __restrict__ pai
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 56; ++k) d[k] = relu(d[k]);
+                if (hact && t < nrows) {
+                    float* o = hact + (size_t)(lo + t) * HACT_STRIDE + (l + 1) * 52;
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]));
+                }
                 if (l < NL - 1) {
                     tmem_store_split<7>(tmem, TM_AHI, TM_ALO, d);
                     tmem_st_wait();
