@@ -334,9 +334,10 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
     if (tc) {
         int rc = refresh_wtc(h, tc);
         if (rc) return rc;
-        const long long ptiles = ((long long)h->pair_cap + 127) / 128;
+        const int tiles_per_cta = (tc == NPE_PRECISION_TF32X3_TC) ? 2 : 1;   // the 3xTF32 kernels run two tile groups per CTA
+        const long long ptiles = (((long long)h->pair_cap + 127) / 128 + tiles_per_cta - 1) / tiles_per_cta;
         const int pg = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
-        const int ft = (F + 127) / 128;
+        const int ft = ((F + 127) / 128 + tiles_per_cta - 1) / tiles_per_cta;
         const int fg = ft < h->num_sms ? ft : h->num_sms;
         if (tc == NPE_PRECISION_TF32_TC) {
             k_pair_forward_tc<<<pg, NT, sizeof(PairTcSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
