@@ -258,6 +258,15 @@ int ensure_batch_buffers(npe_handle* h, int F) {
     return NPE_OK;
 }
 
+// Pair builder launch: sub-warp variants when every scene has at most 9 / 17 objects.
+template <typename... Args>
+void launch_build_pairs(npe_handle* h, int nblk, int nmax, Args... args) {
+    if (nmax - 1 <= 8) k_build_pairs<8><<<nblk, 512, 0, h->stream>>>(args...);
+    else if (nmax - 1 <= 16) k_build_pairs<16><<<nblk, 1024, 0, h->stream>>>(args...);
+    else k_build_pairs<32><<<nblk, NT_PAIRS, 0, h->stream>>>(args...);
+    h->launches++;
+}
+
 int build_pairs(npe_handle* h) {
     if (h->pairs_valid) return NPE_OK;
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
@@ -266,11 +275,9 @@ int build_pairs(npe_handle* h) {
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
         const int nblk = (h->F + FPB - 1) / FPB;
-        k_build_pairs<<<nblk, NT_PAIRS, 0, h->stream>>>(h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p,
-                                                  h->block_sums.p, h->foc_row.p, h->batch_form ? nullptr : h->y.p,
-                                                  h->active_total, h->pair_start.p, h->pair_foc.p, h->pair_crow.p,
-                                                  h->pair_cap, h->info_dev);
-        h->launches++;
+        launch_build_pairs(h, nblk, h->Nmax, h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
+                           h->foc_row.p, h->batch_form ? nullptr : h->y.p, h->active_total, h->pair_start.p, h->pair_foc.p,
+                           h->pair_crow.p, h->pair_cap, h->info_dev);
         if (nblk > 1) {
             k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
                                                               h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
@@ -1032,10 +1039,9 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
-            k_build_pairs<<<nblk, NT_PAIRS, 0, h->stream>>>(src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
-                                                      h->foc_row.p, nullptr, h->active_total, h->pair_start.p, h->pair_foc.p,
-                                                      h->pair_crow.p, h->pair_cap, h->info_dev);
-            h->launches++;
+            launch_build_pairs(h, nblk, h->Nmax, src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
+                               h->foc_row.p, (float*)nullptr, h->active_total, h->pair_start.p, h->pair_foc.p, h->pair_crow.p,
+                               h->pair_cap, h->info_dev);
             if (nblk > 1) {
                 k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(src, h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
                                                                   h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
@@ -1046,7 +1052,7 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
         A.step = step;
         {
             ProfScope ps__(h, NPE_K_ROLLOUT);
-            k_rollout_post<<<(SN + 255) / 256, 256, 0, h->stream>>>(A);
+            k_rollout_post<<<(SN + POST_OBJ - 1) / POST_OBJ, 256, 0, h->stream>>>(A);
             h->launches++;
         }
     }

@@ -154,40 +154,89 @@ __device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, 
     nbr = (u64)m0 | ((u64)m1 << 32);
 }
 
-// K1 (+K7): one warp per focus (8 foci per warp, 64 per CTA): pair bits, focus row offset, the relative target
-// y = frame(t0+2) with columns 0..5 minus frame(t0+1) (relative_pair, data_process.lua:87-96), and the first level of
-// the active-pair scan: exclusive prefix of the counts inside the CTA + the CTA total.
+// Sub-warp variant of warp_pairs for small scenes: a group of LANES (8 or 16) lanes handles one focus with at most
+// LANES contexts, so a warp builds 32 / LANES pair tables at once (8-ball scenes: 4 foci per warp instead of 1 with 7
+// of 32 lanes busy).  Same arithmetic, same tie rule, bit-identical results.
+template <int LANES>
+__device__ __forceinline__ void group_pairs(const float* pos, int stride, int N, int n, int kmax, float thr_px, bool active,
+                                            u64& keep, u64& nbr) {
+    const int lane = threadIdx.x & 31, gl = lane & (LANES - 1), gbase = lane & ~(LANES - 1);
+    const int Cn = active ? N - 1 : 0;
+    const bool valid = gl < Cn;
+    float d = __int_as_float(0x7f800000);
+    if (valid) {
+        const float fx = pos[(size_t)n * stride], fy = pos[(size_t)n * stride + 1];
+        const int j = gl + (gl >= n);
+        const float dx = __fsub_rn(pos[(size_t)j * stride], fx);
+        const float dy = __fsub_rn(pos[(size_t)j * stride + 1], fy);
+        d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    }
+    const int k = (kmax > 0 && kmax < Cn) ? kmax : Cn;
+    int rank = 0;
+#pragma unroll
+    for (int cp = 0; cp < LANES; ++cp) {
+        const float dp = __shfl_sync(0xffffffffu, d, gbase + cp);
+        if (cp < Cn) rank += (dp < d) || (dp == d && cp < gl);
+    }
+    const bool kp = valid && (k >= Cn || rank < k);
+    const unsigned bk = __ballot_sync(0xffffffffu, kp);
+    const unsigned bm = __ballot_sync(0xffffffffu, kp && (__fmul_rn(d, 800.f) <= thr_px));
+    const unsigned gm = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
+    keep = (u64)((bk >> gbase) & gm);
+    nbr = (u64)((bm >> gbase) & gm);
+}
+
+// K1 (+K7): pair bits, focus row offset, the relative target y = frame(t0+2) with columns 0..5 minus frame(t0+1)
+// (relative_pair, data_process.lua:87-96), and the first level of the active-pair scan (exclusive prefix of the counts
+// inside the CTA + the CTA total).  64 foci per CTA.  LANES = 32: one warp per focus (up to 63 contexts), two foci per
+// warp in turn, 1024 threads; LANES = 16 / 8: 2 / 4 foci per warp at once (scenes with at most 17 / 9 objects).
 constexpr int FPB = 64;   // foci per CTA of the pair builder
-constexpr int NT_PAIRS = 1024;   // 32 warps: two foci per warp, so the dependent global loads of the 64 foci overlap
+constexpr int NT_PAIRS = 1024;
+template <int LANES>
 __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
-                                                    u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
-                                                    int* __restrict__ block_sums, long long* __restrict__ foc_row,
-                                                    float* __restrict__ y, u64* __restrict__ active_total,
-                                                    int* __restrict__ pair_start, int* __restrict__ pair_foc,
-                                                    long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
+                                                          u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
+                                                          int* __restrict__ block_sums, long long* __restrict__ foc_row,
+                                                          float* __restrict__ y, u64* __restrict__ active_total,
+                                                          int* __restrict__ pair_start, int* __restrict__ pair_foc,
+                                                          long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
     __shared__ int s_cnt[FPB];
     __shared__ int s_pre[FPB];
     __shared__ u64 s_nbr[FPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = 0; i < FPB / (NT_PAIRS / 32); ++i) {
-        const int fl = warp * (FPB / (NT_PAIRS / 32)) + i;
+    constexpr int GPW = 32 / LANES;                       // foci per warp per pass
+    const int nwarps = blockDim.x >> 5;
+    const int gl = lane & (LANES - 1), grp = lane / LANES;
+    for (int base = 0; base < FPB; base += nwarps * GPW) {
+        const int fl = base + warp * GPW + grp;
         const int f = blockIdx.x * FPB + fl;
+        const bool active = fl < FPB && f < src.F;
         int c = 0;
-        if (f < src.F) {
-            const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
-            u64 keep, nbr;
-            warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
-            const size_t ro = row_off(src, s, n, t0);
-            if (y && lane < D) {
+        u64 keep = 0, nbr = 0;
+        size_t ro = 0;
+        if (LANES == 32) {
+            if (active) {
+                const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
+                warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
+                ro = row_off(src, s, n, t0);
+            }
+        } else {
+            int s = 0, n = 0, t0 = 0, N = 1;
+            if (active) { s = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f]; N = src.n_obj[s]; ro = row_off(src, s, n, t0); }
+            group_pairs<LANES>(src.states + row_off(src, s, 0, t0 + 1), src.T * D, N, n, kmax, thr_px, active, keep, nbr);
+        }
+        if (active) {
+            if (y) {
                 const float* p = src.states + ro;
-                float v = p[2 * D + lane];
-                if (lane < 6) v = __fsub_rn(v, p[D + lane]);
-                y[(size_t)f * D + lane] = v;
+                for (int col = gl; col < D; col += LANES) {
+                    float v = p[2 * D + col];
+                    if (col < 6) v = __fsub_rn(v, p[D + col]);
+                    y[(size_t)f * D + col] = v;
+                }
             }
             c = __popcll(nbr);
-            if (lane == 0) { keep_out[f] = keep; nbr_out[f] = nbr; foc_row[f] = (long long)ro; s_nbr[fl] = nbr; }
+            if (gl == 0) { keep_out[f] = keep; nbr_out[f] = nbr; foc_row[f] = (long long)ro; s_nbr[fl] = nbr; }
         }
-        if (lane == 0) s_cnt[fl] = c;
+        if (gl == 0 && fl < FPB) s_cnt[fl] = c;
     }
     __syncthreads();
     if (warp == 0) {

@@ -567,40 +567,45 @@ struct RollPostArgs {
     double* metrics;          // (steps, 7) or null
 };
 
-__global__ void __launch_bounds__(256) k_rollout_post(RollPostArgs A) {
+// One thread per (object, state column): 22 consecutive threads touch 22 consecutive floats (coalesced); the thread of
+// column 0 also computes the object's step metrics.
+constexpr int POST_OBJ = 11, POST_NT = POST_OBJ * D;   // 242 threads: a CTA owns whole objects (the shift is in place)
+__global__ void __launch_bounds__(256) k_rollout_post(RollPostArgs A) {   // 256 threads, the last 14 idle
     __shared__ double red[7][8];
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gid = (long long)blockIdx.x * POST_NT + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
     double mt[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (idx < A.S * A.Nmax) {
-        const int s = idx / A.Nmax, ob = idx - s * A.Nmax;
+    const long long idx = gid / D;
+    const int c = (int)(gid - idx * D);
+    bool live = false;
+    float q = 0.f, lc = 0.f, gtc = 0.f;
+    float* w = nullptr;
+    if (threadIdx.x < POST_NT && idx < (long long)A.S * A.Nmax) {
+        const int s = (int)(idx / A.Nmax), ob = (int)(idx - (long long)s * A.Nmax);
         if (ob < A.n_obj[s]) {
-            float* w = A.roll + (size_t)idx * 2 * D;
-            float last[D];
-#pragma unroll
-            for (int c = 0; c < D; ++c) last[c] = w[D + c];
+            live = true;
+            w = A.roll + (size_t)idx * 2 * D;
+            const float* last = w + D;
+            lc = last[c];
             const float* gt = A.use_gt ? A.states + (((size_t)idx * A.T) + A.t0 + 2 + A.step) * D : nullptr;
+            if (gt) gtc = gt[c];
             const int f = A.foc_of_obj[idx];
-            float q[D];
             if (f < 0) {
-#pragma unroll
-                for (int c = 0; c < D; ++c) q[c] = gt ? gt[c] : last[c];
+                q = gt ? gt[c] : lc;
             } else {
                 const float* o = A.pred + (size_t)f * OUT;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) q[c] = __fadd_rn(o[c], last[c]);
-#pragma unroll
-                for (int c = 6; c < D; ++c) q[c] = last[c];
-                q[0] = __fdiv_rn(__fadd_rn(__fmul_rn(last[0], 800.f), __fmul_rn(last[2], 60.f)), 800.f);
-                q[1] = __fdiv_rn(__fadd_rn(__fmul_rn(last[1], 800.f), __fmul_rn(last[3], 60.f)), 800.f);
-                float ang = __fadd_rn(__fmul_rn(last[4], PI_F), __fmul_rn(last[5], PI_F));
-                const float gtpi = ang > PI_F ? 1.f : 0.f, lepi = ang <= -PI_F ? 1.f : 0.f;
-                ang = __fadd_rn(ang, __fmul_rn(-TWO_PI_F, gtpi));
-                ang = __fadd_rn(ang, __fmul_rn(TWO_PI_F, lepi));
-                q[4] = __fdiv_rn(ang, PI_F);
-                if (A.ball_zero && last[10] == 1.f) { q[4] = 0.f; q[5] = 0.f; }
-                if (gt) {
+                if (c < 2) q = __fdiv_rn(__fadd_rn(__fmul_rn(lc, 800.f), __fmul_rn(last[c + 2], 60.f)), 800.f);
+                else if (c == 4) {
+                    float ang = __fadd_rn(__fmul_rn(lc, PI_F), __fmul_rn(last[5], PI_F));
+                    const float gtpi = ang > PI_F ? 1.f : 0.f, lepi = ang <= -PI_F ? 1.f : 0.f;
+                    ang = __fadd_rn(ang, __fmul_rn(-TWO_PI_F, gtpi));
+                    ang = __fadd_rn(ang, __fmul_rn(TWO_PI_F, lepi));
+                    q = __fdiv_rn(ang, PI_F);
+                } else if (c < 6) q = __fadd_rn(o[c], lc);
+                else q = lc;
+                if ((c == 4 || c == 5) && A.ball_zero && last[10] == 1.f) q = 0.f;
+                if (c == 0 && gt) {
                     const float y2 = __fsub_rn(gt[2], last[2]), y3 = __fsub_rn(gt[3], last[3]), y5 = __fsub_rn(gt[5], last[5]);
                     const float e2 = o[2] - y2, e3 = o[3] - y3, e5 = o[5] - y5;
                     const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
@@ -616,17 +621,13 @@ __global__ void __launch_bounds__(256) k_rollout_post(RollPostArgs A) {
                     }
                 }
             }
-            if (A.traj) {
-                float* dst = A.traj + (((size_t)idx * A.steps) + A.step) * D;
-#pragma unroll
-                for (int c = 0; c < D; ++c) dst[c] = q[c];
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                w[c] = last[c];
-                w[D + c] = (A.teacher && gt) ? gt[c] : q[c];
-            }
+            if (A.traj) A.traj[(((size_t)idx * A.steps) + A.step) * D + c] = q;
         }
+    }
+    __syncthreads();   // all reads of the object's last frame (by its 22 threads, same CTA) precede the in-place shift
+    if (live) {
+        w[c] = lc;
+        w[D + c] = (A.teacher && A.use_gt) ? gtc : q;
     }
     if (A.metrics && A.use_gt) {
 #pragma unroll

@@ -417,3 +417,15 @@ def test_tf32x3_forward_is_fp32_grade(model, trained_like_params):
     ref, mref = model.rollout(0, 12, use_gt=True, teacher=False)
     assert np.max(np.abs(traj - ref)) < 1e-4
     assert np.allclose(met, mref, rtol=1e-3, atol=1e-9)
+
+
+def test_pair_builder_16_lane_groups(model, trained_like_params):
+    """Scenes with 10..17 objects take the 16-lane sub-warp pair builder: bit-exact table, forward parity."""
+    st = scenes.raw_to_state(scenes.gen_balls(50, 12, 6, seed=77, world=(1600, 1200)))
+    this = st[:, 0, 1:3]; ctx = st[:, 1:, 1:3]; y = batcher.relative_pair(this, st[:, 0, 3:4])
+    l, pred, lv, lw = npe.fp(trained_like_params, (this, ctx, y))
+    gl, gpred, _, _ = model.fp(trained_like_params, (this, ctx, y))
+    idx, mask, cnt = model.pair_table()
+    oidx, omask, _ = oracle_pairs(this, ctx)
+    assert np.array_equal(idx, oidx.astype(np.int32)) and np.array_equal(mask, omask.astype(np.uint8))
+    assert omask.sum() > 0 and rel_err(gpred[:, :6], pred[:, :6]) < TOL
