@@ -176,6 +176,86 @@ __global__ void __launch_bounds__(128, 1) k2(const float* A, const float* W, flo
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
+// ---- variant 3: input-gradient product.  D[m][k] = sum_n A[m][n] * W[n][k]: B operand = the SAME weight tile
+// ([k-chunk][n][4 floats], built for the forward as a K-major operand) read as an MN-MAJOR operand (N' = k, K' = n):
+// descriptor SBO = ROWS_N * 16 (next 4 k), LBO = 128 (next 8 n); idesc b_major = 1.  A in tensor memory, single pass.
+__global__ void __launch_bounds__(128, 1) k3(const float* A64, const float* W, float* D, long long* cycles, int variant) {
+    __shared__ __align__(128) float sB[16 * N * 4];
+    __shared__ __align__(128) float sA3[14 * M * 4];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int c = 0; c < 14; ++c) *reinterpret_cast<float4*>(sA3 + (c * M + t) * 4) = *reinterpret_cast<const float4*>(A64 + t * N + 4 * c);
+    for (int c = 0; c < 16; ++c)
+        if (t < N) *reinterpret_cast<float4*>(sB + (c * N + t) * 4) = c < KC ? *reinterpret_cast<const float4*>(W + t * K + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 8) {   // A row: 64 values (reduction index n), columns 64..127 of tensor memory
+        uint32_t h[8];
+        for (int i = 0; i < 8; ++i) h[i] = __float_as_uint(A64[t * N + c + i]);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(lane_base + 64 + c),
+                     "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (t == 0) {
+        // N' = 56 output columns (k), K' = 64 (n) in 8 steps
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((variant ? 1u : 0u) << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // N' = 64 (N % 16 == 0 for M = 128)
+        for (int s = 0; s < 7; ++s) {
+            const uint64_t db = (variant == 2 || variant == 4) ? make_desc(smem_u32(sB) + s * 128, N * 16, 128)
+                                             : make_desc(smem_u32(sB) + s * 128, /*LBO*/ 128, /*SBO*/ N * 16);
+            const uint32_t acc = s > 0;
+            if (variant < 3) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                    ::"r"(tmem), "r"(tmem + 64 + 8 * s), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            } else {
+                const uint64_t da = make_desc(smem_u32(sA3) + 2 * s * M * 16, M * 16, 128);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+        ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t r[64];
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[c + 0]), "=r"(r[c + 1]), "=r"(r[c + 2]), "=r"(r[c + 3]), "=r"(r[c + 4]), "=r"(r[c + 5]), "=r"(r[c + 6]),
+              "=r"(r[c + 7]), "=r"(r[c + 8]), "=r"(r[c + 9]), "=r"(r[c + 10]), "=r"(r[c + 11]), "=r"(r[c + 12]),
+              "=r"(r[c + 13]), "=r"(r[c + 14]), "=r"(r[c + 15])
+            : "r"(lane_base + c));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int c = 0; c < K; ++c) D[t * 64 + c] = __uint_as_float(r[c]);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
 static float tf32_trunc(float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; }
 
 int main() {
@@ -217,6 +297,39 @@ int main() {
             for (int i = 0; i < M * N; ++i) e3 = fmax(e3, fabs(D2[i] - ref[i]));
             printf("k2 max err vs fp64(fp32 inputs) %.3e (rel %.2e)  cycles (st A + 21 MMA + commit + ld) %lld\n", e3, e3 / mx, c2);
             printf("k2 D[5][0..3] = %f %f %f %f   ref %f %f %f %f\n", D2[5 * N], D2[5 * N + 1], D2[5 * N + 2], D2[5 * N + 3], ref[5 * N], ref[5 * N + 1], ref[5 * N + 2], ref[5 * N + 3]);
+        }
+    }
+    {
+        // dgrad check: A64 (128 x 64), D3[m][k] = sum_n A64[m][n] * W[n][k]
+        std::vector<float> A64(M * N), D3(M * 64, 0.f);
+        for (auto& v : A64) v = (rand() % 2001 - 1000) / 1000.f;
+        float* dA64; cudaMalloc(&dA64, A64.size() * 4); cudaMemcpy(dA64, A64.data(), A64.size() * 4, cudaMemcpyHostToDevice);
+        for (int variant = 0; variant < 5; ++variant) {
+        cudaMemset(dD, 0, D.size() * 4);
+        k3<<<1, 128>>>(dA64, dW, dD, dc, variant);
+        cudaError_t e3 = cudaDeviceSynchronize();
+        printf("k3 variant %d (MN-major B, dgrad): %s\n", variant, cudaGetErrorString(e3));
+        if (e3 == cudaSuccess) {
+            cudaMemcpy(D3.data(), dD, D3.size() * 4, cudaMemcpyDeviceToHost);
+            double emax = 0, rmax = 0;
+            for (int m = 0; m < M; ++m)
+                for (int k = 0; k < K; ++k) {
+                    double sref = 0;
+                    for (int n = 0; n < 56; ++n) sref += (double)tf32_trunc(A64[m * N + n]) * tf32_trunc(W[n * K + k]);
+                    emax = fmax(emax, fabs(D3[m * 64 + k] - sref)); rmax = fmax(rmax, fabs(sref));
+                }
+            printf("k3 max err vs fp64(tf32-truncated inputs) %.3e (max|ref| %.3f)\n", emax, rmax);
+            for (int k = 0; k < 6; ++k) {
+                double sref = 0; for (int n = 0; n < 56; ++n) sref += (double)A64[3 * N + n] * W[n * K + k];
+                printf("  D3[3][%d] = %f ref %f\n", k, D3[3 * 64 + k], sref);
+            }
+            // hypothesis tests: which (n,k) pairing reproduces D3[3][0]?
+            for (int swap = 0; swap < 2; ++swap) {
+                double s2 = 0;
+                for (int n = 0; n < 8; ++n) s2 += (double)A64[3 * N + n] * (swap ? W[0 * K + n] : W[n * K + 0]);
+                printf("  partial(first 8 n) swap=%d: %f\n", swap, s2);
+            }
+        }
         }
     }
     printf("D[77][60..63] = %f %f %f %f   ref %f %f %f %f\n", D[77 * N + 60], D[77 * N + 61], D[77 * N + 62], D[77 * N + 63], ref[77 * N + 60], ref[77 * N + 61], ref[77 * N + 62], ref[77 * N + 63]);
