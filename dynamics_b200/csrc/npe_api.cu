@@ -137,6 +137,8 @@ struct npe_handle {
     // rollout
     DevBuf<float> traj;
     DevBuf<double> metrics;
+    DevBuf<double> slot_metrics;
+    bool want_slots = false;   // set by npe_rollout_slots around one rollout
 
     // kernel-class profiling (roofline): event pairs around launches of one selected kernel class
     int prof_kernel = -1;
@@ -631,7 +633,7 @@ int npe_destroy(npe_handle* h) {
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
-    h->traj.release(); h->metrics.release();
+    h->traj.release(); h->metrics.release(); h->slot_metrics.release();
     h->roll.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
@@ -982,6 +984,12 @@ static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teache
         CK(cudaMemsetAsync(h->metrics.p, 0, (size_t)steps * 7 * sizeof(double), h->stream));
         A.metrics = h->metrics.p;
     }
+    A.slot_metrics = nullptr;
+    if (want_metrics && h->want_slots) {
+        CK(h->slot_metrics.ensure((size_t)steps * h->Nmax * 7));
+        CK(cudaMemsetAsync(h->slot_metrics.p, 0, (size_t)steps * h->Nmax * 7 * sizeof(double), h->stream));
+        A.slot_metrics = h->slot_metrics.p;
+    }
     const int G = TILE / h->Nmax;
     const int ngroups = (h->S + G - 1) / G;
     const int grid = ngroups < h->num_sms ? ngroups : h->num_sms;
@@ -1027,6 +1035,12 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
         CK(h->metrics.ensure((size_t)steps * 7));
         CK(cudaMemsetAsync(h->metrics.p, 0, (size_t)steps * 7 * sizeof(double), h->stream));
         A.metrics = h->metrics.p;
+    }
+    A.slot_metrics = nullptr;
+    if (want_metrics && h->want_slots) {
+        CK(h->slot_metrics.ensure((size_t)steps * h->Nmax * 7));
+        CK(cudaMemsetAsync(h->slot_metrics.p, 0, (size_t)steps * h->Nmax * 7 * sizeof(double), h->stream));
+        A.slot_metrics = h->slot_metrics.p;
     }
     k_rollout_init<<<(SN * 2 * D + 255) / 256, 256, 0, h->stream>>>(h->roll.p, h->states.p, SN, h->T, t0);
     CKL();
@@ -1074,6 +1088,19 @@ int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_
     if (rc) return rc;
     if (traj_out) CK(cudaMemcpyAsync(traj_out, h->traj.p, (size_t)h->S * h->Nmax * steps * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (metrics_out) CK(cudaMemcpyAsync(metrics_out, h->metrics.p, (size_t)steps * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
+
+int npe_rollout_slots(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* slot_metrics_out) {
+    NEED(h);
+    if (!slot_metrics_out) return fail(h, NPE_ERR_INVALID, "rollout_slots: slot_metrics_out is NULL");
+    h->want_slots = true;
+    int rc = rollout_dispatch(h, t0, steps, use_gt, teacher, traj_out != nullptr, true);
+    h->want_slots = false;
+    if (rc) return rc;
+    if (traj_out) CK(cudaMemcpyAsync(traj_out, h->traj.p, (size_t)h->S * h->Nmax * steps * D * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(slot_metrics_out, h->slot_metrics.p, (size_t)steps * h->Nmax * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return NPE_OK;
 }

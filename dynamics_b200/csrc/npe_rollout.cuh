@@ -47,6 +47,7 @@ struct RollArgs {
     const float* wpack;       // packed weight image
     float* traj;              // (S, Nmax, steps, 22) or null
     double* metrics;          // (steps, 7) or null
+    double* slot_metrics;     // (steps, Nmax, 7) or null: the same sums kept per object slot (eval.lua:348-358)
 };
 
 __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
@@ -202,6 +203,12 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                             mt[6] = 1.0;
                         }
                     }
+                }
+                if (A.slot_metrics && mt[3] != 0.0) {
+                    double* m = A.slot_metrics + ((size_t)step * A.Nmax + ob) * 7;
+#pragma unroll
+                    for (int i = 0; i < 7; ++i)
+                        if (mt[i] != 0.0) atomicAdd(m + i, mt[i]);
                 }
 #pragma unroll
                 for (int c = 0; c < D; ++c) S.New[t * 24 + c] = q[c];

@@ -565,6 +565,7 @@ struct RollPostArgs {
     int S, Nmax, T, t0, step, steps, use_gt, teacher, ball_zero;
     float* traj;              // (S, Nmax, steps, 22) or null
     double* metrics;          // (steps, 7) or null
+    double* slot_metrics;     // (steps, Nmax, 7) or null
 };
 
 // One thread per (object, state column): 22 consecutive threads touch 22 consecutive floats (coalesced); the thread of
@@ -618,6 +619,12 @@ __global__ void __launch_bounds__(256) k_rollout_post(RollPostArgs A) {   // 256
                         mt[4] = __fdiv_rn(__fadd_rn(__fmul_rn(pvx, gvx), __fmul_rn(pvy, gvy)), __fmul_rn(pm, gm));
                         mt[5] = fabsf(__fsub_rn(1.f, __fdiv_rn(pm, gm)));
                         mt[6] = 1.0;
+                    }
+                    if (A.slot_metrics) {
+                        double* m = A.slot_metrics + ((size_t)A.step * A.Nmax + ob) * 7;
+#pragma unroll
+                        for (int i = 0; i < 7; ++i)
+                            if (mt[i] != 0.0) atomicAdd(m + i, mt[i]);
                     }
                 }
             }

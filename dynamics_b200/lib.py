@@ -60,6 +60,7 @@ SIGNATURES = {
     "npe_train_step": (C.c_int, [_H, C.c_int32, C.c_float, C.c_int32, _fp]),
     "npe_train_steps": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _fp]),
     "npe_rollout": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),
+    "npe_rollout_slots": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),
     "npe_rollout_resident": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "npe_set_precision": (C.c_int, [_H, C.c_int32]),
     "npe_set_rollout_mode": (C.c_int, [_H, C.c_int32]),

@@ -39,6 +39,7 @@ int npe_optim_reset(npe_handle* h, float rmsprop_m_init);
 int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out);
 int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr, int32_t divisor_batch, float* losses_out);
 int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* metrics_out);
+int npe_rollout_slots(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* slot_metrics_out);
 int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out);
 int npe_set_precision(npe_handle* h, int32_t mode);
 int npe_set_rollout_mode(npe_handle* h, int32_t mode);

@@ -157,6 +157,8 @@ class NPEModel:
 
     # ---- batch form (reference batch tuple) -------------------------------------------------------------------
     def _upload(self, batch):
+        if hasattr(batch, "select"):            # loader.DeviceBatch: examples already resident, only the triples travel
+            return batch.select(self)
         this, context, y = batch[0], batch[1], batch[2]
         this = L.f32(this); context = L.f32(context)
         B = this.shape[0]
@@ -278,6 +280,15 @@ class NPEModel:
         self._ck(self.lib.npe_rollout(self.h, t0, steps, int(use_gt), int(teacher), L.fptr(traj), mp))
         return traj, met
 
+    def rollout_slots(self, t0, steps, use_gt=True, teacher=False, want_traj=True):
+        """rollout() with the metric sums kept per object slot: (traj, slot_metrics (steps,Nmax,7))."""
+        S, Nmax, T = self.scene_shape
+        traj = np.empty((S, Nmax, steps, L.OBJ_DIM), np.float32) if want_traj else None
+        met = np.zeros((steps, Nmax, 7), np.float64)
+        self._ck(self.lib.npe_rollout_slots(self.h, t0, steps, int(use_gt), int(teacher), L.fptr(traj),
+                                            met.ctypes.data_as(C.POINTER(C.c_double))))
+        return traj, met
+
     def rollout_resident(self, t0, steps):
         n = C.c_int64()
         self._ck(self.lib.npe_rollout_resident(self.h, t0, steps, C.byref(n)))
@@ -338,6 +349,19 @@ class NPEModel:
 
     def allreduce_grads(self):
         self._ck(self.lib.npe_allreduce_grads(self.h))
+
+
+def slot_metrics_to_batch_row(slot_met, n_examples):
+    """One batch's row of the *_through_time_all_batches tables (eval.lua:337-358,385-391) from per-slot sums
+    (steps,Nmax,7): sum over slots of the mean over valid examples, divided by the summed valid fractions."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nv, na = slot_met[:, :, 3], slot_met[:, :, 6]
+        def col(k, n):
+            means = np.where(n > 0, slot_met[:, :, k] / n, 0.0)
+            # a slot with valid foci but no valid angle mask contributes 0/0 = nan in the reference as well
+            means = np.where((n == 0) & (nv > 0), np.nan, means) if n is na else means
+            return means.sum(1) / (n.sum(1) / n_examples)
+        return {"loss": col(0, nv), "vel": col(1, nv), "angvel": col(2, nv), "cos": col(4, na), "mag": col(5, na)}
 
 
 def rollout_metrics_to_logs(met):

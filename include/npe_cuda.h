@@ -174,6 +174,13 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
  */
 int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out,
                 double* metrics_out);
+/*
+ * npe_rollout with the metric sums kept per object slot: slot_metrics_out (steps,Nmax,7), same 7 columns.  This is what
+ * simulate_all's per-batch average needs when some slots hold obstacles in only some examples: it sums the per-slot
+ * MEANS over valid examples and divides by the summed valid FRACTIONS (eval.lua:337-358,385-391).
+ */
+int npe_rollout_slots(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out,
+                      double* slot_metrics_out);
 /* Device-resident rollout for throughput runs: no host copies; object-steps advanced are returned. */
 int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* object_steps_out);
 
