@@ -126,6 +126,13 @@ struct npe_handle {
     int stage_idx = 0;
     int foci_B = -1, foci_N = -1;     // shape the iota focus arrays / n_obj were last built for
     DevBuf<float> loss_hist;          // per-step {loss, vel, angvel, overflow} of npe_train_steps
+    // pair tables of a whole chunk of scheduled steps (k_build_pairs_sched), sliced per step by npe_train_steps
+    struct Sched {
+        DevBuf<u64> keep, nbr, total;
+        DevBuf<int> cnt, block_sums, pair_start, pair_foc, info, step_first, step_F;
+        DevBuf<long long> foc_row, pair_crow;
+        DevBuf<float> y;
+    } sched;
     float* loss4_override = nullptr;  // when set, the fused loss reduction writes here instead of the mapped buffer
     float* loss4_host = nullptr;      // host-mapped {loss, vel, angvel, overflow}
     float* loss4_devptr = nullptr;
@@ -634,6 +641,7 @@ int npe_destroy(npe_handle* h) {
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release(); h->slot_metrics.release();
+    { auto& q = h->sched; q.keep.release(); q.nbr.release(); q.total.release(); q.cnt.release(); q.block_sums.release(); q.pair_start.release(); q.pair_foc.release(); q.info.release(); q.step_first.release(); q.step_F.release(); q.foc_row.release(); q.pair_crow.release(); q.y.release(); }
     h->roll.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
@@ -937,16 +945,97 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     return NPE_OK;
 }
 
+// Pair tables of steps [s0, s0 + n) of the schedule in one launch (CTA s = step s); false when a step does not fit one
+// builder CTA (more than 64 foci), in which case the caller builds the tables step by step.
+constexpr int SCHED_CHUNK = 1024;
+static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* fmax_out, int* cap_out) {
+    std::vector<int> sf((size_t)n), sF((size_t)n);
+    int fmax = 0;
+    for (int i = 0; i < n; ++i) {
+        const int w = first + (s0 + i) * batch;
+        sf[(size_t)i] = h->win_start[(size_t)w];
+        sF[(size_t)i] = h->win_start[(size_t)w + batch] - sf[(size_t)i];
+        if (sF[(size_t)i] <= 0) return fail(h, NPE_ERR_INVALID, "train_steps: empty batch");
+        fmax = sF[(size_t)i] > fmax ? sF[(size_t)i] : fmax;
+    }
+    int per = ctx_slots(h);
+    per = per > 16 ? 16 : (per < 1 ? 1 : per);
+    const int cap = fmax * per;
+    auto& q = h->sched;
+    const size_t nf = (size_t)n * fmax, np = (size_t)n * cap;
+    CK(q.keep.ensure(nf)); CK(q.nbr.ensure(nf)); CK(q.cnt.ensure(nf)); CK(q.foc_row.ensure(nf)); CK(q.y.ensure(nf * D));
+    CK(q.block_sums.ensure(n)); CK(q.total.ensure(n)); CK(q.info.ensure((size_t)2 * n));
+    CK(q.pair_start.ensure((size_t)n * (fmax + 1))); CK(q.pair_foc.ensure(np)); CK(q.pair_crow.ensure(np));
+    CK(q.step_first.ensure(n)); CK(q.step_F.ensure(n));
+    CK(cudaMemcpyAsync(q.step_first.p, sf.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(q.step_F.p, sF.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(q.total.p, 0, (size_t)n * sizeof(u64), h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
+    SchedOut o;
+    o.keep = q.keep.p; o.nbr = q.nbr.p; o.cnt = q.cnt.p; o.block_sums = q.block_sums.p; o.foc_row = q.foc_row.p; o.y = q.y.p;
+    o.total = q.total.p; o.pair_start = q.pair_start.p; o.pair_foc = q.pair_foc.p; o.pair_crow = q.pair_crow.p; o.info = q.info.p;
+    FocusSrc src = h->src();
+    src.foc_scene = h->foc_scene.p; src.foc_obj = h->foc_obj.p; src.foc_t0 = h->foc_t0.p;
+    const float thr = h->cfg.nbrhdsize * 60.f;
+    {
+        ProfScope ps__(h, NPE_K_BUILD_PAIRS);
+        if (h->Nmax - 1 <= 8) k_build_pairs_sched<8><<<n, 512, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
+        else if (h->Nmax - 1 <= 16) k_build_pairs_sched<16><<<n, 1024, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
+        else k_build_pairs_sched<32><<<n, NT_PAIRS, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
+        h->launches++;
+    }
+    CKL();
+    *fmax_out = fmax; *cap_out = cap;
+    return NPE_OK;
+}
+
 int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr,
                     int32_t divisor_batch, float* losses_out) {
     NEED(h);
     if (batch <= 0 || nsteps <= 0 || first < 0) return fail(h, NPE_ERR_INVALID, "train_steps: bad arguments");
+    const int W = (int)h->win_start.size() - 1;
+    if (W <= 0) return fail(h, NPE_ERR_STATE, "train_steps: no focus / window schedule uploaded");
+    if ((long long)first + (long long)nsteps * batch > W) return fail(h, NPE_ERR_INVALID, "train_steps: schedule has %d entries", W);
     if (losses_out) CK(h->loss_hist.ensure((size_t)nsteps * 4));
     int rc = NPE_OK;
-    for (int s = 0; s < nsteps && rc == NPE_OK; ++s) {
-        if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
-        h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
-        rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
+    // The batcher runs one chunk of steps ahead of the training kernels: ONE launch builds the pair tables of up to
+    // SCHED_CHUNK steps, each step then works on its slice.
+    int Fmax = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        const int w = first + s * batch;
+        const int Fs = h->win_start[(size_t)w + batch] - h->win_start[(size_t)w];
+        Fmax = Fs > Fmax ? Fs : Fmax;
+    }
+    const bool sched = Fmax <= FPB;
+    if ((rc = ensure_batch_buffers(h, Fmax))) return rc;   // no reallocation while the per-step slices are installed
+    for (int s0 = 0; s0 < nsteps && rc == NPE_OK; s0 += SCHED_CHUNK) {
+        const int n = nsteps - s0 < SCHED_CHUNK ? nsteps - s0 : SCHED_CHUNK;
+        int fmax = 0, cap = 0;
+        if (sched && (rc = sched_build(h, first, batch, s0, n, &fmax, &cap))) break;
+        // base pointers of the per-batch buffers; restored after the chunk
+        u64* const b_keep = h->keep.p; u64* const b_nbr = h->nbr.p; int* const b_cnt = h->cnt.p; int* const b_bs = h->block_sums.p;
+        long long* const b_row = h->foc_row.p; float* const b_y = h->y.p; int* const b_ps = h->pair_start.p;
+        int* const b_pf = h->pair_foc.p; long long* const b_pc = h->pair_crow.p; int* const b_info = h->info_dev;
+        u64* const b_tot = h->active_total;
+        for (int i = 0; i < n && rc == NPE_OK; ++i) {
+            const int s = s0 + i;
+            if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
+            if (sched) {
+                auto& q = h->sched;
+                const size_t fo = (size_t)i * fmax, po = (size_t)i * cap;
+                h->keep.p = q.keep.p + fo; h->nbr.p = q.nbr.p + fo; h->cnt.p = q.cnt.p + fo; h->block_sums.p = q.block_sums.p + i;
+                h->foc_row.p = q.foc_row.p + fo; h->y.p = q.y.p + fo * D; h->pair_start.p = q.pair_start.p + (size_t)i * (fmax + 1);
+                h->pair_foc.p = q.pair_foc.p + po; h->pair_crow.p = q.pair_crow.p + po; h->info_dev = q.info.p + 2 * i;
+                h->active_total = q.total.p + i;
+                h->pair_cap = cap;
+                h->pairs_valid = true; h->hact_valid = false;
+            }
+            h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
+            rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
+        }
+        h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
+        h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
+        if (sched) { h->pairs_valid = false; h->fwd_valid = false; h->F = 0; }
     }
     h->loss4_override = nullptr;
     if (rc) return rc;

@@ -193,12 +193,13 @@ __device__ __forceinline__ void group_pairs(const float* pos, int stride, int N,
 constexpr int FPB = 64;   // foci per CTA of the pair builder
 constexpr int NT_PAIRS = 1024;
 template <int LANES>
-__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
-                                                          u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
-                                                          int* __restrict__ block_sums, long long* __restrict__ foc_row,
-                                                          float* __restrict__ y, u64* __restrict__ active_total,
-                                                          int* __restrict__ pair_start, int* __restrict__ pair_foc,
-                                                          long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
+__device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, float thr_px, u64* __restrict__ keep_out,
+                                                 u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
+                                                 int* __restrict__ block_sums, long long* __restrict__ foc_row,
+                                                 float* __restrict__ y, u64* __restrict__ active_total,
+                                                 int* __restrict__ pair_start, int* __restrict__ pair_foc,
+                                                 long long* __restrict__ pair_crow, int cap, int* __restrict__ info,
+                                                 const int blk, const bool single) {
     __shared__ int s_cnt[FPB];
     __shared__ int s_pre[FPB];
     __shared__ u64 s_nbr[FPB];
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax
     const int gl = lane & (LANES - 1), grp = lane / LANES;
     for (int base = 0; base < FPB; base += nwarps * GPW) {
         const int fl = base + warp * GPW + grp;
-        const int f = blockIdx.x * FPB + fl;
+        const int f = blk * FPB + fl;
         const bool active = fl < FPB && f < src.F;
         int c = 0;
         u64 keep = 0, nbr = 0;
@@ -247,16 +248,16 @@ __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax
             if (lane >= off) { i0 += v0; i1 += v1; }
         }
         const int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-        const int f = blockIdx.x * FPB + lane;
+        const int f = blk * FPB + lane;
         if (f < src.F) local_prefix[f] = i0 - c0;
         if (f + 32 < src.F) local_prefix[f + 32] = tot0 + i1 - c1;
         s_pre[lane] = i0 - c0; s_pre[lane + 32] = tot0 + i1 - c1;
         if (lane == 0) {
-            block_sums[blockIdx.x] = tot0 + tot1;
+            block_sums[blk] = tot0 + tot1;
             atomicAdd(active_total, (u64)(tot0 + tot1));
         }
     }
-    if (gridDim.x > 1) return;
+    if (!single) return;
     // single-CTA batch (F <= 64, e.g. the reference's batch of 50): build the dense pair list here and save a launch
     __syncthreads();
     if (threadIdx.x < FPB && (int)threadIdx.x < src.F) {
@@ -275,6 +276,37 @@ __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax
         }
         if (f == src.F - 1) { pair_start[src.F] = min(base, cap); info[0] = min(base, cap); info[1] = base > cap; }
     }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
+                                                          u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
+                                                          int* __restrict__ block_sums, long long* __restrict__ foc_row,
+                                                          float* __restrict__ y, u64* __restrict__ active_total,
+                                                          int* __restrict__ pair_start, int* __restrict__ pair_foc,
+                                                          long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
+    build_pairs_body<LANES>(src, kmax, thr_px, keep_out, nbr_out, local_prefix, block_sums, foc_row, y, active_total, pair_start,
+                            pair_foc, pair_crow, cap, info, (int)blockIdx.x, gridDim.x == 1);
+}
+
+// The batcher for a whole SCHEDULE of small batches (train(): main.lua:299-304 over a device-resident schedule): CTA s
+// builds the complete pair table of step s (at most 64 foci) into slice s of the schedule buffers, so the per-step
+// launch of the pair builder disappears from the training loop.  fmax = slice stride in foci, cap = in pairs.
+struct SchedOut {
+    u64* keep; u64* nbr; int* cnt; int* block_sums; long long* foc_row; float* y; u64* total;
+    int* pair_start; int* pair_foc; long long* pair_crow; int* info;
+};
+template <int LANES>
+__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs_sched(FocusSrc src, const int* __restrict__ step_first,
+                                                                const int* __restrict__ step_F, int fmax, int cap, int kmax,
+                                                                float thr_px, SchedOut o) {
+    const int s = blockIdx.x;
+    const int first = step_first[s];
+    src.foc_scene += first; src.foc_obj += first; src.foc_t0 += first; src.F = step_F[s];
+    const size_t fo = (size_t)s * fmax, po = (size_t)s * cap;
+    build_pairs_body<LANES>(src, kmax, thr_px, o.keep + fo, o.nbr + fo, o.cnt + fo, o.block_sums + s, o.foc_row + fo, o.y + fo * D,
+                            o.total + s, o.pair_start + (size_t)s * (fmax + 1), o.pair_foc + po, o.pair_crow + po, cap,
+                            o.info + 2 * s, 0, true);
 }
 
 // K1b: second level of the scan + the dense pair list: for pair p of focus f (contexts in ascending index order)

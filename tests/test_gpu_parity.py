@@ -429,3 +429,29 @@ def test_pair_builder_16_lane_groups(model, trained_like_params):
     oidx, omask, _ = oracle_pairs(this, ctx)
     assert np.array_equal(idx, oidx.astype(np.int32)) and np.array_equal(mask, omask.astype(np.uint8))
     assert omask.sum() > 0 and rel_err(gpred[:, :6], pred[:, :6]) < TOL
+
+
+def test_schedule_batcher_chunks_and_fallback(model, params):
+    """npe_train_steps builds the pair tables of a whole chunk of steps in one launch (1024 steps per chunk); the
+    result is bit-identical to selecting and stepping one batch at a time, across a chunk boundary, with mixed object
+    counts, and for batches too large for the one-CTA builder (fallback to per-step tables)."""
+    st = np.zeros((40, 6, 12, 22), np.float32)
+    st[:20, :6] = scenes.raw_to_state(scenes.gen_balls(20, 6, 12, seed=61))
+    st[20:, :3] = scenes.raw_to_state(scenes.gen_balls(20, 3, 12, seed=62))
+    n_obj = np.r_[np.full(20, 6), np.full(20, 3)]
+    rng = np.random.default_rng(5)
+    for batch, nsteps in ((6, 1030), (70, 3)):
+        n = batch * nsteps
+        sc = rng.integers(0, 40, n); ob = rng.integers(0, 3, n); t0 = rng.integers(0, 9, n)
+        model.upload_scenes(st, n_obj)
+        model.upload_foci(sc, ob, t0)
+        model.set_params(params); model.optim_reset(0.0)
+        losses = model.train_steps(0, batch, nsteps, "adam", 3e-4, want_losses=True)
+        p_multi = model.get_params()
+        model.set_params(params); model.optim_reset(0.0)
+        for s in range(nsteps):
+            model.select_foci(s * batch, batch)
+            l = model.train_step("adam", 3e-4, want_loss=(s == nsteps - 1))
+        assert np.array_equal(model.get_params(), p_multi)
+        assert np.array_equal(losses[-1], l)
+        assert np.isfinite(losses).all()
