@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -149,6 +150,8 @@ struct npe_handle {
 
     // kernel-class profiling (roofline): event pairs around launches of one selected kernel class
     int prof_kernel = -1;
+    int prof_period = 1;              // bracket every prof_period-th launch of the selected class
+    long long prof_seen = 0;
     std::vector<cudaEvent_t> prof_events;   // pairs
     size_t prof_used = 0;
 
@@ -201,6 +204,7 @@ int fail(npe_handle* h, int code, const char* fmt, ...) {
 struct ProfScope {
     npe_handle* h; bool on;
     ProfScope(npe_handle* hh, int kid) : h(hh), on(hh->prof_kernel == kid) {
+        if (on) on = (h->prof_seen++ % h->prof_period) == 0;
         if (!on) return;
         if (h->prof_used + 2 > h->prof_events.size()) {
             for (int i = 0; i < 256; ++i) { cudaEvent_t e; cudaEventCreate(&e); h->prof_events.push_back(e); }
@@ -1006,7 +1010,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         const int Fs = h->win_start[(size_t)w + batch] - h->win_start[(size_t)w];
         Fmax = Fs > Fmax ? Fs : Fmax;
     }
-    const bool sched = Fmax <= FPB;
+    const bool sched = Fmax <= FPB && !getenv("NPE_NO_SCHED");   // env switch: A/B measurements only
     if ((rc = ensure_batch_buffers(h, Fmax))) return rc;   // no reallocation while the per-step slices are installed
     for (int s0 = 0; s0 < nsteps && rc == NPE_OK; s0 += SCHED_CHUNK) {
         const int n = nsteps - s0 < SCHED_CHUNK ? nsteps - s0 : SCHED_CHUNK;
@@ -1299,6 +1303,13 @@ int npe_profile_select(npe_handle* h, int32_t kernel_id) {
     CK(cudaStreamSynchronize(h->stream));
     h->prof_kernel = kernel_id;
     h->prof_used = 0;
+    h->prof_seen = 0;
+    return NPE_OK;
+}
+int npe_profile_period(npe_handle* h, int32_t period) {
+    NEED(h);
+    if (period < 1) return fail(h, NPE_ERR_INVALID, "profile_period: must be >= 1");
+    h->prof_period = period;
     return NPE_OK;
 }
 int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out) {

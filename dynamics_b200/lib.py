@@ -73,6 +73,7 @@ SIGNATURES = {
     "npe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "npe_host_free": (None, [C.c_void_p]),
     "npe_profile_select": (C.c_int, [_H, C.c_int32]),
+    "npe_profile_period": (C.c_int, [_H, C.c_int32]),
     "npe_profile_read": (C.c_int, [_H, _ip, C.POINTER(C.c_double)]),
     "npe_event_record": (C.c_int, [_H, C.c_int32]),
     "npe_event_elapsed_ms": (C.c_int, [_H, C.c_int32, C.c_int32, _fp]),

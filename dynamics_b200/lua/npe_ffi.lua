@@ -52,6 +52,7 @@ int npe_sync(npe_handle* h);
 void* npe_host_alloc(size_t bytes);
 void npe_host_free(void* p);
 int npe_profile_select(npe_handle* h, int32_t kernel_id);
+int npe_profile_period(npe_handle* h, int32_t period);
 int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out);
 int npe_event_record(npe_handle* h, int32_t slot);
 int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* ms_out);

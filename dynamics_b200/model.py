@@ -314,7 +314,8 @@ class NPEModel:
         self._ck(self.lib.npe_event_elapsed_ms(self.h, a, b, C.byref(ms)))
         return ms.value
 
-    def profile_select(self, kernel):
+    def profile_select(self, kernel, period=1):
+        self._ck(self.lib.npe_profile_period(self.h, period))
         self._ck(self.lib.npe_profile_select(self.h, -1 if kernel is None else L.KERNEL_IDS[kernel]))
 
     def profile_read(self):

@@ -236,6 +236,9 @@ void npe_host_free(void* p);
 #define NPE_K_TARGETS 7
 #define NPE_K_COUNT 8
 int npe_profile_select(npe_handle* h, int32_t kernel_id);
+/* Bracket only every `period`-th launch of the selected class (default 1): an event between two kernels disables their
+ * programmatic-dependent-launch overlap, so a long timed region samples instead of bracketing every launch. */
+int npe_profile_period(npe_handle* h, int32_t period);
 int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out);
 /* CUDA-event timing on the handle's stream (bench/roofline): record marks, read elapsed ms between two marks. */
 int npe_event_record(npe_handle* h, int32_t slot);
