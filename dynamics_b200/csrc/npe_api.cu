@@ -72,6 +72,8 @@ struct DevBuf {
 
 }  // namespace
 
+constexpr int LOSS_RING = 64;
+
 struct npe_handle {
     npe_config cfg;
     int device = 0, num_sms = 0;
@@ -110,6 +112,8 @@ struct npe_handle {
     int foc_first = 0, F = 0;
     bool batch_form = false;
     bool have_y = false;
+    const float* y_view = nullptr;    // batch form: the targets sit behind the packed scenes in `states` (no copy)
+    const float* yptr() const { return y_view ? y_view : y.p; }
 
     // per-batch buffers
     DevBuf<float> y, pred, loss_ex, ds, this_rows, Hp, hact;
@@ -137,6 +141,7 @@ struct npe_handle {
     float* loss4_override = nullptr;  // when set, the fused loss reduction writes here instead of the mapped buffer
     float* loss4_host = nullptr;      // host-mapped {loss, vel, angvel, overflow}
     float* loss4_devptr = nullptr;
+    cudaEvent_t ring_ev[64] = {};     // npe_train_step_async / npe_loss_wait: one event per ring slot (slot i at loss4_host + 16 + 4 i)
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
     DevBuf<int> ctx_idx_out, cnt_out;
@@ -283,7 +288,7 @@ void launch_build_pairs(npe_handle* h, int nblk, int nmax, Args... args) {
 int build_pairs(npe_handle* h) {
     if (h->pairs_valid) return NPE_OK;
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
-    CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));
+    if (h->F > FPB) CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));   // one CTA stores its total
     const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
@@ -400,7 +405,7 @@ int run_forward(npe_handle* h, bool training, bool fused = false) {
     // training forward: FP32 FFMA kernels, or (train_fwd_tc) the FP32-grade tcgen05 pair kernel; never single-pass TF32
     const int tc = training ? (h->train_fwd_tc && !small_batch(h, h->F) ? NPE_PRECISION_TF32X3_TC : 0) : h->precision;
     float* stash = (training && h->have_y) ? training_stash(h) : nullptr;
-    rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->y.p : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
+    rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->yptr() : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused);
     if (rc) return rc;
     h->fwd_valid = (tc != NPE_PRECISION_TF32_TC);
@@ -432,11 +437,11 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
         if (small)
             CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
                           fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         else
             CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->y.p, h->ds.p, h->partial, sv, sw,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
                           fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         h->launches++;
     }
@@ -601,7 +606,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaHostAlloc((void**)&h->loss4_host, 16 * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostAlloc((void**)&h->loss4_host, (16 + 4 * LOSS_RING) * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&h->loss4_devptr, h->loss4_host, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (int i = 0; i < 2; ++i)
         if ((e = cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -638,6 +643,7 @@ int npe_destroy(npe_handle* h) {
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
     if (h->info_dev) cudaFree(h->info_dev);
+    for (int i = 0; i < LOSS_RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->loss4_host) cudaFreeHost(h->loss4_host);
     for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
@@ -721,7 +727,7 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     if (y) memcpy(sg + n_state, y, n_y * sizeof(float));
     CK(cudaMemcpyAsync(h->states.p, sg, (n_state + n_y) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->stage_ev[si], h->stream));
-    if (y) CK(cudaMemcpyAsync(h->y.p, h->states.p + n_state, n_y * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    h->y_view = y ? h->states.p + n_state : nullptr;
     if (h->foci_B != B || h->foci_N != N) {
         k_batch_foci<<<(B + 255) / 256, 256, 0, h->stream>>>(h->foc_scene.p, h->foc_obj.p, h->foc_t0.p, h->n_obj.p, B, N);
         CKL();
@@ -758,7 +764,7 @@ int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, 
     CK(cudaStreamSynchronize(h->stream));
     h->S = S; h->Nmax = Nmax; h->T = T;
     h->F = 0; h->foc_first = 0;
-    h->batch_form = false; h->have_y = false;
+    h->batch_form = false; h->have_y = false; h->y_view = nullptr;
     h->pairs_valid = false; h->fwd_valid = false;
     h->win_start.clear();
     return NPE_OK;
@@ -840,7 +846,7 @@ int npe_batch_download(npe_handle* h, float* this_past_out, float* y_out) {
     if (y_out) {
         if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
         { int rc = build_pairs(h); if (rc) return rc; }
-        CK(cudaMemcpyAsync(y_out, h->y.p, (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(y_out, h->yptr(), (size_t)h->F * OUT * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     return NPE_OK;
@@ -990,6 +996,28 @@ static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* 
     }
     CKL();
     *fmax_out = fmax; *cap_out = cap;
+    return NPE_OK;
+}
+
+int npe_train_step_async(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, int32_t slot) {
+    NEED(h);
+    if (slot < 0 || slot >= LOSS_RING) return fail(h, NPE_ERR_INVALID, "train_step_async: slot must be in [0, %d)", LOSS_RING);
+    if (!h->ring_ev[slot]) CK(cudaEventCreateWithFlags(&h->ring_ev[slot], cudaEventDisableTiming));
+    h->loss4_override = h->loss4_devptr + 16 + 4 * slot;
+    const int rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
+    h->loss4_override = nullptr;
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ring_ev[slot], h->stream));
+    return NPE_OK;
+}
+
+int npe_loss_wait(npe_handle* h, int32_t slot, float* loss3_out) {
+    NEED(h);
+    if (slot < 0 || slot >= LOSS_RING || !h->ring_ev[slot]) return fail(h, NPE_ERR_INVALID, "loss_wait: slot %d was never issued", slot);
+    CK(cudaEventSynchronize(h->ring_ev[slot]));
+    const volatile float* r = h->loss4_host + 16 + 4 * slot;
+    if (r[3] != 0.f) return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
+    if (loss3_out) { loss3_out[0] = r[0]; loss3_out[1] = r[1]; loss3_out[2] = r[2]; }
     return NPE_OK;
 }
 

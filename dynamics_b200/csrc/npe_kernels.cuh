@@ -254,7 +254,7 @@ __device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, 
         s_pre[lane] = i0 - c0; s_pre[lane + 32] = tot0 + i1 - c1;
         if (lane == 0) {
             block_sums[blk] = tot0 + tot1;
-            atomicAdd(active_total, (u64)(tot0 + tot1));
+            if (single) *active_total = (u64)(tot0 + tot1); else atomicAdd(active_total, (u64)(tot0 + tot1));
         }
     }
     if (!single) return;

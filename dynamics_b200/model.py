@@ -215,6 +215,15 @@ class NPEModel:
         self._ck(self.lib.npe_train_step(self.h, 0 if opt == "adam" else 1, lr, divisor_batch, L.fptr(loss3)))
         return loss3
 
+    def train_step_async(self, slot, opt="adam", lr=3e-4, divisor_batch=0):
+        """train_step without the host wait; the loss lands in ring slot `slot` (0..63), see loss_wait."""
+        self._ck(self.lib.npe_train_step_async(self.h, 0 if opt == "adam" else 1, lr, divisor_batch, slot))
+
+    def loss_wait(self, slot):
+        loss3 = np.empty(3, np.float32)
+        self._ck(self.lib.npe_loss_wait(self.h, slot, L.fptr(loss3)))
+        return loss3
+
     def train_steps(self, first, batch, nsteps, opt="adam", lr=3e-4, divisor_batch=0, want_losses=False):
         """The inner loop of train() (main.lua:299-304) over the uploaded schedule, one host call for all steps."""
         losses = np.empty((nsteps, 3), np.float32) if want_losses else None

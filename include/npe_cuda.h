@@ -165,6 +165,15 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
                     int32_t divisor_batch, float* losses_out);
 
 /*
+ * npe_train_step without the host wait: the step is enqueued, its {loss, vel_loss, angvel_loss} land in ring slot `slot`
+ * (0..63) of host-mapped memory and npe_loss_wait(slot) returns them once that step has finished.  A caller that reads
+ * the loss of step s-1 after enqueueing step s (trainLogger / update_batch_weight one iteration late, main.lua:306)
+ * keeps the GPU queue non-empty across iterations.
+ */
+int npe_train_step_async(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, int32_t slot);
+int npe_loss_wait(npe_handle* h, int32_t slot, float* loss3_out);
+
+/*
  * simulate_all (eval.lua:237-454) in scene form on the uploaded scenes: past = frames t0,t0+1; `steps` autoregressive
  * steps.  use_gt != 0: frames t0+2.. are ground truth (obstacles copied from it, metrics computed against it);
  * otherwise obstacles stay static and metrics are zero.

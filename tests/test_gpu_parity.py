@@ -455,3 +455,26 @@ def test_schedule_batcher_chunks_and_fallback(model, params):
         assert np.array_equal(model.get_params(), p_multi)
         assert np.array_equal(losses[-1], l)
         assert np.isfinite(losses).all()
+
+
+def test_async_train_step_ring(model, params):
+    """npe_train_step_async + npe_loss_wait (loss read one iteration late) == the blocking npe_train_step."""
+    _, batches = balls_batches(60, 4, seed=71)
+    bl = [batcher.make_batch(*batches[i % len(batches)], offset=i % 20) for i in range(70)]
+    model.set_params(params); model.optim_reset(0.0)
+    ref = []
+    for b in bl:
+        model._upload(b)
+        ref.append(model.train_step("adam", 3e-4))
+    p_ref = model.get_params()
+    model.set_params(params); model.optim_reset(0.0)
+    got = []
+    for i, b in enumerate(bl):                       # 70 steps wrap the 64-slot ring
+        model._upload(b)
+        model.train_step_async(i % 64, "adam", 3e-4)
+        if i:
+            got.append(model.loss_wait((i - 1) % 64))
+    got.append(model.loss_wait(69 % 64))
+    assert np.array_equal(model.get_params(), p_ref) and np.array_equal(np.stack(got), np.stack(ref))
+    with pytest.raises(Exception):
+        model.train_step_async(64)
