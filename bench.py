@@ -161,7 +161,7 @@ def make_training_data(rank):
     offs = []
     for i, n in enumerate(SETS):
         a = i * SCENES_PER_SET
-        states[a:a + SCENES_PER_SET, :n] = synth.ball_scenes(SCENES_PER_SET, n, T_FRAMES, seed=n + 100 * rank)
+        states[a:a + SCENES_PER_SET, :n] = synth.ball_scenes(SCENES_PER_SET, n, T_FRAMES, seed=n + 100 * (0 if os.environ.get("NPE_BENCH_SAME_BATCHES") else rank))
         n_obj[a:a + SCENES_PER_SET] = n
         offs.append(a)
     return states, n_obj, offs
@@ -388,7 +388,8 @@ def run_ours(args):
 
     states, n_obj, offs = make_training_data(rank)
     total = args.warmup + args.steps
-    sc, ob, tt = synth.reference_batch_schedule(SCENES_PER_SET, SETS, total, BATCH, 11 + rank, offs)
+    sc, ob, tt = synth.reference_batch_schedule(SCENES_PER_SET, SETS, total, BATCH,
+                                                 11 + (0 if os.environ.get("NPE_BENCH_SAME_BATCHES") else rank), offs)   # env: skew diagnostics
     m = NPEModel(ModelParams(device=local_rank))
     m.set_params(init_params(1234)); m.optim_reset(0.0)
     if world > 1:

@@ -164,8 +164,7 @@ struct npe_handle {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // NVLink peer exchange (fused DP step)
-    float* xregion = nullptr;         // xgrad[2][NPARAM] + 2 ready counters (+ pad)
-    unsigned* xcounter = nullptr;     // block counter of k_reduce_publish
+    float* xregion = nullptr;         // exchange region of k_dp_step ({value, stamp} cells of every source rank)
     void* peer_ptr[MAX_PEERS] = {};
     bool peer_opened[MAX_PEERS] = {};
     bool peer_ready = false;
@@ -470,24 +469,19 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
             const int buf = (int)(h->peer_step & 1u);
             const unsigned stamp = h->peer_step + 1u;
             h->peer_step += 1u;
-            unsigned* flags = reinterpret_cast<unsigned*>(h->xregion + 2 * NPARAM);
-            CK(launch_pdl(k_reduce_publish, nb, 256, 0, h->stream, h->partial, gp, gd, h->xregion + (size_t)buf * NPARAM,
-                          flags + buf, stamp, h->xcounter, L));
-            PeerPtrs P;
+            DpArgs P;
             P.nranks = h->nranks; P.rank = h->rank;
-            for (int r = 0; r < MAX_PEERS; ++r) P.x[r] = r < h->nranks ? (const float*)h->peer_ptr[r] : nullptr;
-            const int nb2 = (NPARAM + 255) / 256;
+            for (int r = 0; r < MAX_PEERS; ++r) P.region[r] = r < h->nranks ? (uint2*)h->peer_ptr[r] : nullptr;
             if (peer_opt == 1) {
                 h->adam_t += 1;
                 const double t = (double)h->adam_t;
                 o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
-                CK(launch_pdl(k_peer_allreduce_opt<1>, nb2, 256, 0, h->stream, P, buf, stamp, h->grads, o));
+                CK(launch_pdl(k_dp_step<1>, nb, 256, 0, h->stream, h->partial, gp, gd, P, buf, stamp, h->grads, o, L));
             } else {
                 o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
-                CK(launch_pdl(k_peer_allreduce_opt<2>, nb2, 256, 0, h->stream, P, buf, stamp, h->grads, o));
+                CK(launch_pdl(k_dp_step<2>, nb, 256, 0, h->stream, h->partial, gp, gd, P, buf, stamp, h->grads, o, L));
             }
             h->wtc_dirty = true; h->wtc3_dirty = true;
-            h->launches++;
         } else if (fuse_opt == 1) {
             h->adam_t += 1;
             const double t = (double)h->adam_t;
@@ -637,7 +631,6 @@ int npe_destroy(npe_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int r = 0; r < MAX_PEERS; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
     if (h->xregion) cudaFree(h->xregion);
-    if (h->xcounter) cudaFree(h->xcounter);
     float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
@@ -1277,10 +1270,8 @@ int npe_peer_export(npe_handle* h, void* handle64_out) {
     if (!handle64_out) return fail(h, NPE_ERR_INVALID, "peer_export: null output");
     static_assert(sizeof(cudaIpcMemHandle_t) == NPE_PEER_HANDLE_BYTES, "IPC handle size");
     if (!h->xregion) {
-        CK(cudaMalloc((void**)&h->xregion, (2 * (size_t)NPARAM + 64) * sizeof(float)));
-        CK(cudaMemset(h->xregion, 0, (2 * (size_t)NPARAM + 64) * sizeof(float)));
-        CK(cudaMalloc((void**)&h->xcounter, 64));
-        CK(cudaMemset(h->xcounter, 0, 64));
+        CK(cudaMalloc((void**)&h->xregion, DP_REGION_BYTES));
+        CK(cudaMemset(h->xregion, 0, DP_REGION_BYTES));
     }
     cudaIpcMemHandle_t hd;
     CK(cudaIpcGetMemHandle(&hd, h->xregion));

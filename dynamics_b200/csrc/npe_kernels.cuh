@@ -946,69 +946,64 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Data-parallel exchange over NVLink peer memory.  Region layout per rank: xgrad[2][NPARAM] floats (double-buffered by
-// step parity) followed by one 32-bit ready counter per buffer.  k_reduce_publish reduces this rank's CTA partials into
-// its own buffer and, when the last block has finished, publishes `stamp` with a system-scope release.
-// k_peer_allreduce_opt waits (system-scope acquire over NVLink) until every peer has published the same stamp, sums
-// the peers' vectors in rank order and applies the optimiser.  Double buffering makes a "done" handshake unnecessary:
-// a rank can only overwrite buffer b two steps later, after every peer has passed the next step's ready barrier.
+// Data-parallel step over NVLink peer memory: local reduction of the CTA partials, gradient exchange, optimiser and
+// weight-image write-through in ONE kernel.  Every rank owns an exchange region (CUDA IPC) of 8-byte cells
+//     cell[2 buffers][MAX_PEERS source ranks][DP_NPAD]  =  {gradient bits, step stamp}
+// Thread i of rank q reduces parameter i over the CTA partials and PUSHES {value, stamp} into cell [buf][q][i] of every
+// rank's region with ONE aligned 8-byte store per peer (posted NVLink writes; value and flag travel together, so no
+// fence, no separate flag and no read round trip — the idea of NCCL's LL protocol).  It then polls the cells [buf][r][i]
+// of its OWN region until every rank's stamp has arrived, sums the values in rank order (the same sum on every rank:
+// replicas stay bit-identical) and applies Adam / RMSprop.  Parameters are independent: no barrier of any kind.
+// Buffers alternate by step parity; a rank can only push step s+2 into a buffer after it has consumed every peer's
+// step s+1 cell, which that peer pushed after finishing step s, so no "done" handshake is needed.  Every thread pushes
+// before it waits, so ranks cannot deadlock each other.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int MAX_PEERS = 8;
-struct PeerPtrs {
-    const float* x[MAX_PEERS];            // peer exchange regions (own region at index `rank`)
+constexpr int DP_NBLK = (NPARAM + 255) / 256;       // 111 CTAs
+constexpr int DP_NPAD = DP_NBLK * 256;
+constexpr size_t DP_REGION_BYTES = 2ull * MAX_PEERS * DP_NPAD * sizeof(uint2);
+struct DpArgs {
+    uint2* region[MAX_PEERS];             // exchange regions of all ranks (own region at index `rank`)
     int nranks, rank;
 };
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void st_cell(uint2* p, float v, unsigned stamp) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(stamp) : "memory");
+}
+__device__ __forceinline__ uint2 ld_cell(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__global__ void k_reduce_publish(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ xbuf,
-                                 unsigned* __restrict__ ready_flag, unsigned stamp, unsigned* __restrict__ block_counter,
-                                 LossArgs L) {
-    pdl_launch_dependents();   // the all-reduce kernel may start spinning on the ready flags right away
-    pdl_wait();
-    if (L.loss4_out && blockIdx.x == gridDim.x - 1) {
-        block_loss_reduce(L);
-    } else {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < NPARAM) {
-            const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-            float a = 0.f;
-            for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
-            xbuf[i] = a;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(block_counter, 1u) + 1u;
-        if (done == gridDim.x) {
-            *block_counter = 0u;
-            __threadfence_system();
-            st_release_sys(ready_flag, stamp);
-        }
-    }
 }
 
 template <int OPT>
-__global__ void k_peer_allreduce_opt(PeerPtrs P, int buf, unsigned stamp, float* __restrict__ grad, OptArgs o) {
-    if (threadIdx.x == 0) {
-        for (int r = 0; r < P.nranks; ++r) {
-            const unsigned* flag = reinterpret_cast<const unsigned*>(P.x[r] + 2 * NPARAM) + buf;
-            while (ld_acquire_sys(flag) != stamp) { __nanosleep(40); }
-        }
-    }
-    __syncthreads();
+__global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
+                                                 unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
+    const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     float a = 0.f;
-    for (int r = 0; r < P.nranks; ++r) a += __ldcv(P.x[r] + (size_t)buf * NPARAM + i);   // rank order: same sum everywhere
-    grad[i] = a;
+    for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
+    const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
+    for (int r = 1; r < P.nranks; ++r) {                 // remote ranks first, own region last
+        const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
+        st_cell(P.region[q] + mine, a, stamp);
+    }
+    const uint2* in = P.region[P.rank] + (size_t)buf * MAX_PEERS * DP_NPAD + i;
+    float g = 0.f;
+    for (int r = 0; r < P.nranks; ++r) {                 // rank order
+        float v = a;
+        if (r != P.rank) {
+            uint2 c = ld_cell(in + (size_t)r * DP_NPAD);
+            while (c.y != stamp) c = ld_cell(in + (size_t)r * DP_NPAD);
+            v = __uint_as_float(c.x);
+        }
+        g += v;
+    }
+    grad[i] = g;
+    a = g;
     if (OPT == 1) {
         const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
         const float vi = __fadd_rn(__fmul_rn(o.b2, o.v[i]), __fmul_rn(o.omb2, __fmul_rn(a, a)));
