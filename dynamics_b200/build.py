@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnpe_cuda.so")
 SOURCES = ["npe_api.cu"]
-HEADERS = ["npe_layout.h", "npe_tile.cuh", "npe_kernels.cuh", "npe_rollout.cuh", "npe_umma.cuh", "npe_tc.cuh",
+HEADERS = ["npe_layout.h", "npe_tile.cuh", "npe_mma16.cuh", "npe_kernels.cuh", "npe_rollout.cuh", "npe_umma.cuh", "npe_tc.cuh",
            os.path.join("..", "..", "include", "npe_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-shared"]

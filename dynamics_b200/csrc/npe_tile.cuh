@@ -296,17 +296,26 @@ __device__ __noinline__ void gemm_nn16(const float* __restrict__ dZ, const float
     (void)nrows;
 }
 
-// ROWS-dispatching wrappers used by the kernels (ROWS = 64: throughput mapping, ROWS = 16: latency mapping).
+}  // namespace npe
+#include "npe_mma16.cuh"
+namespace npe {
+
+// ROWS-dispatching wrappers used by the kernels (ROWS = 64: throughput mapping on the FFMA pipe, ROWS = 16: latency
+// mapping on mma.sync with the 3xTF32 split, npe_mma16.cuh; gemm_nt16 / gemm_nn16 above are its FP32 predecessors, kept
+// for tools/microbench).  kc / nc are literals at every call site, so the dispatch folds at compile time.
 template <int ROWS, int NI, int LDA, int LDW>
 __device__ __forceinline__ void gemm_nt_r(const float* A, const float* W, int kc, int nrows, EpiNT e) {
     if (ROWS == 64) gemm_nt<NI, LDA, LDW>(A, W, kc, nrows, e);
-    else gemm_nt16<NI, LDA, LDW>(A, W, kc, nrows, e);
+    else if (kc == 24) mma_nt16<NI, 24, LDA, LDW>(A, W, e);
+    else if (kc == 13) mma_nt16<NI, 13, LDA, LDW>(A, W, e);
+    else mma_nt16<NI, 11, LDA, LDW>(A, W, e);
 }
-// nc = reduction length in chunks of 4 n (64-row mapping); the 16-row mapping walks it in steps of 8 n.
+// nc = reduction length in chunks of 4 n.
 template <int ROWS, int KCO, int LDZ, int LDW>
 __device__ __forceinline__ void gemm_nn_r(const float* dZ, const float* W, int nc, int nrows, EpiNN e) {
     if (ROWS == 64) gemm_nn<KCO, LDZ, LDW>(dZ, W, nc, nrows, e);
-    else gemm_nn16<KCO, LDZ, LDW>(dZ, W, (nc + 1) / 2, nrows, e);
+    else if (nc == 13) mma_nn16<KCO, 13, LDZ, LDW>(dZ, W, e);
+    else mma_nn16<KCO, 6, LDZ, LDW>(dZ, W, e);
 }
 
 // acc[4 i + j] += sum_{r < nrows} dZ[r][zoff + 4 a + i] * Hm[r][4 b + j];  (a, b) = (tile / KCH, tile % KCH).

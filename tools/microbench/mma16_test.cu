@@ -1,0 +1,122 @@
+// Correctness (vs the FP32 micro-kernels and an fp64 product) and cycle cost of the mma.sync 16-row tile passes.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cmath>
+#include "../../dynamics_b200/csrc/npe_tile.cuh"
+using namespace npe;
+
+struct Smem {
+    float W[56 * LD];
+    float A[16 * LD];
+    float B[16 * LD];
+    float C[16 * LD];
+    float H[16 * LD];
+};
+
+__device__ float rnd(unsigned& s) { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.f - 0.5f; }
+
+__global__ void __launch_bounds__(NT, 1) k(long long* cyc, float* err, int iters) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    Smem& S = *reinterpret_cast<Smem*>(raw);
+    unsigned seed = 1234u + threadIdx.x * 77u;
+    for (int i = threadIdx.x; i < 56 * LD; i += NT) { const int n = i / LD, kk = i % LD; S.W[i] = (n < 50 && kk < 52) ? 0.3f * rnd(seed) : 0.f; }
+    for (int i = threadIdx.x; i < 16 * LD; i += NT) { S.A[i] = (i % LD) < 52 ? rnd(seed) : __int_as_float(0x7fc00000); S.H[i] = rnd(seed) ; S.B[i] = 0.f; S.C[i] = 0.f; }
+    __syncthreads();
+    // ---- correctness: nt ----
+    float e_nt = 0.f, e_nn = 0.f, e_wg = 0.f;
+    mma_nt16<7, 13, LD, LD>(S.A, S.W, EpiNT{S.B, LD, 52, 1});
+    gemm_nt16<7, LD, LD>(S.A, S.W, 13, 16, EpiNT{S.C, LD, 52, 1});
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * 52; i += NT) {
+        const int r = i / 52, n = i % 52;
+        double ref = 0; for (int kk = 0; kk < 52; ++kk) ref += (double)S.A[r * LD + kk] * S.W[n * LD + kk];
+        ref = ref > 0 ? ref : 0;
+        e_nt = fmaxf(e_nt, fabsf((float)(S.B[r * LD + n] - ref)));
+        e_nn = fmaxf(e_nn, fabsf((float)(S.C[r * LD + n] - ref)));      // the FP32 path's own error for scale
+    }
+    if (e_nt > 0) atomicMax((int*)&err[0], __float_as_int(e_nt));
+    if (e_nn > 0) atomicMax((int*)&err[1], __float_as_int(e_nn));
+    __syncthreads();
+    // ---- correctness: nn (dA = dZ W, masked by H > 0), dZ = A restricted to 52 columns ----
+    for (int i = threadIdx.x; i < 16 * LD; i += NT) if ((i % LD) >= 52) S.A[i] = 0.f;
+    __syncthreads();
+    mma_nn16<13, 13, LD, LD>(S.A, S.W, EpiNN{S.B, LD, S.H, 13});
+    __syncthreads();
+    e_nn = 0.f;
+    for (int i = threadIdx.x; i < 13 * 52; i += NT) {
+        const int r = i / 52, kk = i % 52;
+        double ref = 0; for (int n = 0; n < 52; ++n) ref += (double)S.A[r * LD + n] * S.W[n * LD + kk];
+        if (!(S.H[r * LD + kk] > 0.f)) ref = 0;
+        e_nn = fmaxf(e_nn, fabsf((float)(S.B[r * LD + kk] - ref)));
+    }
+    if (e_nn > 0) atomicMax((int*)&err[2], __float_as_int(e_nn));
+    __syncthreads();
+    // ---- correctness: wgrad, 28 tiles (4 m16 x 7 n8) over 8 warps, 13 valid rows ----
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int tile = warp; tile < 28; tile += 8) {
+        float cm[4] = {0, 0, 0, 0}, cc[4] = {0, 0, 0, 0};
+        const int n0 = 16 * (tile / 7), k0 = 8 * (tile % 7);
+        if (n0 < 52) mma_wgrad16<LD, LD>(cm, S.A, S.H, n0, k0, 13, 52);
+        for (int h = 0; h < 2; ++h)
+            for (int j = 0; j < 2; ++j) {
+                const int n = n0 + g + 8 * h, kk = k0 + 2 * t + j;
+                if (n < 52 && kk < 52) {
+                    double ref = 0; for (int r = 0; r < 13; ++r) ref += (double)S.A[r * LD + n] * S.H[r * LD + kk];
+                    e_wg = fmaxf(e_wg, fabsf((float)(cm[2 * h + j] + cc[2 * h + j] - ref)));
+                }
+            }
+    }
+    if (e_wg > 0) atomicMax((int*)&err[3], __float_as_int(e_wg));
+    __syncthreads();
+    // ---- timing ----
+    for (int i = threadIdx.x; i < 16 * LD; i += NT) { S.A[i] = 0.01f * (i % 13); S.B[i] = 0.f; }
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        mma_nt16<7, 13, LD, LD>(S.A, S.W, EpiNT{S.B, LD, 52, 1});
+        __syncthreads();
+        mma_nt16<7, 13, LD, LD>(S.B, S.W, EpiNT{S.A, LD, 52, 1});
+        __syncthreads();
+    }
+    long long t1 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        mma_nn16<13, 13, LD, LD>(S.A, S.W, EpiNN{S.B, LD, S.H, 16});
+        __syncthreads();
+        mma_nn16<13, 13, LD, LD>(S.B, S.W, EpiNN{S.A, LD, S.H, 16});
+        __syncthreads();
+    }
+    long long t2 = clock64();
+    float keep = 0.f;
+    float cm[4][4] = {}, cc[4][4] = {};
+    for (int it = 0; it < iters; ++it) {
+        int q = 0;
+        for (int tile = warp; tile < 28; tile += 8, ++q) mma_wgrad16<LD, LD>(cm[q], S.A, S.H, 16 * (tile / 7), 8 * (tile % 7), 16, 52);
+        __syncthreads();
+    }
+    long long t3 = clock64();
+    for (int q = 0; q < 4; ++q) for (int i = 0; i < 4; ++i) keep += cm[q][i] + cc[q][i];
+    long long t4 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        gemm_nt16<7, LD, LD>(S.A, S.W, 13, 16, EpiNT{S.B, LD, 52, 1});
+        __syncthreads();
+        gemm_nt16<7, LD, LD>(S.B, S.W, 13, 16, EpiNT{S.A, LD, 52, 1});
+        __syncthreads();
+    }
+    long long t5 = clock64();
+    if (threadIdx.x == 0) { cyc[0] = (t1 - t0) / (2 * iters); cyc[1] = (t2 - t1) / (2 * iters); cyc[2] = (t3 - t2) / iters; cyc[3] = (t5 - t4) / (2 * iters); }
+    if (keep == 12345.f) cyc[0] = 0;
+}
+
+int main() {
+    long long* cyc; float* err;
+    cudaMalloc(&cyc, 4 * sizeof(long long)); cudaMalloc(&err, 4 * sizeof(float)); cudaMemset(err, 0, 4 * sizeof(float));
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    k<<<1, NT, sizeof(Smem)>>>(cyc, err, 200);
+    cudaDeviceSynchronize();
+    long long hc[4]; float he[4];
+    cudaMemcpy(hc, cyc, sizeof hc, cudaMemcpyDeviceToHost); cudaMemcpy(he, err, sizeof he, cudaMemcpyDeviceToHost);
+    printf("status %s\n", cudaGetErrorString(cudaGetLastError()));
+    printf("max abs err vs fp64: mma_nt16 %.3e (fp32 gemm_nt16 %.3e)  mma_nn16 %.3e  mma_wgrad16 %.3e\n", he[0], he[1], he[2], he[3]);
+    printf("cycles/pass: mma_nt16 %lld  mma_nn16 %lld  mma_wgrad16 (52x52, 28 tiles) %lld  | fp32 gemm_nt16 %lld\n", hc[0], hc[1], hc[2], hc[3]);
+    return 0;
+}
