@@ -978,7 +978,7 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
 template <int OPT>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
-    pdl_launch_dependents();
+    // no early griddepcontrol.launch_dependents here: the next kernel stages the weight image this kernel writes
     pdl_wait();
     if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

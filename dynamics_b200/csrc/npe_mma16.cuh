@@ -58,7 +58,7 @@ __device__ __forceinline__ void mma_tf32x3_1(float (&c)[4], const float (&a)[4],
 // Same contract as gemm_nt16.  Columns k >= 4 KC of A are never read as values (they may be uninitialised).
 // Even and odd k-steps accumulate separately: six independent chains of at most four dependent MMAs.
 template <int NI, int KC, int LDA, int LDW>
-__device__ __noinline__ void mma_nt16(const float* __restrict__ A, const float* __restrict__ W, EpiNT e) {
+__device__ __forceinline__ void mma_nt16(const float* __restrict__ A, const float* __restrict__ W, EpiNT e) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     if (warp >= NI) return;
     constexpr int K = 4 * KC, STEPS = (K + 7) / 8;
@@ -96,7 +96,7 @@ __device__ __noinline__ void mma_nt16(const float* __restrict__ A, const float* 
 // dA[r][k] = mask(sum_{n < 4 NC} dZ[r][n] * W[n][k]) for r < 16, k < 4 KCO; warp w owns output columns 8 w .. 8 w + 7.
 // Same contract as gemm_nn16 (hmask: ReLU derivative taken from hmask[r][k] > 0; rows >= e.nrows are not stored).
 template <int KCO, int NC, int LDZ, int LDW>
-__device__ __noinline__ void mma_nn16(const float* __restrict__ dZ, const float* __restrict__ W, EpiNN e) {
+__device__ __forceinline__ void mma_nn16(const float* __restrict__ dZ, const float* __restrict__ W, EpiNN e) {
     constexpr int NT8 = (4 * KCO + 7) / 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     if (warp >= NT8) return;

@@ -65,8 +65,31 @@ def run(mode, rank, local, world):
     allp = [torch.zeros(got.size) for _ in range(world)]
     dist.all_gather(allp, torch.from_numpy(got))
     assert all(torch.equal(allp[0], p) for p in allp), f"[{mode}] replicas diverged"
+    # the free-running loop (npe_train_steps: no host wait between steps, kernels of consecutive steps overlap through
+    # programmatic dependent launch) must give the same bits as stepping with a host wait after every step
+    from oracle import scenes
+    stt = scenes.raw_to_state(scenes.gen_balls(60, 4, 12, seed=200 + rank))
+    rng = np.random.default_rng(300 + rank)
+    nb, nsteps = 7 + rank % 2, 60
+    sc = rng.integers(0, 60, nb * nsteps); ob = rng.integers(0, 4, nb * nsteps); t0 = rng.integers(0, 9, nb * nsteps)
+    gB = int(sum(7 + r % 2 for r in range(world)))
+    m.upload_scenes(stt); m.upload_foci(sc, ob, t0)
+    m.set_params(params); m.optim_reset(0.0)
+    m.train_steps(0, nb, nsteps, "adam", 3e-4, divisor_batch=gB)
+    free = m.get_params()
+    dist.barrier()
+    m.set_params(params); m.optim_reset(0.0)
+    for s_ in range(nsteps):
+        m.select_foci(s_ * nb, nb)
+        m.train_step("adam", 3e-4, divisor_batch=gB, want_loss=True)
+    stepped = m.get_params()
+    assert np.array_equal(free, stepped), f"rank {rank} [{mode}]: free-running loop differs from stepped loop"
+    allp = [torch.zeros(free.size) for _ in range(world)]
+    dist.all_gather(allp, torch.from_numpy(free))
+    assert all(torch.equal(allp[0], p) for p in allp), f"[{mode}] replicas diverged in the free-running loop"
     if rank == 0:
-        print(f"dp_gpu_check ok [{mode}]: world={world} param error after 20 steps {worst:.2e}, replicas bit-identical")
+        print(f"dp_gpu_check ok [{mode}]: world={world} param error after 20 steps {worst:.2e}, replicas bit-identical, "
+              f"free-running == stepped")
     dist.barrier()
     m.close()
 
