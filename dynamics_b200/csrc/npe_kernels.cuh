@@ -93,6 +93,20 @@ struct WeightStage {
     unsigned long long bar;
 };
 // Thread 0 arms the barrier and issues the bulk copies; everyone waits with stage_wait() before the first use.
+__device__ __forceinline__ void stage_init(WeightStage& st) {
+    if (threadIdx.x == 0) mbar_init(&st.bar, 1);
+}
+// after stage_init + a CTA barrier
+__device__ __forceinline__ void stage_copy(WeightStage& st, float* sWp, float* sWd, const float* __restrict__ wpack) {
+    if (threadIdx.x == 0) {
+        unsigned bytes = 0;
+        if (sWp) bytes += SW_PAIR_TOTAL * 4;
+        if (sWd) bytes += SW_DEC_TOTAL * 4;
+        mbar_expect_tx(&st.bar, bytes);
+        if (sWp) bulk_g2s(sWp, wpack, SW_PAIR_TOTAL * 4, &st.bar);
+        if (sWd) bulk_g2s(sWd, wpack + SW_PAIR_TOTAL, SW_DEC_TOTAL * 4, &st.bar);
+    }
+}
 __device__ __forceinline__ void stage_issue(WeightStage& st, float* sWp, float* sWd, const float* __restrict__ wpack) {
     if (threadIdx.x == 0) mbar_init(&st.bar, 1);
     __syncthreads();
@@ -502,21 +516,37 @@ k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_fo
                float* __restrict__ Hp, float* __restrict__ hact) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairFwdSmem<ROWS>& S = *reinterpret_cast<PairFwdSmem<ROWS>*>(smem_raw);
-    pdl_launch_dependents();
-    stage_issue(S.W, S.Wp, nullptr, wpack);
-    pdl_wait();
+    // Programmatic dependent launch.  This kernel's predecessor is either the pair builder (tables complete before
+    // any CTA of this grid starts) or the previous step's reduce + optimiser kernel, which releases its dependents at
+    // once: everything that does not depend on the NEW weights -- pair list, gathered state rows -- is loaded while
+    // that kernel is still running.  The weight image is staged after griddepcontrol.wait, and only then are this
+    // kernel's own dependents released (they stage weights in their prologues).
+    stage_init(S.W);
     const int P = info[0];
-    if ((int)blockIdx.x * ROWS >= P) { stage_wait(S.W); return; }   // never exit with a bulk copy in flight
+    const int lo0 = blockIdx.x * ROWS;
+    if (lo0 < P) {
+        load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo0, min(ROWS, P - lo0));
+        __syncthreads();
+        gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, min(ROWS, P - lo0));
+        gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, min(ROWS, P - lo0));
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_launch_dependents();
+    stage_copy(S.W, S.Wp, nullptr, wpack);
+    if (lo0 >= P) { stage_wait(S.W); return; }   // never exit with a bulk copy in flight
     bool staged = false;
     float* const bufs[NL + 1] = {S.P0, S.P1, S.P0, S.P1, S.P0, S.P1};
-    for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
+    for (int lo = lo0; lo < P; lo += gridDim.x * ROWS) {
         const int nrows = min(ROWS, P - lo);
-        __syncthreads();
-        load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
-        __syncthreads();
-        gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
-        gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
-        __syncthreads();
+        if (lo != lo0) {
+            __syncthreads();
+            load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
+            __syncthreads();
+            gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
+            gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
+            __syncthreads();
+        }
         if (!staged) { stage_wait(S.W); staged = true; }
         pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs, hact, lo);
         for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
@@ -650,16 +680,12 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
     DecBwdSmem<ROWS>& S = *reinterpret_cast<DecBwdSmem<ROWS>*>(smem_raw);
     pdl_launch_dependents();
     for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) S.Db[idx] = 0.f;   // pad columns 52..55 are read by the 16-row mapping
+    // the predecessor (pair forward) releases this grid only after the previous optimiser step is complete, so the
+    // weight image and the static inputs of the first tile (focus rows, pair ranges) load while it runs
     stage_issue(S.W, nullptr, S.Wd, wpack);
-    pdl_wait();
-    bool staged = false;
-    float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
-    float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
     const int t = threadIdx.x;
     const int ntiles = (F + ROWS - 1) / ROWS;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    auto load_tile_inputs = [&](int tile) {
         const int f0 = tile * ROWS;
         const int nf = min(ROWS, F - f0);
         __syncthreads();
@@ -669,6 +695,18 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
         load_focus_tile<ROWS>(S.Z, states, S.foff, nf);
         for (int idx = t; idx < ROWS * LD; idx += NT) S.Da[idx] = 0.f;
         __syncthreads();
+    };
+    if ((int)blockIdx.x < ntiles) load_tile_inputs(blockIdx.x);
+    pdl_wait();
+    bool staged = false;
+    float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
+    float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int f0 = tile * ROWS;
+        const int nf = min(ROWS, F - f0);
+        if (tile != (int)blockIdx.x) load_tile_inputs(tile);
         focus_sums(S.Z, S.pstart, Hp, nf);
         __syncthreads();
         if (!staged) { stage_wait(S.W); staged = true; }
@@ -791,9 +829,17 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
     pdl_launch_dependents();
     for (int idx = threadIdx.x; idx < ROWS * LD; idx += NT) { S.Da[idx] = 0.f; S.Db[idx] = 0.f; }   // pad columns stay zero
     stage_issue(S.W, S.Wp, nullptr, wpack);
-    pdl_wait();
     const int P = info[0];
     const int t = threadIdx.x;
+    const int lo0 = blockIdx.x * ROWS;
+    if (lo0 < P) {   // static inputs of the first tile load while the decoder kernel runs
+        load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo0, min(ROWS, P - lo0));
+        __syncthreads();
+        gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, min(ROWS, P - lo0));
+        gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, min(ROWS, P - lo0));
+        __syncthreads();
+    }
+    pdl_wait();
     float acc[NL][16];
 #pragma unroll
     for (int l = 0; l < NL; ++l)
@@ -804,14 +850,16 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
     if ((int)blockIdx.x * ROWS >= P) stage_wait(S.W);   // never exit with a bulk copy in flight
     if ((int)blockIdx.x * ROWS < P) {
         bool staged = false;
-        for (int lo = blockIdx.x * ROWS; lo < P; lo += gridDim.x * ROWS) {
+        for (int lo = lo0; lo < P; lo += gridDim.x * ROWS) {
             const int nrows = min(ROWS, P - lo);
-            __syncthreads();
-            load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
-            __syncthreads();
-            gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
-            gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
-            __syncthreads();
+            if (lo != lo0) {
+                __syncthreads();
+                load_pair_meta(S.M, pair_foc, pair_crow, foc_row, lo, nrows);
+                __syncthreads();
+                gather_rows<ROWS, LD>(S.Xf, states, S.M.frow, nrows);
+                gather_rows<ROWS, LD>(S.Xc, states, S.M.crow, nrows);
+                __syncthreads();
+            }
             if (!staged) { stage_wait(S.W); staged = true; }
             if (hact) {
                 // activations of this tile from the forward kernel's stash (rows >= nrows and pad columns zero)
@@ -921,6 +969,9 @@ __device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
 template <int OPT>
 __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o,
                                LossArgs L) {
+    // dependents are released at once: the pair forward kernel of the next step loads its (static) pair list and state
+    // rows while this kernel runs and touches the weight image only after its own griddepcontrol.wait
+    pdl_launch_dependents();
     pdl_wait();
     if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -978,7 +1029,7 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
 template <int OPT>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
-    // no early griddepcontrol.launch_dependents here: the next kernel stages the weight image this kernel writes
+    pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
     pdl_wait();
     if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
