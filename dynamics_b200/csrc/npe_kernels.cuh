@@ -966,6 +966,20 @@ __device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
     }
 }
 
+// Sum of partial[b][i] over b < np in CTA order (deterministic), eight loads in flight at a time: the additions keep
+// their sequential order (padding with +0 does not change a sum), only the L2 latencies overlap.
+__device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i) {
+    float a = 0.f;
+    for (int b0 = 0; b0 < np; b0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (b0 + j < np) ? partial[(size_t)(b0 + j) * NPARAM + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a += v[j];
+    }
+    return a;
+}
+
 template <int OPT>
 __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o,
                                LossArgs L) {
@@ -977,8 +991,7 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-    float a = 0.f;
-    for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
+    const float a = ordered_partial_sum(partial, np, i);
     grad[i] = a;
     if (OPT == 1) {
         const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
@@ -1035,8 +1048,7 @@ __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ parti
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-    float a = 0.f;
-    for (int b = 0; b < np; ++b) a += partial[(size_t)b * NPARAM + i];
+    float a = ordered_partial_sum(partial, np, i);
     const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
     for (int r = 1; r < P.nranks; ++r) {                 // remote ranks first, own region last
         const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
