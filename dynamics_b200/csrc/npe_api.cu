@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/npe_cuda.h"
@@ -123,6 +124,24 @@ struct npe_handle {
     DevBuf<long long> foc_row, pair_crow;
     int pair_cap = 0;
     int* info_dev = nullptr;          // {P, overflow}
+    // Batch form is double-buffered: npe_batch_upload copies the batch and builds its pair table on `stream2` into the
+    // slot that is NOT in use, so an upload overlaps the training kernels of the previous batch (npe_train_step_async).
+    // `alt` holds the other slot's buffers; slot_ready is signalled on stream2, slot_free on the main stream.
+    struct BatchSlot {
+        DevBuf<float> states;
+        DevBuf<u64> keep, nbr;
+        DevBuf<int> cnt, block_sums, pair_start, pair_foc;
+        DevBuf<long long> foc_row, pair_crow;
+        DevBuf<int> n_obj, foc_scene, foc_obj, foc_t0;   // per slot: batches of different object counts alternate
+        int foci_B = -1, foci_N = -1;
+        int* info_dev = nullptr;
+        u64* active_total = nullptr;
+    } alt;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t slot_ready = nullptr;          // upload + pair table of the current slot complete (stream2)
+    cudaEvent_t slot_free[2] = {nullptr, nullptr};   // main-stream work on that slot enqueued so far is complete
+    int slot = 0;
+    bool slot_free_valid[2] = {false, false};
     // batch-form staging: the three host arrays are packed into the scene layout in page-locked memory and shipped
     // with ONE async copy (two buffers alternate; an event guards reuse)
     float* stage[2] = {nullptr, nullptr};
@@ -600,6 +619,14 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->alt.active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->alt.info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(h->alt.info_dev, 0, 4 * sizeof(int));
+    cudaMemset(h->alt.active_total, 0, sizeof(u64));
+    if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->slot_ready, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreateWithFlags(&h->slot_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void**)&h->loss4_host, (16 + 4 * LOSS_RING) * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&h->loss4_devptr, h->loss4_host, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (int i = 0; i < 2; ++i)
@@ -636,6 +663,14 @@ int npe_destroy(npe_handle* h) {
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
     if (h->info_dev) cudaFree(h->info_dev);
+    if (h->alt.active_total) cudaFree(h->alt.active_total);
+    if (h->alt.info_dev) cudaFree(h->alt.info_dev);
+    { auto& a = h->alt; a.states.release(); a.keep.release(); a.nbr.release(); a.cnt.release(); a.block_sums.release();
+      a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release();
+      a.n_obj.release(); a.foc_scene.release(); a.foc_obj.release(); a.foc_t0.release(); }
+    if (h->slot_ready) cudaEventDestroy(h->slot_ready);
+    for (int i = 0; i < 2; ++i) if (h->slot_free[i]) cudaEventDestroy(h->slot_free[i]);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     for (int i = 0; i < LOSS_RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->loss4_host) cudaFreeHost(h->loss4_host);
     for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
@@ -688,11 +723,29 @@ int npe_grads_set(npe_handle* h, const float* host, int32_t n) {
     return NPE_OK;
 }
 
+// Exchanges the current batch slot with `alt` (buffers and their capacities travel together).
+static void swap_batch_slot(npe_handle* h) {
+    auto& a = h->alt;
+    std::swap(h->states, a.states); std::swap(h->keep, a.keep); std::swap(h->nbr, a.nbr); std::swap(h->cnt, a.cnt);
+    std::swap(h->block_sums, a.block_sums); std::swap(h->pair_start, a.pair_start); std::swap(h->pair_foc, a.pair_foc);
+    std::swap(h->foc_row, a.foc_row); std::swap(h->pair_crow, a.pair_crow);
+    std::swap(h->info_dev, a.info_dev); std::swap(h->active_total, a.active_total);
+    std::swap(h->n_obj, a.n_obj); std::swap(h->foc_scene, a.foc_scene); std::swap(h->foc_obj, a.foc_obj); std::swap(h->foc_t0, a.foc_t0);
+    std::swap(h->foci_B, a.foci_B); std::swap(h->foci_N, a.foci_N);
+    h->slot ^= 1;
+}
+
 int npe_batch_upload(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C) {
     NEED(h);
     if (!this_past || B <= 0 || C < 0 || (C > 0 && !context)) return fail(h, NPE_ERR_INVALID, "batch_upload: bad arguments");
     if (C + 1 > MAXOBJ) return fail(h, NPE_ERR_INVALID, "batch_upload: at most %d contexts", MAXOBJ - 1);
     const int N = C + 1;
+    // everything enqueued so far works on the current slot: mark its release point, then move to the other slot
+    CK(cudaEventRecord(h->slot_free[h->slot], h->stream));
+    h->slot_free_valid[h->slot] = true;
+    swap_batch_slot(h);
+    if (h->slot_free_valid[h->slot]) CK(cudaStreamWaitEvent(h->stream2, h->slot_free[h->slot], 0));
+    const bool reshape = h->foci_B != B || h->foci_N != N;   // this slot's focus / object-count arrays are rewritten below
     CK(h->n_obj.ensure(B));
     CK(h->foc_scene.ensure(B)); CK(h->foc_obj.ensure(B)); CK(h->foc_t0.ensure(B));
     h->S = B; h->Nmax = N; h->T = 2;
@@ -718,12 +771,14 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     }
     CK(h->states.ensure(n_state + (size_t)B * OUT));
     if (y) memcpy(sg + n_state, y, n_y * sizeof(float));
-    CK(cudaMemcpyAsync(h->states.p, sg, (n_state + n_y) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaEventRecord(h->stage_ev[si], h->stream));
+    cudaStream_t main_stream = h->stream;
+    h->stream = h->stream2;            // the copy and the pair builder of this slot run on the upload stream
+    cudaError_t e = cudaMemcpyAsync(h->states.p, sg, (n_state + n_y) * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(h->stage_ev[si], h->stream);
     h->y_view = y ? h->states.p + n_state : nullptr;
-    if (h->foci_B != B || h->foci_N != N) {
+    if (e == cudaSuccess && reshape) {
         k_batch_foci<<<(B + 255) / 256, 256, 0, h->stream>>>(h->foc_scene.p, h->foc_obj.p, h->foc_t0.p, h->n_obj.p, B, N);
-        CKL();
+        e = cudaGetLastError();
         h->foci_B = B; h->foci_N = N;
     }
     h->foc_first = 0; h->F = B;
@@ -731,6 +786,12 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     h->pairs_valid = false; h->fwd_valid = false;
     h->win_start.clear();
     h->scene_foci.clear();
+    rc = (e == cudaSuccess) ? build_pairs(h) : NPE_OK;
+    if (e == cudaSuccess && rc == NPE_OK) e = cudaEventRecord(h->slot_ready, h->stream);
+    h->stream = main_stream;
+    if (e != cudaSuccess) return fail(h, NPE_ERR_CUDA, "batch_upload: %s", cudaGetErrorString(e));
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(h->stream, h->slot_ready, 0));   // later work on the main stream sees the new batch
     return NPE_OK;
 }
 
@@ -738,6 +799,7 @@ int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, 
     NEED(h);
     if (!states || !n_obj || S <= 0 || Nmax <= 0 || T < 2) return fail(h, NPE_ERR_INVALID, "scenes_upload: bad arguments");
     if (Nmax > MAXOBJ) return fail(h, NPE_ERR_INVALID, "scenes_upload: at most %d objects per scene", MAXOBJ);
+    CK(cudaStreamSynchronize(h->stream2));
     const size_t n = (size_t)S * Nmax * T * D;
     CK(h->states.ensure(n));
     CK(h->n_obj.ensure(S));
