@@ -478,3 +478,45 @@ def test_async_train_step_ring(model, params):
     assert np.array_equal(model.get_params(), p_ref) and np.array_equal(np.stack(got), np.stack(ref))
     with pytest.raises(Exception):
         model.train_step_async(64)
+
+
+def test_double_buffered_uploads_mixed_shapes(model, params):
+    """Uploads alternate between two device slots and run on their own stream; batches of different object counts and
+    sizes, scene-form work in between and the pipelined loop must give the bits of the blocking loop."""
+    sets = {n: balls_batches(60, n, seed=80 + n)[1] for n in (3, 4, 6, 9)}
+    order = [3, 4, 4, 6, 3, 9, 9, 4, 6, 3, 3, 9]
+    bl = []
+    for i, n in enumerate(order):
+        foc, ctx = sets[n][i % len(sets[n])]
+        nb = 50 if i % 3 else 23                                        # batch size changes too
+        bl.append(batcher.make_batch(foc[:nb], ctx[:nb], offset=i % 20))
+    st = scenes.raw_to_state(scenes.gen_balls(20, 5, 6, seed=3))
+
+    def run(pipelined):
+        model.set_params(params); model.optim_reset(0.0)
+        losses = []
+        for i, b in enumerate(bl):
+            if i == 5:                                                  # a scene-form interlude between two uploads
+                model.upload_scenes(st)
+                model.upload_foci(np.arange(20), np.zeros(20, np.int32), np.ones(20, np.int32))
+                model.select_foci(0, 20)
+                losses.append(model.train_step("adam", 3e-4))
+            model._upload(b)
+            if pipelined:
+                model.train_step_async(i % 64, "adam", 3e-4)
+                if i and i != 5:
+                    losses.append(model.loss_wait((i - 1) % 64))
+                elif i == 5:
+                    losses.insert(-1, model.loss_wait(4))
+            else:
+                losses.append(model.train_step("adam", 3e-4))
+        if pipelined:
+            losses.append(model.loss_wait((len(bl) - 1) % 64))
+        return model.get_params(), np.stack(losses)
+
+    p_block, l_block = run(False)
+    p_pipe, l_pipe = run(True)
+    assert np.array_equal(p_block, p_pipe) and np.array_equal(l_block, l_pipe)
+    # and the blocking loop agrees with the oracle on the first batch
+    l_ref = npe.fp(params, bl[0])[0]
+    assert abs(l_block[0][0] - l_ref) <= 1e-4 * abs(l_ref)
