@@ -15,6 +15,7 @@
 
 #include "../../include/npe_cuda.h"
 #include "npe_kernels.cuh"
+#include "npe_step16.cuh"
 #include "npe_rollout.cuh"
 #include "npe_tc.cuh"
 
@@ -123,6 +124,8 @@ struct npe_handle {
     DevBuf<int> cnt, block_sums, pair_start, pair_foc;   // cnt = CTA-local exclusive prefix of active counts
     DevBuf<long long> foc_row, pair_crow;
     int pair_cap = 0;
+    unsigned* step_flags = nullptr;   // k_step_fused: per-tile arrival flags (2 x SM count), stamped per launch
+    unsigned step_stamp = 0;
     int* info_dev = nullptr;          // {P, overflow}
     // Batch form is double-buffered: npe_batch_upload copies the batch and builds its pair table on `stream2` into the
     // slot that is NOT in use, so an upload overlaps the training kernels of the previous batch (npe_train_step_async).
@@ -437,45 +440,8 @@ int run_loss_reduce(npe_handle* h) {
     return NPE_OK;
 }
 
-// fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
-// peer_opt: 1 / 2 = fused NVLink all-reduce + Adam / RMSprop (requires npe_peer_attach)
-int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0,
-                 bool fused_fwd = false) {
-    if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
-    if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
-    const int B = divisor_batch > 0 ? divisor_batch : h->F;
-    // d_vel = 2 (p - y) * vlambda / (2B); d_ang_vel = 2 (p - y) * lambda / B   (npe.lua:304-315)
-    const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
-    const float sw = 2.f * h->cfg.lambda / (float)B;
-    const bool small = small_batch(h, h->F);
-    const int rows = small ? 16 : 64;
-    const int gd = focus_grid(h, h->F, rows);
-    const int gp = pair_grid(h, rows);
-    {
-        ProfScope ps__(h, NPE_K_DEC_BACKWARD);
-        if (small)
-            CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
-                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
-        else
-            CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
-                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
-                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
-        h->launches++;
-    }
-    {
-        ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
-        if (small)
-            CK(launch_pdl(k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->stream, h->states.p, h->pair_foc.p,
-                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
-                          h->hact_valid ? h->hact.p : nullptr));
-        else
-            CK(launch_pdl(k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->stream, h->states.p, h->pair_foc.p,
-                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
-                          h->hact_valid ? h->hact.p : nullptr));
-        h->launches++;
-    }
-    CK(cudaGetLastError());
+// Fixed-order reduction of the CTA partials (+ optimiser / peer exchange / batch loss, see run_backward).
+int launch_reduce(npe_handle* h, int gp, int gd, int fuse_opt, float lr, bool want_loss, int peer_opt) {
     {
         ProfScope ps__(h, NPE_K_REDUCE);
         OptArgs o;
@@ -518,6 +484,81 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
     }
     CK(cudaGetLastError());
     return NPE_OK;
+}
+
+// fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
+// peer_opt: 1 / 2 = fused NVLink all-reduce + Adam / RMSprop (requires npe_peer_attach)
+int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0,
+                 bool fused_fwd = false) {
+    if (!h->fwd_valid) return fail(h, NPE_ERR_STATE, "npe_backward must follow npe_forward on the same batch");
+    if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
+    const int B = divisor_batch > 0 ? divisor_batch : h->F;
+    // d_vel = 2 (p - y) * vlambda / (2B); d_ang_vel = 2 (p - y) * lambda / B   (npe.lua:304-315)
+    const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
+    const float sw = 2.f * h->cfg.lambda / (float)B;
+    const bool small = small_batch(h, h->F);
+    const int rows = small ? 16 : 64;
+    const int gd = focus_grid(h, h->F, rows);
+    const int gp = pair_grid(h, rows);
+    {
+        ProfScope ps__(h, NPE_K_DEC_BACKWARD);
+        if (small)
+            CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
+                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
+        else
+            CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
+                          h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
+                          fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
+        h->launches++;
+    }
+    {
+        ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
+        if (small)
+            CK(launch_pdl(k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->stream, h->states.p, h->pair_foc.p,
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
+                          h->hact_valid ? h->hact.p : nullptr));
+        else
+            CK(launch_pdl(k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->stream, h->states.p, h->pair_foc.p,
+                          h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
+                          h->hact_valid ? h->hact.p : nullptr));
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return launch_reduce(h, gp, gd, fuse_opt, lr, want_loss, peer_opt);
+}
+
+// Forward + backward of a small batch as ONE grid of tiles (npe_step16.cuh) followed by the reduce kernel.  Taken by
+// npe_train_step when every pair tile and decoder tile gets its own SM; same results as run_forward + run_backward.
+bool step_fused_ok(const npe_handle* h) {
+    if (!small_batch(h, h->F) || !h->have_y) return false;
+    static const bool off = getenv("NPE_NO_FUSED_STEP") != nullptr;   // A/B measurements only
+    if (off) return false;
+    const int gp = (h->pair_cap + SR - 1) / SR, gd = (h->F + SR - 1) / SR;
+    return gp >= 1 && gp + gd <= h->num_sms && gp + gd <= 512;
+}
+int run_step_fused(npe_handle* h, int divisor_batch, int fuse_opt, float lr, bool want_loss, int peer_opt) {
+    int rc = build_pairs(h);
+    if (rc) return rc;
+    const int B = divisor_batch > 0 ? divisor_batch : h->F;
+    const int gp = (h->pair_cap + SR - 1) / SR, gd = (h->F + SR - 1) / SR;
+    StepArgs A;
+    A.states = h->states.p; A.pair_foc = h->pair_foc.p; A.pair_crow = h->pair_crow.p; A.foc_row = h->foc_row.p;
+    A.pair_start = h->pair_start.p; A.info = h->info_dev; A.wpack = h->wpack; A.y = h->yptr();
+    A.Hp = h->Hp.p; A.ds = h->ds.p; A.partial = h->partial; A.pred = h->pred.p; A.loss_ex = h->loss_ex.p;
+    A.F = h->F; A.gp = gp;
+    A.scale_v = 2.f * h->cfg.vlambda / (float)(2 * B);      // npe.lua:304-315, as in run_backward
+    A.scale_w = 2.f * h->cfg.lambda / (float)B;
+    A.flags = h->step_flags; A.stamp = ++h->step_stamp;
+    A.abort = h->info_dev + 1;
+    {
+        ProfScope ps__(h, NPE_K_STEP_FUSED);
+        CK(launch_pdl(k_step_fused, gp + gd, NT, sizeof(StepSmem), h->stream, A));
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    h->hact_valid = false;
+    return launch_reduce(h, gp, gd, fuse_opt, lr, want_loss, peer_opt);
 }
 
 int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
@@ -620,6 +661,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->alt.active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->step_flags, 512 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(h->step_flags, 0, 512 * sizeof(unsigned));
     if ((e = cudaMalloc((void**)&h->alt.info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(h->alt.info_dev, 0, 4 * sizeof(int));
     cudaMemset(h->alt.active_total, 0, sizeof(u64));
@@ -641,6 +684,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_dec_forward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecFwdSmem<16>))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecBwdSmem<16>))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_backward<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairBwdSmem<16>))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_step_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StepSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
@@ -664,6 +708,7 @@ int npe_destroy(npe_handle* h) {
     if (h->active_total) cudaFree(h->active_total);
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
+    if (h->step_flags) cudaFree(h->step_flags);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
     { auto& a = h->alt; a.states.release(); a.keep.release(); a.nbr.release(); a.cnt.release(); a.block_sums.release();
       a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release();
@@ -984,10 +1029,16 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
     int rc;
     if (!h->have_y) return fail(h, NPE_ERR_STATE, "batch has no targets");
-    if ((rc = run_forward(h, true, /*fused=*/true))) return rc;
     if (opt != 0 && opt != 1) return fail(h, NPE_ERR_INVALID, "train_step: opt must be 0 (adam) or 1 (rmsprop)");
     const bool want_loss = loss3_out != nullptr || h->loss4_override != nullptr;
-    if (h->peer_ready) {
+    const bool one_grid = (h->peer_ready || !h->comm) && step_fused_ok(h);
+    if (one_grid) {
+        // small batch: every tile of the forward and the backward is a CTA of one grid, then reduce (+ exchange) + optimiser
+        if ((rc = run_step_fused(h, divisor_batch, h->peer_ready ? 0 : (opt == 0 ? 1 : 2), lr, want_loss,
+                                 h->peer_ready ? (opt == 0 ? 1 : 2) : 0))) return rc;
+    } else if ((rc = run_forward(h, true, /*fused=*/true))) {
+        return rc;
+    } else if (h->peer_ready) {
         // data parallel over NVLink peer memory: local reduce + publish, then all-reduce fused with the optimiser
         if ((rc = run_backward(h, divisor_batch, 0, lr, want_loss, opt == 0 ? 1 : 2, true))) return rc;
     } else if (!h->comm) {
@@ -1003,6 +1054,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     if (want_loss && !h->loss4_override) {
         // the loss kernel wrote {loss, vel, angvel, overflow} straight into host-mapped memory: one sync, no copy
         CK(cudaStreamSynchronize(h->stream));
+        if (h->loss4_host[3] == 2.f) return fail(h, NPE_ERR_CUDA, "k_step_fused: a tile waited too long for its producer; results are invalid");
         if (h->loss4_host[3] != 0.f)
             return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
         loss3_out[0] = h->loss4_host[0]; loss3_out[1] = h->loss4_host[1]; loss3_out[2] = h->loss4_host[2];

@@ -653,6 +653,57 @@ __global__ void k_loss_reduce(const float* __restrict__ loss_ex, int F, float* _
     }
 }
 
+// Decoder weight-gradient register tiles -> this CTA's partial (reference flat layout).  Thread t owns tiles t and
+// t + NT of layer 1 (13 x 24 tiles of 4 x 4), tile t of layers 2..4 (13 x 13) and tile t - 169 of layer 5 (6 x 13).
+__device__ __forceinline__ void dec_partials_store(float* __restrict__ out, const float (&a1a)[16], const float (&a1b)[16],
+                                                   const float (&a2)[16], const float (&a3)[16], const float (&a4)[16],
+                                                   const float (&a5)[16]) {
+    const int t = threadIdx.x;
+    auto put1 = [&](const float (&acc)[16], int tileid) {
+        const int a = tileid / 24, b = tileid - a * 24;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * a + i, zc = 4 * b + j;
+                if (n < H) {
+                    if (zc < H) out[OFF_DEC1_W + n * DEC_IN + zc] = acc[4 * i + j];
+                    else if (zc == ONE_COL) out[OFF_DEC1_B + n] = acc[4 * i + j];
+                    else if (zc >= ZCOL_F) out[OFF_DEC1_W + n * DEC_IN + zc - 2] = acc[4 * i + j];
+                }
+            }
+    };
+    put1(a1a, t);
+    if (t + NT < 13 * 24) put1(a1b, t + NT);
+    auto putm = [&](const float (&acc)[16], int layer) {   // layer = 2..4
+        const int a = t / 13, b = t - a * 13;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * a + i, k = 4 * b + j;
+                if (n < H) {
+                    if (k < H) out[off_dec_w(layer) + n * H + k] = acc[4 * i + j];
+                    else if (k == ONE_COL) out[off_dec_b(layer) + n] = acc[4 * i + j];
+                }
+            }
+    };
+    if (t < 169) { putm(a2, 2); putm(a3, 3); putm(a4, 4); }
+    if (t >= 169 && t < 169 + 78) {
+        const int e = t - 169, a = e / 13, b = e - a * 13;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 4 * a + i, k = 4 * b + j;
+                if (n < OUT) {
+                    if (k < H) out[OFF_DEC5_W + n * H + k] = a5[4 * i + j];
+                    else if (k == ONE_COL) out[OFF_DEC5_B + n] = a5[4 * i + j];
+                }
+            }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // K4a: decoder backward.  d_pred = 2 (p - y) vlambda / (2B) on cols 2,3; 2 (p - y) lambda / B on col 5; zero
 // elsewhere (npe.lua:301-320).  Weight-gradient tiles live in registers for the whole kernel.
@@ -755,48 +806,34 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
         if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Da, S.Z, t + NT, nf);
         gemm_nn_r<ROWS, 13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, nf, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
     }
-    // write the register tiles into this CTA's partial (reference flat layout)
-    float* out = partial + (size_t)blockIdx.x * NPARAM;
-    auto put1 = [&](const float (&acc)[16], int tileid) {
-        const int a = tileid / 24, b = tileid - a * 24;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, zc = 4 * b + j;
-                if (n < H) {
-                    if (zc < H) out[OFF_DEC1_W + n * DEC_IN + zc] = acc[4 * i + j];
-                    else if (zc == ONE_COL) out[OFF_DEC1_B + n] = acc[4 * i + j];
-                    else if (zc >= ZCOL_F) out[OFF_DEC1_W + n * DEC_IN + zc - 2] = acc[4 * i + j];
-                }
-            }
-    };
-    put1(a1a, t);
-    if (t + NT < 13 * 24) put1(a1b, t + NT);
-    auto putm = [&](const float (&acc)[16], int layer) {   // layer = 2..4
+    dec_partials_store(partial + (size_t)blockIdx.x * NPARAM, a1a, a1b, a2, a3, a4, a5);
+}
+
+// Pair-MLP weight-gradient register tiles -> this CTA's partial.  Thread t < 169 owns tile t of every pairwise layer;
+// threads 169..245 own one tile of each encoder (acc[0] = context encoder, acc[1] = focus encoder).
+__device__ __forceinline__ void pair_partials_store(float* __restrict__ out, const float (&acc)[NL][16]) {
+    const int t = threadIdx.x;
+    if (t < 169) {
         const int a = t / 13, b = t - a * 13;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int l = 0; l < NL; ++l)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, k = 4 * b + j;
-                if (n < H) {
-                    if (k < H) out[off_dec_w(layer) + n * H + k] = acc[4 * i + j];
-                    else if (k == ONE_COL) out[off_dec_b(layer) + n] = acc[4 * i + j];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = 4 * a + i, k = 4 * b + j;
+                    if (n < H && k < H) out[OFF_PAIR + l * 2500 + n * H + k] = acc[l][4 * i + j];
                 }
-            }
-    };
-    if (t < 169) { putm(a2, 2); putm(a3, 3); putm(a4, 4); }
-    if (t >= 169 && t < 169 + 78) {
-        const int e = t - 169, a = e / 13, b = e - a * 13;
+    } else if (t < 169 + 77) {
+        const int e = t - 169, a = e / 11, b = e - a * 11;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int n = 4 * a + i, k = 4 * b + j;
-                if (n < OUT) {
-                    if (k < H) out[OFF_DEC5_W + n * H + k] = a5[4 * i + j];
-                    else if (k == ONE_COL) out[OFF_DEC5_B + n] = a5[4 * i + j];
+                if (n < H2) {
+                    out[OFF_ENC_C + n * IN + k] = acc[0][4 * i + j];
+                    out[OFF_ENC_T + n * IN + k] = acc[1][4 * i + j];
                 }
             }
     }
@@ -904,31 +941,7 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
             }
         }
     }
-    float* out = partial + (size_t)blockIdx.x * NPARAM;
-    if (t < 169) {
-        const int a = t / 13, b = t - a * 13;
-#pragma unroll
-        for (int l = 0; l < NL; ++l)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = 4 * a + i, k = 4 * b + j;
-                    if (n < H && k < H) out[OFF_PAIR + l * 2500 + n * H + k] = acc[l][4 * i + j];
-                }
-    } else if (enc_thread) {
-        const int e = t - 169, a = e / 11, b = e - a * 11;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, k = 4 * b + j;
-                if (n < H2) {
-                    out[OFF_ENC_C + n * IN + k] = acc[0][4 * i + j];
-                    out[OFF_ENC_T + n * IN + k] = acc[1][4 * i + j];
-                }
-            }
-    }
+    pair_partials_store(partial + (size_t)blockIdx.x * NPARAM, acc);
 }
 
 // grad[i] = sum over CTA partials in CTA order (deterministic); pair part and decoder part have their own grids.

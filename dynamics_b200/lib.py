@@ -119,7 +119,7 @@ def load_library(path=LIB_PATH):
 
 
 KERNEL_IDS = {"build_pairs": 0, "forward": 1, "dec_backward": 2, "pair_backward": 3, "reduce": 4, "optim": 5,
-              "rollout": 6, "targets": 7}
+              "rollout": 6, "targets": 7, "step_fused": 8}
 
 
 def pinned_array(lib, shape, dtype=np.float32):

@@ -243,7 +243,8 @@ void npe_host_free(void* p);
 #define NPE_K_OPTIM 5
 #define NPE_K_ROLLOUT 6
 #define NPE_K_TARGETS 7
-#define NPE_K_COUNT 8
+#define NPE_K_STEP_FUSED 8   /* forward + backward of a small batch as one grid of tiles (k_step_fused) */
+#define NPE_K_COUNT 9
 int npe_profile_select(npe_handle* h, int32_t kernel_id);
 /* Bracket only every `period`-th launch of the selected class (default 1): an event between two kernels disables their
  * programmatic-dependent-launch overlap, so a long timed region samples instead of bracketing every launch. */
