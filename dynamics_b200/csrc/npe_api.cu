@@ -440,48 +440,48 @@ int run_loss_reduce(npe_handle* h) {
     return NPE_OK;
 }
 
+// Arguments of the reduction + optimiser (+ peer exchange) stage; advances the optimiser / exchange step counters.
+struct ReducePlan {
+    OptArgs o; LossArgs L; DpArgs P; int buf = 0; unsigned stamp = 0; int opt = 0; bool peer = false;
+};
+ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss, int peer_opt) {
+    ReducePlan r;
+    OptArgs& o = r.o;
+    o.x = h->params; o.m = h->adam_m; o.v = h->adam_v; o.wpack = h->wpack;
+    o.b1 = 0.9f; o.omb1 = (float)(1.0 - 0.9); o.b2 = 0.999f; o.omb2 = (float)(1.0 - 0.999); o.eps = 1e-8f; o.step = lr;
+    r.L.loss_ex = h->loss_ex.p; r.L.F = h->F;
+    r.L.loss4_out = want_loss ? (h->loss4_override ? h->loss4_override : h->loss4_devptr) : nullptr; r.L.info = h->info_dev;
+    r.opt = peer_opt ? peer_opt : fuse_opt;
+    r.peer = peer_opt != 0;
+    r.P.nranks = h->nranks; r.P.rank = h->rank;
+    for (int q = 0; q < MAX_PEERS; ++q) r.P.region[q] = (r.peer && q < h->nranks) ? (uint2*)h->peer_ptr[q] : nullptr;
+    if (r.peer) {
+        r.buf = (int)(h->peer_step & 1u);
+        r.stamp = h->peer_step + 1u;
+        h->peer_step += 1u;
+    }
+    if (r.opt == 1) {
+        h->adam_t += 1;
+        const double t = (double)h->adam_t;
+        o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
+    } else if (r.opt == 2) {
+        o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
+    }
+    if (r.opt) { h->wtc_dirty = true; h->wtc3_dirty = true; }
+    return r;
+}
+
 // Fixed-order reduction of the CTA partials (+ optimiser / peer exchange / batch loss, see run_backward).
 int launch_reduce(npe_handle* h, int gp, int gd, int fuse_opt, float lr, bool want_loss, int peer_opt) {
-    {
-        ProfScope ps__(h, NPE_K_REDUCE);
-        OptArgs o;
-        o.x = h->params; o.m = h->adam_m; o.v = h->adam_v; o.wpack = h->wpack;
-        o.b1 = 0.9f; o.omb1 = (float)(1.0 - 0.9); o.b2 = 0.999f; o.omb2 = (float)(1.0 - 0.999); o.eps = 1e-8f; o.step = lr;
-        LossArgs L;
-        L.loss_ex = h->loss_ex.p; L.F = h->F; L.loss4_out = want_loss ? (h->loss4_override ? h->loss4_override : h->loss4_devptr) : nullptr; L.info = h->info_dev;
-        const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
-        if (peer_opt) {
-            const int buf = (int)(h->peer_step & 1u);
-            const unsigned stamp = h->peer_step + 1u;
-            h->peer_step += 1u;
-            DpArgs P;
-            P.nranks = h->nranks; P.rank = h->rank;
-            for (int r = 0; r < MAX_PEERS; ++r) P.region[r] = r < h->nranks ? (uint2*)h->peer_ptr[r] : nullptr;
-            if (peer_opt == 1) {
-                h->adam_t += 1;
-                const double t = (double)h->adam_t;
-                o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
-                CK(launch_pdl(k_dp_step<1>, nb, 256, 0, h->stream, h->partial, gp, gd, P, buf, stamp, h->grads, o, L));
-            } else {
-                o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
-                CK(launch_pdl(k_dp_step<2>, nb, 256, 0, h->stream, h->partial, gp, gd, P, buf, stamp, h->grads, o, L));
-            }
-            h->wtc_dirty = true; h->wtc3_dirty = true;
-        } else if (fuse_opt == 1) {
-            h->adam_t += 1;
-            const double t = (double)h->adam_t;
-            o.step = (float)((double)lr * std::sqrt(1.0 - std::pow(0.999, t)) / (1.0 - std::pow(0.9, t)));
-            CK(launch_pdl(k_reduce_grads<1>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
-            h->wtc_dirty = true; h->wtc3_dirty = true;
-        } else if (fuse_opt == 2) {
-            o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
-            CK(launch_pdl(k_reduce_grads<2>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
-            h->wtc_dirty = true; h->wtc3_dirty = true;
-        } else {
-            CK(launch_pdl(k_reduce_grads<0>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, o, L));
-        }
-        h->launches++;
-    }
+    ProfScope ps__(h, NPE_K_REDUCE);
+    const ReducePlan r = prepare_reduce(h, fuse_opt, lr, want_loss, peer_opt);
+    const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
+    if (r.peer && r.opt == 1) CK(launch_pdl(k_dp_step<1>, nb, 256, 0, h->stream, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
+    else if (r.peer) CK(launch_pdl(k_dp_step<2>, nb, 256, 0, h->stream, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
+    else if (r.opt == 1) CK(launch_pdl(k_reduce_grads<1>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
+    else if (r.opt == 2) CK(launch_pdl(k_reduce_grads<2>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
+    else CK(launch_pdl(k_reduce_grads<0>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
+    h->launches++;
     CK(cudaGetLastError());
     return NPE_OK;
 }
@@ -535,7 +535,7 @@ bool step_fused_ok(const npe_handle* h) {
     static const bool off = getenv("NPE_NO_FUSED_STEP") != nullptr;   // A/B measurements only
     if (off) return false;
     const int gp = (h->pair_cap + SR - 1) / SR, gd = (h->F + SR - 1) / SR;
-    return gp >= 1 && gp + gd <= h->num_sms && gp + gd <= 512;
+    return gp >= 1 && gp + gd <= h->num_sms && gp + gd <= 500;
 }
 int run_step_fused(npe_handle* h, int divisor_batch, int fuse_opt, float lr, bool want_loss, int peer_opt) {
     int rc = build_pairs(h);

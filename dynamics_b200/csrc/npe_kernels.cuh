@@ -960,8 +960,8 @@ __device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
     __shared__ double sv[256], sw[256];
     double av = 0.0, aw = 0.0;
     for (int f = threadIdx.x; f < L.F; f += 256) {
-        av += 2.0 * (double)L.loss_ex[(size_t)f * 3 + 1];
-        aw += (double)L.loss_ex[(size_t)f * 3 + 2];
+        av += 2.0 * (double)__ldcg(L.loss_ex + (size_t)f * 3 + 1);
+        aw += (double)__ldcg(L.loss_ex + (size_t)f * 3 + 2);
     }
     sv[threadIdx.x] = av; sw[threadIdx.x] = aw;
     __syncthreads();
@@ -979,6 +979,27 @@ __device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
     }
 }
 
+// Adam (OPT = 1) / RMSprop (OPT = 2) update of parameter i with gradient a, one rounding per operation (upstream optim
+// semantics, main.lua:135-144,301-302), plus the write-through to the packed weight image.  OPT = 0: nothing.
+template <int OPT>
+__device__ __forceinline__ void opt_update(int i, float a, const OptArgs& o) {
+    // state is read through L2 (__ldcg): in the one-grid step a parameter may be updated by a different SM every step
+    if (OPT == 1) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, __ldcg(o.m + i)), __fmul_rn(o.omb1, a));
+        const float vi = __fadd_rn(__fmul_rn(o.b2, __ldcg(o.v + i)), __fmul_rn(o.omb2, __fmul_rn(a, a)));
+        o.m[i] = mi; o.v[i] = vi;
+        const float xn = __fsub_rn(__ldcg(o.x + i), __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    } else if (OPT == 2) {
+        const float mi = __fadd_rn(__fmul_rn(o.b1, __ldcg(o.m + i)), __fmul_rn(o.omb1, __fmul_rn(a, a)));
+        o.m[i] = mi;
+        const float xn = __fsub_rn(__ldcg(o.x + i), __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
+        o.x[i] = xn;
+        o.wpack[pack_index(i)] = xn;
+    }
+}
+
 // Sum of partial[b][i] over b < np in CTA order (deterministic), eight loads in flight at a time: the additions keep
 // their sequential order (padding with +0 does not change a sum), only the L2 latencies overlap.
 __device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i) {
@@ -986,7 +1007,7 @@ __device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ p
     for (int b0 = 0; b0 < np; b0 += 8) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (b0 + j < np) ? partial[(size_t)(b0 + j) * NPARAM + i] : 0.f;
+        for (int j = 0; j < 8; ++j) v[j] = (b0 + j < np) ? __ldcg(partial + (size_t)(b0 + j) * NPARAM + i) : 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) a += v[j];
     }
@@ -1006,20 +1027,7 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     const float a = ordered_partial_sum(partial, np, i);
     grad[i] = a;
-    if (OPT == 1) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
-        const float vi = __fadd_rn(__fmul_rn(o.b2, o.v[i]), __fmul_rn(o.omb2, __fmul_rn(a, a)));
-        o.m[i] = mi; o.v[i] = vi;
-        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
-        o.x[i] = xn;
-        o.wpack[pack_index(i)] = xn;
-    } else if (OPT == 2) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, __fmul_rn(a, a)));
-        o.m[i] = mi;
-        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
-        o.x[i] = xn;
-        o.wpack[pack_index(i)] = xn;
-    }
+    opt_update<OPT>(i, a, o);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1052,18 +1060,10 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
     return v;
 }
 
-template <int OPT>
-__global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
-                                                 unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
-    pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
-    pdl_wait();
-    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NPARAM) return;
-    const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-    float a = ordered_partial_sum(partial, np, i);
+// Pushes this rank's value of parameter i into every peer's region and returns the rank-order sum over all ranks.
+__device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, int buf, unsigned stamp) {
     const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
-    for (int r = 1; r < P.nranks; ++r) {                 // remote ranks first, own region last
+    for (int r = 1; r < P.nranks; ++r) {                 // remote ranks
         const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
         st_cell(P.region[q] + mine, a, stamp);
     }
@@ -1078,22 +1078,22 @@ __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ parti
         }
         g += v;
     }
-    grad[i] = g;
-    a = g;
-    if (OPT == 1) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, a));
-        const float vi = __fadd_rn(__fmul_rn(o.b2, o.v[i]), __fmul_rn(o.omb2, __fmul_rn(a, a)));
-        o.m[i] = mi; o.v[i] = vi;
-        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
-        o.x[i] = xn;
-        o.wpack[pack_index(i)] = xn;
-    } else if (OPT == 2) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, o.m[i]), __fmul_rn(o.omb1, __fmul_rn(a, a)));
-        o.m[i] = mi;
-        const float xn = __fsub_rn(o.x[i], __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
-        o.x[i] = xn;
-        o.wpack[pack_index(i)] = xn;
-    }
+    return g;
+}
+
+template <int OPT>
+__global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
+                                                 unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
+    pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
+    pdl_wait();
+    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NPARAM) return;
+    const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
+    float a = ordered_partial_sum(partial, np, i);
+    a = peer_exchange(i, a, P, buf, stamp);
+    grad[i] = a;
+    opt_update<OPT>(i, a, o);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

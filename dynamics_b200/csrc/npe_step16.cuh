@@ -77,7 +77,9 @@ __device__ __forceinline__ void publish_flag(unsigned* flag, unsigned stamp) {
     if (threadIdx.x == 0) { __threadfence(); st_release_gpu(flag, stamp); }
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-
+// The reduction of the partials + optimiser stays a separate kernel (k_reduce_grads / k_dp_step, 111 CTAs, one
+// parameter per thread): folded into this grid behind an all-CTA barrier it was slower (17 CTAs x 256 threads walk
+// 6-7 parameters each, i.e. 6-7 serial L2 latency chains: 39 us per launch against 30 + 4).
 __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     StepSmem& U_ = *reinterpret_cast<StepSmem*>(smem_raw);
@@ -148,8 +150,7 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
             }
         }
         pair_partials_store(A.partial + (size_t)blockIdx.x * NPARAM, acc);
-        return;
-    }
+    } else {
     // ---------------------------------------------------- decoder tile ----------------------------------------------------
     StepDecSmem& S = U_.dec;
     const int tile = blockIdx.x - A.gp;
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
     wgrad<24, LD, LD1, true>(a1a, S.Dz[0], S.Z, t, nf);
     if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Dz[0], S.Z, t + NT, nf);
     dec_partials_store(A.partial + (size_t)tile * NPARAM, a1a, a1b, a2, a3, a4, a5);
+    }
 }
 
 }  // namespace npe
