@@ -126,6 +126,7 @@ struct npe_handle {
     int pair_cap = 0;
     unsigned* step_flags = nullptr;   // k_step_fused: per-tile arrival flags (2 x SM count), stamped per launch
     unsigned step_stamp = 0;
+    unsigned long long* step_trace = nullptr;   // npe_step_trace: device buffer of phase time stamps (tools only)
     int* info_dev = nullptr;          // {P, overflow}
     // Batch form is double-buffered: npe_batch_upload copies the batch and builds its pair table on `stream2` into the
     // slot that is NOT in use, so an upload overlaps the training kernels of the previous batch (npe_train_step_async).
@@ -551,6 +552,7 @@ int run_step_fused(npe_handle* h, int divisor_batch, int fuse_opt, float lr, boo
     A.scale_w = 2.f * h->cfg.lambda / (float)B;
     A.flags = h->step_flags; A.stamp = ++h->step_stamp;
     A.abort = h->info_dev + 1;
+    A.trace = h->step_trace;
     {
         ProfScope ps__(h, NPE_K_STEP_FUSED);
         CK(launch_pdl(k_step_fused, gp + gd, NT, sizeof(StepSmem), h->stream, A));
@@ -709,6 +711,7 @@ int npe_destroy(npe_handle* h) {
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
+    if (h->step_trace) cudaFree(h->step_trace);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
     { auto& a = h->alt; a.states.release(); a.keep.release(); a.nbr.release(); a.cnt.release(); a.block_sums.release();
       a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release();
@@ -1429,6 +1432,19 @@ void* npe_host_alloc(size_t bytes) {
     return p;
 }
 void npe_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int npe_step_trace(npe_handle* h, uint64_t* stamps_out, int32_t max_ctas) {
+    NEED(h);
+    if (!h->step_trace) {
+        CK(cudaMalloc((void**)&h->step_trace, 512 * 8 * sizeof(unsigned long long)));
+        CK(cudaMemset(h->step_trace, 0, 512 * 8 * sizeof(unsigned long long)));
+    }
+    if (stamps_out && max_ctas > 0) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(stamps_out, h->step_trace, (size_t)(max_ctas < 512 ? max_ctas : 512) * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    return NPE_OK;
+}
 
 int npe_profile_select(npe_handle* h, int32_t kernel_id) {
     NEED(h);

@@ -981,35 +981,44 @@ __device__ __forceinline__ void block_loss_reduce(const LossArgs& L) {
 
 // Adam (OPT = 1) / RMSprop (OPT = 2) update of parameter i with gradient a, one rounding per operation (upstream optim
 // semantics, main.lua:135-144,301-302), plus the write-through to the packed weight image.  OPT = 0: nothing.
+// The optimiser state of parameter i; it does not depend on the gradient kernels, so the reduce kernels fetch it
+// BEFORE griddepcontrol.wait (through L2: a parameter may be updated by a different SM every step).
+struct OptState { float m, v, x; };
 template <int OPT>
-__device__ __forceinline__ void opt_update(int i, float a, const OptArgs& o) {
-    // state is read through L2 (__ldcg): in the one-grid step a parameter may be updated by a different SM every step
+__device__ __forceinline__ OptState opt_load(int i, const OptArgs& o) {
+    OptState s{0.f, 0.f, 0.f};
+    if (OPT != 0) { s.m = __ldcg(o.m + i); s.x = __ldcg(o.x + i); }
+    if (OPT == 1) s.v = __ldcg(o.v + i);
+    return s;
+}
+template <int OPT>
+__device__ __forceinline__ void opt_update(int i, float a, const OptArgs& o, const OptState& s) {
     if (OPT == 1) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, __ldcg(o.m + i)), __fmul_rn(o.omb1, a));
-        const float vi = __fadd_rn(__fmul_rn(o.b2, __ldcg(o.v + i)), __fmul_rn(o.omb2, __fmul_rn(a, a)));
+        const float mi = __fadd_rn(__fmul_rn(o.b1, s.m), __fmul_rn(o.omb1, a));
+        const float vi = __fadd_rn(__fmul_rn(o.b2, s.v), __fmul_rn(o.omb2, __fmul_rn(a, a)));
         o.m[i] = mi; o.v[i] = vi;
-        const float xn = __fsub_rn(__ldcg(o.x + i), __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
+        const float xn = __fsub_rn(s.x, __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
         o.x[i] = xn;
         o.wpack[pack_index(i)] = xn;
     } else if (OPT == 2) {
-        const float mi = __fadd_rn(__fmul_rn(o.b1, __ldcg(o.m + i)), __fmul_rn(o.omb1, __fmul_rn(a, a)));
+        const float mi = __fadd_rn(__fmul_rn(o.b1, s.m), __fmul_rn(o.omb1, __fmul_rn(a, a)));
         o.m[i] = mi;
-        const float xn = __fsub_rn(__ldcg(o.x + i), __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
+        const float xn = __fsub_rn(s.x, __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
         o.x[i] = xn;
         o.wpack[pack_index(i)] = xn;
     }
 }
 
-// Sum of partial[b][i] over b < np in CTA order (deterministic), eight loads in flight at a time: the additions keep
+// Sum of partial[b][i] over b < np in CTA order (deterministic), sixteen loads in flight at a time: the additions keep
 // their sequential order (padding with +0 does not change a sum), only the L2 latencies overlap.
 __device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i) {
     float a = 0.f;
-    for (int b0 = 0; b0 < np; b0 += 8) {
-        float v[8];
+    for (int b0 = 0; b0 < np; b0 += 16) {
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (b0 + j < np) ? __ldcg(partial + (size_t)(b0 + j) * NPARAM + i) : 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < np) ? __ldcg(partial + (size_t)(b0 + j) * NPARAM + i) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a += v[j];
+        for (int j = 0; j < 16; ++j) a += v[j];
     }
     return a;
 }
@@ -1020,14 +1029,17 @@ __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pai
     // dependents are released at once: the pair forward kernel of the next step loads its (static) pair list and state
     // rows while this kernel runs and touches the weight image only after its own griddepcontrol.wait
     pdl_launch_dependents();
-    pdl_wait();
-    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
+    OptState st{0.f, 0.f, 0.f};
+    if (!loss_block && i < NPARAM) st = opt_load<OPT>(i, o);
+    pdl_wait();
+    if (loss_block) { block_loss_reduce(L); return; }
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     const float a = ordered_partial_sum(partial, np, i);
     grad[i] = a;
-    opt_update<OPT>(i, a, o);
+    opt_update<OPT>(i, a, o, st);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -1085,15 +1097,18 @@ template <int OPT>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
     pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
-    pdl_wait();
-    if (L.loss4_out && blockIdx.x == gridDim.x - 1) { block_loss_reduce(L); return; }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
+    OptState st{0.f, 0.f, 0.f};
+    if (!loss_block && i < NPARAM) st = opt_load<OPT>(i, o);
+    pdl_wait();
+    if (loss_block) { block_loss_reduce(L); return; }
     if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     float a = ordered_partial_sum(partial, np, i);
     a = peer_exchange(i, a, P, buf, stamp);
     grad[i] = a;
-    opt_update<OPT>(i, a, o);
+    opt_update<OPT>(i, a, o, st);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -34,6 +34,7 @@ struct StepArgs {
     unsigned* flags;                // [0, gp): pair tile forward done; [gp, gp + gd): decoder tile ds done
     unsigned stamp;
     int* abort;
+    unsigned long long* trace;      // optional (tools): 8 globaltimer stamps per CTA at the phase boundaries
 };
 
 struct StepDecSmem {
@@ -76,6 +77,13 @@ __device__ __forceinline__ void publish_flag(unsigned* flag, unsigned stamp) {
     __syncthreads();                                   // the CTA's global writes precede the release (cumulativity)
     if (threadIdx.x == 0) { __threadfence(); st_release_gpu(flag, stamp); }
 }
+__device__ __forceinline__ void trace_mark(const StepArgs& A, int slot) {
+    if (A.trace && threadIdx.x == 0) {
+        unsigned long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        A.trace[(size_t)blockIdx.x * 8 + slot] = tns;
+    }
+}
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 // The reduction of the partials + optimiser stays a separate kernel (k_reduce_grads / k_dp_step, 111 CTAs, one
 // parameter per thread): folded into this grid behind an all-CTA barrier it was slower (17 CTAs x 256 threads walk
@@ -100,7 +108,9 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
             gather_rows<SR, LD>(S.Xc, A.states, S.M.crow, nrows);
         }
         __syncthreads();
+        trace_mark(A, 0);
         pdl_wait();
+        trace_mark(A, 1);
         pdl_launch_dependents();
         float acc[NL][16];
 #pragma unroll
@@ -119,9 +129,11 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
             }
         }
         publish_flag(A.flags + blockIdx.x, A.stamp);       // inactive tiles publish too (nobody waits on them)
+        trace_mark(A, 2);
         if (active) {
             // the decoder tiles that own this tile's foci (the pair list is sorted by focus)
             wait_flags(A.flags + A.gp, S.M.pf[0] / SR, S.M.pf[nrows - 1] / SR, A.stamp, A.abort);
+            trace_mark(A, 3);
             for (int idx = t; idx < SR * (LD / 4); idx += NT) {
                 const int r = idx / (LD / 4), c4 = idx - r * (LD / 4);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -149,7 +161,9 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
                 wgrad<11, LD, LD, true>(acc[1], da, S.Xf, t - 169, nrows, 0);
             }
         }
+        trace_mark(A, 4);
         pair_partials_store(A.partial + (size_t)blockIdx.x * NPARAM, acc);
+        trace_mark(A, 5);
     } else {
     // ---------------------------------------------------- decoder tile ----------------------------------------------------
     StepDecSmem& S = U_.dec;
@@ -163,11 +177,14 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
     __syncthreads();
     load_focus_tile<SR>(S.Z, A.states, S.foff, nf);
     __syncthreads();
+    trace_mark(A, 0);
     pdl_wait();
+    trace_mark(A, 1);
     pdl_launch_dependents();
     stage_copy(S.W, nullptr, S.Wd, A.wpack);
     const int p_lo = S.pstart[0], p_hi = S.pstart[nf];
     if (p_hi > p_lo) wait_flags(A.flags, p_lo / SR, (p_hi - 1) / SR, A.stamp, A.abort);
+    trace_mark(A, 2);
     // per-focus sums of the pair outputs in list order (focus_sums, reading through L2: the rows were written by other SMs)
     for (int idx = t; idx < nf * 13; idx += NT) {
         const int f = idx / 13, c4 = idx - f * 13;
@@ -213,6 +230,7 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
     __syncthreads();
     gemm_nn_r<SR, 13, LD, LD1>(S.Dz[0], S.Wd + SW_DEC1, 13, nf, EpiNN{A.ds + (size_t)f0 * 52, 52, nullptr, nf});
     publish_flag(A.flags + A.gp + tile, A.stamp);
+    trace_mark(A, 3);
     // weight gradients (off the critical path of the step: the pair tiles run their backward meanwhile)
     float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
 #pragma unroll
@@ -225,7 +243,9 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
     }
     wgrad<24, LD, LD1, true>(a1a, S.Dz[0], S.Z, t, nf);
     if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Dz[0], S.Z, t + NT, nf);
+    trace_mark(A, 4);
     dec_partials_store(A.partial + (size_t)tile * NPARAM, a1a, a1b, a2, a3, a4, a5);
+    trace_mark(A, 5);
     }
 }
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "npe_sync": (C.c_int, [_H]),
     "npe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "npe_host_free": (None, [C.c_void_p]),
+    "npe_step_trace": (C.c_int, [_H, C.POINTER(C.c_uint64), C.c_int32]),
     "npe_profile_select": (C.c_int, [_H, C.c_int32]),
     "npe_profile_period": (C.c_int, [_H, C.c_int32]),
     "npe_profile_read": (C.c_int, [_H, _ip, C.POINTER(C.c_double)]),

@@ -53,6 +53,7 @@ int npe_peer_attach(npe_handle* h, int32_t rank, int32_t nranks, const void* all
 int npe_sync(npe_handle* h);
 void* npe_host_alloc(size_t bytes);
 void npe_host_free(void* p);
+int npe_step_trace(npe_handle* h, uint64_t* stamps_out, int32_t max_ctas);
 int npe_profile_select(npe_handle* h, int32_t kernel_id);
 int npe_profile_period(npe_handle* h, int32_t period);
 int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out);

@@ -245,6 +245,10 @@ void npe_host_free(void* p);
 #define NPE_K_TARGETS 7
 #define NPE_K_STEP_FUSED 8   /* forward + backward of a small batch as one grid of tiles (k_step_fused) */
 #define NPE_K_COUNT 9
+/* Tools: the first call switches on phase time stamps (globaltimer, ns) in k_step_fused; stamps_out (max_ctas, 8) receives
+ * the stamps of the last launch: {static loads done, wait done, first hand-over, second hand-over, gradients done,
+ * partial stored, 0, 0} per CTA (pair tiles first, then decoder tiles). */
+int npe_step_trace(npe_handle* h, uint64_t* stamps_out, int32_t max_ctas);
 int npe_profile_select(npe_handle* h, int32_t kernel_id);
 /* Bracket only every `period`-th launch of the selected class (default 1): an event between two kernels disables their
  * programmatic-dependent-launch overlap, so a long timed region samples instead of bracketing every launch. */
