@@ -47,6 +47,9 @@ KERNEL_FLOPS = {                       # algorithmic FLOPs: maske
     "step_fused": lambda F, P: 79800.0 * F + 79400.0 * P,      # forward + both backward passes in one grid of tiles
 }
 STEP_FLOPS = lambda F, P: 79800.0 * F + 79400.0 * P
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture (cold caches under the
+# profiler: mostly the two weight images, which the real loop serves from L2) -- profiles/r1_final_step_fused_kernel.md
+NCU_TRAFFIC_BYTES = {"step_fused": 290304}
 
 
 def _load_peaks():
@@ -536,9 +539,9 @@ def run_ours(args):
                     "blocking_ms_per_step": ms_e2e_sync / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_" + dom, "bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / FP32_PEAK_TFLOPS, "traffic": NCU_TRAFFIC_BYTES.get(dom),
                          "kernel_ms": k_ms, "launches_timed": nprof, "peak_source": FP32_PEAK_NOTE,
-                         "note": "batch 50 -> one 64-row tile on one SM: latency-bound by construction; see extra.stress64"},
+                         "note": "batch 50 = 4 decoder tiles + ~10 pair tiles of 16 rows on 148 SMs, a chain of ~30 dependent passes: latency-bound by construction (see extra.stress64 for the throughput regime); kernel_ms is measured on every 16th launch, bracketed by events, i.e. WITHOUT the overlap with the neighbouring kernels that the loop has"},
             "kernel_ms_prepass": kern,
             "step_tflops": STEP_FLOPS(BATCH, P_mean) * world * args.steps / (ms * 1e-3) / 1e12}
     m.close()
