@@ -89,7 +89,7 @@ struct npe_handle {
     float* allreduce_buf = nullptr;   // NPARAM + 4 floats: gradient + {sum_v, sum_w, F}
     int adam_t = 0;
     float rms_m_init = 0.f;
-    float* partial = nullptr;         // [num_sms][NPARAM]
+    float* partial = nullptr;         // [num_sms][PT_TOTAL], tile-major (npe_layout.h)
     float* wpack = nullptr;           // packed (shared-memory layout) weight image, kept in sync with params
     float* wtc = nullptr;             // tensor-core (K-major canonical layout, TF32-rounded) weight image
     bool wtc_dirty = true;
@@ -650,7 +650,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         if ((e = cudaMalloc((void**)b, NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
         cudaMemset(*b, 0, NPARAM * sizeof(float));
     }
-    if ((e = cudaMalloc((void**)&h->partial, (size_t)h->num_sms * NPARAM * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->partial, (size_t)h->num_sms * PT_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->wpack, WPACK_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     k_pack_zero<<<(WPACK_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wpack);
     if ((e = cudaMalloc((void**)&h->wtc, TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);

@@ -653,55 +653,26 @@ __global__ void k_loss_reduce(const float* __restrict__ loss_ex, int F, float* _
     }
 }
 
-// Decoder weight-gradient register tiles -> this CTA's partial (reference flat layout).  Thread t owns tiles t and
+// Register tile -> 16 consecutive floats of the tile-major partial.
+__device__ __forceinline__ void tile_store(float* __restrict__ dst, const float (&acc)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st4(dst + 4 * q, make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]));
+}
+
+// Decoder weight-gradient register tiles -> this CTA's partial (tile-major, npe_layout.h).  Thread t owns tiles t and
 // t + NT of layer 1 (13 x 24 tiles of 4 x 4), tile t of layers 2..4 (13 x 13) and tile t - 169 of layer 5 (6 x 13).
 __device__ __forceinline__ void dec_partials_store(float* __restrict__ out, const float (&a1a)[16], const float (&a1b)[16],
                                                    const float (&a2)[16], const float (&a3)[16], const float (&a4)[16],
                                                    const float (&a5)[16]) {
     const int t = threadIdx.x;
-    auto put1 = [&](const float (&acc)[16], int tileid) {
-        const int a = tileid / 24, b = tileid - a * 24;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, zc = 4 * b + j;
-                if (n < H) {
-                    if (zc < H) out[OFF_DEC1_W + n * DEC_IN + zc] = acc[4 * i + j];
-                    else if (zc == ONE_COL) out[OFF_DEC1_B + n] = acc[4 * i + j];
-                    else if (zc >= ZCOL_F) out[OFF_DEC1_W + n * DEC_IN + zc - 2] = acc[4 * i + j];
-                }
-            }
-    };
-    put1(a1a, t);
-    if (t + NT < 13 * 24) put1(a1b, t + NT);
-    auto putm = [&](const float (&acc)[16], int layer) {   // layer = 2..4
-        const int a = t / 13, b = t - a * 13;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, k = 4 * b + j;
-                if (n < H) {
-                    if (k < H) out[off_dec_w(layer) + n * H + k] = acc[4 * i + j];
-                    else if (k == ONE_COL) out[off_dec_b(layer) + n] = acc[4 * i + j];
-                }
-            }
-    };
-    if (t < 169) { putm(a2, 2); putm(a3, 3); putm(a4, 4); }
-    if (t >= 169 && t < 169 + 78) {
-        const int e = t - 169, a = e / 13, b = e - a * 13;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, k = 4 * b + j;
-                if (n < OUT) {
-                    if (k < H) out[OFF_DEC5_W + n * H + k] = a5[4 * i + j];
-                    else if (k == ONE_COL) out[OFF_DEC5_B + n] = a5[4 * i + j];
-                }
-            }
+    tile_store(out + PT_DEC1A + t * 16, a1a);
+    if (t + NT < 13 * 24) tile_store(out + PT_DEC1B + t * 16, a1b);
+    if (t < 169) {
+        tile_store(out + PT_DEC2 + t * 16, a2);
+        tile_store(out + PT_DEC2 + PT_LAYER + t * 16, a3);
+        tile_store(out + PT_DEC2 + 2 * PT_LAYER + t * 16, a4);
     }
+    if (t >= 169 && t < 169 + 78) tile_store(out + PT_DEC5 + (t - 169) * 16, a5);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -806,36 +777,19 @@ k_dec_backward(const float* __restrict__ states, const long long* __restrict__ f
         if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Da, S.Z, t + NT, nf);
         gemm_nn_r<ROWS, 13, LD, LD1>(S.Da, S.Wd + SW_DEC1, 13, nf, EpiNN{ds_out + (size_t)f0 * 52, 52, nullptr, nf});
     }
-    dec_partials_store(partial + (size_t)blockIdx.x * NPARAM, a1a, a1b, a2, a3, a4, a5);
+    dec_partials_store(partial + (size_t)blockIdx.x * PT_TOTAL, a1a, a1b, a2, a3, a4, a5);
 }
 
-// Pair-MLP weight-gradient register tiles -> this CTA's partial.  Thread t < 169 owns tile t of every pairwise layer;
-// threads 169..245 own one tile of each encoder (acc[0] = context encoder, acc[1] = focus encoder).
+// Pair-MLP weight-gradient register tiles -> this CTA's partial (tile-major).  Thread t < 169 owns tile t of every
+// pairwise layer; threads 169..245 own one tile of each encoder (acc[0] = context encoder, acc[1] = focus encoder).
 __device__ __forceinline__ void pair_partials_store(float* __restrict__ out, const float (&acc)[NL][16]) {
     const int t = threadIdx.x;
     if (t < 169) {
-        const int a = t / 13, b = t - a * 13;
 #pragma unroll
-        for (int l = 0; l < NL; ++l)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = 4 * a + i, k = 4 * b + j;
-                    if (n < H && k < H) out[OFF_PAIR + l * 2500 + n * H + k] = acc[l][4 * i + j];
-                }
+        for (int l = 0; l < NL; ++l) tile_store(out + PT_PAIR + l * PT_LAYER + t * 16, acc[l]);
     } else if (t < 169 + 77) {
-        const int e = t - 169, a = e / 11, b = e - a * 11;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = 4 * a + i, k = 4 * b + j;
-                if (n < H2) {
-                    out[OFF_ENC_C + n * IN + k] = acc[0][4 * i + j];
-                    out[OFF_ENC_T + n * IN + k] = acc[1][4 * i + j];
-                }
-            }
+        tile_store(out + PT_ENC_C + (t - 169) * 16, acc[0]);
+        tile_store(out + PT_ENC_T + (t - 169) * 16, acc[1]);
     }
 }
 
@@ -941,7 +895,7 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
             }
         }
     }
-    pair_partials_store(partial + (size_t)blockIdx.x * NPARAM, acc);
+    pair_partials_store(partial + (size_t)blockIdx.x * PT_TOTAL, acc);
 }
 
 // grad[i] = sum over CTA partials in CTA order (deterministic); pair part and decoder part have their own grids.
@@ -1009,14 +963,43 @@ __device__ __forceinline__ void opt_update(int i, float a, const OptArgs& o, con
     }
 }
 
+// Flat (reference) parameter index -> offset inside a CTA's tile-major partial: element (n, k) of a layer lives in tile
+// (n / 4, k / 4) of the thread mapping of wgrad, at 4 (n % 4) + (k % 4).  Decoder biases are column 50 (the constant-1
+// activation column); decoder layer 1 skips the pad column 51 (z = [s(50) | 1 | 0 | this_past(44)]).
+__device__ __forceinline__ int partial_index(int i) {
+    int base, n, k, kt;                                   // kt = tiles per row of the layer
+    if (i < OFF_PAIR) {                                   // encoders, 25 x 44
+        const int r = i < OFF_ENC_C ? i : i - OFF_ENC_C;
+        base = i < OFF_ENC_C ? PT_ENC_T : PT_ENC_C; n = r / IN; k = r - n * IN; kt = 11;
+    } else if (i < OFF_DEC1_W) {                          // pairwise layers, 50 x 50
+        const int r0 = i - OFF_PAIR, l = r0 / 2500, r = r0 - l * 2500;
+        base = PT_PAIR + l * PT_LAYER; n = r / H; k = r - n * H; kt = 13;
+    } else if (i < OFF_DEC2_W) {                          // decoder layer 1, 50 x 94 + bias
+        if (i < OFF_DEC1_B) { const int r = i - OFF_DEC1_W; n = r / DEC_IN; k = r - n * DEC_IN; if (k >= H) k += 2; }
+        else { n = i - OFF_DEC1_B; k = ONE_COL; }
+        const int tile = (n >> 2) * 24 + (k >> 2);
+        return (tile < NT ? PT_DEC1A + tile * 16 : PT_DEC1B + (tile - NT) * 16) + 4 * (n & 3) + (k & 3);
+    } else if (i < OFF_DEC5_W) {                          // decoder layers 2..4, 50 x 50 + bias
+        const int r0 = i - OFF_DEC2_W, l = r0 / 2550, r = r0 - l * 2550;
+        base = PT_DEC2 + l * PT_LAYER; kt = 13;
+        if (r < 2500) { n = r / H; k = r - n * H; } else { n = r - 2500; k = ONE_COL; }
+    } else {                                              // decoder layer 5, 22 x 50 + bias
+        const int r = i - OFF_DEC5_W;
+        base = PT_DEC5; kt = 13;
+        if (r < OUT * H) { n = r / H; k = r - n * H; } else { n = r - OUT * H; k = ONE_COL; }
+    }
+    return base + ((n >> 2) * kt + (k >> 2)) * 16 + 4 * (n & 3) + (k & 3);
+}
+
 // Sum of partial[b][i] over b < np in CTA order (deterministic), sixteen loads in flight at a time: the additions keep
 // their sequential order (padding with +0 does not change a sum), only the L2 latencies overlap.
 __device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i) {
+    const float* src = partial + partial_index(i);
     float a = 0.f;
     for (int b0 = 0; b0 < np; b0 += 16) {
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < np) ? __ldcg(partial + (size_t)(b0 + j) * NPARAM + i) : 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < np) ? __ldcg(src + (size_t)(b0 + j) * PT_TOTAL) : 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) a += v[j];
     }

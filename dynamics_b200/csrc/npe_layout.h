@@ -54,6 +54,20 @@ constexpr int SW_DEC2 = SW_DEC1 + 56 * LD1;       // 3 x (56 x 56)
 constexpr int SW_DEC5 = SW_DEC2 + 3 * SW_PAIR_SZ; // 24 x 56
 constexpr int SW_DEC_TOTAL = SW_DEC5 + 24 * LD;   // 16576 floats = 66304 B
 
+// ---- per-CTA gradient partials: TILE-MAJOR layout ----
+// A CTA writes its weight-gradient register tiles (4 x 4 per thread) as they are: 16 consecutive floats per thread per
+// accumulator array, i.e. four 16-byte stores, coalesced over the warp, no index arithmetic on the critical path.  The
+// reduce kernels (one parameter per thread) translate a flat parameter index into this layout (partial_index).
+constexpr int PT_PAIR = 0;                          // 5 layers x 169 tiles (13 x 13) x 16
+constexpr int PT_LAYER = 169 * 16;
+constexpr int PT_ENC_C = PT_PAIR + NL * PT_LAYER;   // 77 tiles (7 x 11) x 16
+constexpr int PT_ENC_T = PT_ENC_C + 77 * 16;
+constexpr int PT_DEC1A = PT_ENC_T + 77 * 16;        // decoder layer 1: tiles 0..255 of 13 x 24
+constexpr int PT_DEC1B = PT_DEC1A + 256 * 16;       //                  tiles 256..311
+constexpr int PT_DEC2 = PT_DEC1B + 56 * 16;         // decoder layers 2..4: 169 tiles each
+constexpr int PT_DEC5 = PT_DEC2 + 3 * PT_LAYER;     // decoder layer 5: 78 tiles (6 x 13)
+constexpr int PT_TOTAL = PT_DEC5 + 78 * 16;         // 30336 floats per CTA
+
 constexpr int TILE = 64;            // rows (foci or pairs) per shared-memory tile
 constexpr int NT = 256;             // threads per CTA
 constexpr int MAXOBJ = 64;          // objects per scene

@@ -162,90 +162,90 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
             }
         }
         trace_mark(A, 4);
-        pair_partials_store(A.partial + (size_t)blockIdx.x * NPARAM, acc);
+        pair_partials_store(A.partial + (size_t)blockIdx.x * PT_TOTAL, acc);
         trace_mark(A, 5);
     } else {
-    // ---------------------------------------------------- decoder tile ----------------------------------------------------
-    StepDecSmem& S = U_.dec;
-    const int tile = blockIdx.x - A.gp;
-    const int f0 = tile * SR;
-    const int nf = min(SR, A.F - f0);
-    for (int idx = t; idx < 5 * SR * LD; idx += NT) (&S.Dz[0][0])[idx] = 0.f;
-    stage_init(S.W);
-    if (t < nf) S.foff[t] = A.foc_row[f0 + t];
-    if (t <= nf) S.pstart[t] = A.pair_start[f0 + t];
-    __syncthreads();
-    load_focus_tile<SR>(S.Z, A.states, S.foff, nf);
-    __syncthreads();
-    trace_mark(A, 0);
-    pdl_wait();
-    trace_mark(A, 1);
-    pdl_launch_dependents();
-    stage_copy(S.W, nullptr, S.Wd, A.wpack);
-    const int p_lo = S.pstart[0], p_hi = S.pstart[nf];
-    if (p_hi > p_lo) wait_flags(A.flags, p_lo / SR, (p_hi - 1) / SR, A.stamp, A.abort);
-    trace_mark(A, 2);
-    // per-focus sums of the pair outputs in list order (focus_sums, reading through L2: the rows were written by other SMs)
-    for (int idx = t; idx < nf * 13; idx += NT) {
-        const int f = idx / 13, c4 = idx - f * 13;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = S.pstart[f]; p < S.pstart[f + 1]; ++p) {
-            const float4 v = ldcg4(A.Hp + (size_t)p * 52 + 4 * c4);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        // ---------------------------------------------------- decoder tile ----------------------------------------------------
+        StepDecSmem& S = U_.dec;
+        const int tile = blockIdx.x - A.gp;
+        const int f0 = tile * SR;
+        const int nf = min(SR, A.F - f0);
+        for (int idx = t; idx < 5 * SR * LD; idx += NT) (&S.Dz[0][0])[idx] = 0.f;
+        stage_init(S.W);
+        if (t < nf) S.foff[t] = A.foc_row[f0 + t];
+        if (t <= nf) S.pstart[t] = A.pair_start[f0 + t];
+        __syncthreads();
+        load_focus_tile<SR>(S.Z, A.states, S.foff, nf);
+        __syncthreads();
+        trace_mark(A, 0);
+        pdl_wait();
+        trace_mark(A, 1);
+        pdl_launch_dependents();
+        stage_copy(S.W, nullptr, S.Wd, A.wpack);
+        const int p_lo = S.pstart[0], p_hi = S.pstart[nf];
+        if (p_hi > p_lo) wait_flags(A.flags, p_lo / SR, (p_hi - 1) / SR, A.stamp, A.abort);
+        trace_mark(A, 2);
+        // per-focus sums of the pair outputs in list order (focus_sums, reading through L2: the rows were written by other SMs)
+        for (int idx = t; idx < nf * 13; idx += NT) {
+            const int f = idx / 13, c4 = idx - f * 13;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = S.pstart[f]; p < S.pstart[f + 1]; ++p) {
+                const float4 v = ldcg4(A.Hp + (size_t)p * 52 + 4 * c4);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            if (c4 == 12) { a.z = 1.f; a.w = 0.f; }
+            st4(S.Z + f * LD1 + 4 * c4, a);
         }
-        if (c4 == 12) { a.z = 1.f; a.w = 0.f; }
-        st4(S.Z + f * LD1 + 4 * c4, a);
-    }
-    __syncthreads();
-    stage_wait(S.W);
-    float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
-    decoder_forward<SR>(S.Wd, S.Z, ubufs, S.O, nf);
-    for (int idx = t; idx < nf * OUT; idx += NT) {
-        const int r = idx / OUT, n = idx - r * OUT;
-        float v = S.O[r * LD + n];
-        if (n >= 6) v = 1.f / (1.f + expf(-v));
-        A.pred[(size_t)(f0 + r) * OUT + n] = v;
-    }
-    float* dz5 = S.Dz[4];
-    if (t < nf) {
-        const float* yy = A.y + (size_t)(f0 + t) * OUT;
-        const float e2 = S.O[t * LD + 2] - yy[2], e3 = S.O[t * LD + 3] - yy[3], e5 = S.O[t * LD + 5] - yy[5];
-        const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
-        A.loss_ex[(size_t)(f0 + t) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
-        A.loss_ex[(size_t)(f0 + t) * 3 + 1] = __fdiv_rn(lv, 2.f);
-        A.loss_ex[(size_t)(f0 + t) * 3 + 2] = lw;
-        dz5[t * LD + 2] = e2 * A.scale_v;
-        dz5[t * LD + 3] = e3 * A.scale_v;
-        dz5[t * LD + 5] = e5 * A.scale_w;
-    }
-    __syncthreads();
-    // input-gradient chain first: ds is what the pair tiles are waiting for
-    gemm_nn_r<SR, 13, LD, LD>(S.Dz[4], S.Wd + SW_DEC5, 6, nf, EpiNN{S.Dz[3], LD, S.U[3], SR});
-    __syncthreads();
-    gemm_nn_r<SR, 13, LD, LD>(S.Dz[3], S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, nf, EpiNN{S.Dz[2], LD, S.U[2], SR});
-    __syncthreads();
-    gemm_nn_r<SR, 13, LD, LD>(S.Dz[2], S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, nf, EpiNN{S.Dz[1], LD, S.U[1], SR});
-    __syncthreads();
-    gemm_nn_r<SR, 13, LD, LD>(S.Dz[1], S.Wd + SW_DEC2, 13, nf, EpiNN{S.Dz[0], LD, S.U[0], SR});
-    __syncthreads();
-    gemm_nn_r<SR, 13, LD, LD1>(S.Dz[0], S.Wd + SW_DEC1, 13, nf, EpiNN{A.ds + (size_t)f0 * 52, 52, nullptr, nf});
-    publish_flag(A.flags + A.gp + tile, A.stamp);
-    trace_mark(A, 3);
-    // weight gradients (off the critical path of the step: the pair tiles run their backward meanwhile)
-    float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
+        __syncthreads();
+        stage_wait(S.W);
+        float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
+        decoder_forward<SR>(S.Wd, S.Z, ubufs, S.O, nf);
+        for (int idx = t; idx < nf * OUT; idx += NT) {
+            const int r = idx / OUT, n = idx - r * OUT;
+            float v = S.O[r * LD + n];
+            if (n >= 6) v = 1.f / (1.f + expf(-v));
+            A.pred[(size_t)(f0 + r) * OUT + n] = v;
+        }
+        float* dz5 = S.Dz[4];
+        if (t < nf) {
+            const float* yy = A.y + (size_t)(f0 + t) * OUT;
+            const float e2 = S.O[t * LD + 2] - yy[2], e3 = S.O[t * LD + 3] - yy[3], e5 = S.O[t * LD + 5] - yy[5];
+            const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 1] = __fdiv_rn(lv, 2.f);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 2] = lw;
+            dz5[t * LD + 2] = e2 * A.scale_v;
+            dz5[t * LD + 3] = e3 * A.scale_v;
+            dz5[t * LD + 5] = e5 * A.scale_w;
+        }
+        __syncthreads();
+        // input-gradient chain first: ds is what the pair tiles are waiting for
+        gemm_nn_r<SR, 13, LD, LD>(S.Dz[4], S.Wd + SW_DEC5, 6, nf, EpiNN{S.Dz[3], LD, S.U[3], SR});
+        __syncthreads();
+        gemm_nn_r<SR, 13, LD, LD>(S.Dz[3], S.Wd + SW_DEC2 + 2 * SW_PAIR_SZ, 13, nf, EpiNN{S.Dz[2], LD, S.U[2], SR});
+        __syncthreads();
+        gemm_nn_r<SR, 13, LD, LD>(S.Dz[2], S.Wd + SW_DEC2 + SW_PAIR_SZ, 13, nf, EpiNN{S.Dz[1], LD, S.U[1], SR});
+        __syncthreads();
+        gemm_nn_r<SR, 13, LD, LD>(S.Dz[1], S.Wd + SW_DEC2, 13, nf, EpiNN{S.Dz[0], LD, S.U[0], SR});
+        __syncthreads();
+        gemm_nn_r<SR, 13, LD, LD1>(S.Dz[0], S.Wd + SW_DEC1, 13, nf, EpiNN{A.ds + (size_t)f0 * 52, 52, nullptr, nf});
+        publish_flag(A.flags + A.gp + tile, A.stamp);
+        trace_mark(A, 3);
+        // weight gradients (off the critical path of the step: the pair tiles run their backward meanwhile)
+        float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
-    if (t >= 169 && t < 169 + 78) wgrad<13, LD, LD, true>(a5, S.Dz[4], S.U[3], t - 169, nf);
-    if (t < 169) {
-        wgrad<13, LD, LD, true>(a4, S.Dz[3], S.U[2], t, nf);
-        wgrad<13, LD, LD, true>(a3, S.Dz[2], S.U[1], t, nf);
-        wgrad<13, LD, LD, true>(a2, S.Dz[1], S.U[0], t, nf);
-    }
-    wgrad<24, LD, LD1, true>(a1a, S.Dz[0], S.Z, t, nf);
-    if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Dz[0], S.Z, t + NT, nf);
-    trace_mark(A, 4);
-    dec_partials_store(A.partial + (size_t)tile * NPARAM, a1a, a1b, a2, a3, a4, a5);
-    trace_mark(A, 5);
+        for (int i = 0; i < 16; ++i) { a1a[i] = a1b[i] = a2[i] = a3[i] = a4[i] = a5[i] = 0.f; }
+        if (t >= 169 && t < 169 + 78) wgrad<13, LD, LD, true>(a5, S.Dz[4], S.U[3], t - 169, nf);
+        if (t < 169) {
+            wgrad<13, LD, LD, true>(a4, S.Dz[3], S.U[2], t, nf);
+            wgrad<13, LD, LD, true>(a3, S.Dz[2], S.U[1], t, nf);
+            wgrad<13, LD, LD, true>(a2, S.Dz[1], S.U[0], t, nf);
+        }
+        wgrad<24, LD, LD1, true>(a1a, S.Dz[0], S.Z, t, nf);
+        if (t + NT < 13 * 24) wgrad<24, LD, LD1, true>(a1b, S.Dz[0], S.Z, t + NT, nf);
+        trace_mark(A, 4);
+        dec_partials_store(A.partial + (size_t)tile * PT_TOTAL, a1a, a1b, a2, a3, a4, a5);
+        trace_mark(A, 5);
     }
 }
 
