@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
 #pragma unroll
             for (int l = NL - 1; l >= 0; --l) {
                 const float* hin = S.Hh[l];
-                if (t < 169) wgrad<13, LD, LD, true>(acc[l], da, hin, t, nrows);
+                if (t < 169) wgrad16<13, LD, LD, true>(acc[l], da, hin, t);   // rows >= nrows: dz rows are zero
                 gemm_nn_r<SR, 13, LD, LD>(da, S.Wp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNN{db, LD, hin, SR});
                 __syncthreads();
                 float* tmp = da; da = db; db = tmp;
@@ -200,20 +200,10 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
         stage_wait(S.W);
         float* const ubufs[4] = {S.U[0], S.U[1], S.U[2], S.U[3]};
         decoder_forward<SR>(S.Wd, S.Z, ubufs, S.O, nf);
-        for (int idx = t; idx < nf * OUT; idx += NT) {
-            const int r = idx / OUT, n = idx - r * OUT;
-            float v = S.O[r * LD + n];
-            if (n >= 6) v = 1.f / (1.f + expf(-v));
-            A.pred[(size_t)(f0 + r) * OUT + n] = v;
-        }
         float* dz5 = S.Dz[4];
         if (t < nf) {
             const float* yy = A.y + (size_t)(f0 + t) * OUT;
             const float e2 = S.O[t * LD + 2] - yy[2], e3 = S.O[t * LD + 3] - yy[3], e5 = S.O[t * LD + 5] - yy[5];
-            const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
-            A.loss_ex[(size_t)(f0 + t) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
-            A.loss_ex[(size_t)(f0 + t) * 3 + 1] = __fdiv_rn(lv, 2.f);
-            A.loss_ex[(size_t)(f0 + t) * 3 + 2] = lw;
             dz5[t * LD + 2] = e2 * A.scale_v;
             dz5[t * LD + 3] = e3 * A.scale_v;
             dz5[t * LD + 5] = e5 * A.scale_w;
@@ -231,6 +221,21 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
         gemm_nn_r<SR, 13, LD, LD1>(S.Dz[0], S.Wd + SW_DEC1, 13, nf, EpiNN{A.ds + (size_t)f0 * 52, 52, nullptr, nf});
         publish_flag(A.flags + A.gp + tile, A.stamp);
         trace_mark(A, 3);
+        // model:fp outputs (prediction with the sigmoid split, per-example losses): nobody in this grid waits for them
+        for (int idx = t; idx < nf * OUT; idx += NT) {
+            const int r = idx / OUT, n = idx - r * OUT;
+            float v = S.O[r * LD + n];
+            if (n >= 6) v = 1.f / (1.f + expf(-v));
+            A.pred[(size_t)(f0 + r) * OUT + n] = v;
+        }
+        if (t < nf) {
+            const float* yy = A.y + (size_t)(f0 + t) * OUT;
+            const float e2 = S.O[t * LD + 2] - yy[2], e3 = S.O[t * LD + 3] - yy[3], e5 = S.O[t * LD + 5] - yy[5];
+            const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 1] = __fdiv_rn(lv, 2.f);
+            A.loss_ex[(size_t)(f0 + t) * 3 + 2] = lw;
+        }
         // weight gradients (off the critical path of the step: the pair tiles run their backward meanwhile)
         float a1a[16], a1b[16], a2[16], a3[16], a4[16], a5[16];
 #pragma unroll

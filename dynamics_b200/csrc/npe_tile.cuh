@@ -340,6 +340,28 @@ __device__ __forceinline__ void wgrad(float (&acc)[16], const float* __restrict_
     }
 }
 
+// wgrad over ALL rows of a 16-row tile, fully unrolled: rows beyond the tile's valid rows must hold zeros in dZ and
+// finite values in Hm (the one-grid step guarantees both), so the result equals wgrad(..., nrows).  Being one basic
+// block, the compiler interleaves these FFMAs with the HMMA chain of the input-gradient pass issued right after it.
+template <int KCH, int LDZ, int LDH, bool ZALIGNED>
+__device__ __forceinline__ void wgrad16(float (&acc)[16], const float* __restrict__ dZ, const float* __restrict__ Hm,
+                                        int tile, int zoff = 0) {
+    const int a = tile / KCH, b = tile - a * KCH;
+    const float* zp = dZ + zoff + 4 * a;
+    const float* hp = Hm + 4 * b;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        float4 z;
+        if (ZALIGNED) z = ld4(zp + r * LDZ);
+        else { z.x = zp[r * LDZ]; z.y = zp[r * LDZ + 1]; z.z = zp[r * LDZ + 2]; z.w = zp[r * LDZ + 3]; }
+        const float4 h = ld4(hp + r * LDH);
+        acc[0] = fmaf(z.x, h.x, acc[0]);   acc[1] = fmaf(z.x, h.y, acc[1]);   acc[2] = fmaf(z.x, h.z, acc[2]);   acc[3] = fmaf(z.x, h.w, acc[3]);
+        acc[4] = fmaf(z.y, h.x, acc[4]);   acc[5] = fmaf(z.y, h.y, acc[5]);   acc[6] = fmaf(z.y, h.z, acc[6]);   acc[7] = fmaf(z.y, h.w, acc[7]);
+        acc[8] = fmaf(z.z, h.x, acc[8]);   acc[9] = fmaf(z.z, h.y, acc[9]);   acc[10] = fmaf(z.z, h.z, acc[10]); acc[11] = fmaf(z.z, h.w, acc[11]);
+        acc[12] = fmaf(z.w, h.x, acc[12]); acc[13] = fmaf(z.w, h.y, acc[13]); acc[14] = fmaf(z.w, h.z, acc[14]); acc[15] = fmaf(z.w, h.w, acc[15]);
+    }
+}
+
 // ---- TMA bulk copy (global -> shared, 1-D) with mbarrier completion: stages the packed weight image ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
