@@ -189,9 +189,18 @@ __global__ void __launch_bounds__(NT, 1) k_step_fused(StepArgs A) {
         for (int idx = t; idx < nf * 13; idx += NT) {
             const int f = idx / 13, c4 = idx - f * 13;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int p = S.pstart[f]; p < S.pstart[f + 1]; ++p) {
-                const float4 v = ldcg4(A.Hp + (size_t)p * 52 + 4 * c4);
-                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            const int p1 = S.pstart[f + 1];
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int p = S.pstart[f]; p < p1; p += 4) {       // four rows in flight; added in list order
+                const float* src = A.Hp + (size_t)p * 52 + 4 * c4;
+                const float4 v0 = ldcg4(src);
+                const float4 v1 = p + 1 < p1 ? ldcg4(src + 52) : zero4;
+                const float4 v2 = p + 2 < p1 ? ldcg4(src + 104) : zero4;
+                const float4 v3 = p + 3 < p1 ? ldcg4(src + 156) : zero4;
+                a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w;
+                a.x += v1.x; a.y += v1.y; a.z += v1.z; a.w += v1.w;
+                a.x += v2.x; a.y += v2.y; a.z += v2.z; a.w += v2.w;
+                a.x += v3.x; a.y += v3.y; a.z += v3.z; a.w += v3.w;
             }
             if (c4 == 12) { a.z = 1.f; a.w = 0.f; }
             st4(S.Z + f * LD1 + 4 * c4, a);
