@@ -500,7 +500,7 @@ def run_ours(args):
     def e2e_run(n0, n1):                 # pipelined form: the loss of step s-1 is read after step s is enqueued
         for s in range(n0, n1):
             a, b, c, cn = argp[s % ring]
-            rc = lib.npe_batch_upload(hdl, a, b, c, BATCH, cn) or lib.npe_train_step_async(hdl, 0, LR, gB, s % 64)
+            rc = lib.npe_train_batch_async(hdl, a, b, c, BATCH, cn, 0, LR, gB, s % 64)
             if s > n0:
                 rc = rc or lib.npe_loss_wait(hdl, (s - 1) % 64, loss_p)
             if rc:
@@ -535,7 +535,7 @@ def run_ours(args):
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "npe_batch_upload (pinned host arrays) + npe_train_step_async + npe_loss_wait of the previous step",
+                    "api": "npe_train_batch_async (pinned host arrays: upload + step) + npe_loss_wait of the previous step",
                     "blocking_ms_per_step": ms_e2e_sync / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_" + dom, "bound": "fp32", "achieved": ach, "peak": FP32_PEAK_TFLOPS,

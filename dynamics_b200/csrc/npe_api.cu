@@ -1121,6 +1121,12 @@ int npe_train_step_async(npe_handle* h, int32_t opt, float lr, int32_t divisor_b
     return NPE_OK;
 }
 
+int npe_train_batch_async(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C,
+                          int32_t opt, float lr, int32_t divisor_batch, int32_t slot) {
+    const int rc = npe_batch_upload(h, this_past, context, y, B, C);
+    return rc ? rc : npe_train_step_async(h, opt, lr, divisor_batch, slot);
+}
+
 int npe_loss_wait(npe_handle* h, int32_t slot, float* loss3_out) {
     NEED(h);
     if (slot < 0 || slot >= LOSS_RING || !h->ring_ev[slot]) return fail(h, NPE_ERR_INVALID, "loss_wait: slot %d was never issued", slot);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "npe_train_step": (C.c_int, [_H, C.c_int32, C.c_float, C.c_int32, _fp]),
     "npe_train_step_async": (C.c_int, [_H, C.c_int32, C.c_float, C.c_int32, C.c_int32]),
     "npe_loss_wait": (C.c_int, [_H, C.c_int32, _fp]),
+    "npe_train_batch_async": (C.c_int, [_H, _fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32]),
     "npe_train_steps": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _fp]),
     "npe_rollout": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),
     "npe_rollout_slots": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _fp, C.POINTER(C.c_double)]),

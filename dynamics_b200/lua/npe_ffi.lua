@@ -39,6 +39,7 @@ int npe_optim_reset(npe_handle* h, float rmsprop_m_init);
 int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, float* loss3_out);
 int npe_train_step_async(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, int32_t slot);
 int npe_loss_wait(npe_handle* h, int32_t slot, float* loss3_out);
+int npe_train_batch_async(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C, int32_t opt, float lr, int32_t divisor_batch, int32_t slot);
 int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr, int32_t divisor_batch, float* losses_out);
 int npe_rollout(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* metrics_out);
 int npe_rollout_slots(npe_handle* h, int32_t t0, int32_t steps, int32_t use_gt, int32_t teacher, float* traj_out, double* slot_metrics_out);

@@ -219,6 +219,13 @@ class NPEModel:
         """train_step without the host wait; the loss lands in ring slot `slot` (0..63), see loss_wait."""
         self._ck(self.lib.npe_train_step_async(self.h, 0 if opt == "adam" else 1, lr, divisor_batch, slot))
 
+    def train_batch_async(self, batch, slot, opt="adam", lr=3e-4, divisor_batch=0):
+        """Upload a host batch {this, context, y} and enqueue its training step in one call (loss: loss_wait(slot))."""
+        this, context, y = L.f32(batch[0]), L.f32(batch[1]), L.f32(np.asarray(batch[2]).reshape(len(batch[0]), -1))
+        self._ck(self.lib.npe_train_batch_async(self.h, L.fptr(this), L.fptr(context), L.fptr(y), this.shape[0],
+                                                context.shape[1] if context.ndim >= 2 else 0,
+                                                0 if opt == "adam" else 1, lr, divisor_batch, slot))
+
     def loss_wait(self, slot):
         loss3 = np.empty(3, np.float32)
         self._ck(self.lib.npe_loss_wait(self.h, slot, L.fptr(loss3)))

@@ -470,8 +470,11 @@ def test_async_train_step_ring(model, params):
     model.set_params(params); model.optim_reset(0.0)
     got = []
     for i, b in enumerate(bl):                       # 70 steps wrap the 64-slot ring
-        model._upload(b)
-        model.train_step_async(i % 64, "adam", 3e-4)
+        if i % 2:
+            model._upload(b)
+            model.train_step_async(i % 64, "adam", 3e-4)
+        else:
+            model.train_batch_async(b, i % 64, "adam", 3e-4)      # the same two calls behind one entry point
         if i:
             got.append(model.loss_wait((i - 1) % 64))
     got.append(model.loss_wait(69 % 64))
