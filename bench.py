@@ -265,14 +265,46 @@ def timed_loop(model, step_fn, warmup, steps, barrier):
     return model.event_elapsed_ms(0, 1)
 
 
-def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_step=1024):
-    """configs[3]: 64-ball scenes, all-pairs with the 210-px mask (12-NN trim off), 1024 scenes per GPU per step."""
+def attach_dp(m, dist, rank, world, mode):
+    """Joins the data-parallel group of the launch: NVLink peer memory (CUDA IPC handles all-gathered over the launcher's
+    gloo group) or an NCCL communicator inside the library."""
+    if world <= 1:
+        return
+    import torch
+    if mode == "nccl":
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
+        dist.broadcast(idt, 0)
+        m.comm_init(rank, world, bytes(idt.tolist()))
+    else:
+        mine = torch.tensor(list(m.peer_export()), dtype=torch.uint8)
+        allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        m.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
+
+
+def max_over_ranks(dist, ms):
+    if dist is None:
+        return ms
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_step=1024, dist=None, rank=0, world=1,
+                   dp_mode="p2p"):
+    """configs[3]: 64-ball scenes, all-pairs with the 210-px mask (12-NN trim off), 1024 scenes per GPU per step;
+    data-parallel over `world` GPUs (own scenes per rank, gradient exchange every step, max time over ranks)."""
     from dynamics_b200 import synth
     from dynamics_b200.model import init_params
-    st = synth.ball_scenes(scenes_per_step * 2, 64, 3, seed=64, world=(3200, 2400), collide=False)
+    st = synth.ball_scenes(scenes_per_step * 2, 64, 3, seed=64 + 1000 * rank, world=(3200, 2400), collide=False)
     m = model_cls(mp_cls(max_ctx=0, device=device))
+    barrier = (lambda: dist.barrier()) if dist else (lambda: None)
     try:
         m.set_params(init_params(1234)); m.optim_reset(0.0)
+        attach_dp(m, dist, rank, world, dp_mode)
         m.upload_scenes(st)
         W = scenes_per_step * 2
         m.upload_windows(np.arange(W), np.zeros(W, np.int32))
@@ -284,13 +316,14 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
 
         def step(s):
             m.select_windows((s % 2) * scenes_per_step, scenes_per_step)
-            m.train_step("adam", LR, want_loss=False)
+            m.train_step("adam", LR, divisor_batch=F * world, want_loss=False)
         out = {}
-        ms = timed_loop(m, step, warmup, steps, lambda: None)
-        out.update({"value": F * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps,
-                    "config": {"workload": "configs[3]: 64-ball scenes, 12-NN trim off, 1024 scenes/step",
-                               "foci_per_step": F, "active_pairs_per_step": P},
-                    "step_tflops": STEP_FLOPS(F, P) * steps / (ms * 1e-3) / 1e12})
+        ms = max_over_ranks(dist, timed_loop(m, step, warmup, steps, barrier))
+        out.update({"value": F * world * steps / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "n_gpus": world,
+                    "config": {"workload": "configs[3]: 64-ball scenes, 12-NN trim off, 1024 scenes/step per GPU",
+                               "foci_per_step_per_gpu": F, "active_pairs_per_step": P,
+                               "grad_exchange": dp_mode if world > 1 else None},
+                    "step_tflops": STEP_FLOPS(F, P) * world * steps / (ms * 1e-3) / 1e12})
         kern = {}
         for k in ("build_pairs", "forward", "dec_backward", "pair_backward", "step_fused", "reduce", "optim"):
             m.profile_select(k)
@@ -309,14 +342,16 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
         m.close()
 
 
-def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
-    """configs[4]-style rollout: `scenes` 8-ball scenes advanced `steps` steps, three variants:
-    fp32 persistent kernel (window on chip), fp32 by kernels (window in HBM), tf32 tcgen05 by kernels."""
+def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200, dist=None, rank=0, world=1):
+    """configs[4]-style rollout: `scenes` 8-ball scenes PER GPU advanced `steps` steps (scenes sharded by trajectory, no
+    collective: the aggregate is world x scenes over the slowest rank's time), four variants: fp32 persistent kernel
+    (window on chip), fp32 by kernels (window in HBM), tcgen05 3xTF32 and single-pass TF32 by kernels."""
     from dynamics_b200 import synth
     from dynamics_b200.model import init_params
-    st = synth.ball_scenes(scenes, balls, 2, seed=5)
+    st = synth.ball_scenes(scenes, balls, 2, seed=5 + 1000 * rank)
     m = model_cls(mp_cls(device=device))
-    out = {"config": {"workload": f"configs[4]-style: {scenes} x {balls}-ball scenes x {steps} steps, no ground truth"}}
+    out = {"n_gpus": world,
+           "config": {"workload": f"configs[4]-style: {scenes} x {balls}-ball scenes per GPU x {steps} steps, no ground truth"}}
     try:
         m.set_params(init_params(1234))
         m.upload_scenes(st)
@@ -324,11 +359,14 @@ def bench_rollout(model_cls, mp_cls, device, scenes=16384, balls=8, steps=200):
                                          ("tf32x3_tcgen05", "tf32x3", "kernels", steps), ("tf32_tcgen05", "tf32", "kernels", steps)):
             m.set_precision(prec); m.set_rollout_mode(mode)
             m.rollout_resident(0, 3); m.sync()
+            if dist:
+                dist.barrier()
             m.event_record(0)
             n = m.rollout_resident(0, nsteps)
             m.event_record(1); m.sync()
-            ms = m.event_elapsed_ms(0, 1)
-            out[name] = {"value": n / (ms * 1e-3), "unit": "object-steps/s", "ms": ms, "steps": nsteps, "object_steps": n}
+            ms = max_over_ranks(dist, m.event_elapsed_ms(0, 1))
+            out[name] = {"value": n * world / (ms * 1e-3), "unit": "object-steps/s", "ms": ms, "steps": nsteps,
+                         "object_steps": n * world}
         # kernel-level view of the tcgen05 pair kernel: active pairs per step from one build
         m.set_precision("tf32"); m.set_rollout_mode("kernels")
         m.profile_select("forward")
@@ -396,19 +434,7 @@ def run_ours(args):
                                                  11 + (0 if os.environ.get("NPE_BENCH_SAME_BATCHES") else rank), offs)   # env: skew diagnostics
     m = NPEModel(ModelParams(device=local_rank))
     m.set_params(init_params(1234)); m.optim_reset(0.0)
-    if world > 1:
-        import torch
-        if args.dp == "nccl":
-            idt = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
-            dist.broadcast(idt, 0)
-            m.comm_init(rank, world, bytes(idt.tolist()))
-        else:   # fused all-reduce + optimiser over NVLink peer memory (CUDA IPC handles exchanged by the launcher)
-            mine = torch.tensor(list(m.peer_export()), dtype=torch.uint8)
-            allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            m.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
+    attach_dp(m, dist, rank, world, args.dp)
     m.upload_scenes(states, n_obj)
     m.upload_foci(sc, ob, tt)
     gB = BATCH * world
@@ -545,14 +571,21 @@ def run_ours(args):
             "kernel_ms_prepass": kern,
             "step_tflops": STEP_FLOPS(BATCH, P_mean) * world * args.steps / (ms * 1e-3) / 1e12}
     m.close()
-    if rank == 0 and world == 1 and not args.no_extra:
+    if not args.no_extra:
+        # the other workloads of BASELINE.json: every rank takes part (configs[3] exchanges gradients, configs[4] is sharded)
         try:
-            line["extra"] = {"stress64": bench_stress64(NPEModel, ModelParams, local_rank),
-                             "forward_stress64": bench_forward_stress(NPEModel, ModelParams, local_rank),
-                             "rollout": bench_rollout(NPEModel, ModelParams, local_rank)}
+            extra = {"stress64": bench_stress64(NPEModel, ModelParams, local_rank, dist=dist, rank=rank, world=world,
+                                                dp_mode=args.dp)}
+            if world == 1:
+                extra["forward_stress64"] = bench_forward_stress(NPEModel, ModelParams, local_rank)
+            extra["rollout"] = bench_rollout(NPEModel, ModelParams, local_rank, dist=dist, rank=rank, world=world)
+            line["extra"] = extra
         except Exception as e:  # the headline must still print
             line["extra"] = {"error": repr(e)}
-        line["cpu_baseline"] = cpu_baseline_leg(hb, seconds=args.cpu_seconds)
+            if dist:
+                raise
+        if rank == 0 and world == 1:
+            line["cpu_baseline"] = cpu_baseline_leg(hb, seconds=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line))
     if dist:
