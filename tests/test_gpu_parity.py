@@ -523,3 +523,34 @@ def test_double_buffered_uploads_mixed_shapes(model, params):
     # and the blocking loop agrees with the oracle on the first batch
     l_ref = npe.fp(params, bl[0])[0]
     assert abs(l_block[0][0] - l_ref) <= 1e-4 * abs(l_ref)
+
+
+@pytest.mark.parametrize("nfoci,far", [(1, False), (17, False), (50, True), (33, False)])
+def test_one_grid_step_edge_shapes(model, trained_like_params, nfoci, far):
+    """npe_train_step on the one-grid path (k_step_fused) at its edges: a single focus, a decoder tile with one valid
+    row, no active pair at all; the gradient it leaves in grad_params and the parameters after the Adam step match the
+    oracle, and so does the separate-kernel path (fp + bp) on the same batch."""
+    st = scenes.raw_to_state(scenes.gen_balls(max(nfoci, 4), 6, 8, seed=40 + nfoci))
+    this = st[:nfoci, 0, 0:2].copy(); ctx = st[:nfoci, 1:, 0:2].copy()
+    if far:
+        ctx[..., 0:2] += 5.0
+    y = batcher.relative_pair(this, st[:nfoci, 0, 2:3])
+    batch = (this, ctx, y)
+    g_ref, _ = npe.bp(trained_like_params, batch)
+    l_ref = npe.fp(trained_like_params, batch)[0]
+    x = trained_like_params.copy()
+    optim.adam_step(x, g_ref, optim.adam_init(x.size), 3e-4)
+    model.set_params(trained_like_params); model.optim_reset(0.0)
+    model._upload(batch)
+    loss3 = model.train_step("adam", 3e-4)
+    g = model.get_grads()
+    assert abs(loss3[0] - l_ref) <= TOL * abs(l_ref)
+    assert grad_err(g, g_ref) < TOL
+    if far:
+        assert np.all(g[:14700] == 0)
+    assert np.max(np.abs(model.get_params() - x)) / np.max(np.abs(x)) < TOL
+    # separate kernels on the same batch: same gradient up to the summation order of the partial reduction
+    model.set_params(trained_like_params)
+    model.fp(None, batch)
+    g2 = model.bp()
+    assert np.array_equal(g2, g)
