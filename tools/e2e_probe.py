@@ -22,11 +22,13 @@ for this, ctx, y in hb:
 loss3 = np.zeros(3, np.float32)
 tu = ts = tw = 0.0
 N = 4000
+SKIP_UPLOAD = bool(os.environ.get('PROBE_SKIP_UPLOAD'))
 t00 = time.perf_counter()
 for s in range(N):
     this, ctx, y = pinned[s % ring]
     t0 = time.perf_counter()
-    m._ck(m.lib.npe_batch_upload(m.h, L.fptr(this), L.fptr(ctx), L.fptr(y), 50, ctx.shape[1]))
+    if not SKIP_UPLOAD or s == 0:
+        m._ck(m.lib.npe_batch_upload(m.h, L.fptr(this), L.fptr(ctx), L.fptr(y), 50, ctx.shape[1]))
     t1 = time.perf_counter()
     m._ck(m.lib.npe_train_step_async(m.h, 0, 3e-4, 50, s % 64))
     t2 = time.perf_counter()
