@@ -49,7 +49,7 @@ KERNEL_FLOPS = {                       # algorithmic FLOPs: maske
 STEP_FLOPS = lambda F, P: 79800.0 * F + 79400.0 * P
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture (cold caches under the
 # profiler: mostly the two weight images, which the real loop serves from L2) -- profiles/r1_final_step_fused_kernel.md
-NCU_TRAFFIC_BYTES = {"step_fused": 290304}
+NCU_TRAFFIC_BYTES = {"step_fused": 287488}
 
 
 def _load_peaks():
