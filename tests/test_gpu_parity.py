@@ -554,3 +554,19 @@ def test_one_grid_step_edge_shapes(model, trained_like_params, nfoci, far):
     model.fp(None, batch)
     g2 = model.bp()
     assert np.array_equal(g2, g)
+
+
+def test_one_grid_step_walls(model, trained_like_params):
+    """configs[2] shape on the one-grid path: 50 ball foci among 33 objects (12 nearest kept), ~40 pair tiles whose
+    foci span several decoder tiles; gradient and loss of npe_train_step against the oracle."""
+    st = scenes.raw_to_state(scenes.gen_walls(25, 8, seed=13, variant="U"))
+    foc, ctx, _, _ = batcher.expand_for_each_object(st)
+    batch = batcher.make_batch(foc, ctx, offset=3)
+    g_ref, _ = npe.bp(trained_like_params, batch)
+    l_ref = npe.fp(trained_like_params, batch)[0]
+    model.set_params(trained_like_params); model.optim_reset(0.0)
+    model._upload((batch[5][0], batch[5][1], batch[2]))          # untrimmed contexts: the device trims to 12
+    loss3 = model.train_step("adam", 3e-4)
+    assert abs(loss3[0] - l_ref) <= TOL * abs(l_ref)
+    assert grad_err(model.get_grads(), g_ref) < TOL
+    assert model.batch_stats()[1] > 64                             # more than four pair tiles were active
