@@ -1184,6 +1184,16 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
         h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
         if (sched) { h->pairs_valid = false; h->fwd_valid = false; h->F = 0; }
+        if (sched && rc == NPE_OK) {
+            // one look at the chunk's {P, flag} words: a dropped pair (1) or a timed-out hand-over (2) must not pass silently
+            std::vector<int> info((size_t)2 * n);
+            CK(cudaMemcpyAsync(info.data(), h->sched.info.p, info.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < n; ++i) {
+                if (info[(size_t)2 * i + 1] == 2) return fail(h, NPE_ERR_CUDA, "train_steps: step %d: a tile waited too long for its producer; results are invalid", s0 + i);
+                if (info[(size_t)2 * i + 1] != 0) return fail(h, NPE_ERR_NOMEM, "train_steps: active-pair list overflow in step %d (capacity %d pairs)", s0 + i, cap);
+            }
+        }
     }
     h->loss4_override = nullptr;
     if (rc) return rc;
