@@ -98,7 +98,7 @@ class Clocks:
                 self.rows.append((float(sm), int(reasons)))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def start(self):
         try:
