@@ -21,3 +21,31 @@ end
 
 function optim.npe_adam(opfunc, x, state) return step('adam', opfunc, x, state, state.network) end
 function optim.npe_rmsprop(opfunc, x, state) return step('rmsprop', opfunc, x, state, state.network) end
+
+-- Fast path for train() with -rs (main.lua:299-306): one call per iteration uploads the sampled batch and enqueues
+-- forward + backward + optimiser (npe_train_batch_async); the loss of iteration t-1 is read after iteration t has been
+-- enqueued, so the GPU never waits for the host.  `batch` is the loader's tuple {this, context, y, ...}; returns the
+-- loss of the PREVIOUS iteration (nil on the first call).  Call optim.npe_flush(state) before reading theta.params.
+function optim.npe_train_async(batch, state, kind)
+    local h = state.network.handle
+    local this, context, y = batch[1]:contiguous(), batch[2]:contiguous(), batch[3]:contiguous()
+    local B, Cn = this:size(1), context:size(2)
+    state.t = (state.t or 0) + 1
+    npeffi.check(h, C.npe_train_batch_async(h, npeffi.fptr(this), npeffi.fptr(context), npeffi.fptr(y), B, Cn,
+                                            kind == 'rmsprop' and 1 or 0, state.learningRate or 3e-4, B, state.t % 64))
+    local prev
+    if state.t > 1 then
+        state.loss3 = state.loss3 or torch.FloatTensor(3)
+        npeffi.check(h, C.npe_loss_wait(h, (state.t - 1) % 64, npeffi.fptr(state.loss3)))
+        prev = state.loss3[1]
+    end
+    return prev
+end
+
+function optim.npe_flush(state)
+    local h = state.network.handle
+    state.loss3 = state.loss3 or torch.FloatTensor(3)
+    if (state.t or 0) > 0 then npeffi.check(h, C.npe_loss_wait(h, state.t % 64, npeffi.fptr(state.loss3))) end
+    state.network:pull()
+    return state.loss3[1]
+end
