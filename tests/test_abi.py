@@ -61,3 +61,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".lua", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_plain_c_client(tmp_path):
+    """The header is C, the library links from C and reports errors as codes + messages; with a GPU the same binary runs
+    a tiny batch end to end (tests/c_abi_check.c).  Runs on the CPU box (expects the loud no-GPU failure) and on the B200."""
+    import shutil
+    import subprocess
+    from dynamics_b200.build import build
+    lib = build(force=False)
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    exe = tmp_path / "c_abi_check"
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c_abi_check.c")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-O1", src, "-o", str(exe), lib, "-lm",
+                    "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip() in ("gpu", "nogpu")
