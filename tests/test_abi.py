@@ -79,3 +79,22 @@ def test_plain_c_client(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() in ("gpu", "nogpu")
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under dynamics_b200/ (Python, CUDA, Lua) may import, link or execute it, and
+    bench.py / __graft_entry__.py only in their checker legs (cpu_baseline / --impl reference / smoke)."""
+    pkg = os.path.join(ROOT, "dynamics_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".lua")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "oracle/" not in text and "oracle." not in text.replace("the oracle.", ""), f
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle|import oracle", bench)]
+    assert uses, "bench.py times the CPU port in its cpu_baseline / reference legs"
+    for pos in uses:                                            # every use sits inside one of the two checker functions
+        head = bench[:pos]
+        fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]
+        assert fn in ("cpu_baseline_leg", "run_reference"), fn
