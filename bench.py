@@ -266,22 +266,7 @@ def timed_loop(model, step_fn, warmup, steps, barrier):
 
 
 def attach_dp(m, dist, rank, world, mode):
-    """Joins the data-parallel group of the launch: NVLink peer memory (CUDA IPC handles all-gathered over the launcher's
-    gloo group) or an NCCL communicator inside the library."""
-    if world <= 1:
-        return
-    import torch
-    if mode == "nccl":
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            idt = torch.tensor(list(m.unique_id()), dtype=torch.uint8)
-        dist.broadcast(idt, 0)
-        m.comm_init(rank, world, bytes(idt.tolist()))
-    else:
-        mine = torch.tensor(list(m.peer_export()), dtype=torch.uint8)
-        allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
-        dist.all_gather(allh, mine)
-        m.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
+    m.attach_data_parallel(dist, rank, world, mode)
 
 
 def max_over_ranks(dist, ms):

@@ -364,6 +364,25 @@ class NPEModel:
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
         self._ck(self.lib.npe_peer_attach(self.h, rank, nranks, C.cast(buf, C.c_void_p)))
 
+    def attach_data_parallel(self, dist, rank, world, mode="p2p"):
+        """Joins the data-parallel group of a one-process-per-GPU launch.  `dist` is torch.distributed with any CPU
+        backend (gloo): it only carries the 64-byte CUDA-IPC handles (mode 'p2p': gradient exchange over NVLink peer
+        memory inside the reduce + optimiser kernel) or the 128-byte NCCL id (mode 'nccl')."""
+        if world <= 1:
+            return
+        import torch
+        if mode == "nccl":
+            idt = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                idt = torch.tensor(list(self.unique_id()), dtype=torch.uint8)
+            dist.broadcast(idt, 0)
+            self.comm_init(rank, world, bytes(idt.tolist()))
+        else:
+            mine = torch.tensor(list(self.peer_export()), dtype=torch.uint8)
+            allh = [torch.zeros(64, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            self.peer_attach(rank, world, bytes(torch.cat(allh).tolist()))
+
     def allreduce_grads(self):
         self._ck(self.lib.npe_allreduce_grads(self.h))
 

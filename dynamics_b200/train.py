@@ -10,6 +10,11 @@ the per-iteration work (sample -> fp -> bp -> optimizer) enqueued on the GPU thr
   train                       main.lua:271-396        test / validate        main.lua:398-437
   run_experiment(_load)       main.lua:456-540        modes                  main.lua:563-574
 
+Data parallel (the reference is single-process): launched with one process per GPU
+(`python -m torch.distributed.run --nproc-per-node N -m dynamics_b200.train ...`), every rank samples its own batches
+from the same folders, back-propagates with the GLOBAL batch (N x batch_size) as divisor and the gradient is exchanged
+inside the optimiser kernel, so the replicas stay bit-identical; rank 0 alone prints, logs and writes checkpoints.
+
 With -rs (uniform batch sampling) and -L2 0 the samples of the next chunk of iterations are drawn up front (they do
 not depend on the losses), their focus triples are uploaded once and the whole chunk runs as ONE npe_train_steps call;
 a chunk ends wherever the reference prints, validates, saves or decays the learning rate, so every host-visible event
@@ -58,6 +63,7 @@ def build_parser():
     a("-val_every", type=int, default=100000); a("-lrdecay_every", type=int, default=2500)
     a("-lrdecayafter", type=int, default=50000); a("-fast", action="store_true")
     a("-device", type=int, default=0)
+    a("-dp", default="p2p", choices=["p2p", "nccl"], help="gradient exchange when launched with one process per GPU")
     return p
 
 
@@ -83,14 +89,19 @@ def chunk_len(done, periods, remaining, cap=MAX_CHUNK):
 
 
 class Logger:
-    """optim.Logger: a header of tab-separated names, then one tab-separated row per add()."""
+    """optim.Logger: a header of tab-separated names, then one tab-separated row per add().  path None: discard (the
+    ranks other than 0 of a data-parallel run)."""
 
     def __init__(self, path):
-        os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
-        self.fh = open(path, "w")
+        self.fh = None
+        if path is not None:
+            os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+            self.fh = open(path, "w")
         self.names = None
 
     def add(self, row):
+        if self.fh is None:
+            return
         if self.names is None:
             self.names = list(row)
             self.fh.write("\t".join(self.names) + "\t\n")
@@ -109,47 +120,70 @@ class Experiment:
         self.mp = mp
         self.train_losses, self.val_losses, self.test_losses = [], [], []
         self.model = None
-        self.rng = np.random.default_rng(mp.seed)
+        # one process per GPU under torchrun: RANK / LOCAL_RANK / WORLD_SIZE
+        self.rank = int(os.environ.get("RANK", 0)); self.world = int(os.environ.get("WORLD_SIZE", 1))
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group("gloo", rank=self.rank, world_size=self.world)
+            self.dist = dist
+            mp.device = int(os.environ.get("LOCAL_RANK", self.rank))
+        self.rng = np.random.default_rng(mp.seed + 1000 * self.rank)      # training batches differ per rank
+        self.rng_eval = np.random.default_rng(mp.seed)                    # validation order is the same on every rank
+        self.global_batch = mp.batch_size * self.world
         self.lr = mp.lr
+        self.say = print if self.rank == 0 else (lambda *a, **k: None)
         self.stepwise = False          # True: one device call per iteration even with -rs (what priority sampling does)
         self.history = None            # set to [] to record (dataset, sampled_id, lr, loss) of every iteration
 
     # ---- main.lua:216-245 ----
     def initsavebatches(self):
         mp = self.mp
+        if self.rank != 0:                      # rank 0 writes the batch files, the others wait for them
+            self.dist.barrier()
+            return
         for folder in list(mp.dataset_folders) + list(mp.test_dataset_folders):
             root = os.path.join(mp.data_root, folder)
             if os.path.isdir(os.path.join(root, "batches")):
-                print(f"Batches for {folder} already made")
+                self.say(f"Batches for {folder} already made")
                 continue
             jsons = sorted(glob.glob(os.path.join(root, "jsons", "*.json")))
-            print(f"Saving batches of size {mp.batch_size} from {root}/jsons into {root}/batches")
+            self.say(f"Saving batches of size {mp.batch_size} from {root}/jsons into {root}/batches")
             dataprep.json_to_batch_files(jsons, root, batch_size=mp.batch_size, seed=mp.seed)
+        if self.dist is not None:
+            self.dist.barrier()
 
     # ---- main.lua:154-214 ----
     def inittrain(self, preload=False, model_path=None, iters=None):
         mp = self.mp
-        print("Network parameters:"); print(vars(mp))
+        self.say("Network parameters:"); self.say(vars(mp))
         mparams = ModelParams(batch_size=mp.batch_size, rnn_dim=mp.rnn_dim, layers=mp.layers, num_past=mp.num_past,
                               num_future=mp.num_future, nbrhd=mp.nbrhd, nbrhdsize=mp.nbrhdsize, vlambda=mp.vlambda,
                               lambda_=mp.lambda_, model=mp.model, device=mp.device)
         self.model = NPEModel.create(mparams, preload, model_path, None if preload else init_params(mp.seed))
+        if self.world > 1:
+            self.model.attach_data_parallel(self.dist, self.rank, self.world, mp.dp)
         args = {"data_root": mp.data_root, "dataset_folders": mp.dataset_folders, "maxwinsize": CONFIG_ARGS["maxwinsize"],
                 "winsize": mp.winsize, "num_past": mp.num_past, "num_future": mp.num_future, "relative": True,
                 "sim": False, "subdivide": CONFIG_ARGS["subdivide"], "shuffle": CONFIG_ARGS["shuffle"],
                 "model": self.model, "batch_size": mp.batch_size, "rng": self.rng}
-        test_args = dict(args); test_args["dataset_folders"] = mp.test_dataset_folders
+        eval_args = dict(args); eval_args["rng"] = self.rng_eval
+        test_args = dict(eval_args); test_args["dataset_folders"] = mp.test_dataset_folders
         self.train_loader = GeneralDataSampler.create("trainset", dict(args))
-        self.val_loader = GeneralDataSampler.create("valset", dict(args))
+        self.val_loader = GeneralDataSampler.create("valset", dict(eval_args))
         self.test_loader = GeneralDataSampler.create("testset", test_args)
-        self.train_test_loader = GeneralDataSampler.create("trainset", dict(args))
-        os.makedirs(mp.savedir, exist_ok=True)
-        self.train_logger = Logger(os.path.join(mp.savedir, f"train_{iters}.log" if iters else "train.log"))
-        self.experiment_logger = Logger(os.path.join(mp.savedir, "experiment.log"))
-        t7.save(os.path.join(mp.savedir, f"args{iters}.t7" if iters else "args.t7"),
-                {"mp": _plain(vars(mp)), "config_args": dict(CONFIG_ARGS)})
+        self.train_test_loader = GeneralDataSampler.create("trainset", dict(eval_args))
+        lead = self.rank == 0
+        if lead:
+            os.makedirs(mp.savedir, exist_ok=True)
+        self.train_logger = Logger(os.path.join(mp.savedir, f"train_{iters}.log" if iters else "train.log") if lead else None)
+        self.experiment_logger = Logger(os.path.join(mp.savedir, "experiment.log") if lead else None)
+        if lead:
+            t7.save(os.path.join(mp.savedir, f"args{iters}.t7" if iters else "args.t7"),
+                    {"mp": _plain(vars(mp)), "config_args": dict(CONFIG_ARGS)})
         self.model.optim_reset(0.0)
-        print("Initialized Network")
+        self.say("Initialized Network")
 
     # ---- one reference iteration: feval_train + optimizer (main.lua:247-269,301-304) ----
     def _sample(self):
@@ -161,6 +195,8 @@ class Experiment:
         m, mp = self.model, self.mp
         batch = self._sample()
         if mp.L2 > 0:
+            if self.world > 1:
+                raise NotImplementedError("-L2 > 0 runs the optimiser from a host-edited gradient: single GPU only")
             loss, _, _, _ = m.fp(None, batch)
             grad = m.bp(batch)
             params = m.get_params()
@@ -169,7 +205,7 @@ class Experiment:
             (m.adam_step if mp.opt == "adam" else m.rmsprop_step)(self.lr)
         else:
             batch.select(m)
-            loss = float(m.train_step(mp.opt, self.lr)[0])
+            loss = float(m.train_step(mp.opt, self.lr, divisor_batch=self.global_batch)[0])
         self.train_loader.update_batch_weight(loss)
         if self.history is not None:
             self.history.append((self.train_loader.current_dataset, self.train_loader.current_sampled_id, self.lr, loss))
@@ -185,7 +221,8 @@ class Experiment:
         b.store.commit()
         scene = np.concatenate(scene); t0 = np.concatenate(t0)
         m.upload_foci(scene, np.zeros_like(scene), t0)
-        losses = m.train_steps(0, self.mp.batch_size, n, self.mp.opt, self.lr, want_losses=True)[:, 0]
+        losses = m.train_steps(0, self.mp.batch_size, n, self.mp.opt, self.lr, divisor_batch=self.global_batch,
+                               want_losses=True)[:, 0]
         for (ds, sid), loss in zip(who, losses):                  # update_batch_weight of every iteration, in order
             tl.datasamplers[ds - 1].priority_sampler.update_batch_weight(sid, float(loss))
             if self.history is not None:
@@ -195,7 +232,7 @@ class Experiment:
     # ---- main.lua:271-396 ----
     def train(self, start_iter=1, epoch_num=1):
         mp, m = self.mp, self.model
-        print("Start iter:", start_iter); print("Start epoch num:", epoch_num)
+        self.say("Start iter:", start_iter); self.say("Start epoch num:", epoch_num)
         if start_iter == 1:
             self._validate_and_record()
             self._save(epoch_num, 0, self.val_losses[-1], 0)
@@ -212,7 +249,7 @@ class Experiment:
             k = t_last - start_iter + 1
             if k % mp.print_every == 0:
                 hb = self.train_loader.get_hardest_batch()
-                print("epoch %2d  iteration %2d  loss = %6.8f  gradnorm = %6.4e  batch = %d-%d    hardest batch: %d-%d    "
+                self.say("epoch %2d  iteration %2d  loss = %6.8f  gradnorm = %6.4e  batch = %d-%d    hardest batch: %d-%d    "
                       "with loss %6.8f lr = %6.4e" % (epoch_num, t_last, losses[-1], float(np.linalg.norm(m.get_grads())),
                                                      self.train_loader.current_dataset, self.train_loader.current_sampled_id,
                                                      hb[2], hb[1], hb[0], self.lr))
@@ -226,7 +263,7 @@ class Experiment:
             if t_last >= mp.lrdecayafter and k % mp.lrdecay_every == 0:
                 self.lr *= mp.lrdecay
                 mp.lr = self.lr
-                print(f"Learning rate is now {self.lr}")
+                self.say(f"Learning rate is now {self.lr}")
             nb = self.train_loader.num_batches
             if t_last // nb > (t - 1) // nb:                        # some iteration of this chunk had t % nb == 0
                 epoch_num = (t_last // nb) + 1
@@ -237,22 +274,24 @@ class Experiment:
         mp = self.mp
         w = np.asarray(self.val_losses[-mp.val_window:], np.float64)
         delta = float(np.mean(w[1:] - w[:-1]))
-        print(f"Average change in val loss over {mp.val_window} validations: {delta}")
-        print("Loss is decreasing" if delta < 0 and int(np.argmax(w)) < int(np.argmin(w)) else "Loss is increasing")
+        self.say(f"Average change in val loss over {mp.val_window} validations: {delta}")
+        self.say("Loss is decreasing" if delta < 0 and int(np.argmax(w)) < int(np.argmin(w)) else "Loss is increasing")
         spread = float(w.max() - w.min())
-        print(f"Val loss difference in a window of {mp.val_window}: {spread}")
+        self.say(f"Val loss difference in a window of {mp.val_window}: {spread}")
         if spread < mp.val_eps:
-            print(f"That is less than {mp.val_eps}. Converged.")
+            self.say(f"That is less than {mp.val_eps}. Converged.")
             return True
         return False
 
     def _save(self, epoch_num, step, val_loss, iters):              # main.lua:288-296,333-346
         path = "%s/epoch%d_step%d_%.7f.t7" % (self.mp.savedir, epoch_num, step, val_loss)
-        print("saving checkpoint to " + path)
+        if self.rank != 0:
+            return path
+        self.say("saving checkpoint to " + path)
         t7.save(path, {"model": {"theta": {"params": self.model.get_params()}}, "mp": _plain(vars(self.mp)),
                        "train_losses": list(self.train_losses), "val_losses": list(self.val_losses),
                        "test_losses": list(self.test_losses), "iters": iters})
-        print("Saved model")
+        self.say("Saved model")
         return path
 
     # ---- main.lua:398-437 ----
@@ -260,7 +299,7 @@ class Experiment:
         num_batches = num_batches or loader.num_batches
         if self.mp.fast:
             num_batches = min(5000, num_batches)
-        print(f"Testing {num_batches} batches")
+        self.say(f"Testing {num_batches} batches")
         total = 0.0
         for _ in range(num_batches):
             batch, _ = loader.sample_sequential_batch(False)
@@ -271,7 +310,7 @@ class Experiment:
         tr = self.test(self.train_test_loader, min(5000, self.val_loader.num_batches))
         va = self.test(self.val_loader, self.val_loader.num_batches)
         te = self.test(self.test_loader, self.test_loader.num_batches)
-        print(f"train loss\t{tr}\tval loss\t{va}\ttest_loss\t{te}")
+        self.say(f"train loss\t{tr}\tval loss\t{va}\ttest_loss\t{te}")
         self.experiment_logger.add({"log MSE loss (train set)": math.log(tr), "log MSE loss (val set)": math.log(va),
                                     "log MSE loss (test set)": math.log(te)})
         return tr, va, te
@@ -290,7 +329,7 @@ class Experiment:
         snapshot = get_last_snapshot(mp.savedir)
         if snapshot is None:
             raise FileNotFoundError(f"no epoch*.t7 snapshot under {mp.savedir}")
-        print(snapshot)
+        self.say(snapshot)
         ck = t7.load(snapshot)
         for k, v in dict(ck["mp"]).items():                         # "completely overwrite" (main.lua:497)
             setattr(mp, k, v)
@@ -308,7 +347,7 @@ class Experiment:
         if (iters - 1) >= mp.lrdecayafter and (iters - 1) % mp.lrdecay_every == 0:
             mp.lr = mp.lr * mp.lrdecay
         self.lr = mp.lr
-        print(f"Learning rate is now {self.lr}")
+        self.say(f"Learning rate is now {self.lr}")
         self.inittrain(True, snapshot, iters)
         for tr, va, te in zip(self.train_losses, self.val_losses, self.test_losses):
             self.experiment_logger.add({"log MSE loss (train set)": math.log(tr), "log MSE loss (val set)": math.log(va),
