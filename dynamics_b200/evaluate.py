@@ -49,8 +49,10 @@ def save_ex_pred_json(scenes, traj, numsteps, jsonfile, dataset_name, subfolder,
     dataprep.record_trajectories(scenes[:, :, :num_past + numsteps], os.path.join(subfolder, "gt_" + jsonfile), config)
 
 
-def simulate_all(model, sampler, numsteps, savedir, ns=3, saveoutput=True):
-    """eval.lua:237-454 for one dataset's sampler.  Returns the (total_batches, numsteps) tables by log column."""
+def simulate_all(model, sampler, numsteps, savedir, ns=3, saveoutput=True, dist=None, rank=0, world=1):
+    """eval.lua:237-454 for one dataset's sampler.  Returns the (total_batches, numsteps) tables by log column.
+    Under a one-process-per-GPU launch the batch files are sharded by trajectory (file i goes to rank i mod world; no
+    collective on the data path), the tables are summed over ranks at the end and rank 0 writes the log."""
     name = os.path.basename(os.path.normpath(sampler.dataset_folder))
     subfolder = os.path.join(savedir, name + "_predictions")
     os.makedirs(subfolder, exist_ok=True)
@@ -58,7 +60,9 @@ def simulate_all(model, sampler, numsteps, savedir, ns=3, saveoutput=True):
         f"Number of predictive steps should be less than {sampler.maxwinsize - sampler.num_past + 1}"
     tables = {k: np.zeros((sampler.total_batches, numsteps)) for _, k in LOG_COLUMNS}
     for i in range(sampler.total_batches):
-        sampler.sample_sequential_batch()
+        sampler.sample_sequential_batch()                          # every rank walks the same order
+        if i % world != rank:
+            continue
         file_id = int(sampler.batch_idxs[sampler.current_batch - 1])
         scenes = sampler.file_scenes(file_id)                      # (B, N, T, 22): object 0 = focus, then contexts
         model.upload_scenes(scenes)
@@ -70,7 +74,13 @@ def simulate_all(model, sampler, numsteps, savedir, ns=3, saveoutput=True):
         if saveoutput and i < ns:
             save_ex_pred_json(scenes, traj, numsteps, f"batch{file_id}.json", name, subfolder, sampler.num_past,
                               sampler.num_future)
-    logger = Logger(os.path.join(subfolder, "gt_divergence.log"))
+    if dist is not None:
+        import torch
+        for _, k in LOG_COLUMNS:                                   # each row was filled by exactly one rank
+            t = torch.from_numpy(np.nan_to_num(tables[k], nan=0.0)); nanmask = torch.from_numpy(np.isnan(tables[k]).astype(np.float64))
+            dist.all_reduce(t); dist.all_reduce(nanmask)
+            tables[k] = np.where(nanmask.numpy() > 0, np.nan, t.numpy())
+    logger = Logger(os.path.join(subfolder, "gt_divergence.log") if rank == 0 else None)
     means = {k: tables[k].mean(0) for _, k in LOG_COLUMNS}
     for tt in range(numsteps):
         row = {"Timesteps": tt + 1}
@@ -81,6 +91,13 @@ def simulate_all(model, sampler, numsteps, savedir, ns=3, saveoutput=True):
 
 def predict_simulate_all(mp):
     """eval.lua:513-526."""
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+        mp.device = int(os.environ.get("LOCAL_RANK", rank))
     savedir = os.path.join(mp.logs_root, mp.name)
     snapshot = get_last_snapshot(savedir)
     if snapshot is None:
@@ -99,7 +116,7 @@ def predict_simulate_all(mp):
     out = {}
     for folder, sampler in zip(test_loader.dataset_folders, test_loader.datasamplers):
         print("Evaluating " + folder)
-        out[folder] = simulate_all(model, sampler, mp.steps, savedir, mp.ns, True)
+        out[folder] = simulate_all(model, sampler, mp.steps, savedir, mp.ns, True, dist, rank, world)
     model.close()
     return out
 

@@ -53,6 +53,22 @@ def main():
             print(f"dp_train_check ok [{mode}]: world={world}, 23 iterations, replicas bit-identical, val losses {vals[0]}")
         e.model.close()
         dist.barrier()
+    # eval.lua -mode sim on the p2p run's newest checkpoint: batch files sharded over the ranks == all files on one rank
+    from dynamics_b200 import evaluate
+    argv = ["-mode", "sim", "-name", "dp_p2p", "-test_dataset_folders", "{'balls_n4_t60_ex100_m'}", "-data_root", root,
+            "-logs_root", os.path.join(root, "logs"), "-ns", "1", "-steps", "6"]
+    sharded = evaluate.main(argv)["balls_n4_t60_ex100_m"]
+    dist.barrier()
+    if rank == 0:
+        os.environ["WORLD_SIZE"] = "1"                       # the same driver, unsharded, on rank 0's GPU
+        single = evaluate.main(argv)["balls_n4_t60_ex100_m"]
+        os.environ["WORLD_SIZE"] = str(world)
+        for k in sharded:
+            assert np.array_equal(sharded[k], single[k], equal_nan=True), k
+        log = open(os.path.join(root, "logs", "dp_p2p", "balls_n4_t60_ex100_m_predictions", "gt_divergence.log")).read()
+        assert len(log.splitlines()) == 7
+        print(f"dp_train_check ok [rollout]: {sharded['loss'].shape[0]} batch files sharded over {world} ranks == one rank")
+    dist.barrier()
     dist.destroy_process_group()
 
 
