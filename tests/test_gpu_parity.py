@@ -570,3 +570,49 @@ def test_one_grid_step_walls(model, trained_like_params):
     assert abs(loss3[0] - l_ref) <= TOL * abs(l_ref)
     assert grad_err(model.get_grads(), g_ref) < TOL
     assert model.batch_stats()[1] > 64                             # more than four pair tiles were active
+
+
+# ---- the CUDA path against the committed golden fixtures (tests/golden/*.npz, frozen oracle outputs) ------------------------
+def test_cuda_against_golden_fixtures(model):
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    params = npe.init_params(1234).copy()
+    rng = np.random.default_rng(7)
+    params += (0.05 * rng.standard_normal(params.shape)).astype(np.float32) * np.abs(params).mean()
+    params = params.astype(np.float32)
+    # n4, batch 50: forward, losses, pair table, gradient, one Adam / RMSprop step
+    z = np.load(os.path.join(gold, "n4_b50.npz"))
+    batch = (z["this"], z["context"], z["y"])
+    loss, pred, lv, lw = model.fp(params, batch)
+    assert rel_err(pred[:, :6], z["pred"][:, :6]) < TOL and np.max(np.abs(pred[:, 6:] - z["pred"][:, 6:])) < 1e-5
+    assert rel_err([loss, lv, lw], z["loss3"]) < TOL
+    le, _, lve, lwe = model.fp_batch(None, batch)
+    assert np.max(np.abs(np.stack([le, lve, lwe], 1) - z["loss_per_example"])) < 1e-6
+    idx, mask, cnt = model.pair_table()
+    k = z["closest_indices"].shape[1]
+    assert np.array_equal(idx[:, :k], np.tile(np.arange(k, dtype=np.int32), (50, 1)))     # fixture contexts are already trimmed
+    assert np.array_equal(mask[:, :k], z["nbr_mask"])
+    model.fp(None, batch)
+    g = model.bp()
+    assert np.max(np.abs(g[z["grad_idx"]] - z["grad_sel"])) <= TOL * float(z["grad_absmax"])
+    assert abs(float(g.astype(np.float64).sum()) - float(z["grad_sum"])) <= 1e-3 * float(z["grad_absmax"]) * 50
+    for opt, key in (("adam", "adam_sel"), ("rmsprop", "rmsprop_sel")):
+        model.set_params(params); model.optim_reset(0.0)
+        model._upload(batch)
+        model.train_step(opt, 3e-4)
+        got = model.get_params()[z["grad_idx"]]
+        assert np.max(np.abs(got - z[key])) <= 2e-6 + 1e-4 * 3e-4, opt
+    # walls U: 12 nearest of 32 contexts, bit-exact indices and masks
+    w = np.load(os.path.join(gold, "walls_u_trim.npz"))
+    model.set_params(params)
+    _, wpred, _, _ = model.fp(None, (w["this"], w["context_full"], np.zeros((50, 1, 22), np.float32)))
+    widx, wmask, wcnt = model.pair_table()
+    assert np.array_equal(widx[:, :12], w["closest_indices"].astype(np.int32)) and np.all(wcnt == 12)
+    assert np.array_equal(wmask[:, :12], w["nbr_mask"])
+    assert rel_err(wpred[:, :6], w["pred"][:, :6]) < TOL
+    # rollout n3, 10 steps against ground truth
+    r = np.load(os.path.join(gold, "rollout_n3.npz"))
+    model.upload_scenes(r["states"])
+    traj, met = model.rollout(0, 10, use_gt=True)
+    assert np.max(np.abs(traj[..., 0:4] - r["traj"][..., 0:4])) < 1e-3
+    assert np.allclose(met[:, 0] / met[:, 3], r["m_loss"], rtol=2e-3)
