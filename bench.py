@@ -6,11 +6,15 @@ Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` pri
   workload   = BASELINE.json configs[1]: balls n3/n4/n5, variable mass, batch 50 (reference batch composition)
   value      = samples/s with scenes and the example schedule resident in HBM (device batcher + fwd + bwd + Adam)
   e2e        = the same metric through the reference-facing batch API with HOST buffers: per step H2D of
-               {this, context, y} from pinned memory, train step, D2H of the loss
-  roofline   = dominant kernel of the timed region, bracketed by CUDA events on its stream
-  extra      = the compute-bound shapes (configs[3] S-64 training, configs[4]-style rollout) with their own rooflines
-Multi-GPU (torchrun): weak scaling, one process per GPU, scenes sharded per rank, one NCCL all-reduce of the flat
-gradient per step (divisor = global batch); timing = max over ranks.
+               {this, context, y} from pinned memory + pair builder (second stream, double-buffered slots), train step,
+               loss read back one iteration late (npe_train_batch_async / npe_loss_wait); `blocking_ms_per_step` is the
+               same loop with the loss read before the next step is issued
+  roofline   = dominant kernel of the timed region, every 16th launch bracketed by CUDA events on its stream
+  extra      = the other BASELINE workloads at every N: configs[3] S-64 training (data parallel), configs[4]-style
+               rollout (sharded by trajectory), with their own rooflines
+Multi-GPU (torchrun): weak scaling, one process per GPU, scenes sharded per rank, the flat gradient exchanged every step
+over NVLink peer memory inside the reduce + optimiser kernel (--dp nccl: one ncclAllReduce instead); divisor = global
+batch; timing = max over ranks.
 """
 import argparse
 import json
