@@ -217,10 +217,10 @@ int npe_comm_unique_id(void* id128_out);
 int npe_comm_init(npe_handle* h, int32_t rank, int32_t nranks, const void* id128);
 int npe_allreduce_grads(npe_handle* h); /* sum of flat gradients (+3 loss sums) over ranks, in place */
 /*
- * Fused data-parallel step over NVLink peer memory (replaces reduce + ncclAllReduce + optimiser with two small kernels):
- * every rank exposes an exchange region (its locally reduced gradient, double-buffered, + a ready flag) through CUDA
- * IPC; the optimiser kernel of each rank reads all peers' gradients directly over NVLink, sums them in rank order
- * (identical on every rank -> replicas stay bit-identical) and applies Adam / RMSprop.
+ * Data-parallel step over NVLink peer memory (replaces reduce + ncclAllReduce + optimiser with ONE kernel): every rank
+ * owns an exchange region of 8-byte {gradient, step stamp} cells that the peers map through CUDA IPC; the reduce +
+ * optimiser kernel of each rank pushes its reduced gradient into every peer's region (posted NVLink stores), waits for
+ * the peers' cells in its own region, sums them in rank order (replicas stay bit-identical) and applies Adam / RMSprop.
  *   npe_peer_export: writes this rank's 64-byte IPC handle.  The launcher all-gathers the handles (nranks * 64 bytes).
  *   npe_peer_attach: opens every peer's region.  After it, npe_train_step uses the fused path (NCCL stays available
  *   through npe_allreduce_grads).
