@@ -215,3 +215,33 @@ def test_golden_walls_trim_and_rollout():
     tr, met = rollout.rollout_scenes(_gold_params(), r["states"][:, :, :2], np.full(8, 3), 10, gt=r["states"][:, :, 2:])
     assert np.allclose(tr, r["traj"], rtol=1e-4, atol=1e-5)
     assert np.allclose(met["loss"], r["m_loss"], rtol=1e-3)
+
+
+# ---- property tests (hypothesis): the integer / bit outputs on lattices where ties are common -------------------------------
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(hst.integers(0, 2 ** 31 - 1), hst.integers(2, 30), hst.integers(1, 14))
+def test_trim_and_mask_against_brute_force(seed, n_ctx, k_max):
+    """k_nearest_indices == a per-focus Python sort by (float32 distance, index) on an 80-px lattice (equidistant contexts
+    everywhere); the neighbourhood mask == d*800 <= 210 in float32 on the kept contexts."""
+    rng = np.random.default_rng(seed)
+    B = 6
+    pos = (rng.integers(0, 10, (B, n_ctx + 1, 2)) * 80).astype(np.float32) / np.float32(800)
+    st = np.zeros((B, n_ctx + 1, 2, 22), np.float32)
+    st[:, :, :, 0:2] = pos[:, :, None, :]
+    st[..., 10] = 1                                               # balls
+    this, ctx = st[:, 0], st[:, 1:]
+    idx, d = batcher.k_nearest_indices(this, ctx, k_max)
+    k = min(k_max, n_ctx)
+    for b in range(B):
+        dist_b = [np.sqrt((ctx[b, c, -1, 0] - this[b, -1, 0]) ** 2 + (ctx[b, c, -1, 1] - this[b, -1, 1]) ** 2, dtype=np.float32)
+                  for c in range(n_ctx)]
+        order = sorted(range(n_ctx), key=lambda c: (dist_b[c], c))[:k]
+        assert sorted(order) == idx[b].tolist()
+        assert np.array_equal(np.asarray(dist_b, np.float32), d[b])
+    tctx = np.take_along_axis(ctx, idx[:, :, None, None], axis=1)
+    mask = npe.neighbor_mask(this, tctx, check_focus=False)
+    want = (np.take_along_axis(d, idx, axis=1) * np.float32(800) <= np.float32(210))
+    assert np.array_equal(mask.astype(bool), want)
