@@ -616,3 +616,23 @@ def test_cuda_against_golden_fixtures(model):
     traj, met = model.rollout(0, 10, use_gt=True)
     assert np.max(np.abs(traj[..., 0:4] - r["traj"][..., 0:4])) < 1e-3
     assert np.allclose(met[:, 0] / met[:, 3], r["m_loss"], rtol=2e-3)
+
+
+@pytest.mark.parametrize("n_ctx", [2, 5, 8, 9, 15, 16, 17, 30, 45, 63])
+def test_pair_builder_bit_exact_on_lattices(model, n_ctx):
+    """Pair indices, kept counts and neighbourhood masks of the CUDA builder == the oracle on an 80-px lattice where
+    equidistant contexts are everywhere (tie rule: smaller distance, then lower index), for every lane-group variant of
+    the builder (8 / 16 / 32 lanes per focus), with the 12-nearest trim active from 13 contexts on."""
+    rng = np.random.default_rng(100 + n_ctx)
+    B = 64
+    pos = (rng.integers(0, 10, (B, n_ctx + 1, 2)) * 80).astype(np.float32) / np.float32(800)
+    st = np.zeros((B, n_ctx + 1, 2, 22), np.float32)
+    st[:, :, :, 0:2] = pos[:, :, None, :]
+    st[..., 6] = 1; st[..., 10] = 1; st[..., 14] = 1; st[..., 16] = 1; st[..., 18] = 1; st[..., 20] = 1
+    this, ctx = st[:, 0], st[:, 1:]
+    model.fp(npe.init_params(1), (this, ctx, np.zeros((B, 1, 22), np.float32)))
+    idx, mask, cnt = model.pair_table()
+    oidx, omask, _ = oracle_pairs(this, ctx, 12)
+    k = oidx.shape[1]
+    assert np.all(cnt == k) and np.array_equal(idx[:, :k], oidx.astype(np.int32))
+    assert np.array_equal(mask[:, :k], omask.astype(np.uint8))
