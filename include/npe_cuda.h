@@ -172,7 +172,8 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
  */
 int npe_train_step_async(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, int32_t slot);
 int npe_loss_wait(npe_handle* h, int32_t slot, float* loss3_out);
-/* feval_train + optimiser of one host batch in one call: npe_batch_upload followed by npe_train_step_async. */
+/* feval_train + optimiser (main.lua:247-269,301-302) of one host batch in one call: npe_batch_upload followed by
+ * npe_train_step_async. */
 int npe_train_batch_async(npe_handle* h, const float* this_past, const float* context, const float* y, int32_t B, int32_t C,
                           int32_t opt, float lr, int32_t divisor_batch, int32_t slot);
 
