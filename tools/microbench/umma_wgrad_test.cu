@@ -42,25 +42,34 @@ __global__ void __launch_bounds__(128, 1) k_wgrad(const float* dZ, const float* 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&S.tmem_slot)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&S.tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = S.tmem_slot;
+    // the rows are in registers when the timing starts (in the chain kernels they come out of the epilogue)
+    float zr[NN], hr[KK];
+#pragma unroll
+    for (int n = 0; n < NN; ++n) { zr[n] = dZ[t * NN + n]; hr[n] = H[t * KK + n]; }
+    __syncthreads();
     long long t0 = clock64();
     // transposed, split stores: thread t = row r; the column order is rotated by r / 4 so that the 8 threads of a warp that
     // share r % 4 hit different banks
     {
         const int r = t;
         const int base = (r >> 2) * (NN * 4) + (r & 3);
+#pragma unroll
         for (int j = 0; j < NN; ++j) {
             const int n = (j + (r >> 2)) & (NN - 1);
-            const float z = dZ[r * NN + n], h = H[r * KK + n];
+            float z = 0.f, h = 0.f;
+#pragma unroll
+            for (int q = 0; q < NN; ++q) { if (q == j) { z = zr[q]; h = hr[q]; } }     // static register index; rotation by address only
+            (void)n;
             const float zh = tf32_hi(z), hh = tf32_hi(h);
-            S.Ah[base + n * 4] = zh; S.Al[base + n * 4] = z - zh;
-            S.Bh[base + n * 4] = hh; S.Bl[base + n * 4] = h - hh;
+            S.Ah[base + j * 4] = zh; S.Al[base + j * 4] = z - zh;
+            S.Bh[base + j * 4] = hh; S.Bl[base + j * 4] = h - hh;
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -92,6 +101,31 @@ __global__ void __launch_bounds__(128, 1) k_wgrad(const float* dZ, const float* 
         ::"r"(smem_u32(&S.bar)) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     long long t2 = clock64();
+    // the same 48 MMAs twice into two INDEPENDENT accumulators (two layers of a tile in flight): issue-bound or chain-bound?
+    if (t == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KK >> 3) << 17) | ((uint32_t)(m_val >> 4) << 24);
+        for (int pass = 0; pass < 3; ++pass) {
+            const float* sA = pass == 2 ? S.Al : S.Ah;
+            const float* sB = pass == 1 ? S.Bl : S.Bh;
+            for (int s = 0; s < R / 8; ++s) {
+                const uint64_t da = make_desc(smem_u32(sA) + 2 * s * NN * 16, NN * 16, 128);
+                const uint64_t db = make_desc(smem_u32(sB) + 2 * s * KK * 16, KK * 16, 128);
+                const uint32_t acc = (pass > 0 || s > 0);
+                for (int which = 0; which < 2; ++which)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem + 64 + 64 * which), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&S.bar)) : "memory");
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT2_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 1;\n\t@p bra DONE2_%=;\n\tbra WAIT2_%=;\n\tDONE2_%=:\n\t}"
+        ::"r"(smem_u32(&S.bar)) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    long long t3 = clock64();
     // dump all 128 lanes x 64 columns: the host finds where row n of the accumulator lives
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t v[64];
@@ -106,10 +140,10 @@ __global__ void __launch_bounds__(128, 1) k_wgrad(const float* dZ, const float* 
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     for (int c = 0; c < 64; ++c) dump[t * 64 + c] = __uint_as_float(v[c]);
-    if (t == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t1; }
+    if (t == 0) { cycles[0] = t1 - t0; cycles[1] = t2 - t1; cycles[2] = t3 - t2; }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
 }
 
 int main() {
@@ -125,7 +159,7 @@ int main() {
             ref[n * KK + k] = (float)s; mx = fmax(mx, fabs(s));
         }
     float *dz, *dh, *dd; long long* dc;
-    cudaMalloc(&dz, dZ.size() * 4); cudaMalloc(&dh, H.size() * 4); cudaMalloc(&dd, dump.size() * 4); cudaMalloc(&dc, 16);
+    cudaMalloc(&dz, dZ.size() * 4); cudaMalloc(&dh, H.size() * 4); cudaMalloc(&dd, dump.size() * 4); cudaMalloc(&dc, 24);
     cudaMemcpy(dz, dZ.data(), dZ.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dh, H.data(), H.size() * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
@@ -136,7 +170,7 @@ int main() {
         printf("M = %d: %s\n", m_val, cudaGetErrorString(e));
         if (e != cudaSuccess) return 1;
         cudaMemcpy(dump.data(), dd, dump.size() * 4, cudaMemcpyDeviceToHost);
-        long long cyc[2]; cudaMemcpy(cyc, dc, 16, cudaMemcpyDeviceToHost);
+        long long cyc[3]; cudaMemcpy(cyc, dc, 24, cudaMemcpyDeviceToHost);
         // locate every accumulator row: the TMEM lane whose 64 columns match ref[n][:]
         int found = 0; double emax = 0; int lane_of[NN];
         for (int n = 0; n < NN; ++n) {
@@ -147,8 +181,8 @@ int main() {
                 if (e2 < 1e-3 * mx) { lane_of[n] = lane; emax = fmax(emax, e2); ++found; break; }
             }
         }
-        printf("  rows located %d / %d, max err vs fp64 %.3e (rel %.2e), cycles: transpose+split %lld, 48 MMA + commit %lld\n",
-               found, NN, emax, emax / mx, cyc[0], cyc[1]);
+        printf("  rows located %d / %d, max err vs fp64 %.3e (rel %.2e), cycles: transpose+split (rows in registers) %lld, 48 MMA + commit %lld, 2 x 48 MMA into two accumulators %lld\n",
+               found, NN, emax, emax / mx, cyc[0], cyc[1], cyc[2]);
         printf("  lane of row n: n=0 -> %d, 1 -> %d, 15 -> %d, 16 -> %d, 17 -> %d, 31 -> %d, 32 -> %d, 47 -> %d, 48 -> %d, 63 -> %d\n",
                lane_of[0], lane_of[1], lane_of[15], lane_of[16], lane_of[17], lane_of[31], lane_of[32], lane_of[47], lane_of[48], lane_of[63]);
     }
