@@ -7,8 +7,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnpe_cuda.so")
 SOURCES = ["npe_api.cu"]
-HEADERS = ["npe_layout.h", "npe_tile.cuh", "npe_mma16.cuh", "npe_kernels.cuh", "npe_rollout.cuh", "npe_umma.cuh", "npe_tc.cuh",
-           os.path.join("..", "..", "include", "npe_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -17,7 +15,9 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "npe_cuda.h"))
+    return any(os.path.getmtime(f) > t for f in deps)
 
 
 def build(force=False, verbose=False):

@@ -97,6 +97,9 @@ struct npe_handle {
     bool wtc3_dirty = true;
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
+    int train_stash = 1;              // forward writes the pair activations for the backward kernels (0: recompute)
+    int bwd_tc = 1;                   // large training batches: backward (input + weight gradients) on tcgen05
+    int small_batch_max = -1;         // foci up to which the 16-row latency mapping is used (-1: 4 * SM count)
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
     int roll_F = 0;
@@ -167,6 +170,10 @@ struct npe_handle {
     cudaEvent_t ring_ev[64] = {};     // npe_train_step_async / npe_loss_wait: one event per ring slot (slot i at loss4_host + 16 + 4 i)
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
+    // The last launch on the main stream was a pair builder: the next kernel must not be a programmatic dependent of it
+    // (it would read the pair tables before griddepcontrol.wait, and only the wait guarantees the builder's writes are
+    // visible).  launch_pdl drops the attribute once and clears the flag.
+    bool after_builder = false;
     DevBuf<int> ctx_idx_out, cnt_out;
     DevBuf<unsigned char> mask_out;
 
@@ -192,6 +199,7 @@ struct npe_handle {
     bool peer_opened[MAX_PEERS] = {};
     bool peer_ready = false;
     unsigned peer_step = 0;
+    int peer_timeout_ms = 10000;      // k_dp_step gives up on a peer's gradient cell after this long (NPE_OPT_PEER_TIMEOUT_MS)
 
     FocusSrc src() const {
         FocusSrc s;
@@ -259,13 +267,17 @@ __global__ void k_batch_foci(int* scene, int* obj, int* t0, int* n_obj, int B, i
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; it calls
 // griddepcontrol.wait before touching predecessor outputs.
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+cudaError_t launch_pdl(npe_handle* h, void (*kernel)(KArgs...), int grid, int block, size_t smem, Args... args) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.attrs = attr;
+    // directly after a pair builder: a plain (fully serialised) launch, because the kernels below read the builder's
+    // outputs in their prologue, before griddepcontrol.wait
+    cfg.numAttrs = h->after_builder ? 0 : 1;
+    h->after_builder = false;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -305,6 +317,7 @@ void launch_build_pairs(npe_handle* h, int nblk, int nmax, Args... args) {
     else if (nmax - 1 <= 16) k_build_pairs<16><<<nblk, 1024, 0, h->stream>>>(args...);
     else k_build_pairs<32><<<nblk, NT_PAIRS, 0, h->stream>>>(args...);
     h->launches++;
+    h->after_builder = true;
 }
 
 int build_pairs(npe_handle* h) {
@@ -339,8 +352,20 @@ int check_pair_overflow(npe_handle* h) {
     return NPE_OK;
 }
 
+// After a synchronisation point in peer mode: k_dp_step sets info[1] = 3 when a peer's gradient never arrived.
+int check_peer_timeout(npe_handle* h) {
+    int info[2] = {0, 0};
+    CK(cudaMemcpy(info, h->info_dev, sizeof info, cudaMemcpyDeviceToHost));
+    if (info[1] == 3) {
+        cudaMemset(h->info_dev + 1, 0, sizeof(int));
+        return fail(h, NPE_ERR_CUDA, "data-parallel step: a peer rank did not deliver its gradient within %d ms "
+                                     "(rank fault, or ranks issued different numbers of steps); results are invalid", h->peer_timeout_ms);
+    }
+    return NPE_OK;
+}
+
 // Small batches take the 16-row (latency) mapping: more CTAs, each pass ~3x shorter; large ones the 64-row mapping.
-bool small_batch(const npe_handle* h, int F) { return F <= 16 * h->num_sms / 4; }
+bool small_batch(const npe_handle* h, int F) { return F <= (h->small_batch_max >= 0 ? h->small_batch_max : 16 * h->num_sms / 4); }
 
 int pair_grid(const npe_handle* h, int rows) {
     const long long tiles = ((long long)h->pair_cap + rows - 1) / rows;
@@ -401,16 +426,16 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
         if (small_batch(h, F)) {
-            CK(launch_pdl(k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>), h->stream,
+            CK(launch_pdl(h, k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>),
                           st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
             if (!skip_decoder)
-                CK(launch_pdl(k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>), h->stream,
+                CK(launch_pdl(h, k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>),
                               st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         } else {
-            CK(launch_pdl(k_pair_forward<64>, pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>), h->stream,
+            CK(launch_pdl(h, k_pair_forward<64>, pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>),
                           st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
             if (!skip_decoder)
-                CK(launch_pdl(k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>), h->stream,
+                CK(launch_pdl(h, k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>),
                               st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         }
         h->launches += skip_decoder ? 1 : 2;
@@ -426,7 +451,7 @@ int run_forward(npe_handle* h, bool training, bool fused = false) {
     if (rc) return rc;
     // training forward: FP32 FFMA kernels, or (train_fwd_tc) the FP32-grade tcgen05 pair kernel; never single-pass TF32
     const int tc = training ? (h->train_fwd_tc && !small_batch(h, h->F) ? NPE_PRECISION_TF32X3_TC : 0) : h->precision;
-    float* stash = (training && h->have_y) ? training_stash(h) : nullptr;
+    float* stash = (training && h->have_y && h->train_stash) ? training_stash(h) : nullptr;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->yptr() : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused);
     if (rc) return rc;
@@ -455,6 +480,7 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
     r.opt = peer_opt ? peer_opt : fuse_opt;
     r.peer = peer_opt != 0;
     r.P.nranks = h->nranks; r.P.rank = h->rank;
+    r.P.abort = h->info_dev + 1; r.P.timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
     for (int q = 0; q < MAX_PEERS; ++q) r.P.region[q] = (r.peer && q < h->nranks) ? (uint2*)h->peer_ptr[q] : nullptr;
     if (r.peer) {
         r.buf = (int)(h->peer_step & 1u);
@@ -477,11 +503,11 @@ int launch_reduce(npe_handle* h, int gp, int gd, int fuse_opt, float lr, bool wa
     ProfScope ps__(h, NPE_K_REDUCE);
     const ReducePlan r = prepare_reduce(h, fuse_opt, lr, want_loss, peer_opt);
     const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
-    if (r.peer && r.opt == 1) CK(launch_pdl(k_dp_step<1>, nb, 256, 0, h->stream, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
-    else if (r.peer) CK(launch_pdl(k_dp_step<2>, nb, 256, 0, h->stream, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
-    else if (r.opt == 1) CK(launch_pdl(k_reduce_grads<1>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
-    else if (r.opt == 2) CK(launch_pdl(k_reduce_grads<2>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
-    else CK(launch_pdl(k_reduce_grads<0>, nb, 256, 0, h->stream, h->partial, gp, gd, h->grads, r.o, r.L));
+    if (r.peer && r.opt == 1) CK(launch_pdl(h, k_dp_step<1>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
+    else if (r.peer) CK(launch_pdl(h, k_dp_step<2>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
+    else if (r.opt == 1) CK(launch_pdl(h, k_reduce_grads<1>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
+    else if (r.opt == 2) CK(launch_pdl(h, k_reduce_grads<2>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
+    else CK(launch_pdl(h, k_reduce_grads<0>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
     h->launches++;
     CK(cudaGetLastError());
     return NPE_OK;
@@ -504,11 +530,11 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
     {
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
         if (small)
-            CK(launch_pdl(k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->stream, h->states.p, h->foc_row.p, h->F,
+            CK(launch_pdl(h, k_dec_backward<16>, gd, NT, sizeof(DecBwdSmem<16>), h->states.p, h->foc_row.p, h->F,
                           h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
                           fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         else
-            CK(launch_pdl(k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->stream, h->states.p, h->foc_row.p, h->F,
+            CK(launch_pdl(h, k_dec_backward<64>, gd, NT, sizeof(DecBwdSmem<64>), h->states.p, h->foc_row.p, h->F,
                           h->pair_start.p, h->Hp.p, h->wpack, h->yptr(), h->ds.p, h->partial, sv, sw,
                           fused_fwd ? h->pred.p : nullptr, fused_fwd ? h->loss_ex.p : nullptr));
         h->launches++;
@@ -516,11 +542,11 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
         if (small)
-            CK(launch_pdl(k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->stream, h->states.p, h->pair_foc.p,
+            CK(launch_pdl(h, k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->states.p, h->pair_foc.p,
                           h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
                           h->hact_valid ? h->hact.p : nullptr));
         else
-            CK(launch_pdl(k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->stream, h->states.p, h->pair_foc.p,
+            CK(launch_pdl(h, k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->states.p, h->pair_foc.p,
                           h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
                           h->hact_valid ? h->hact.p : nullptr));
         h->launches++;
@@ -555,7 +581,7 @@ int run_step_fused(npe_handle* h, int divisor_batch, int fuse_opt, float lr, boo
     A.trace = h->step_trace;
     {
         ProfScope ps__(h, NPE_K_STEP_FUSED);
-        CK(launch_pdl(k_step_fused, gp + gd, NT, sizeof(StepSmem), h->stream, A));
+        CK(launch_pdl(h, k_step_fused, gp + gd, NT, sizeof(StepSmem), A));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -837,6 +863,7 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
     rc = (e == cudaSuccess) ? build_pairs(h) : NPE_OK;
     if (e == cudaSuccess && rc == NPE_OK) e = cudaEventRecord(h->slot_ready, h->stream);
     h->stream = main_stream;
+    h->after_builder = false;   // the builder ran on the upload stream; the event wait below is a full dependency
     if (e != cudaSuccess) return fail(h, NPE_ERR_CUDA, "batch_upload: %s", cudaGetErrorString(e));
     if (rc) return rc;
     CK(cudaStreamWaitEvent(h->stream, h->slot_ready, 0));   // later work on the main stream sees the new batch
@@ -1057,6 +1084,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
     if (want_loss && !h->loss4_override) {
         // the loss kernel wrote {loss, vel, angvel, overflow} straight into host-mapped memory: one sync, no copy
         CK(cudaStreamSynchronize(h->stream));
+        if (h->peer_ready) { int rcp = check_peer_timeout(h); if (rcp) return rcp; }
         if (h->loss4_host[3] == 2.f) return fail(h, NPE_ERR_CUDA, "k_step_fused: a tile waited too long for its producer; results are invalid");
         if (h->loss4_host[3] != 0.f)
             return fail(h, NPE_ERR_NOMEM, "active-pair list overflow (capacity %d pairs); results are invalid", h->pair_cap);
@@ -1103,6 +1131,7 @@ static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* 
         else if (h->Nmax - 1 <= 16) k_build_pairs_sched<16><<<n, 1024, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
         else k_build_pairs_sched<32><<<n, NT_PAIRS, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
         h->launches++;
+        h->after_builder = true;
     }
     CKL();
     *fmax_out = fmax; *cap_out = cap;
@@ -1181,6 +1210,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
         }
+        h->loss4_override = nullptr;   // only the npe_train_step calls above may see it (every return path below is clean)
         h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
         h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
         if (sched) { h->pairs_valid = false; h->fwd_valid = false; h->F = 0; }
@@ -1190,8 +1220,10 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             CK(cudaMemcpyAsync(info.data(), h->sched.info.p, info.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CK(cudaStreamSynchronize(h->stream));
             for (int i = 0; i < n; ++i) {
+                if (info[(size_t)2 * i + 1] == 0) continue;
                 if (info[(size_t)2 * i + 1] == 2) return fail(h, NPE_ERR_CUDA, "train_steps: step %d: a tile waited too long for its producer; results are invalid", s0 + i);
-                if (info[(size_t)2 * i + 1] != 0) return fail(h, NPE_ERR_NOMEM, "train_steps: active-pair list overflow in step %d (capacity %d pairs)", s0 + i, cap);
+                if (info[(size_t)2 * i + 1] == 3) return fail(h, NPE_ERR_CUDA, "train_steps: step %d: a peer rank did not deliver its gradient in time; results are invalid", s0 + i);
+                return fail(h, NPE_ERR_NOMEM, "train_steps: active-pair list overflow in step %d (capacity %d pairs)", s0 + i, cap);
             }
         }
     }
@@ -1419,8 +1451,11 @@ int npe_peer_attach(npe_handle* h, int32_t rank, int32_t nranks, const void* all
     if (!h->xregion) return fail(h, NPE_ERR_STATE, "peer_attach: call npe_peer_export first");
     for (int r = 0; r < nranks; ++r) {
         if (r == rank) { h->peer_ptr[r] = h->xregion; continue; }
-        cudaIpcMemHandle_t hd;
+        cudaIpcMemHandle_t hd, own;
         memcpy(&hd, (const char*)all_handles + (size_t)r * NPE_PEER_HANDLE_BYTES, sizeof hd);
+        // a handle that names this rank's own region (single-process tests of the missing-peer path): no IPC open
+        CK(cudaIpcGetMemHandle(&own, h->xregion));
+        if (memcmp(&hd, &own, sizeof hd) == 0) { h->peer_ptr[r] = h->xregion; continue; }
         CK(cudaIpcOpenMemHandle(&h->peer_ptr[r], hd, cudaIpcMemLazyEnablePeerAccess));
         h->peer_opened[r] = true;
     }
@@ -1439,6 +1474,23 @@ int npe_allreduce_grads(npe_handle* h) {
 int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
+    if (h->peer_ready) return check_peer_timeout(h);
+    return NPE_OK;
+}
+
+int npe_set_option(npe_handle* h, int32_t option, int32_t value) {
+    NEED(h);
+    switch (option) {
+        case NPE_OPT_TRAIN_FWD_TC: h->train_fwd_tc = value != 0; break;
+        case NPE_OPT_TRAIN_STASH: h->train_stash = value != 0; break;
+        case NPE_OPT_BWD_TC: h->bwd_tc = value != 0; break;
+        case NPE_OPT_PEER_TIMEOUT_MS:
+            if (value < 1) return fail(h, NPE_ERR_INVALID, "set_option: peer timeout must be >= 1 ms");
+            h->peer_timeout_ms = value; break;
+        case NPE_OPT_SMALL_BATCH_MAX: h->small_batch_max = value; break;
+        default: return fail(h, NPE_ERR_INVALID, "set_option: unknown option %d", option);
+    }
+    h->fwd_valid = false; h->hact_valid = false;
     return NPE_OK;
 }
 

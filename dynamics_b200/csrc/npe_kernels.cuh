@@ -1045,7 +1045,14 @@ constexpr size_t DP_REGION_BYTES = 2ull * MAX_PEERS * DP_NPAD * sizeof(uint2);
 struct DpArgs {
     uint2* region[MAX_PEERS];             // exchange regions of all ranks (own region at index `rank`)
     int nranks, rank;
+    int* abort;                           // info[1]: set to 3 when a peer's cell does not arrive within timeout_ns
+    unsigned long long timeout_ns;
 };
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void st_cell(uint2* p, float v, unsigned stamp) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(stamp) : "memory");
 }
@@ -1067,8 +1074,21 @@ __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, 
     for (int r = 0; r < P.nranks; ++r) {                 // rank order
         float v = a;
         if (r != P.rank) {
+            // Bounded wait (like wait_flags of the one-grid step): a peer that faulted, stopped stepping or issued a
+            // different number of steps must surface as an error on this rank, not as a wedged GPU.  Ranks have to issue
+            // the same number of npe_train_step calls.
             uint2 c = ld_cell(in + (size_t)r * DP_NPAD);
-            while (c.y != stamp) c = ld_cell(in + (size_t)r * DP_NPAD);
+            if (c.y != stamp) {
+                const unsigned long long t0 = global_ns();
+                int spins = 0;
+                while ((c = ld_cell(in + (size_t)r * DP_NPAD)).y != stamp) {
+                    if (++spins > 64) {
+                        __nanosleep(64);
+                        if ((spins & 255) == 0 &&
+                            (*(volatile int*)P.abort == 3 || global_ns() - t0 > P.timeout_ns)) { *P.abort = 3; break; }
+                    }
+                }
+            }
             v = __uint_as_float(c.x);
         }
         g += v;

@@ -67,6 +67,7 @@ SIGNATURES = {
     "npe_rollout_resident": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "npe_set_precision": (C.c_int, [_H, C.c_int32]),
     "npe_set_rollout_mode": (C.c_int, [_H, C.c_int32]),
+    "npe_set_option": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "npe_comm_unique_id": (C.c_int, [C.c_void_p]),
     "npe_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "npe_allreduce_grads": (C.c_int, [_H]),
@@ -120,6 +121,7 @@ def load_library(path=LIB_PATH):
     return _LIB
 
 
+OPTIONS = {"train_fwd_tc": 0, "train_stash": 1, "bwd_tc": 2, "peer_timeout_ms": 3, "small_batch_max": 4}
 KERNEL_IDS = {"build_pairs": 0, "forward": 1, "dec_backward": 2, "pair_backward": 3, "reduce": 4, "optim": 5,
               "rollout": 6, "targets": 7, "step_fused": 8}
 

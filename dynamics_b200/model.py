@@ -314,6 +314,11 @@ class NPEModel:
         """'fp32' (FFMA kernels, default), 'tf32' (tcgen05, single pass) or 'tf32x3' (tcgen05, FP32-grade split)."""
         self._ck(self.lib.npe_set_precision(self.h, {"fp32": 0, "tf32": 1, "tf32x3": 2}[mode]))
 
+    def set_option(self, name, value):
+        """Kernel-dispatch switches (include/npe_cuda.h NPE_OPT_*): 'train_fwd_tc', 'train_stash', 'bwd_tc',
+        'peer_timeout_ms', 'small_batch_max'."""
+        self._ck(self.lib.npe_set_option(self.h, L.OPTIONS[name], int(value)))
+
     def set_rollout_mode(self, mode):
         """'persistent' (one kernel, window on chip) or 'kernels' (window in HBM, 5 launches per step)."""
         self._ck(self.lib.npe_set_rollout_mode(self.h, {"persistent": 0, "kernels": 1}[mode]))

@@ -212,6 +212,21 @@ int npe_rollout_resident(npe_handle* h, int32_t t0, int32_t steps, int64_t* obje
 #define NPE_ROLLOUT_BY_KERNELS 1
 int npe_set_precision(npe_handle* h, int32_t mode);
 int npe_set_rollout_mode(npe_handle* h, int32_t mode);
+/*
+ * Kernel-dispatch switches of the training step (model:fp + model:bp, npe.lua:225-336).  Every combination computes the
+ * same function; they exist so that each kernel family can be compared with the oracle and with the others.
+ *   NPE_OPT_TRAIN_FWD_TC     1 (default): large batches run the pair forward on the FP32-grade 3xTF32 tcgen05 kernel; 0: FFMA
+ *   NPE_OPT_TRAIN_STASH      1 (default): the forward writes the pair activations for the backward; 0: the backward recomputes
+ *   NPE_OPT_BWD_TC           1 (default): large batches run input- and weight-gradients on tcgen05 (3xTF32); 0: FFMA kernels
+ *   NPE_OPT_PEER_TIMEOUT_MS  how long the data-parallel step waits for a peer's gradient before failing (default 10000)
+ *   NPE_OPT_SMALL_BATCH_MAX  foci up to which the 16-row latency mapping is used (-1 = default, 4 x SM count)
+ */
+#define NPE_OPT_TRAIN_FWD_TC 0
+#define NPE_OPT_TRAIN_STASH 1
+#define NPE_OPT_BWD_TC 2
+#define NPE_OPT_PEER_TIMEOUT_MS 3
+#define NPE_OPT_SMALL_BATCH_MAX 4
+int npe_set_option(npe_handle* h, int32_t option, int32_t value);
 
 /* Data-parallel: one handle per GPU/process.  id = 128-byte ncclUniqueId from npe_comm_unique_id on rank 0. */
 int npe_comm_unique_id(void* id128_out);

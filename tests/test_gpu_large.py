@@ -1,0 +1,223 @@
+"""-m gpu parity tests of the THROUGHPUT regime (more than 592 foci): every kernel family that the large-batch training
+step, the large forward and the rollout-by-kernels dispatch to is compared with the CPU oracle, at sizes where the
+persistent tile loops of each kernel wrap (more tiles than resident CTAs / tile groups on a 148-SM part).
+
+  configs[1]/[4]-style data: 5120 eight-ball scenes -> 40 960 foci, ~80 k active pairs
+      64-row FFMA tiles: 640 focus tiles, > 1 200 pair tiles (148 CTAs)
+      128-row tcgen05 tiles: 320 focus tiles, > 600 pair tiles (296 tile groups)
+  configs[3]-style data: 64-ball scenes, 12-NN trim off (63 context slots, 32-lane pair builder), 4 096 foci
+
+Dispatches of npe_train_step / npe_forward + npe_backward (include/npe_cuda.h NPE_OPT_*):
+  default      tcgen05 3xTF32 forward + activation stash + tcgen05 backward
+  ffma_bwd     tcgen05 3xTF32 forward + activation stash + FFMA <64> backward kernels
+  ffma         FFMA <64> forward + stash + FFMA <64> backward
+  recompute    FFMA <64> forward, no stash: the backward recomputes the pair chain
+Tolerances: masks bit-exact, pred / loss 1e-4 relative, gradient 1e-4 of ||g||_inf, parameters after one
+Adam step 1e-4 of ||x||_inf; single-pass TF32 forward 2e-3.  The achieved errors are printed (pytest -s shows them).
+"""
+import numpy as np
+import pytest
+
+from oracle import batcher, npe, optim, rollout, scenes
+from tests.util import grad_err, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+TOL_TF32 = 2e-3
+DISPATCH = {
+    "default": dict(train_fwd_tc=1, train_stash=1, bwd_tc=1),
+    "ffma_bwd": dict(train_fwd_tc=1, train_stash=1, bwd_tc=0),
+    "ffma": dict(train_fwd_tc=0, train_stash=1, bwd_tc=0),
+    "recompute": dict(train_fwd_tc=0, train_stash=0, bwd_tc=0),
+}
+
+
+def scene_examples(st, t0):
+    """(this (F,2,22), ctx (F,N-1,2,22), y (F,1,22)) of every object of every scene at window t0, scene-major /
+    object-minor: the order of npe_select_windows."""
+    S, N = st.shape[:2]
+    others = np.array([[j for j in range(N) if j != o] for o in range(N)])
+    this = st[:, :, t0:t0 + 2].reshape(S * N, 2, 22)
+    ctx = st[:, others][:, :, :, t0:t0 + 2].reshape(S * N, N - 1, 2, 22)
+    y = batcher.relative_pair(this, st[:, :, t0 + 2:t0 + 3].reshape(S * N, 1, 22))
+    return this, ctx, y
+
+
+def oracle_chunked(params, this, ctx, y, chunk=4096):
+    """npe.fp_batch / npe.bp over chunks of foci (examples are independent; the gradient is a sum with the FULL batch
+    as divisor, npe.lua:304-315)."""
+    F = this.shape[0]
+    preds, les, masks = [], [], []
+    g = np.zeros(params.size, np.float64)
+    for a in range(0, F, chunk):
+        b = (this[a:a + chunk], ctx[a:a + chunk], y[a:a + chunk])
+        gi, pred = npe.bp(params, b, divisor_batch=F)
+        g += gi
+        le, lv, lw = npe.losses_per_example(pred, b[2].reshape(len(pred), -1))
+        preds.append(pred); les.append(np.stack([le, lv, lw], 1)); masks.append(npe.neighbor_mask(b[0], b[1]))
+    pred = np.concatenate(preds); le = np.concatenate(les)
+    lv = np.float64(2.0) * le[:, 1].astype(np.float64).sum(); lw = le[:, 2].astype(np.float64).sum()
+    loss3 = np.array([(lv + lw) / (3 * F), lv / (2 * F), lw / F])
+    return dict(pred=pred, le=le, loss3=loss3, grad=g.astype(np.float32), mask=np.concatenate(masks))
+
+
+@pytest.fixture(scope="module")
+def n8(trained_like_params):
+    st = scenes.raw_to_state(scenes.gen_balls(5120, 8, 4, seed=88))
+    this, ctx, y = scene_examples(st, 0)
+    ref = oracle_chunked(trained_like_params, this, ctx, y)
+    x = trained_like_params.copy()
+    optim.adam_step(x, ref["grad"], optim.adam_init(x.size), 3e-4)
+    ref["adam"] = x
+    return st, ref
+
+
+@pytest.fixture(scope="module")
+def s64(trained_like_params):
+    st = scenes.raw_to_state(scenes.gen_big(64, 64, 3, seed=66))
+    this, ctx, y = scene_examples(st, 0)
+    ref = oracle_chunked(trained_like_params, this, ctx, y, chunk=1024)
+    x = trained_like_params.copy()
+    optim.adam_step(x, ref["grad"], optim.adam_init(x.size), 3e-4)
+    ref["adam"] = x
+    return st, ref
+
+
+def make_model(max_ctx, opts):
+    from dynamics_b200 import ModelParams, NPEModel
+    m = NPEModel(ModelParams(max_ctx=max_ctx))
+    for k, v in opts.items():
+        m.set_option(k, v)
+    return m
+
+
+def run_training_checks(m, st, ref, params, tag):
+    S = st.shape[0]
+    m.set_params(params); m.optim_reset(0.0)
+    m.upload_scenes(st)
+    m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+    F = m.select_windows(0, S)
+    assert F == ref["pred"].shape[0] and F > 592
+    idx, mask, cnt = m.pair_table()
+    assert np.array_equal(mask[:, :ref["mask"].shape[1]], ref["mask"].astype(np.uint8))          # bit-exact
+    f, p = m.batch_stats()
+    assert p == int(ref["mask"].sum())
+    # model:fp + model:bp as separate calls (training forward: FP32-grade kernels whatever the inference precision)
+    pred, loss3 = m.forward_current()
+    e_pred = rel_err(pred[:, :6], ref["pred"][:, :6]); e_loss = rel_err(loss3, ref["loss3"], 1e-6)
+    g = m.bp()
+    e_g = grad_err(g, ref["grad"])
+    ents, _ = npe.param_layout()
+    worst = max((grad_err(g[o:o + int(np.prod(s))], ref["grad"][o:o + int(np.prod(s))]), n) for n, o, s in ents)
+    # run-to-run determinism of the whole path
+    m.forward_current()
+    assert np.array_equal(m.bp(), g), "gradient not run-to-run deterministic"
+    # feval_train + optimiser in one call
+    l3 = m.train_step("adam", 3e-4)
+    e_l3 = rel_err(l3, ref["loss3"], 1e-6)
+    e_gs = grad_err(m.get_grads(), ref["grad"])
+    e_x = float(np.max(np.abs(m.get_params() - ref["adam"])) / np.max(np.abs(ref["adam"])))
+    print(f"[{tag}] F={F} P={p}: pred {e_pred:.2e} loss {e_loss:.2e} grad {e_g:.2e} (worst block {worst[0]:.2e} {worst[1]}) "
+          f"step: loss {e_l3:.2e} grad {e_gs:.2e} params {e_x:.2e}")
+    assert e_pred < TOL and e_loss < TOL
+    assert e_g < TOL and worst[0] < 5e-4, worst
+    assert e_l3 < TOL and e_gs < TOL and e_x < TOL
+
+
+@pytest.mark.parametrize("dispatch", list(DISPATCH))
+def test_large_train_step_n8(n8, trained_like_params, dispatch):
+    """40 960 foci / ~80 k active pairs: every persistent loop of the training kernels wraps at least twice."""
+    st, ref = n8
+    m = make_model(12, DISPATCH[dispatch])
+    try:
+        run_training_checks(m, st, ref, trained_like_params, f"n8/{dispatch}")
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("dispatch", list(DISPATCH))
+def test_large_train_step_s64(s64, trained_like_params, dispatch):
+    """configs[3] shape: 64-ball scenes, trim off, 4 096 foci (7x the small-batch switch)."""
+    st, ref = s64
+    m = make_model(0, DISPATCH[dispatch])
+    try:
+        run_training_checks(m, st, ref, trained_like_params, f"s64/{dispatch}")
+    finally:
+        m.close()
+
+
+@pytest.mark.parametrize("dispatch", ["default", "ffma"])
+def test_forced_large_path_on_reference_batch(model, trained_like_params, dispatch):
+    """The reference's batch of 50 pushed through the large-batch kernels (NPE_OPT_SMALL_BATCH_MAX = 0): partial
+    tiles, a single CTA, and the golden n4 fixture as the anchor."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "n4_b50.npz"))
+    batch = (z["this"], z["context"], z["y"])
+    for k, v in DISPATCH[dispatch].items():
+        model.set_option(k, v)
+    model.set_option("small_batch_max", 0)
+    loss, pred, lv, lw = model.fp(trained_like_params, batch)
+    assert rel_err(pred[:, :6], z["pred"][:, :6]) < TOL and rel_err([loss, lv, lw], z["loss3"]) < TOL
+    g = model.bp()
+    g_ref, _ = npe.bp(trained_like_params, batch)
+    assert grad_err(g, g_ref) < TOL
+    assert np.max(np.abs(g[z["grad_idx"]] - z["grad_sel"])) <= TOL * float(z["grad_absmax"])
+    model.set_params(trained_like_params); model.optim_reset(0.0)
+    model._upload(batch)
+    l3 = model.train_step("adam", 3e-4)
+    assert rel_err(l3, z["loss3"]) < TOL and grad_err(model.get_grads(), g_ref) < TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", TOL), ("tf32x3", TOL), ("tf32", TOL_TF32)])
+def test_large_forward_and_rollout_each_precision(n8, trained_like_params, precision, tol):
+    """Inference forward on 40 960 foci and two rollout-by-kernels steps on 5 120 scenes for each arithmetic variant."""
+    st, ref = n8
+    S = st.shape[0]
+    m = make_model(12, {})
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+        m.select_windows(0, S)
+        m.set_precision(precision)
+        pred, le = m.forward_per_example_current()
+        scale = np.abs(ref["pred"][:, :6]).max()
+        e = float(np.abs(pred[:, :6] - ref["pred"][:, :6]).max() / scale) if precision == "tf32" else rel_err(pred[:, :6], ref["pred"][:, :6])
+        e_le = float(np.max(np.abs(le - ref["le"])))
+        idx, mask, cnt = m.pair_table()
+        assert np.array_equal(mask[:, :7], ref["mask"].astype(np.uint8))
+        # rollout by kernels, teacher forced (one-step predictions at every step against the oracle's)
+        m.set_rollout_mode("kernels")
+        steps = 2
+        traj, met = m.rollout(0, steps, use_gt=True, teacher=True)
+        rtraj, rmet = rollout.rollout_scenes(trained_like_params, st[:, :, 0:2], np.full(S, 8), steps, gt=st[:, :, 2:],
+                                             teacher=st[:, :, 2:])
+        vs = np.abs(rtraj[..., 2:4]).max()
+        e_roll = float(np.max(np.abs(traj[..., 2:4] - rtraj[..., 2:4])) / vs)
+        print(f"[n8/{precision}] forward {e:.2e} per-example loss abs {e_le:.2e} rollout velocities {e_roll:.2e}")
+        assert e < tol and e_roll < max(tol, 2e-4)
+        assert e_le < (1e-6 if precision != "tf32" else 1e-3)
+        assert np.array_equal(traj[..., 0:2], rtraj[..., 0:2])          # positions integrate the PREVIOUS velocity: exact
+        assert met[:, 3].min() == S * 8
+    finally:
+        m.close()
+
+
+def test_missing_peer_times_out_instead_of_hanging(model, params):
+    """The data-parallel step waits for every peer's gradient cell with a bound: a rank whose peer never steps gets
+    NPE_ERR_CUDA, not a wedged GPU.  Single process: rank 0 of 2 with its own region standing in for the absent peer."""
+    import ctypes as C
+    from dynamics_b200 import NPEError
+    from tests.util import balls_batches
+    _, batches = balls_batches(60, 4, seed=5)
+    batch = batcher.make_batch(*batches[0], offset=1)
+    buf = C.create_string_buffer(64)
+    model._ck(model.lib.npe_peer_export(model.h, buf))
+    both = C.create_string_buffer(buf.raw + buf.raw, 128)
+    model._ck(model.lib.npe_peer_attach(model.h, 0, 2, both))
+    model.set_option("peer_timeout_ms", 50)
+    model.set_params(params); model.optim_reset(0.0)
+    model._upload(batch)
+    with pytest.raises(NPEError) as ei:
+        model.train_step("adam", 3e-4, divisor_batch=100)
+    assert "peer" in str(ei.value)
