@@ -18,6 +18,7 @@
 #include "npe_step16.cuh"
 #include "npe_rollout.cuh"
 #include "npe_tc.cuh"
+#include "npe_tcbwd.cuh"
 
 using namespace npe;
 
@@ -95,6 +96,11 @@ struct npe_handle {
     bool wtc_dirty = true;
     float* wtc3 = nullptr;            // hi | lo images for the 3xTF32 variant (2 * TC_TOTAL floats)
     bool wtc3_dirty = true;
+    float* wtt3 = nullptr;            // hi | lo TRANSPOSED images for the tcgen05 input-gradient chains (2 * TT_TOTAL floats)
+    bool wtt3_dirty = true;
+    DevBuf<float> dzact, dact, ddz;   // tcgen05 backward: pair gradient stash, decoder activation / gradient stashes
+    DevBuf<long long> pair_frow;      // focus-window offset of every active pair (encoder weight gradient)
+    bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
     int train_stash = 1;              // forward writes the pair activations for the backward kernels (0: recompute)
@@ -339,7 +345,7 @@ int build_pairs(npe_handle* h) {
     }
     CK(cudaGetLastError());
     h->pairs_valid = true;
-    h->hact_valid = false;
+    h->hact_valid = false; h->dact_valid = false;
     return NPE_OK;
 }
 
@@ -401,7 +407,7 @@ float* training_stash(npe_handle* h) {
 // stash: activation stash for a following backward (training) or nullptr; skip_decoder: the fused training step lets
 // k_dec_backward produce pred / losses.
 int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, int tc,
-                           float* stash = nullptr, bool skip_decoder = false) {
+                           float* stash = nullptr, bool skip_decoder = false, float* dact = nullptr) {
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
         int rc = refresh_wtc(h, tc);
@@ -421,7 +427,7 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
                                                                          h->info_dev, h->wtc3, h->Hp.p, stash);
             if (!skip_decoder)
                 k_dec_forward_tc3<<<fg, NT, sizeof(DecTc3Smem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc3,
-                                                                             y, h->pred.p, loss_ex);
+                                                                             y, h->pred.p, loss_ex, dact);
         }
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
@@ -452,11 +458,18 @@ int run_forward(npe_handle* h, bool training, bool fused = false) {
     // training forward: FP32 FFMA kernels, or (train_fwd_tc) the FP32-grade tcgen05 pair kernel; never single-pass TF32
     const int tc = training ? (h->train_fwd_tc && !small_batch(h, h->F) ? NPE_PRECISION_TF32X3_TC : 0) : h->precision;
     float* stash = (training && h->have_y && h->train_stash) ? training_stash(h) : nullptr;
+    // tcgen05 backward (large batches): it consumes the pair stash AND a decoder stash, so the decoder forward runs here
+    // (with the stash) instead of inside k_dec_backward
+    float* dact = nullptr;
+    if (training && h->bwd_tc && tc == NPE_PRECISION_TF32X3_TC && stash &&
+        h->dact.ensure((size_t)h->F * DACT_STRIDE) == cudaSuccess)
+        dact = h->dact.p;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->yptr() : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
-                                stash, fused);
+                                stash, fused && !dact, dact);
     if (rc) return rc;
     h->fwd_valid = (tc != NPE_PRECISION_TF32_TC);
     h->hact_valid = stash != nullptr;
+    h->dact_valid = dact != nullptr;
     return NPE_OK;
 }
 
@@ -494,7 +507,7 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
     } else if (r.opt == 2) {
         o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
     }
-    if (r.opt) { h->wtc_dirty = true; h->wtc3_dirty = true; }
+    if (r.opt) { h->wtc_dirty = true; h->wtc3_dirty = true; h->wtt3_dirty = true; }
     return r;
 }
 
@@ -513,6 +526,87 @@ int launch_reduce(npe_handle* h, int gp, int gd, int fuse_opt, float lr, bool wa
     return NPE_OK;
 }
 
+int refresh_wtt(npe_handle* h) {
+    if (!h->wtt3_dirty) return NPE_OK;
+    k_pack_tt3_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtt3, h->wtt3 + TT_TOTAL);
+    CKL();
+    h->wtt3_dirty = false;
+    return NPE_OK;
+}
+
+WJob wjob_layer(const float* G, long long gs, int gcols, const float* X, long long xs, int tmem_col, int pt_base, int n_valid) {
+    WJob J = {};
+    J.G = G; J.g_stride = gs; J.g_cols = gcols;
+    J.x[0].base = X; J.x[0].offs = nullptr; J.x[0].stride = xs; J.x[0].cols_valid = 52; J.x[0].cols_store = 56; J.x[0].col0 = 0;
+    J.nx = 1; J.nb = 56; J.tmem_col = tmem_col; J.kind = 0; J.pt_base = pt_base; J.kt = 13; J.n_valid = n_valid;
+    return J;
+}
+
+// model:bp for large batches on tcgen05 (npe_tcbwd.cuh): decoder input-gradient chain -> ds, pair input-gradient chain,
+// then the weight gradients of the pair part and of the decoder part (accumulators in tensor memory per CTA) into the
+// per-CTA partials that the reduce / optimiser / exchange kernel consumes.
+int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out) {
+    int rc = refresh_wtt(h);
+    if (rc) return rc;
+    const int F = h->F;
+    CK(h->ddz.ensure((size_t)F * DACT_STRIDE));
+    CK(h->dzact.ensure((size_t)h->pair_cap * HACT_STRIDE));
+    CK(h->pair_frow.ensure((size_t)h->pair_cap));
+    const int ftiles = (F + 127) / 128;
+    const long long ptiles = ((long long)h->pair_cap + 127) / 128;
+    const int fg = (ftiles + 1) / 2 < h->num_sms ? (ftiles + 1) / 2 : h->num_sms;
+    const int pg = (int)((ptiles + 1) / 2 < h->num_sms ? ((ptiles + 1) / 2 > 0 ? (ptiles + 1) / 2 : 1) : h->num_sms);
+    const int gd = ftiles < h->num_sms ? ftiles : h->num_sms;
+    const int gp = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
+    {
+        ProfScope ps__(h, NPE_K_DEC_BACKWARD);
+        k_dec_dgrad_tc3<<<fg, NT, sizeof(DecDgradSmem), h->stream>>>(F, h->pred.p, h->yptr(), h->dact.p, h->wtt3, sv, sw,
+                                                                     h->ddz.p, h->ds.p);
+        h->launches++;
+    }
+    {
+        ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
+        k_pair_dgrad_tc3<<<pg, NT, sizeof(PairDgradSmem), h->stream>>>(h->pair_foc.p, h->foc_row.p, h->info_dev, h->hact.p, h->ds.p,
+                                                                       h->wtt3, h->dzact.p, h->pair_frow.p);
+        h->launches++;
+    }
+    {
+        ProfScope ps__(h, NPE_K_WGRAD);
+        WArgs A = {};
+        for (int l = NL; l >= 1; --l)   // pairwise layer l: G = dz_l, X = h_{l-1}
+            A.job[NL - l] = wjob_layer(h->dzact.p + l * 52, HACT_STRIDE, 52, h->hact.p + (l - 1) * 52, HACT_STRIDE, 64 * (NL - l),
+                                       PT_PAIR + (l - 1) * PT_LAYER, H);
+        WJob& E = A.job[NL];            // both encoders: G = dz0, X = [focus window (48) | context window (48)]
+        E = WJob{};
+        E.G = h->dzact.p; E.g_stride = HACT_STRIDE; E.g_cols = 52;
+        E.x[0].base = h->states.p; E.x[0].offs = h->pair_frow.p; E.x[0].cols_valid = IN; E.x[0].cols_store = 48; E.x[0].col0 = 0;
+        E.x[1].base = h->states.p; E.x[1].offs = h->pair_crow.p; E.x[1].cols_valid = IN; E.x[1].cols_store = 48; E.x[1].col0 = 48;
+        E.nx = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
+        A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial;
+        k_wgrad_tc<<<gp, WG_NT, sizeof(WgradSmem), h->stream>>>(A);
+        h->launches++;
+        WArgs B = {};
+        // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
+        // constant 1, i.e. accumulator column 50 is the bias gradient
+        B.job[0] = wjob_layer(h->ddz.p + 4 * 52, DACT_STRIDE, 24, h->dact.p + 4 * 52, DACT_STRIDE, 0, PT_DEC5, OUT);
+        for (int l = 4; l >= 2; --l)
+            B.job[5 - l] = wjob_layer(h->ddz.p + (l - 1) * 52, DACT_STRIDE, 52, h->dact.p + (l - 1) * 52, DACT_STRIDE, 64 * (5 - l),
+                                      PT_DEC2 + (l - 2) * PT_LAYER, H);
+        WJob& D1 = B.job[4];            // layer 1: G = dz1, X = z = [pair sum (50) | 1 | 0 | focus window (44)]
+        D1 = WJob{};
+        D1.G = h->ddz.p; D1.g_stride = DACT_STRIDE; D1.g_cols = 52;
+        D1.x[0].base = h->dact.p; D1.x[0].offs = nullptr; D1.x[0].stride = DACT_STRIDE; D1.x[0].cols_valid = 52; D1.x[0].cols_store = 52; D1.x[0].col0 = 0;
+        D1.x[1].base = h->states.p; D1.x[1].offs = h->foc_row.p; D1.x[1].cols_valid = IN; D1.x[1].cols_store = IN; D1.x[1].col0 = ZCOL_F;
+        D1.nx = 2; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
+        B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial;
+        k_wgrad_tc<<<gd, WG_NT, sizeof(WgradSmem), h->stream>>>(B);
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    *gp_out = gp; *gd_out = gd;
+    return NPE_OK;
+}
+
 // fuse_opt: 0 = reduction only; 1 = + Adam; 2 = + RMSprop (single-GPU train step)
 // peer_opt: 1 / 2 = fused NVLink all-reduce + Adam / RMSprop (requires npe_peer_attach)
 int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 0.f, bool want_loss = false, int peer_opt = 0,
@@ -524,6 +618,12 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
     const float sv = 2.f * h->cfg.vlambda / (float)(2 * B);
     const float sw = 2.f * h->cfg.lambda / (float)B;
     const bool small = small_batch(h, h->F);
+    if (h->dact_valid && h->hact_valid && !small) {
+        int gpt = 0, gdt = 0;
+        const int rc = run_backward_tc(h, sv, sw, &gpt, &gdt);
+        if (rc) return rc;
+        return launch_reduce(h, gpt, gdt, fuse_opt, lr, want_loss, peer_opt);
+    }
     const int rows = small ? 16 : 64;
     const int gd = focus_grid(h, h->F, rows);
     const int gp = pair_grid(h, rows);
@@ -591,8 +691,8 @@ int run_step_fused(npe_handle* h, int divisor_batch, int fuse_opt, float lr, boo
 
 int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
     h->adam_t += 1;
-    h->wtc_dirty = true; h->wtc3_dirty = true;
-    h->fwd_valid = false; h->hact_valid = false;   // parameters change: forward state is stale
+    h->wtc_dirty = true; h->wtc3_dirty = true; h->wtt3_dirty = true;
+    h->fwd_valid = false; h->hact_valid = false; h->dact_valid = false;   // parameters change: forward state is stale
     const double t = (double)h->adam_t;
     const float step = (float)((double)lr * std::sqrt(1.0 - std::pow((double)b2, t)) / (1.0 - std::pow((double)b1, t)));
     { ProfScope ps__(h, NPE_K_OPTIM); k_adam<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->adam_m, h->adam_v, h->wpack, NPARAM, b1, (float)(1.0 - (double)b1), b2, (float)(1.0 - (double)b2), eps, step);
@@ -602,8 +702,8 @@ int run_adam(npe_handle* h, float lr, float b1, float b2, float eps) {
 }
 
 int run_rmsprop(npe_handle* h, float lr, float alpha, float eps) {
-    h->wtc_dirty = true; h->wtc3_dirty = true;
-    h->fwd_valid = false; h->hact_valid = false;
+    h->wtc_dirty = true; h->wtc3_dirty = true; h->wtt3_dirty = true;
+    h->fwd_valid = false; h->hact_valid = false; h->dact_valid = false;
     { ProfScope ps__(h, NPE_K_OPTIM); k_rmsprop<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->grads, h->rms_m, h->wpack, NPARAM, alpha, (float)(1.0 - (double)alpha), eps, lr);
     h->launches++; }
     { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return fail(h, NPE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); }
@@ -684,6 +784,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->wtc3, 2 * (size_t)TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     k_pack_tc_zero<<<(TC_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wtc3);                 // hi image: unit entries
     cudaMemsetAsync(h->wtc3 + TC_TOTAL, 0, (size_t)TC_TOTAL * sizeof(float), h->stream);   // lo image: zero
+    if ((e = cudaMalloc((void**)&h->wtt3, 2 * (size_t)TT_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->wtt3, 0, 2 * (size_t)TT_TOTAL * sizeof(float), h->stream);
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->loss_sums_dev, 4 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&h->active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -717,7 +819,10 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTc3Smem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTc3Smem))) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k_dec_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTc3Smem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairDgradSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem))) != cudaSuccess)
         return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
     *out = h;
     return NPE_OK;
@@ -730,7 +835,7 @@ int npe_destroy(npe_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int r = 0; r < MAX_PEERS; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
     if (h->xregion) cudaFree(h->xregion);
-    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3};
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3, h->wtt3};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
@@ -751,6 +856,7 @@ int npe_destroy(npe_handle* h) {
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
+    h->dzact.release(); h->dact.release(); h->ddz.release(); h->pair_frow.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release(); h->slot_metrics.release();
     { auto& q = h->sched; q.keep.release(); q.nbr.release(); q.total.release(); q.cnt.release(); q.block_sums.release(); q.pair_start.release(); q.pair_foc.release(); q.info.release(); q.step_first.release(); q.step_F.release(); q.foc_row.release(); q.pair_crow.release(); q.y.release(); }
@@ -771,8 +877,8 @@ int npe_params_set(npe_handle* h, const float* host, int32_t n) {
     k_pack_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wpack);
     CKL();
     CK(cudaStreamSynchronize(h->stream));
-    h->fwd_valid = false; h->hact_valid = false;
-    h->wtc_dirty = true; h->wtc3_dirty = true;
+    h->fwd_valid = false; h->hact_valid = false; h->dact_valid = false;
+    h->wtc_dirty = true; h->wtc3_dirty = true; h->wtt3_dirty = true;
     return NPE_OK;
 }
 int npe_params_get(npe_handle* h, float* host, int32_t n) {
@@ -1205,7 +1311,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
                 h->pair_foc.p = q.pair_foc.p + po; h->pair_crow.p = q.pair_crow.p + po; h->info_dev = q.info.p + 2 * i;
                 h->active_total = q.total.p + i;
                 h->pair_cap = cap;
-                h->pairs_valid = true; h->hact_valid = false;
+                h->pairs_valid = true; h->hact_valid = false; h->dact_valid = false;
             }
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
@@ -1490,7 +1596,7 @@ int npe_set_option(npe_handle* h, int32_t option, int32_t value) {
         case NPE_OPT_SMALL_BATCH_MAX: h->small_batch_max = value; break;
         default: return fail(h, NPE_ERR_INVALID, "set_option: unknown option %d", option);
     }
-    h->fwd_valid = false; h->hact_valid = false;
+    h->fwd_valid = false; h->hact_valid = false; h->dact_valid = false;
     return NPE_OK;
 }
 
@@ -1558,6 +1664,24 @@ int npe_event_elapsed_ms(npe_handle* h, int32_t a, int32_t b, float* ms_out) {
 }
 
 int64_t npe_launch_count(const npe_handle* h) { return h ? h->launches : 0; }
+
+int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats) {
+    NEED(h);
+    const float* src = nullptr; size_t cap = 0;
+    switch (which) {
+        case NPE_DBG_HACT: src = h->hact.p; cap = h->hact.cap; break;
+        case NPE_DBG_DZACT: src = h->dzact.p; cap = h->dzact.cap; break;
+        case NPE_DBG_DACT: src = h->dact.p; cap = h->dact.cap; break;
+        case NPE_DBG_DDZ: src = h->ddz.p; cap = h->ddz.cap; break;
+        case NPE_DBG_DS: src = h->ds.p; cap = h->ds.cap; break;
+        case NPE_DBG_HP: src = h->Hp.p; cap = h->Hp.cap; break;
+        default: return fail(h, NPE_ERR_INVALID, "debug_read: unknown buffer %d", which);
+    }
+    if (!out || nfloats <= 0 || !src || (size_t)nfloats > cap) return fail(h, NPE_ERR_INVALID, "debug_read: buffer %d holds %zu floats", which, cap);
+    CK(cudaMemcpyAsync(out, src, (size_t)nfloats * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return NPE_OK;
+}
 
 int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out) {
     NEED(h);

@@ -454,7 +454,10 @@ struct DecTc3Smem {
 __global__ void __launch_bounds__(NT, 1)
 k_dec_forward_tc3(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
                   const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
-                  const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex) {
+                  const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
+                  float* __restrict__ dact) {
+    // dact != nullptr (training with the tcgen05 backward): row f of the decoder stash [F][5][52] receives
+    // {z[0..51] = pair sum | 1 | 0, u1, u2, u3, u4} for the input- and weight-gradient kernels (npe_tcbwd.cuh)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecTc3Smem& S = *reinterpret_cast<DecTc3Smem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, g = t >> 7, r = t & 127;
@@ -491,6 +494,11 @@ k_dec_forward_tc3(const float* __restrict__ states, const long long* __restrict_
                 }
             }
             tmem_store_split<6>(tm, TM_AHI, TM_ALO, z);
+            if (dact && live) {
+                float* o = dact + (size_t)(f0 + r) * (5 * 52);
+#pragma unroll
+                for (int c = 0; c < 12; ++c) st4(o + 4 * c, make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
+            }
         }
         {   // z columns 48..95: pair sums 48,49 | 1 | 0 | focus window (44)
             float z2[48];
@@ -503,6 +511,7 @@ k_dec_forward_tc3(const float* __restrict__ states, const long long* __restrict_
                 for (int c2 = 0; c2 < 22; ++c2) { const float2 v = ld2(states + foff + 2 * c2); z2[4 + 2 * c2] = v.x; z2[5 + 2 * c2] = v.y; }
             }
             tmem_store_split<6>(tm, TM_AHI + 48, TM_ALO + 48, z2);
+            if (dact && live) st4(dact + (size_t)(f0 + r) * (5 * 52) + 48, make_float4(z2[0], z2[1], z2[2], z2[3]));
         }
         tmem_st_wait();
         if (!staged) { mbar_wait(&S.ctl.wbar, 0); staged = true; }
@@ -522,6 +531,11 @@ k_dec_forward_tc3(const float* __restrict__ states, const long long* __restrict_
                 float d[64];
                 tc_load_relu(tm, d);
                 tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
+                if (dact && live) {
+                    float* o = dact + (size_t)(f0 + r) * (5 * 52) + (l + 1) * 52;
+#pragma unroll
+                    for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]));
+                }
                 tmem_st_wait();
             } else {
                 float o[32];

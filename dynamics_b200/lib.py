@@ -83,6 +83,7 @@ SIGNATURES = {
     "npe_event_record": (C.c_int, [_H, C.c_int32]),
     "npe_event_elapsed_ms": (C.c_int, [_H, C.c_int32, C.c_int32, _fp]),
     "npe_launch_count": (C.c_int64, [_H]),
+    "npe_debug_read": (C.c_int, [_H, C.c_int32, _fp, C.c_int64]),
     "npe_batch_stats": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
@@ -123,7 +124,7 @@ def load_library(path=LIB_PATH):
 
 OPTIONS = {"train_fwd_tc": 0, "train_stash": 1, "bwd_tc": 2, "peer_timeout_ms": 3, "small_batch_max": 4}
 KERNEL_IDS = {"build_pairs": 0, "forward": 1, "dec_backward": 2, "pair_backward": 3, "reduce": 4, "optim": 5,
-              "rollout": 6, "targets": 7, "step_fused": 8}
+              "rollout": 6, "targets": 7, "step_fused": 8, "wgrad": 9}
 
 
 def pinned_array(lib, shape, dtype=np.float32):

@@ -319,6 +319,13 @@ class NPEModel:
         'peer_timeout_ms', 'small_batch_max'."""
         self._ck(self.lib.npe_set_option(self.h, L.OPTIONS[name], int(value)))
 
+    def debug_read(self, which, shape):
+        """Intermediate device buffer of the current batch (tests): 'hact', 'dzact', 'dact', 'ddz', 'ds', 'hp'."""
+        out = np.empty(shape, np.float32)
+        self._ck(self.lib.npe_debug_read(self.h, {"hact": 0, "dzact": 1, "dact": 2, "ddz": 3, "ds": 4, "hp": 5}[which],
+                                         L.fptr(out), out.size))
+        return out
+
     def set_rollout_mode(self, mode):
         """'persistent' (one kernel, window on chip) or 'kernels' (window in HBM, 5 launches per step)."""
         self._ck(self.lib.npe_set_rollout_mode(self.h, {"persistent": 0, "kernels": 1}[mode]))

@@ -263,7 +263,8 @@ void npe_host_free(void* p);
 #define NPE_K_ROLLOUT 6
 #define NPE_K_TARGETS 7
 #define NPE_K_STEP_FUSED 8   /* forward + backward of a small batch as one grid of tiles (k_step_fused) */
-#define NPE_K_COUNT 9
+#define NPE_K_WGRAD 9        /* tcgen05 weight-gradient kernels of the large-batch backward (k_wgrad_tc, two launches) */
+#define NPE_K_COUNT 10
 /* Tools: the first call switches on phase time stamps (globaltimer, ns) in k_step_fused; stamps_out (max_ctas, 8) receives
  * the stamps of the last launch: {static loads done, wait done, first hand-over, second hand-over, gradients done,
  * partial stored, 0, 0} per CTA (pair tiles first, then decoder tiles). */
@@ -276,6 +277,19 @@ int npe_profile_read(npe_handle* h, int32_t* launches_out, double* total_ms_out)
 /* CUDA-event timing on the handle's stream (bench/roofline): record marks, read elapsed ms between two marks. */
 int npe_event_record(npe_handle* h, int32_t slot);
 int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* ms_out);
+/*
+ * Parity checks of intermediate results (tests only): copies the first nfloats of an internal device buffer of the
+ * current batch.  Layouts (csrc/npe_tcbwd.cuh): HACT / DZACT [pair][6][52] = h0..h5 / dz0..dz5 of every active pair in
+ * list order; DACT [focus][5][52] = {pair sum | 1 | 0, u1..u4}; DDZ [focus][5][52] = dz1..dz5; DS [focus][52] = gradient
+ * into the pair sum; HP [pair][52] = h5.
+ */
+#define NPE_DBG_HACT 0
+#define NPE_DBG_DZACT 1
+#define NPE_DBG_DACT 2
+#define NPE_DBG_DDZ 3
+#define NPE_DBG_DS 4
+#define NPE_DBG_HP 5
+int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats);
 /* Counters: kernels launched by this handle since creation; active pairs / foci of the current batch. */
 int64_t npe_launch_count(const npe_handle* h);
 int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out);

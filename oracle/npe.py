@@ -233,7 +233,7 @@ def d_pred(pred, y, vlambda=1.0, lam=1.0, divisor_batch=None):
     return g
 
 
-def bp(params, batch, vlambda=1.0, lam=1.0, layers=C.LAYERS, divisor_batch=None, **kw):
+def bp(params, batch, vlambda=1.0, lam=1.0, layers=C.LAYERS, divisor_batch=None, inter=None, **kw):
     """model:bp (npe.lua:290-336): manual chain rule -> grad_params (flat).  Float32 storage, float64 accumulation
     inside each matrix product (numpy matmul on float32 uses float32 BLAS; we promote the reductions that sum over
     the batch to keep the oracle the more accurate side of the comparison)."""
@@ -247,10 +247,14 @@ def bp(params, batch, vlambda=1.0, lam=1.0, layers=C.LAYERS, divisor_batch=None,
     du = dp.copy()
     du[:, 6:] = 0.0
     us = st["us"]
+    if inter is not None:   # intermediate gradients for kernel-by-kernel parity checks: dz of every layer, ds
+        inter.update(us=us, hs=st["hs"], m=st["m"], dz_dec={}, dz_pair={})
     for i in range(layers, 0, -1):
         u_in = us[i - 1].astype(np.float64)
         if i < layers:
             du = du * (us[i] > 0)
+        if inter is not None:
+            inter["dz_dec"][i] = du.astype(F32)
         gv[f"dec.L{i}.W"][...] = (du.T @ u_in).astype(F32)
         gv[f"dec.L{i}.b"][...] = du.sum(axis=0).astype(F32)
         du = du @ p[f"dec.L{i}.W"].astype(np.float64)
@@ -259,11 +263,17 @@ def bp(params, batch, vlambda=1.0, lam=1.0, layers=C.LAYERS, divisor_batch=None,
     B, Cn, _ = ctx.shape
     dh = np.broadcast_to(ds[:, None, :], (B, Cn, H)) * st["m"]   # CAddTable bwd = copy; apply_mask (npe.lua:326-327)
     hs = st["hs"]
+    if inter is not None:
+        inter["ds"] = ds.astype(F32)
     for l in range(layers, 0, -1):
         dh = dh * (hs[l] > 0)
+        if inter is not None:
+            inter["dz_pair"][l] = dh.astype(F32)
         gv[f"pair.L{l}.W"][...] = np.einsum("bcj,bck->jk", dh, hs[l - 1].astype(np.float64)).astype(F32)
         dh = dh @ p[f"pair.L{l}.W"].astype(np.float64)
     dh = dh * (hs[0] > 0)
+    if inter is not None:
+        inter["dz_pair"][0] = dh.astype(F32)
     h2 = H // 2
     gv["enc.this.W"][...] = np.einsum("bcj,bck->jk", dh[:, :, :h2], st["f_in"].astype(np.float64)).astype(F32)
     gv["enc.ctx.W"][...] = np.einsum("bcj,bck->jk", dh[:, :, h2:], st["c_in"].astype(np.float64)).astype(F32)

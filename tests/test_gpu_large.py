@@ -221,3 +221,67 @@ def test_missing_peer_times_out_instead_of_hanging(model, params):
     with pytest.raises(NPEError) as ei:
         model.train_step("adam", 3e-4, divisor_batch=100)
     assert "peer" in str(ei.value)
+
+
+def test_tcgen05_backward_stage_by_stage(s64, trained_like_params):
+    """The tcgen05 backward kernel by kernel against the oracle's intermediate gradients (npe.bp(inter=...)): decoder
+    stash and input-gradient chain (dz5..dz1, ds), pair stash and chain (dz5..dz0 of every ACTIVE pair, list order =
+    focus-major, context ascending), then the weight gradients.  Localises a fault to one kernel."""
+    st, ref = s64
+    this, ctx, y = scene_examples(st, 0)
+    F = this.shape[0]
+    inter = {}
+    g_ref, _ = npe.bp(trained_like_params, (this, ctx, y), inter=inter)
+    m = make_model(0, DISPATCH["default"])
+    try:
+        S = st.shape[0]
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+        m.select_windows(0, S)
+        m.forward_current()
+        g = m.bp()
+        f, P = m.batch_stats()
+        act = inter["m"][:, :, 0] > 0                                    # (F, C) active pairs, list order = row-major
+        def err(a, b):
+            return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+        dact = m.debug_read("dact", (F, 5, 52))
+        e = {"z": err(dact[:, 0, :50], inter["us"][0][:, :50])}
+        assert np.all(dact[:, :, 50] == 1) and np.all(dact[:, :, 51] == 0)
+        for i in range(1, 5):
+            e[f"u{i}"] = err(dact[:, i, :50], inter["us"][i])
+        ddz = m.debug_read("ddz", (F, 5, 52))
+        e["dz5_dec"] = err(ddz[:, 4, :22], inter["dz_dec"][5])
+        for i in range(4, 0, -1):
+            e[f"dz{i}_dec"] = err(ddz[:, i - 1, :50], inter["dz_dec"][i])
+        ds = m.debug_read("ds", (F, 52))
+        e["ds"] = err(ds[:, :50], inter["ds"])
+        hact = m.debug_read("hact", (P, 6, 52)); dzact = m.debug_read("dzact", (P, 6, 52))
+        # A pre-activation within rounding noise of zero may be > 0 on one side and == 0 on the other; from that layer
+        # down the two gradients of that row legitimately differ.  Rows with such a ReLU flip are counted and excluded.
+        flip_p = np.zeros(P, bool)
+        for l in range(6):
+            flip_p |= ((hact[:, l, :50] > 0) != (inter["hs"][l][act] > 0)).any(axis=1)
+        flip_f = np.zeros(F, bool)
+        for i in range(1, 5):
+            flip_f |= ((dact[:, i, :50] > 0) != (inter["us"][i] > 0)).any(axis=1)
+        pf = np.repeat(np.arange(F), act.sum(axis=1))                    # focus of every active pair
+        flip_p |= flip_f[pf]
+        assert flip_p.mean() < 0.02 and flip_f.mean() < 0.02, (flip_p.mean(), flip_f.mean())
+        okp, okf = ~flip_p, ~flip_f
+        for i in range(4, 0, -1):
+            e[f"dz{i}_dec"] = err(ddz[okf, i - 1, :50], inter["dz_dec"][i][okf])
+        e["ds"] = err(ds[okf, :50], inter["ds"][okf])
+        for l in range(6):
+            e[f"h{l}"] = err(hact[:, l, :50], inter["hs"][l][act])
+            e[f"dz{l}_pair"] = err(dzact[okp, l, :50], inter["dz_pair"][l][act][okp])
+        e["flips"] = float(flip_p.sum() + flip_f.sum())
+        ents, _ = npe.param_layout()
+        for n, o, s in ents:
+            k = int(np.prod(s))
+            e["g:" + n] = grad_err(g[o:o + k], g_ref[o:o + k]) if np.max(np.abs(g_ref[o:o + k])) > 0 else 0.0
+        print("[s64 stage by stage] " + " ".join(f"{k}={v:.1e}" for k, v in e.items()))
+        bad = {k: v for k, v in e.items() if k != "flips" and not v < (5e-4 if k.startswith("g:") else 1e-4)}
+        assert not bad, bad
+    finally:
+        m.close()
