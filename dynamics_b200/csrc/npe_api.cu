@@ -19,6 +19,7 @@
 #include "npe_rollout.cuh"
 #include "npe_tc.cuh"
 #include "npe_tcbwd.cuh"
+#include "npe_chain.cuh"
 
 using namespace npe;
 
@@ -96,11 +97,14 @@ struct npe_handle {
     bool wtc_dirty = true;
     float* wtc3 = nullptr;            // hi | lo images for the 3xTF32 variant (2 * TC_TOTAL floats)
     bool wtc3_dirty = true;
+    float* wenc = nullptr;            // 64-row encoder images of the chain kernels (hi T | hi C | lo T | lo C), refreshed with wtc3
     float* wtt3 = nullptr;            // hi | lo TRANSPOSED images for the tcgen05 input-gradient chains (2 * TT_TOTAL floats)
     bool wtt3_dirty = true;
     DevBuf<float> dzact, dact, ddz;   // tcgen05 backward: pair gradient stash, decoder activation / gradient stashes
     DevBuf<long long> pair_frow;      // focus-window offset of every active pair (encoder weight gradient)
+    DevBuf<u64> hmask, umask;         // ReLU bits of h0..h5 per active pair [6][pair_cap] / of u1..u4 per focus [4][F]
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
+    long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
     int train_stash = 1;              // forward writes the pair activations for the backward kernels (0: recompute)
@@ -390,6 +394,8 @@ int refresh_wtc(npe_handle* h, int mode) {
     } else if (mode == NPE_PRECISION_TF32X3_TC && h->wtc3_dirty) {
         k_pack_tc3_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc3, h->wtc3 + TC_TOTAL);
         CKL();
+        k_pack_enc64<<<(OFF_PAIR + 255) / 256, 256, 0, h->stream>>>(h->params, h->wenc);
+        CKL();
         h->wtc3_dirty = false;
     }
     return NPE_OK;
@@ -397,8 +403,9 @@ int refresh_wtc(npe_handle* h, int mode) {
 
 // Activation stash for training (h0..h5 per active pair); skipped (recompute instead) when it would exceed 2 GB.
 float* training_stash(npe_handle* h) {
-    const size_t need = (size_t)h->pair_cap * HACT_STRIDE;
-    if (need * sizeof(float) > (size_t)2 << 30) return nullptr;
+    h->stash_rows = ((long long)h->pair_cap + 127) / 128 * 128;
+    const size_t need = (size_t)(NL + 1) * h->stash_rows * HSLOT + 128 * HSLOT;   // + slack: tile-granular bulk reads
+    if (need * sizeof(float) > (size_t)4 << 30) return nullptr;
     if (h->hact.ensure(need) != cudaSuccess) return nullptr;
     return h->hact.p;
 }
@@ -423,23 +430,26 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
             k_dec_forward_tc<<<fg, NT, sizeof(DecTcSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y,
                                                                        h->pred.p, loss_ex);
         } else {
-            k_pair_forward_tc3<<<pg, NT, sizeof(PairTc3Smem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                         h->info_dev, h->wtc3, h->Hp.p, stash);
+            // warp-specialised chain kernels (npe_chain.cuh): two tile slots per CTA, two threads per row, one MMA warp
+            k_pair_forward_c2<<<pg, CH_NT, sizeof(PairChainSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                                                                              h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash,
+                                                                              dact ? h->hmask.p : nullptr, h->stash_rows);
             if (!skip_decoder)
-                k_dec_forward_tc3<<<fg, NT, sizeof(DecTc3Smem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc3,
-                                                                             y, h->pred.p, loss_ex, dact);
+                k_dec_forward_c2<<<fg, CH_NT, sizeof(DecChainSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
+                                                                                h->wtc3, y, h->pred.p, loss_ex, dact,
+                                                                                dact ? h->umask.p : nullptr);
         }
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
         if (small_batch(h, F)) {
             CK(launch_pdl(h, k_pair_forward<16>, pair_grid(h, 16), NT, sizeof(PairFwdSmem<16>),
-                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash, h->stash_rows));
             if (!skip_decoder)
                 CK(launch_pdl(h, k_dec_forward<16>, focus_grid(h, F, 16), NT, sizeof(DecFwdSmem<16>),
                               st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
         } else {
             CK(launch_pdl(h, k_pair_forward<64>, pair_grid(h, 64), NT, sizeof(PairFwdSmem<64>),
-                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash));
+                          st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->Hp.p, stash, h->stash_rows));
             if (!skip_decoder)
                 CK(launch_pdl(h, k_dec_forward<64>, focus_grid(h, F, 64), NT, sizeof(DecFwdSmem<64>),
                               st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wpack, y, h->pred.p, loss_ex));
@@ -462,7 +472,8 @@ int run_forward(npe_handle* h, bool training, bool fused = false) {
     // (with the stash) instead of inside k_dec_backward
     float* dact = nullptr;
     if (training && h->bwd_tc && tc == NPE_PRECISION_TF32X3_TC && stash &&
-        h->dact.ensure((size_t)h->F * DACT_STRIDE) == cudaSuccess)
+        h->dact.ensure((size_t)5 * h->F * HSLOT + 128 * HSLOT) == cudaSuccess && h->umask.ensure((size_t)4 * h->F) == cudaSuccess &&
+        h->hmask.ensure((size_t)(NL + 1) * h->stash_rows) == cudaSuccess)
         dact = h->dact.p;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->yptr() : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused && !dact, dact);
@@ -534,23 +545,24 @@ int refresh_wtt(npe_handle* h) {
     return NPE_OK;
 }
 
-WJob wjob_layer(const float* G, long long gs, int gcols, const float* X, long long xs, int tmem_col, int pt_base, int n_valid) {
+WJob wjob_layer(const float* G, int gcols, const float* X, int tmem_col, int pt_base, int n_valid) {
     WJob J = {};
-    J.G = G; J.g_stride = gs; J.g_cols = gcols;
-    J.x[0].base = X; J.x[0].offs = nullptr; J.x[0].stride = xs; J.x[0].cols_valid = 52; J.x[0].cols_store = 56; J.x[0].col0 = 0;
-    J.nx = 1; J.nb = 56; J.tmem_col = tmem_col; J.kind = 0; J.pt_base = pt_base; J.kt = 13; J.n_valid = n_valid;
+    J.G = G; J.g_cols = gcols;
+    J.X0 = X; J.x0_valid = 52; J.x0_store = 56;
+    J.ngs = 0; J.nb = 56; J.tmem_col = tmem_col; J.kind = 0; J.pt_base = pt_base; J.kt = 13; J.n_valid = n_valid;
     return J;
 }
 
-// model:bp for large batches on tcgen05 (npe_tcbwd.cuh): decoder input-gradient chain -> ds, pair input-gradient chain,
-// then the weight gradients of the pair part and of the decoder part (accumulators in tensor memory per CTA) into the
-// per-CTA partials that the reduce / optimiser / exchange kernel consumes.
+// model:bp for large batches on tcgen05 (npe_chain.cuh, npe_tcbwd.cuh): decoder input-gradient chain -> ds, pair
+// input-gradient chain, then the weight gradients of the pair part and of the decoder part (accumulators in tensor memory
+// per CTA) into the per-CTA partials that the reduce / optimiser / exchange kernel consumes.
 int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out) {
     int rc = refresh_wtt(h);
     if (rc) return rc;
     const int F = h->F;
-    CK(h->ddz.ensure((size_t)F * DACT_STRIDE));
-    CK(h->dzact.ensure((size_t)h->pair_cap * HACT_STRIDE));
+    const size_t SR = (size_t)h->stash_rows;
+    CK(h->ddz.ensure((size_t)5 * F * HSLOT + 128 * HSLOT));
+    CK(h->dzact.ensure((size_t)(NL + 1) * SR * HSLOT + 128 * HSLOT));
     CK(h->pair_frow.ensure((size_t)h->pair_cap));
     const int ftiles = (F + 127) / 128;
     const long long ptiles = ((long long)h->pair_cap + 127) / 128;
@@ -560,44 +572,45 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
     const int gp = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
     {
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
-        k_dec_dgrad_tc3<<<fg, NT, sizeof(DecDgradSmem), h->stream>>>(F, h->pred.p, h->yptr(), h->dact.p, h->wtt3, sv, sw,
-                                                                     h->ddz.p, h->ds.p);
+        k_dec_dgrad_c2<<<fg, CH_NT, sizeof(DecDgradChainSmem), h->stream>>>(F, h->pred.p, h->yptr(), h->umask.p, h->wtt3, sv, sw,
+                                                                            h->ddz.p, h->ds.p);
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
-        k_pair_dgrad_tc3<<<pg, NT, sizeof(PairDgradSmem), h->stream>>>(h->pair_foc.p, h->foc_row.p, h->info_dev, h->hact.p, h->ds.p,
-                                                                       h->wtt3, h->dzact.p, h->pair_frow.p);
+        k_pair_dgrad_c2<<<pg, CH_NT, sizeof(PairDgradChainSmem), h->stream>>>(h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
+                                                                              h->stash_rows, h->ds.p, h->wtt3, h->dzact.p,
+                                                                              h->pair_frow.p);
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_WGRAD);
         WArgs A = {};
         for (int l = NL; l >= 1; --l)   // pairwise layer l: G = dz_l, X = h_{l-1}
-            A.job[NL - l] = wjob_layer(h->dzact.p + l * 52, HACT_STRIDE, 52, h->hact.p + (l - 1) * 52, HACT_STRIDE, 64 * (NL - l),
-                                       PT_PAIR + (l - 1) * PT_LAYER, H);
+            A.job[NL - l] = wjob_layer(h->dzact.p + (size_t)l * SR * HSLOT, 52, h->hact.p + (size_t)(l - 1) * SR * HSLOT,
+                                       64 * (NL - l), PT_PAIR + (l - 1) * PT_LAYER, H);
         WJob& E = A.job[NL];            // both encoders: G = dz0, X = [focus window (48) | context window (48)]
         E = WJob{};
-        E.G = h->dzact.p; E.g_stride = HACT_STRIDE; E.g_cols = 52;
-        E.x[0].base = h->states.p; E.x[0].offs = h->pair_frow.p; E.x[0].cols_valid = IN; E.x[0].cols_store = 48; E.x[0].col0 = 0;
-        E.x[1].base = h->states.p; E.x[1].offs = h->pair_crow.p; E.x[1].cols_valid = IN; E.x[1].cols_store = 48; E.x[1].col0 = 48;
-        E.nx = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
+        E.G = h->dzact.p; E.g_cols = 52; E.X0 = nullptr;
+        E.gs[0].base = h->states.p; E.gs[0].offs = h->pair_frow.p; E.gs[0].cols_valid = IN; E.gs[0].cols_store = 48; E.gs[0].col0 = 0;
+        E.gs[1].base = h->states.p; E.gs[1].offs = h->pair_crow.p; E.gs[1].cols_valid = IN; E.gs[1].cols_store = 48; E.gs[1].col0 = 48;
+        E.ngs = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
         A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial;
         k_wgrad_tc<<<gp, WG_NT, sizeof(WgradSmem), h->stream>>>(A);
         h->launches++;
         WArgs B = {};
         // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
         // constant 1, i.e. accumulator column 50 is the bias gradient
-        B.job[0] = wjob_layer(h->ddz.p + 4 * 52, DACT_STRIDE, 24, h->dact.p + 4 * 52, DACT_STRIDE, 0, PT_DEC5, OUT);
+        const size_t FS = (size_t)F * HSLOT;
+        B.job[0] = wjob_layer(h->ddz.p + 4 * FS, 24, h->dact.p + 4 * FS, 0, PT_DEC5, OUT);
         for (int l = 4; l >= 2; --l)
-            B.job[5 - l] = wjob_layer(h->ddz.p + (l - 1) * 52, DACT_STRIDE, 52, h->dact.p + (l - 1) * 52, DACT_STRIDE, 64 * (5 - l),
-                                      PT_DEC2 + (l - 2) * PT_LAYER, H);
+            B.job[5 - l] = wjob_layer(h->ddz.p + (l - 1) * FS, 52, h->dact.p + (l - 1) * FS, 64 * (5 - l), PT_DEC2 + (l - 2) * PT_LAYER, H);
         WJob& D1 = B.job[4];            // layer 1: G = dz1, X = z = [pair sum (50) | 1 | 0 | focus window (44)]
         D1 = WJob{};
-        D1.G = h->ddz.p; D1.g_stride = DACT_STRIDE; D1.g_cols = 52;
-        D1.x[0].base = h->dact.p; D1.x[0].offs = nullptr; D1.x[0].stride = DACT_STRIDE; D1.x[0].cols_valid = 52; D1.x[0].cols_store = 52; D1.x[0].col0 = 0;
-        D1.x[1].base = h->states.p; D1.x[1].offs = h->foc_row.p; D1.x[1].cols_valid = IN; D1.x[1].cols_store = IN; D1.x[1].col0 = ZCOL_F;
-        D1.nx = 2; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
+        D1.G = h->ddz.p; D1.g_cols = 52;
+        D1.X0 = h->dact.p; D1.x0_valid = 52; D1.x0_store = 52;
+        D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
+        D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
         B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial;
         k_wgrad_tc<<<gd, WG_NT, sizeof(WgradSmem), h->stream>>>(B);
         h->launches++;
@@ -644,11 +657,11 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         if (small)
             CK(launch_pdl(h, k_pair_backward<16>, gp, NT, sizeof(PairBwdSmem<16>), h->states.p, h->pair_foc.p,
                           h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
-                          h->hact_valid ? h->hact.p : nullptr));
+                          h->hact_valid ? h->hact.p : nullptr, h->stash_rows));
         else
             CK(launch_pdl(h, k_pair_backward<64>, gp, NT, sizeof(PairBwdSmem<64>), h->states.p, h->pair_foc.p,
                           h->pair_crow.p, h->foc_row.p, h->info_dev, h->wpack, h->ds.p, h->partial,
-                          h->hact_valid ? h->hact.p : nullptr));
+                          h->hact_valid ? h->hact.p : nullptr, h->stash_rows));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -784,6 +797,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->wtc3, 2 * (size_t)TC_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     k_pack_tc_zero<<<(TC_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->wtc3);                 // hi image: unit entries
     cudaMemsetAsync(h->wtc3 + TC_TOTAL, 0, (size_t)TC_TOTAL * sizeof(float), h->stream);   // lo image: zero
+    if ((e = cudaMalloc((void**)&h->wenc, 4 * (size_t)ENC64_SZ * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemsetAsync(h->wenc, 0, 4 * (size_t)ENC64_SZ * sizeof(float), h->stream);
     if ((e = cudaMalloc((void**)&h->wtt3, 2 * (size_t)TT_TOTAL * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemsetAsync(h->wtt3, 0, 2 * (size_t)TT_TOTAL * sizeof(float), h->stream);
     if ((e = cudaMalloc((void**)&h->loss3_dev, 4 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -818,11 +833,11 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pair_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTc3Smem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_forward_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTc3Smem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_dec_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pair_dgrad_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairDgradSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem))) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairChainSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradChainSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairDgradChainSmem))) != cudaSuccess)
         return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);
     *out = h;
     return NPE_OK;
@@ -835,7 +850,7 @@ int npe_destroy(npe_handle* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int r = 0; r < MAX_PEERS; ++r) if (h->peer_opened[r]) cudaIpcCloseMemHandle(h->peer_ptr[r]);
     if (h->xregion) cudaFree(h->xregion);
-    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3, h->wtt3};
+    float* bufs[] = {h->params, h->grads, h->adam_m, h->adam_v, h->rms_m, h->partial, h->loss3_dev, h->allreduce_buf, h->wpack, h->wtc, h->wtc3, h->wtt3, h->wenc};
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
@@ -856,7 +871,7 @@ int npe_destroy(npe_handle* h) {
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
-    h->dzact.release(); h->dact.release(); h->ddz.release(); h->pair_frow.release();
+    h->dzact.release(); h->dact.release(); h->ddz.release(); h->pair_frow.release(); h->hmask.release(); h->umask.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release(); h->slot_metrics.release();
     { auto& q = h->sched; q.keep.release(); q.nbr.release(); q.total.release(); q.cnt.release(); q.block_sums.release(); q.pair_start.release(); q.pair_foc.release(); q.info.release(); q.step_first.release(); q.step_F.release(); q.foc_row.release(); q.pair_crow.release(); q.y.release(); }

@@ -1,0 +1,591 @@
+// Warp-specialised 3xTF32 tcgen05 chain kernels (forward and input-gradient chains of the NPE, reference
+// src/lua/npe.lua:225-336, modules.lua:10-26,46-88) -- successors of the first-generation kernels in npe_tc.cuh.
+//
+// A "chain" is a sequence of small dense layers on a tile of 128 rows (active pairs or foci) whose activations never
+// leave the SM: the A operand of every layer (hi / lo TF32 halves) lives in tensor memory, the B operand is a weight
+// image (hi / lo) resident in shared memory, the accumulator is in tensor memory.
+//
+// What bounded the first generation was NOT the tensor pipe (ncu: 15 % active) but the per-SM L1tex wavefront queue:
+// every thread owned one row and walked it with 16-byte global accesses, so each warp instruction touched 32 different
+// 128-byte lines (32-64 queue cycles per instruction; gather + stash stores = ~34 k queue cycles per 128-row tile against
+// ~5 k cycles of MMA).  Two changes:
+//
+//   * ALL global traffic of a row-owning warp goes through a per-warp shared-memory staging buffer (32 rows x 32 columns,
+//     pitch 36 floats: conflict-free 16-byte accesses) and is issued with a transposed lane mapping -- 8 consecutive
+//     lanes cover 128 contiguous bytes of one row, 4 rows per instruction -- i.e. 4-8 lines per instruction instead of 32.
+//     Gathers of 44-float state windows are staged frame by frame (22 floats, dense) with lane-linear 8-byte accesses.
+//   * a dedicated MMA warp: an elected thread issues the tcgen05.mma of BOTH tile slots as soon as a slot's A operand is
+//     published (mbarrier a_ready, 128 arrivals) and commits to the slot's d_ready mbarrier; it also stages the weights.
+//     The 2 x 128 epilogue threads never issue MMAs or wait for each other.
+//   * both encoders accumulate into ONE 64-column accumulator through 64-row weight images whose real rows sit at 0..24
+//     (focus) and 25..49 (context): h0 comes out in its natural column order
+//   * ReLU bits (one 64-bit word per row and layer, layer-major) are written by the forward kernels so that the
+//     input-gradient chains do not read activations at all
+//
+// Stashes are LAYER-MAJOR [slot][row][HSLOT] (npe_kernels.cuh) so that a tile of one layer is a contiguous block: the
+// weight-gradient kernel fetches it with one TMA bulk copy.
+// TMEM columns per slot (256): [0,64) accumulator, [64,160) A hi, [160,256) A lo.
+#pragma once
+#include "npe_tcbwd.cuh"
+
+namespace npe {
+
+constexpr int CH_EPI = 256;               // epilogue threads: 2 slots x 128 rows
+constexpr int CH_NT = CH_EPI + 32;        // + the MMA warp
+constexpr int ENC64_SZ = 12 * 64 * 4;     // one encoder as a 64-row image: 12 K-chunks x 64 rows x 4 floats
+constexpr int STG_PITCH = 36;             // floats; 16-byte accesses of a quarter-warp hit 8 distinct bank groups
+constexpr int STG_FLOATS = 32 * STG_PITCH;   // per-warp staging buffer: 4608 B
+
+struct ChainCtl {
+    unsigned long long wbar;
+    unsigned long long a_ready[2];
+    unsigned long long d_ready[2];
+    uint32_t tmem, pad;
+};
+
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// ---- 64-row encoder images (hi | lo): [focus encoder: rows 0..24 | context encoder: rows 25..49], K = 44 (+ pad to 48) ----
+__global__ void k_pack_enc64(const float* __restrict__ params, float* __restrict__ w) {   // w: hi T | hi C | lo T | lo C
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= OFF_PAIR) return;
+    const int which = i >= OFF_ENC_C, r = i - which * OFF_ENC_C, n = r / IN, k = r - n * IN;
+    const int o = which * ENC64_SZ + ((k >> 2) * 64 + (n + which * H2)) * 4 + (k & 3);
+    const float x = params[i], h = tf32_hi(x);
+    w[o] = h;
+    w[2 * ENC64_SZ + o] = x - h;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// per-warp staging: coalesced global <-> row-owner registers (lane = row of the warp's 32 rows)
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src) {
+    unsigned long long v = (unsigned long long)p;
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return (const float*)(((unsigned long long)hi << 32) | lo);
+}
+// v[0 .. 31] of every lane (= 32 columns of its row) -> global rows: row q of the warp at g + q * gpitch, the first
+// nchunks 16-byte chunks of it; rows >= nrows are skipped.  8 lanes write 128 contiguous bytes of one row.
+__device__ __forceinline__ void warp_store32(float* stg, const float* v, float* __restrict__ g, long long gpitch, int nrows, int nchunks) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) st4(stg + lane * STG_PITCH + 4 * c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+    __syncwarp();
+    const int ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = (lane >> 3) + 4 * i;
+        const float4 x = ld4(stg + q * STG_PITCH + 4 * ch);
+        if (q < nrows && ch < nchunks) st4(g + (long long)q * gpitch + 4 * ch, x);
+    }
+    __syncwarp();
+}
+// A full 52-column row per lane (d[0 .. 63], columns >= 52 ignored) -> global rows of pitch gpitch
+__device__ __forceinline__ void warp_store_row52(float* stg, const float* d, float* __restrict__ g, long long gpitch, int nrows) {
+    warp_store32(stg, d, g, gpitch, nrows, 8);
+    warp_store32(stg, d + 32, g + 32, gpitch, nrows, 5);
+}
+// inverse: v[0 .. 31] of lane q = the first nchunks chunks (rest zero) of the row at myrow (per-lane pointer, 16-byte aligned)
+__device__ __forceinline__ void warp_load32(float* stg, float* v, const float* myrow, bool live, int nchunks) {
+    const int lane = threadIdx.x & 31, ch = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int q = (lane >> 3) + 4 * i;
+        const float* rp = shfl_ptr(myrow, q);
+        const bool ok = __shfl_sync(0xffffffffu, (int)live, q) != 0;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && ch < nchunks) x = ld4(rp + 4 * ch);
+        st4(stg + q * STG_PITCH + 4 * ch, x);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 x = ld4(stg + lane * STG_PITCH + 4 * c);
+        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+    }
+    __syncwarp();
+}
+// One frame (22 floats, 8-byte aligned) of every lane's window: x[0 .. 21] <- myrow[0 .. 21].  Lane-linear 8-byte accesses:
+// a warp instruction covers 32 consecutive float2 of the (row, column) order, i.e. ~3 rows.
+__device__ __forceinline__ void warp_gather22(float* stg, float* x, const float* myrow, bool live) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        const int e = k * 32 + lane, q = e / 11, c2 = e - q * 11;
+        const float* rp = shfl_ptr(myrow, q);
+        const bool ok = __shfl_sync(0xffffffffu, (int)live, q) != 0;
+        float2 v = make_float2(0.f, 0.f);
+        if (ok) v = ld2(rp + 2 * c2);
+        *reinterpret_cast<float2*>(stg + 2 * e) = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c2 = 0; c2 < 11; ++c2) {
+        const float2 v = *reinterpret_cast<const float2*>(stg + lane * 22 + 2 * c2);
+        x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+    }
+    __syncwarp();
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// slot bookkeeping
+// ----------------------------------------------------------------------------------------------------------------
+struct ChainThread {
+    int slot, row, wq;         // tile slot, row within the tile (TMEM lane), warp within the slot (0..3)
+    uint32_t tm;               // TMEM base of the slot
+    float* stg;                // this warp's staging buffer
+};
+__device__ __forceinline__ ChainThread chain_thread(uint32_t tmem, float* stg_all) {
+    ChainThread c;
+    const int t = threadIdx.x;
+    c.slot = t >> 7; c.row = t & 127; c.wq = (t >> 5) & 3;
+    c.tm = tmem + c.slot * TM_GROUP;
+    c.stg = stg_all + (t >> 5) * STG_FLOATS;
+    return c;
+}
+__device__ __forceinline__ void chain_publish_a(ChainCtl& ctl, int slot) {
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&ctl.a_ready[slot]);
+}
+__device__ __forceinline__ void chain_wait_d(ChainCtl& ctl, int slot, unsigned& nd) {
+    mbar_wait(&ctl.d_ready[slot], nd & 1u);
+    ++nd;
+    tc_fence_after();
+}
+// ReLU bits: bit k = (v[k] > 0) for k < 50
+__device__ __forceinline__ unsigned long long relu_bits64(const float* v) {
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) lo |= (v[k] > 0.f ? 1u : 0u) << k;
+#pragma unroll
+    for (int k = 32; k < H; ++k) hi |= (v[k] > 0.f ? 1u : 0u) << (k - 32);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+// MMA-warp scheduler: issues stage after stage of both slots in the order their A operands become ready.
+template <int NSTAGE, typename IssueFn>
+__device__ __forceinline__ void chain_mma_loop(ChainCtl& ctl, uint32_t tmem, int tiles0, int tiles1, IssueFn issue) {
+    int tiles[2] = {tiles0, tiles1}, stage[2] = {0, 0};
+    unsigned ka[2] = {0u, 0u};
+    while (tiles[0] > 0 || tiles[1] > 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (tiles[s] > 0 && mbar_test(&ctl.a_ready[s], ka[s] & 1u)) {
+                tc_fence_after();
+                issue(stage[s], tmem + s * TM_GROUP);
+                umma_commit(&ctl.d_ready[s]);
+                ++ka[s];
+                if (++stage[s] == NSTAGE) { stage[s] = 0; --tiles[s]; }
+            }
+        }
+    }
+}
+__device__ __forceinline__ void chain_setup(ChainCtl& ctl) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(&ctl.wbar, 1);
+        mbar_init(&ctl.a_ready[0], 128); mbar_init(&ctl.a_ready[1], 128);
+        mbar_init(&ctl.d_ready[0], 1); mbar_init(&ctl.d_ready[1], 1);
+    }
+    if ((t >> 5) == CH_EPI / 32) tmem_alloc<TM_COLS>(&ctl.tmem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
+__device__ __forceinline__ void chain_teardown(ChainCtl& ctl) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == CH_EPI / 32) tmem_dealloc<TM_COLS>(ctl.tmem);
+}
+// number of tiles slot s of this CTA processes: tiles 2 b + s, + 2 G, ...
+__device__ __forceinline__ int chain_tiles(int ntiles, int s) {
+    const int first = 2 * blockIdx.x + s, step = 2 * gridDim.x;
+    return first < ntiles ? (ntiles - 1 - first) / step + 1 : 0;
+}
+
+// ================================================================================================================
+// pair MLP forward: tiles of 128 active pairs.  Stage 0: both encoders into one accumulator; stages 1..5: pairwise layers.
+// Training (hact != nullptr): h0..h5 go to the layer-major stash hact[l][stash_rows][HSLOT], their ReLU bits to hmask[l][stash_rows].
+// ================================================================================================================
+struct PairChainSmem {
+    float Ehi[2 * ENC64_SZ];              // 24576 B   focus | context encoder, 64-row images
+    float Elo[2 * ENC64_SZ];              // 24576 B
+    float Whi[NL * TC_HID_SZ];            // 71680 B
+    float Wlo[NL * TC_HID_SZ];            // 71680 B
+    float stg[8 * STG_FLOATS];            // 36864 B
+    ChainCtl ctl;
+};
+
+__global__ void __launch_bounds__(CH_NT, 1)
+k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
+                  const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wtc3,
+                  const float* __restrict__ wenc, float* __restrict__ Hp, float* __restrict__ hact,
+                  unsigned long long* __restrict__ hmask, long long stash_rows) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PairChainSmem& S = *reinterpret_cast<PairChainSmem*>(smem_raw);
+    const int P = info[0];
+    if ((int)blockIdx.x * 256 >= P) return;
+    chain_setup(S.ctl);
+    const int ntiles = (P + 127) / 128;
+    const int t = threadIdx.x;
+    if (t >= CH_EPI) {
+        if (t == CH_EPI) {
+            mbar_expect_tx(&S.ctl.wbar, (4 * ENC64_SZ + 2 * NL * TC_HID_SZ) * 4);
+            bulk_g2s(S.Ehi, wenc, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+            bulk_g2s(S.Elo, wenc + 2 * ENC64_SZ, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+            bulk_g2s(S.Whi, wtc3 + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
+            bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
+            mbar_wait(&S.ctl.wbar, 0);
+            chain_mma_loop<NL + 1>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
+                if (stage == 0) {
+                    umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Ehi, S.Elo, 64, 64, 6);
+                    // the context encoder accumulates on top (its real rows are 25..49)
+                    const uint32_t idesc = umma_idesc_tf32(64);
+                    const uint32_t bh = smem_u32(S.Ehi + ENC64_SZ), bl = smem_u32(S.Elo + ENC64_SZ);
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint32_t a0 = tm + (pass == 2 ? TM_ALO : TM_AHI) + 48;
+                        const uint32_t b0 = pass == 1 ? bl : bh;
+                        for (int s = 0; s < 6; ++s)
+                            umma_tf32_ts(tm + TM_D, a0 + 8 * s, umma_desc(b0 + 2 * s * 64 * 16, 64 * 16, 128), idesc, 1u);
+                    }
+                } else {
+                    umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + (stage - 1) * TC_HID_SZ,
+                                        S.Wlo + (stage - 1) * TC_HID_SZ, 64, 64, 7);
+                }
+            });
+        }
+    } else {
+        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        unsigned nd = 0;
+        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+            const int lo = tile * 128;
+            const int nrows = min(128, P - lo);
+            const bool live = c.row < nrows;
+            const int wrows = max(0, min(32, nrows - 32 * c.wq));     // valid rows of this warp
+            const size_t p = (size_t)(lo + c.row);
+            const size_t pw = (size_t)(lo + 32 * c.wq);               // first row of this warp
+            {   // gather: focus window -> A columns [0, 48), context window -> [48, 96); frame by frame through the staging buffer
+                const float* fw = states, * cw = states;
+                if (live) { fw = states + foc_row[pair_foc[p]]; cw = states + pair_crow[p]; }
+#pragma unroll
+                for (int which = 0; which < 2; ++which) {
+                    float x[48];
+                    const float* wp = which ? cw : fw;
+                    warp_gather22(c.stg, x, wp, live);
+                    warp_gather22(c.stg, x + 22, wp + 22, live);
+                    x[44] = x[45] = x[46] = x[47] = 0.f;
+                    tmem_store_split<6>(c.tm, TM_AHI + 48 * which, TM_ALO + 48 * which, x);
+                }
+            }
+            chain_publish_a(S.ctl, c.slot);
+#pragma unroll 1
+            for (int l = 0; l <= NL; ++l) {          // epilogue of stage l: h_l
+                chain_wait_d(S.ctl, c.slot, nd);
+                float d[64];
+                tc_load_relu(c.tm, d);
+                if (hmask && live) hmask[(size_t)l * stash_rows + p] = relu_bits64(d);
+                if (hact) warp_store_row52(c.stg, d, hact + ((size_t)l * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                if (l < NL) {
+                    tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+                    chain_publish_a(S.ctl, c.slot);
+                } else {
+                    warp_store_row52(c.stg, d, Hp + pw * 52, 52, wrows);
+                }
+            }
+        }
+    }
+    chain_teardown(S.ctl);
+}
+
+// ================================================================================================================
+// decoder forward: tiles of 128 foci.  Stage 0: z (96) -> u1; stages 1..3: hidden layers; stage 4: output (22 of 32 columns).
+// Training (dact != nullptr): {z[0..51], u1..u4} -> dact[slot][F][HSLOT], ReLU bits of u1..u4 -> umask[i][F].
+// ================================================================================================================
+struct DecChainSmem {
+    float Whi[TC_DEC_TOTAL];       // 74752 B
+    float Wlo[TC_DEC_TOTAL];       // 74752 B
+    float stg[8 * STG_FLOATS];     // 36864 B
+    ChainCtl ctl;
+};
+
+__global__ void __launch_bounds__(CH_NT, 1)
+k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
+                 const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
+                 const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
+                 float* __restrict__ dact, unsigned long long* __restrict__ umask) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DecChainSmem& S = *reinterpret_cast<DecChainSmem*>(smem_raw);
+    chain_setup(S.ctl);
+    const int ntiles = (F + 127) / 128;
+    const int t = threadIdx.x;
+    if (t >= CH_EPI) {
+        if (t == CH_EPI) {
+            mbar_expect_tx(&S.ctl.wbar, 2 * TC_DEC_TOTAL * 4);
+            bulk_g2s(S.Whi, wtc3 + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
+            bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
+            mbar_wait(&S.ctl.wbar, 0);
+            chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
+                if (stage == 0) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC1, S.Wlo + TC_DEC1, TC_HID_ROWS, 64, 12);
+                else if (stage < NL - 1) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC2 + (stage - 1) * TC_HID_SZ,
+                                                             S.Wlo + TC_DEC2 + (stage - 1) * TC_HID_SZ, TC_HID_ROWS, 64, 7);
+                else umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC5, S.Wlo + TC_DEC5, TC_OUT_ROWS, 32, 7);
+            });
+        }
+    } else {
+        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        const int lane = t & 31;
+        unsigned nd = 0;
+        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+            const int f0 = tile * 128;
+            const int nf = min(128, F - f0);
+            const bool live = c.row < nf;
+            const int wrows = max(0, min(32, nf - 32 * c.wq));
+            const size_t f = (size_t)(f0 + c.row);
+            const size_t fw = (size_t)(f0 + 32 * c.wq);
+            {   // z = [pair sum (50) | 1 | 0 | focus window (44)]: columns 0..47, then 48..95
+                float z[52];
+#pragma unroll
+                for (int k = 0; k < 52; ++k) z[k] = 0.f;
+                if (live) {   // per-focus sum of its pairs' h5 rows in list order (fixed order: deterministic)
+                    const int p0 = pair_start[f], p1 = pair_start[f + 1];
+                    for (int p = p0; p < p1; ++p) {
+#pragma unroll
+                        for (int q = 0; q < 13; ++q) {
+                            const float4 h = ld4(Hp + (size_t)p * 52 + 4 * q);
+                            z[4 * q] += h.x; z[4 * q + 1] += h.y; z[4 * q + 2] += h.z; z[4 * q + 3] += h.w;
+                        }
+                    }
+                    z[50] = 1.f; z[51] = 0.f;
+                }
+                tmem_store_split<6>(c.tm, TM_AHI, TM_ALO, z);
+                if (dact) {   // stash slot 0 = z[0..51]
+                    float zz[64];
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) zz[k] = k < 52 ? z[k] : 0.f;
+                    warp_store_row52(c.stg, zz, dact + fw * HSLOT, HSLOT, wrows);
+                }
+                float x[48];
+                x[0] = z[48]; x[1] = z[49]; x[2] = z[50]; x[3] = z[51];
+                const float* wp = live ? states + foc_row[f] : states;
+                float w44[44];
+                warp_gather22(c.stg, w44, wp, live);
+                warp_gather22(c.stg, w44 + 22, wp + 22, live);
+#pragma unroll
+                for (int k = 0; k < 44; ++k) x[4 + k] = w44[k];
+                tmem_store_split<6>(c.tm, TM_AHI + 48, TM_ALO + 48, x);
+            }
+            chain_publish_a(S.ctl, c.slot);
+#pragma unroll 1
+            for (int l = 0; l < NL; ++l) {
+                chain_wait_d(S.ctl, c.slot, nd);
+                if (l < NL - 1) {
+                    float d[64];
+                    tc_load_relu(c.tm, d);
+                    if (umask && live) umask[(size_t)l * F + f] = relu_bits64(d);                  // ReLU bits of u_{l+1}
+                    if (dact) warp_store_row52(c.stg, d, dact + ((size_t)(l + 1) * F + fw) * HSLOT, HSLOT, wrows);
+                    tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+                    chain_publish_a(S.ctl, c.slot);
+                } else {
+                    float o[32];
+                    tmem_ld16(c.tm, 0, o); tmem_ld16(c.tm, 16, o + 16);
+                    tmem_ld_wait();
+                    float e2 = 0.f, e3 = 0.f, e5 = 0.f;
+                    if (live && loss_ex && y) {
+                        const float* yy = y + f * OUT;
+                        e2 = o[2] - yy[2]; e3 = o[3] - yy[3]; e5 = o[5] - yy[5];
+                    }
+#pragma unroll
+                    for (int n = 6; n < OUT; ++n) o[n] = 1.f / (1.f + expf(-o[n]));   // Sigmoid on the property columns (modules.lua:80-86)
+                    // pred rows are dense (22 floats): the warp's 32 rows are 704 consecutive floats -> lane-linear copy
+#pragma unroll
+                    for (int n = 0; n < OUT; ++n) c.stg[lane * OUT + n] = o[n];
+                    __syncwarp();
+                    for (int e = lane; e < wrows * (OUT / 2); e += 32)
+                        *reinterpret_cast<float2*>(pred + fw * OUT + 2 * e) = *reinterpret_cast<const float2*>(c.stg + 2 * e);
+                    __syncwarp();
+                    if (live && loss_ex && y) {
+                        const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
+                        loss_ex[f * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);          // npe.lua:271-274
+                        loss_ex[f * 3 + 1] = __fdiv_rn(lv, 2.f);
+                        loss_ex[f * 3 + 2] = lw;
+                    }
+                }
+            }
+        }
+    }
+    chain_teardown(S.ctl);
+}
+
+// ================================================================================================================
+// decoder input-gradient chain (d_pred -> dz5 -> ... -> dz1 -> ds), tiles of 128 foci; ddz[slot][F][HSLOT] = dz1..dz5
+// ================================================================================================================
+struct DecDgradChainSmem {
+    float Whi[TT_DEC_TOTAL];       // 63488 B
+    float Wlo[TT_DEC_TOTAL];       // 63488 B
+    float stg[8 * STG_FLOATS];
+    ChainCtl ctl;
+};
+
+__global__ void __launch_bounds__(CH_NT, 1)
+k_dec_dgrad_c2(int F, const float* __restrict__ pred, const float* __restrict__ y, const unsigned long long* __restrict__ umask,
+               const float* __restrict__ wtt3, float scale_v, float scale_w, float* __restrict__ ddz,
+               float* __restrict__ ds_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DecDgradChainSmem& S = *reinterpret_cast<DecDgradChainSmem*>(smem_raw);
+    chain_setup(S.ctl);
+    const int ntiles = (F + 127) / 128;
+    const int t = threadIdx.x;
+    if (t >= CH_EPI) {
+        if (t == CH_EPI) {
+            mbar_expect_tx(&S.ctl.wbar, 2 * TT_DEC_TOTAL * 4);
+            bulk_g2s(S.Whi, wtt3 + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
+            bulk_g2s(S.Wlo, wtt3 + TT_TOTAL + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
+            mbar_wait(&S.ctl.wbar, 0);
+            chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
+                // stage 0: dz5 W5 (K = 24); stages 1..3: layers 4..2; stage 4: dz1 W1[:, :50]
+                if (stage == 0) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC5, S.Wlo + TT_DEC5, 64, 64, 3);
+                else if (stage < NL - 1) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC2 + (3 - stage) * TC_HID_SZ,
+                                                             S.Wlo + TT_DEC2 + (3 - stage) * TC_HID_SZ, 64, 64, 7);
+                else umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC1, S.Wlo + TT_DEC1, 64, 64, 7);
+            });
+        }
+    } else {
+        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        unsigned nd = 0;
+        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+            const int f0 = tile * 128;
+            const int nf = min(128, F - f0);
+            const bool live = c.row < nf;
+            const int wrows = max(0, min(32, nf - 32 * c.wq));
+            const size_t f = (size_t)(f0 + c.row);
+            const size_t fw = (size_t)(f0 + 32 * c.wq);
+            unsigned long long um[4] = {0ull, 0ull, 0ull, 0ull};          // ReLU bits of u1..u4 of this focus
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) um[i] = umask[(size_t)i * F + f];
+            }
+            {   // dz5 = d_pred (npe.lua:301-320): columns 2, 3 and 5 of 24
+                float d5[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) d5[k] = 0.f;
+                if (live) {
+                    const float* pp = pred + f * OUT;
+                    const float* yy = y + f * OUT;
+                    d5[2] = (pp[2] - yy[2]) * scale_v;
+                    d5[3] = (pp[3] - yy[3]) * scale_v;
+                    d5[5] = (pp[5] - yy[5]) * scale_w;
+                }
+                warp_store32(c.stg, d5, ddz + ((size_t)4 * F + fw) * HSLOT, HSLOT, wrows, 6);
+                tmem_store_split<3>(c.tm, TM_AHI, TM_ALO, d5);
+            }
+            chain_publish_a(S.ctl, c.slot);
+#pragma unroll 1
+            for (int st = 0; st < NL; ++st) {        // epilogue of stage st: dz_{4 - st} (st < 4) or ds (st == 4)
+                chain_wait_d(S.ctl, c.slot, nd);
+                float d[64];
+                tc_load64(c.tm, d);
+                if (st < NL - 1) {
+                    relu_mask50(d, st == 0 ? um[3] : st == 1 ? um[2] : st == 2 ? um[1] : um[0]);
+                    warp_store_row52(c.stg, d, ddz + ((size_t)(3 - st) * F + fw) * HSLOT, HSLOT, wrows);
+                    tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+                    chain_publish_a(S.ctl, c.slot);
+                } else {
+                    d[50] = 0.f; d[51] = 0.f;        // no gradient into the constant column
+                    warp_store_row52(c.stg, d, ds_out + fw * 52, 52, wrows);
+                }
+            }
+        }
+    }
+    chain_teardown(S.ctl);
+}
+
+// ================================================================================================================
+// pair-MLP input-gradient chain (dz5 = ds[focus] * relu'(h5) -> ... -> dz0), tiles of 128 active pairs;
+// dzact[l][stash_rows][HSLOT] = dz_l.  CAddTable backward = copy; apply_mask is the identity on the active list
+// (npe.lua:326-328).
+// ================================================================================================================
+struct PairDgradChainSmem {
+    float Whi[TT_PAIR_TOTAL];      // 71680 B
+    float Wlo[TT_PAIR_TOTAL];      // 71680 B
+    float stg[8 * STG_FLOATS];
+    ChainCtl ctl;
+};
+
+__global__ void __launch_bounds__(CH_NT, 1)
+k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ foc_row, const int* __restrict__ info,
+                const unsigned long long* __restrict__ hmask, long long stash_rows, const float* __restrict__ ds_in,
+                const float* __restrict__ wtt3, float* __restrict__ dzact, long long* __restrict__ pair_frow) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PairDgradChainSmem& S = *reinterpret_cast<PairDgradChainSmem*>(smem_raw);
+    const int P = info[0];
+    if ((int)blockIdx.x * 256 >= P) return;
+    chain_setup(S.ctl);
+    const int ntiles = (P + 127) / 128;
+    const int t = threadIdx.x;
+    if (t >= CH_EPI) {
+        if (t == CH_EPI) {
+            mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
+            bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
+            bulk_g2s(S.Wlo, wtt3 + TT_TOTAL, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
+            mbar_wait(&S.ctl.wbar, 0);
+            chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
+                const int l = NL - stage;            // dh_{l-1} = dz_l W_l
+                umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_PAIR + (l - 1) * TC_HID_SZ,
+                                    S.Wlo + TT_PAIR + (l - 1) * TC_HID_SZ, 64, 64, 7);
+            });
+        }
+    } else {
+        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        unsigned nd = 0;
+        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+            const int lo = tile * 128;
+            const int nrows = min(128, P - lo);
+            const bool live = c.row < nrows;
+            const int wrows = max(0, min(32, nrows - 32 * c.wq));
+            const size_t p = (size_t)(lo + c.row);
+            const size_t pw = (size_t)(lo + 32 * c.wq);
+            unsigned long long hm[NL + 1];
+#pragma unroll
+            for (int l = 0; l <= NL; ++l) hm[l] = live ? hmask[(size_t)l * stash_rows + p] : 0ull;
+            {
+                float d[64];
+                const float* src = ds_in;
+                if (live) {
+                    const int pf = pair_foc[p];
+                    pair_frow[p] = foc_row[pf];                   // focus-window offset for the encoder weight gradient
+                    src = ds_in + (size_t)pf * 52;
+                }
+                warp_load32(c.stg, d, src, live, 8);
+                warp_load32(c.stg, d + 32, src + 32, live, 5);
+                relu_mask50(d, hm[NL]);
+                warp_store_row52(c.stg, d, dzact + ((size_t)NL * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+            }
+            chain_publish_a(S.ctl, c.slot);
+#pragma unroll 1
+            for (int st = 0; st < NL; ++st) {        // epilogue of stage st: dz_{4 - st}
+                chain_wait_d(S.ctl, c.slot, nd);
+                float d[64];
+                tc_load64(c.tm, d);
+                relu_mask50(d, st == 0 ? hm[4] : st == 1 ? hm[3] : st == 2 ? hm[2] : st == 3 ? hm[1] : hm[0]);
+                warp_store_row52(c.stg, d, dzact + ((size_t)(NL - 1 - st) * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                if (st < NL - 1) {
+                    tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+                    chain_publish_a(S.ctl, c.slot);
+                }
+            }
+        }
+    }
+    chain_teardown(S.ctl);
+}
+
+}  // namespace npe

@@ -467,13 +467,17 @@ struct PairFwdSmem {
 };
 
 // h0 = [relu(Wt f) | relu(Wc c)] into h0buf (cols 50..55 zeroed), then h_l = relu(L_l h_{l-1}) into bufs[l].
-constexpr int HACT_STRIDE = (NL + 1) * 52;   // floats per pair in the activation stash: h0..h5, 52 columns each
+// Activation stashes between forward and backward, LAYER-MAJOR: [slot][row][HSLOT floats] (52 used; 224-byte rows keep
+// every row on 32-byte sector boundaries and make a tile of one layer a contiguous block for TMA bulk copies).
+// Pair stash: slots h0..h5, rows = active pairs (stash_rows = row capacity); decoder stash: slots {pair sum | 1 | 0,
+// u1..u4}, rows = foci (written by the 3xTF32 decoder forward for the tcgen05 backward).
+constexpr int HSLOT = 56;
 
 // Copies rows [0, nrows) x 52 columns of a shared tile to the stash slot `l` of pairs [lo, lo + nrows).
-__device__ __forceinline__ void stash_store(float* __restrict__ hact, int lo, int l, const float* tile, int nrows) {
+__device__ __forceinline__ void stash_store(float* __restrict__ hact, long long stash_rows, int lo, int l, const float* tile, int nrows) {
     for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
         const int r = idx / 13, c4 = idx - r * 13;
-        st4(hact + (size_t)(lo + r) * HACT_STRIDE + l * 52 + 4 * c4, ld4(tile + r * LD + 4 * c4));
+        st4(hact + ((size_t)l * stash_rows + lo + r) * HSLOT + 4 * c4, ld4(tile + r * LD + 4 * c4));
     }
 }
 
@@ -482,18 +486,19 @@ __device__ __forceinline__ void stash_store(float* __restrict__ hact, int lo, in
 // the 2.5 KB/pair round trip (mostly L2) about a quarter of the seven passes it replaces.
 template <int ROWS>
 __device__ __forceinline__ void pair_chain_dense(const float* sWp, const float* sXf, const float* sXc, int nrows,
-                                                 float* const* bufs, float* __restrict__ hact = nullptr, int lo = 0) {
+                                                 float* const* bufs, float* __restrict__ hact = nullptr, int lo = 0,
+                                                 long long stash_rows = 0) {
     float* h0 = bufs[0];
     for (int idx = threadIdx.x; idx < ROWS * 6; idx += NT) h0[(idx / 6) * LD + H + (idx % 6)] = 0.f;
     gemm_nt_r<ROWS, 4, LD, LD>(sXf, sWp + SW_ENC_T, 11, nrows, EpiNT{h0, LD, H2, 1});
     gemm_nt_r<ROWS, 4, LD, LD>(sXc, sWp + SW_ENC_C, 11, nrows, EpiNT{h0 + H2, LD, H2, 1});
     __syncthreads();
-    if (hact) stash_store(hact, lo, 0, h0, nrows);
+    if (hact) stash_store(hact, stash_rows, lo, 0, h0, nrows);
 #pragma unroll 1
     for (int l = 0; l < NL; ++l) {
         gemm_nt_r<ROWS, 7, LD, LD>(bufs[l], sWp + SW_PAIR + l * SW_PAIR_SZ, 13, nrows, EpiNT{bufs[l + 1], LD, 52, 1});
         __syncthreads();
-        if (hact) stash_store(hact, lo, l + 1, bufs[l + 1], nrows);
+        if (hact) stash_store(hact, stash_rows, lo, l + 1, bufs[l + 1], nrows);
     }
 }
 
@@ -513,7 +518,7 @@ template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
-               float* __restrict__ Hp, float* __restrict__ hact) {
+               float* __restrict__ Hp, float* __restrict__ hact, long long stash_rows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairFwdSmem<ROWS>& S = *reinterpret_cast<PairFwdSmem<ROWS>*>(smem_raw);
     // Programmatic dependent launch.  This kernel's predecessor is either the pair builder (tables complete before
@@ -548,7 +553,7 @@ k_pair_forward(const float* __restrict__ states, const int* __restrict__ pair_fo
             __syncthreads();
         }
         if (!staged) { stage_wait(S.W); staged = true; }
-        pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs, hact, lo);
+        pair_chain_dense<ROWS>(S.Wp, S.Xf, S.Xc, nrows, bufs, hact, lo, stash_rows);
         for (int idx = threadIdx.x; idx < nrows * 13; idx += NT) {
             const int r = idx / 13, c4 = idx - r * 13;
             st4(Hp + (size_t)(lo + r) * 52 + 4 * c4, ld4(S.P1 + r * LD + 4 * c4));
@@ -814,7 +819,8 @@ template <int ROWS>
 __global__ void __launch_bounds__(NT, 1)
 k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                 const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wpack,
-                const float* __restrict__ ds_in, float* __restrict__ partial, const float* __restrict__ hact) {
+                const float* __restrict__ ds_in, float* __restrict__ partial, const float* __restrict__ hact,
+                long long stash_rows) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairBwdSmem<ROWS>& S = *reinterpret_cast<PairBwdSmem<ROWS>*>(smem_raw);
     pdl_launch_dependents();
@@ -858,7 +864,7 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
                     const int l = idx / (ROWS * (LD / 4)), rem = idx - l * (ROWS * (LD / 4));
                     const int r = rem / (LD / 4), c4 = rem - r * (LD / 4);
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < nrows && c4 < 13) v = ld4(hact + (size_t)(lo + r) * HACT_STRIDE + l * 52 + 4 * c4);
+                    if (r < nrows && c4 < 13) v = ld4(hact + ((size_t)l * stash_rows + lo + r) * HSLOT + 4 * c4);
                     st4(S.Hh[l] + r * LD + 4 * c4, v);
                 }
                 __syncthreads();

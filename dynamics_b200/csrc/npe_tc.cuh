@@ -306,8 +306,9 @@ k_dec_forward_tc(const float* __restrict__ states, const long long* __restrict__
 // 3xTF32 variant: FP32-grade forward on the tensor cores.  The activations never touch shared memory: each epilogue
 // thread owns one row, reads the accumulator from TMEM, applies ReLU, splits the result into hi / lo TF32 halves and
 // writes them back to TENSOR MEMORY as the A operand of the next layer (tcgen05.st; A-from-TMEM MMA).  Shared memory
-// holds only the hi and lo images of the weights (pair chain 168 KB, decoder 150 KB), which is what makes the split fit.
-// TMEM columns: [0,64) accumulator, [64,160) A hi, [160,256) A lo.
+// holds only the hi and lo images of the weights.  The kernels live in npe_chain.cuh (warp-specialised chains); this
+// file keeps the weight images and the shared helpers.
+// TMEM columns per tile slot: [0,64) accumulator, [64,160) A hi, [160,256) A lo.
 // ================================================================================================================
 constexpr int TM_D = 0, TM_AHI = 64, TM_ALO = 160, TM_GROUP = 256, TM_COLS = 512;
 
@@ -319,249 +320,12 @@ __global__ void k_pack_tc3_scatter(const float* __restrict__ params, float* __re
     w_lo[tc_index(i)] = x - h;
 }
 
-// Two independent 128-thread groups per CTA (warps 0-3 and 4-7) share the weight images and ping-pong on the tensor
-// core: each group owns its own stream of 128-row tiles, its own 256 TMEM columns and its own mbarrier, so the
-// epilogue / input gather of one group overlaps the MMAs of the other (ncu on the single-group version: tensor pipe
-// 12 % active, top stalls long_scoreboard 9.4 and barrier 3.6 per issue).  A group synchronises with a named barrier.
-struct Tc3Ctl {
-    unsigned long long wbar;
-    unsigned long long mbar[2];
-    uint32_t tmem;
-    uint32_t pad;
-};
-__device__ __forceinline__ void tc_group_sync(int g) {
-    tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-    tc_fence_after();
-}
 // ReLU of the 56 leading accumulator columns of this thread's row.
 __device__ __forceinline__ void tc_load_relu(uint32_t tm, float* d) {
     tmem_ld16(tm, 0, d); tmem_ld16(tm, 16, d + 16); tmem_ld16(tm, 32, d + 32); tmem_ld16(tm, 48, d + 48);
     tmem_ld_wait();
 #pragma unroll
     for (int k = 0; k < 56; ++k) d[k] = relu(d[k]);
-}
-
-struct PairTc3Smem {
-    float Whi[TC_PAIR_TOTAL];      // 83968 B
-    float Wlo[TC_PAIR_TOTAL];      // 83968 B
-    Tc3Ctl ctl;
-};
-
-__global__ void __launch_bounds__(NT, 1)
-k_pair_forward_tc3(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
-                   const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wtc3,
-                   float* __restrict__ Hp, float* __restrict__ hact) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PairTc3Smem& S = *reinterpret_cast<PairTc3Smem*>(smem_raw);
-    const int P = info[0];
-    if ((int)blockIdx.x * 256 >= P) return;
-    const int t = threadIdx.x, warp = t >> 5, g = t >> 7, r = t & 127;
-    if (t == 0) { mbar_init(&S.ctl.wbar, 1); mbar_init(&S.ctl.mbar[0], 1); mbar_init(&S.ctl.mbar[1], 1); }
-    if (warp == 0) tmem_alloc<TM_COLS>(&S.ctl.tmem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tm = S.ctl.tmem + g * TM_GROUP;
-    if (t == 0) {
-        mbar_expect_tx(&S.ctl.wbar, 2 * TC_PAIR_TOTAL * 4);
-        bulk_g2s(S.Whi, wtc3, TC_PAIR_TOTAL * 4, &S.ctl.wbar);
-        bulk_g2s(S.Wlo, wtc3 + TC_TOTAL, TC_PAIR_TOTAL * 4, &S.ctl.wbar);
-    }
-    bool staged = false;
-    uint32_t phase = 0;
-    for (int lo = (2 * blockIdx.x + g) * 128; lo < P; lo += 2 * gridDim.x * 128) {
-        const int nrows = min(128, P - lo);
-        // every thread gathers the two windows of ITS pair row straight into tensor memory (hi / lo halves)
-        long long off[2] = {0, 0};
-        if (r < nrows) { off[1] = pair_crow[lo + r]; off[0] = foc_row[pair_foc[lo + r]]; }
-#pragma unroll
-        for (int which = 0; which < 2; ++which) {
-            float x[48];
-#pragma unroll
-            for (int c2 = 0; c2 < 24; ++c2) {
-                float2 v = make_float2(0.f, 0.f);
-                if (c2 < 22 && r < nrows) v = ld2(states + off[which] + 2 * c2);
-                x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
-            }
-            tmem_store_split<6>(tm, TM_AHI + 48 * which, TM_ALO + 48 * which, x);
-        }
-        tmem_st_wait();
-        if (!staged) { mbar_wait(&S.ctl.wbar, 0); staged = true; }
-        tc_group_sync(g);
-        if (r == 0) {
-            umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_ENC_T, S.Wlo + TC_ENC_T, TC_ENC_ROWS, 32, 6);
-            umma_gemm_tf32x3_ts(tm + TM_D + 32, tm + TM_AHI + 48, tm + TM_ALO + 48, S.Whi + TC_ENC_C, S.Wlo + TC_ENC_C, TC_ENC_ROWS, 32, 6);
-            umma_commit(&S.ctl.mbar[g]);
-        }
-        mbar_wait(&S.ctl.mbar[g], phase);
-        tc_fence_after();
-        {
-            float d[64], act[56];
-            tmem_ld16(tm, 0, d); tmem_ld16(tm, 16, d + 16); tmem_ld16(tm, 32, d + 32); tmem_ld16(tm, 48, d + 48);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 56; ++k) act[k] = k < H2 ? relu(d[k]) : (k < H ? relu(d[32 + k - H2]) : 0.f);
-            tmem_store_split<7>(tm, TM_AHI, TM_ALO, act);
-            if (hact && r < nrows) {   // training: activation stash for the backward kernel
-                float* o = hact + (size_t)(lo + r) * HACT_STRIDE;
-#pragma unroll
-                for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(act[4 * c], act[4 * c + 1], act[4 * c + 2], act[4 * c + 3]));
-            }
-            tmem_st_wait();
-        }
-        phase ^= 1;
-        tc_group_sync(g);
-#pragma unroll 1
-        for (int l = 0; l < NL; ++l) {
-            if (r == 0) {
-                umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_PAIR + l * TC_HID_SZ,
-                                    S.Wlo + TC_PAIR + l * TC_HID_SZ, TC_HID_ROWS, 64, 7);
-                umma_commit(&S.ctl.mbar[g]);
-            }
-            mbar_wait(&S.ctl.mbar[g], phase);
-            tc_fence_after();
-            float d[64];
-            tc_load_relu(tm, d);
-            if (hact && r < nrows) {
-                float* o = hact + (size_t)(lo + r) * HACT_STRIDE + (l + 1) * 52;
-#pragma unroll
-                for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]));
-            }
-            if (l < NL - 1) {
-                tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
-                tmem_st_wait();
-            } else if (r < nrows) {
-                float* o = Hp + (size_t)(lo + r) * 52;
-#pragma unroll
-                for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]));
-            }
-            phase ^= 1;
-            tc_group_sync(g);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<TM_COLS>(S.ctl.tmem);
-}
-
-struct DecTc3Smem {
-    float Whi[TC_DEC_TOTAL];       // 74752 B
-    float Wlo[TC_DEC_TOTAL];       // 74752 B
-    Tc3Ctl ctl;
-};
-
-__global__ void __launch_bounds__(NT, 1)
-k_dec_forward_tc3(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
-                  const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
-                  const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
-                  float* __restrict__ dact) {
-    // dact != nullptr (training with the tcgen05 backward): row f of the decoder stash [F][5][52] receives
-    // {z[0..51] = pair sum | 1 | 0, u1, u2, u3, u4} for the input- and weight-gradient kernels (npe_tcbwd.cuh)
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    DecTc3Smem& S = *reinterpret_cast<DecTc3Smem*>(smem_raw);
-    const int t = threadIdx.x, warp = t >> 5, g = t >> 7, r = t & 127;
-    if (t == 0) { mbar_init(&S.ctl.wbar, 1); mbar_init(&S.ctl.mbar[0], 1); mbar_init(&S.ctl.mbar[1], 1); }
-    if (warp == 0) tmem_alloc<TM_COLS>(&S.ctl.tmem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tm = S.ctl.tmem + g * TM_GROUP;
-    if (t == 0) {
-        mbar_expect_tx(&S.ctl.wbar, 2 * TC_DEC_TOTAL * 4);
-        bulk_g2s(S.Whi, wtc3 + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
-        bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
-    }
-    bool staged = false;
-    uint32_t phase = 0;
-    const int ntiles = (F + 127) / 128;
-    for (int tile = 2 * blockIdx.x + g; tile < ntiles; tile += 2 * gridDim.x) {
-        const int f0 = tile * 128;
-        const int nf = min(128, F - f0);
-        const bool live = r < nf;
-        int p0 = 0, p1 = 0;
-        long long foff = 0;
-        if (live) { p0 = pair_start[f0 + r]; p1 = pair_start[f0 + r + 1]; foff = foc_row[f0 + r]; }
-        {   // z columns 0..47: pair sums
-            float z[48];
-#pragma unroll
-            for (int k = 0; k < 48; ++k) z[k] = 0.f;
-            for (int p = p0; p < p1; ++p) {
-#pragma unroll
-                for (int c = 0; c < 12; ++c) {
-                    const float4 h = ld4(Hp + (size_t)p * 52 + 4 * c);
-                    z[4 * c] += h.x; z[4 * c + 1] += h.y; z[4 * c + 2] += h.z; z[4 * c + 3] += h.w;
-                }
-            }
-            tmem_store_split<6>(tm, TM_AHI, TM_ALO, z);
-            if (dact && live) {
-                float* o = dact + (size_t)(f0 + r) * (5 * 52);
-#pragma unroll
-                for (int c = 0; c < 12; ++c) st4(o + 4 * c, make_float4(z[4 * c], z[4 * c + 1], z[4 * c + 2], z[4 * c + 3]));
-            }
-        }
-        {   // z columns 48..95: pair sums 48,49 | 1 | 0 | focus window (44)
-            float z2[48];
-#pragma unroll
-            for (int k = 0; k < 48; ++k) z2[k] = 0.f;
-            for (int p = p0; p < p1; ++p) { const float2 h = ld2(Hp + (size_t)p * 52 + 48); z2[0] += h.x; z2[1] += h.y; }
-            if (live) {
-                z2[2] = 1.f;
-#pragma unroll
-                for (int c2 = 0; c2 < 22; ++c2) { const float2 v = ld2(states + foff + 2 * c2); z2[4 + 2 * c2] = v.x; z2[5 + 2 * c2] = v.y; }
-            }
-            tmem_store_split<6>(tm, TM_AHI + 48, TM_ALO + 48, z2);
-            if (dact && live) st4(dact + (size_t)(f0 + r) * (5 * 52) + 48, make_float4(z2[0], z2[1], z2[2], z2[3]));
-        }
-        tmem_st_wait();
-        if (!staged) { mbar_wait(&S.ctl.wbar, 0); staged = true; }
-        tc_group_sync(g);
-#pragma unroll 1
-        for (int l = 0; l < NL; ++l) {
-            if (r == 0) {
-                if (l == 0) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC1, S.Wlo + TC_DEC1, TC_HID_ROWS, 64, 12);
-                else if (l < NL - 1) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC2 + (l - 1) * TC_HID_SZ,
-                                                         S.Wlo + TC_DEC2 + (l - 1) * TC_HID_SZ, TC_HID_ROWS, 64, 7);
-                else umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC5, S.Wlo + TC_DEC5, TC_OUT_ROWS, 32, 7);
-                umma_commit(&S.ctl.mbar[g]);
-            }
-            mbar_wait(&S.ctl.mbar[g], phase);
-            tc_fence_after();
-            if (l < NL - 1) {
-                float d[64];
-                tc_load_relu(tm, d);
-                tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
-                if (dact && live) {
-                    float* o = dact + (size_t)(f0 + r) * (5 * 52) + (l + 1) * 52;
-#pragma unroll
-                    for (int c = 0; c < 13; ++c) st4(o + 4 * c, make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]));
-                }
-                tmem_st_wait();
-            } else {
-                float o[32];
-                tmem_ld16(tm, 0, o); tmem_ld16(tm, 16, o + 16);
-                tmem_ld_wait();
-                if (live) {
-                    float* pr = pred + (size_t)(f0 + r) * OUT;
-#pragma unroll
-                    for (int n = 0; n < OUT; ++n) pr[n] = n < 6 ? o[n] : 1.f / (1.f + expf(-o[n]));
-                    if (loss_ex && y) {
-                        const float* yy = y + (size_t)(f0 + r) * OUT;
-                        const float e2 = o[2] - yy[2], e3 = o[3] - yy[3], e5 = o[5] - yy[5];
-                        const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
-                        loss_ex[(size_t)(f0 + r) * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);
-                        loss_ex[(size_t)(f0 + r) * 3 + 1] = __fdiv_rn(lv, 2.f);
-                        loss_ex[(size_t)(f0 + r) * 3 + 2] = lw;
-                    }
-                }
-            }
-            phase ^= 1;
-            tc_group_sync(g);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<TM_COLS>(S.ctl.tmem);
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -74,10 +74,10 @@ __global__ void k_pack_tt3_scatter(const float* __restrict__ params, float* __re
     w_lo[o] = x - h;
 }
 
-// ---- stashes (row-major, one row of 52 floats per layer) ----
-// pair:     hact  [pair ][6][52]  h0..h5 (forward), dzact [pair ][6][52]  dz0..dz5 (pair dgrad)
-// decoder:  dact  [focus][5][52]  {z[0..51] = pair sum | 1 | 0, u1..u4} (forward), ddz [focus][5][52] dz1..dz5 (dec dgrad)
-constexpr int DACT_STRIDE = 5 * 52;
+// ---- stashes (row-major, one slot of HSLOT = 56 floats per layer, 52 used; npe_kernels.cuh) ----
+// pair:     hact  [pair ][6 slots]  h0..h5 (forward), dzact [pair ][6 slots]  dz0..dz5 (pair dgrad)
+// decoder:  dact  [focus][5 slots]  {z[0..51] = pair sum | 1 | 0, u1..u4} (forward), ddz [focus][5 slots] dz1..dz5 (dec dgrad)
+// ReLU bits (one 64-bit word per row and layer, layer-major -> coalesced): hmask [6][cap], umask [4][F]
 
 __device__ __forceinline__ void row_load52(float* d, const float* __restrict__ src) {
 #pragma unroll
@@ -95,203 +95,39 @@ __device__ __forceinline__ void tc_load64(uint32_t tm, float* d) {
     tmem_ld16(tm, 0, d); tmem_ld16(tm, 16, d + 16); tmem_ld16(tm, 32, d + 32); tmem_ld16(tm, 48, d + 48);
     tmem_ld_wait();
 }
-// d[k] = d[k] * (h[k] > 0) for k < 50, zero beyond (column 50 is the constant-1 column of the decoder: no gradient)
-__device__ __forceinline__ void relu_mask50(float* d, const float* h) {
+// d[k] = d[k] * (h[k] > 0) for k < 50 with the forward's ReLU bits, zero beyond (column 50 is the constant-1 column of
+// the decoder: no gradient)
+__device__ __forceinline__ void relu_mask50(float* d, unsigned long long bits) {
+    const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32);
 #pragma unroll
-    for (int k = 0; k < 56; ++k) d[k] = (k < H && h[k] > 0.f) ? d[k] : 0.f;
+    for (int k = 0; k < 56; ++k) d[k] = (k < H && (((k < 32 ? lo : hi) >> (k & 31)) & 1u)) ? d[k] : 0.f;
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// decoder input-gradient chain on tiles of 128 foci: d_pred (npe.lua:301-320) -> dz5 -> ... -> dz1 -> ds
+// weight gradients: dW_j[n][k] = sum_r G_j[r][n] * X_j[r][k] for a list of jobs that share the row index r.
+//
+// Pipeline per CTA (persistent over 128-row tiles; unit = 32 rows of one job):
+//   TMA warp        one thread issues cp.async.bulk for the unit's G block and stash X block (32 rows x 224 B, contiguous in the
+//                   layer-major stashes) into a 6-deep raw ring in shared memory (raw_full / raw_empty mbarriers)
+//   8 transposer    read the raw blocks (conflict-free: pitch 56), split hi / lo and store them TRANSPOSED into the K-major
+//   warps           operand images of a 2-deep operand ring; lane mapping 4 rows x 8 columns per instruction, so every store
+//                   instruction writes 32 consecutive floats.  Gathered X segments (state windows addressed through a row
+//                   offset table) are fetched with LDG one unit ahead.
+//   MMA warp        12 x tcgen05.mma.kind::tf32 (M = 64, N = 56 / 96, K = 8; hi*hi + hi*lo + lo*hi) per unit into the job's
+//                   accumulator in tensor memory; tcgen05.commit frees the operand stage
+// The accumulators of all jobs stay in TMEM across the CTA's tiles; one epilogue writes them to the CTA's partial.
 // ----------------------------------------------------------------------------------------------------------------
-struct DecDgradSmem {
-    float Whi[TT_DEC_TOTAL];       // 63488 B
-    float Wlo[TT_DEC_TOTAL];       // 63488 B
-    Tc3Ctl ctl;
-};
-
-__global__ void __launch_bounds__(NT, 1)
-k_dec_dgrad_tc3(int F, const float* __restrict__ pred, const float* __restrict__ y, const float* __restrict__ dact,
-                const float* __restrict__ wtt3, float scale_v, float scale_w, float* __restrict__ ddz,
-                float* __restrict__ ds_out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    DecDgradSmem& S = *reinterpret_cast<DecDgradSmem*>(smem_raw);
-    const int t = threadIdx.x, warp = t >> 5, g = t >> 7, r = t & 127;
-    if (t == 0) { mbar_init(&S.ctl.wbar, 1); mbar_init(&S.ctl.mbar[0], 1); mbar_init(&S.ctl.mbar[1], 1); }
-    if (warp == 0) tmem_alloc<TM_COLS>(&S.ctl.tmem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tm = S.ctl.tmem + g * TM_GROUP;
-    if (t == 0) {
-        mbar_expect_tx(&S.ctl.wbar, 2 * TT_DEC_TOTAL * 4);
-        bulk_g2s(S.Whi, wtt3 + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
-        bulk_g2s(S.Wlo, wtt3 + TT_TOTAL + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
-    }
-    bool staged = false;
-    uint32_t phase = 0;
-    const int ntiles = (F + 127) / 128;
-    for (int tile = 2 * blockIdx.x + g; tile < ntiles; tile += 2 * gridDim.x) {
-        const int f0 = tile * 128;
-        const bool live = r < min(128, F - f0);
-        const size_t f = (size_t)(f0 + r);
-        {   // dz5 = d_pred: columns 2, 3 (velocity) and 5 (angular velocity) only
-            float d5[24];
-#pragma unroll
-            for (int k = 0; k < 24; ++k) d5[k] = 0.f;
-            if (live) {
-                const float* pp = pred + f * OUT;
-                const float* yy = y + f * OUT;
-                d5[2] = (pp[2] - yy[2]) * scale_v;
-                d5[3] = (pp[3] - yy[3]) * scale_v;
-                d5[5] = (pp[5] - yy[5]) * scale_w;
-                float* o = ddz + f * DACT_STRIDE + 4 * 52;
-#pragma unroll
-                for (int c = 0; c < 6; ++c) st4(o + 4 * c, make_float4(d5[4 * c], d5[4 * c + 1], d5[4 * c + 2], d5[4 * c + 3]));
-            }
-            tmem_store_split<3>(tm, TM_AHI, TM_ALO, d5);
-            tmem_st_wait();
-        }
-        if (!staged) { mbar_wait(&S.ctl.wbar, 0); staged = true; }
-        tc_group_sync(g);
-        // layers 5 .. 2: dh_{l-1} = dz_l W_l, dz_{l-1} = dh_{l-1} * (u_{l-1} > 0); then ds = dz1 W1[:, :50]
-#pragma unroll 1
-        for (int l = NL; l >= 1; --l) {
-            if (r == 0) {
-                if (l == NL) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC5, S.Wlo + TT_DEC5, 64, 64, 3);
-                else if (l >= 2) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC2 + (l - 2) * TC_HID_SZ,
-                                                     S.Wlo + TT_DEC2 + (l - 2) * TC_HID_SZ, 64, 64, 7);
-                else umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_DEC1, S.Wlo + TT_DEC1, 64, 64, 7);
-                umma_commit(&S.ctl.mbar[g]);
-            }
-            float h[52];
-            if (l >= 2) {   // u_{l-1} of this focus from the forward stash, fetched while the MMAs run
-                if (live) row_load52(h, dact + f * DACT_STRIDE + (l - 1) * 52);
-                else {
-#pragma unroll
-                    for (int k = 0; k < 52; ++k) h[k] = 0.f;
-                }
-            }
-            mbar_wait(&S.ctl.mbar[g], phase);
-            tc_fence_after();
-            float d[64];
-            tc_load64(tm, d);
-            if (l >= 2) {
-                relu_mask50(d, h);
-                if (live) row_store52(ddz + f * DACT_STRIDE + (l - 2) * 52, d);
-                tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
-                tmem_st_wait();
-            } else if (live) {
-                d[50] = 0.f; d[51] = 0.f;
-                row_store52(ds_out + f * 52, d);
-            }
-            phase ^= 1;
-            tc_group_sync(g);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<TM_COLS>(S.ctl.tmem);
-}
-
-// ----------------------------------------------------------------------------------------------------------------
-// pair-MLP input-gradient chain on tiles of 128 active pairs: dz5 = ds[focus] * (h5 > 0) -> ... -> dz0
-// (CAddTable backward = copy; apply_mask is the identity on the active list, npe.lua:326-328)
-// ----------------------------------------------------------------------------------------------------------------
-struct PairDgradSmem {
-    float Whi[TT_PAIR_TOTAL];      // 71680 B
-    float Wlo[TT_PAIR_TOTAL];      // 71680 B
-    Tc3Ctl ctl;
-};
-
-__global__ void __launch_bounds__(NT, 1)
-k_pair_dgrad_tc3(const int* __restrict__ pair_foc, const long long* __restrict__ foc_row, const int* __restrict__ info,
-                 const float* __restrict__ hact, const float* __restrict__ ds_in, const float* __restrict__ wtt3,
-                 float* __restrict__ dzact, long long* __restrict__ pair_frow) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    PairDgradSmem& S = *reinterpret_cast<PairDgradSmem*>(smem_raw);
-    const int P = info[0];
-    if ((int)blockIdx.x * 256 >= P) return;
-    const int t = threadIdx.x, warp = t >> 5, g = t >> 7, r = t & 127;
-    if (t == 0) { mbar_init(&S.ctl.wbar, 1); mbar_init(&S.ctl.mbar[0], 1); mbar_init(&S.ctl.mbar[1], 1); }
-    if (warp == 0) tmem_alloc<TM_COLS>(&S.ctl.tmem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tm = S.ctl.tmem + g * TM_GROUP;
-    if (t == 0) {
-        mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
-        bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
-        bulk_g2s(S.Wlo, wtt3 + TT_TOTAL, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
-    }
-    bool staged = false;
-    uint32_t phase = 0;
-    for (int lo = (2 * blockIdx.x + g) * 128; lo < P; lo += 2 * gridDim.x * 128) {
-        const bool live = r < min(128, P - lo);
-        const size_t p = (size_t)(lo + r);
-        {
-            float d[56], h[52];
-#pragma unroll
-            for (int k = 0; k < 56; ++k) d[k] = 0.f;
-            if (live) {
-                const int pf = pair_foc[p];
-                pair_frow[p] = foc_row[pf];                 // gather offset of the focus window for the encoder wgrad
-                row_load52(d, ds_in + (size_t)pf * 52);
-                row_load52(h, hact + p * HACT_STRIDE + NL * 52);
-                relu_mask50(d, h);
-                row_store52(dzact + p * HACT_STRIDE + NL * 52, d);
-            }
-            tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
-            tmem_st_wait();
-        }
-        if (!staged) { mbar_wait(&S.ctl.wbar, 0); staged = true; }
-        tc_group_sync(g);
-#pragma unroll 1
-        for (int l = NL; l >= 1; --l) {
-            if (r == 0) {
-                umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_PAIR + (l - 1) * TC_HID_SZ,
-                                    S.Wlo + TT_PAIR + (l - 1) * TC_HID_SZ, 64, 64, 7);
-                umma_commit(&S.ctl.mbar[g]);
-            }
-            float h[52];
-            if (live) row_load52(h, hact + p * HACT_STRIDE + (l - 1) * 52);
-            else {
-#pragma unroll
-                for (int k = 0; k < 52; ++k) h[k] = 0.f;
-            }
-            mbar_wait(&S.ctl.mbar[g], phase);
-            tc_fence_after();
-            float d[64];
-            tc_load64(tm, d);
-            relu_mask50(d, h);
-            if (live) row_store52(dzact + p * HACT_STRIDE + (l - 1) * 52, d);
-            if (l > 1) {
-                tmem_store_split<7>(tm, TM_AHI, TM_ALO, d);
-                tmem_st_wait();
-            }
-            phase ^= 1;
-            tc_group_sync(g);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<TM_COLS>(S.ctl.tmem);
-}
-
-// ----------------------------------------------------------------------------------------------------------------
-// weight gradients: dW_j[n][k] = sum_r G_j[r][n] * X_j[r][k] for a list of jobs that share the row index r
-// ----------------------------------------------------------------------------------------------------------------
-struct WSeg {
-    const float* base;            // value(R, c) = base[(offs ? offs[R] : R * stride) + c]
+struct WGather {
+    const float* base;            // value(R, c) = base[offs[R] + c]
     const long long* offs;
-    long long stride;
     int cols_valid;               // columns c >= cols_valid read as zero
     int cols_store;               // columns c < cols_store are written to the B image at column col0 + c
     int col0;
 };
 struct WJob {
-    const float* G; long long g_stride; int g_cols;   // gradient rows (row-major); columns >= g_cols are zero
-    WSeg x[2]; int nx;                                // input rows: one or two column segments
+    const float* G; int g_cols;                       // gradient rows: stash slot [rows][HSLOT]; columns >= g_cols are zero
+    const float* X0; int x0_valid, x0_store;          // input rows from a stash slot (or nullptr): B image columns [0, x0_store)
+    WGather gs[2]; int ngs;                           // gathered input segments
     int nb;                                           // rows of the B image (k): 56 or 96
     int tmem_col;                                     // accumulator columns [tmem_col, tmem_col + nb)
     int kind;                                         // epilogue: 0 uniform layer, 1 decoder layer 1 (tiles split A / B), 2 encoders
@@ -306,120 +142,154 @@ struct WArgs {
     float* partial;               // [gridDim.x][PT_TOTAL]
 };
 
-constexpr int WG_ROWS = 64;       // rows r per stage (half a 128-row tile): K = 64 per stage = 8 MMA k-steps
-constexpr int WG_NT = 288;        // 8 producer warps + 1 MMA warp
-struct WStage {
+constexpr int WG_ROWS = 32;       // rows per unit: K = 32 = 4 MMA k-steps
+constexpr int WG_NRAW = 4;        // raw ring depth
+constexpr int WG_NOP = 3;         // operand ring depth: transposers run up to 2 units ahead of the MMA warp
+constexpr int WG_NT = 320;        // 8 transposer warps + MMA warp + producer warp
+constexpr int WG_BLOCK = WG_ROWS * HSLOT;            // floats of one stash block (7168 B)
+constexpr int WG_XG_PITCH = 98;   // floats: pitch of gathered X rows in the raw stage (8-byte stores of 32 lanes: conflict-free)
+struct WRaw { float G[WG_BLOCK]; float X[WG_ROWS * WG_XG_PITCH]; };   // 7168 + 12544 B
+struct WOp {
     float Ahi[64 * WG_ROWS], Alo[64 * WG_ROWS];       // G^T: [r / 4][n (64)][r % 4]
     float Bhi[96 * WG_ROWS], Blo[96 * WG_ROWS];       // X^T: [r / 4][k (nb)][r % 4]
 };
 struct WgradSmem {
-    WStage st[2];                                     // 2 x 81920 B
-    unsigned long long full[2], empty[2], done;
+    WOp op[WG_NOP];                                   // 3 x 40960 B
+    WRaw raw[WG_NRAW];                                // 4 x 19712 B
+    unsigned long long raw_full[WG_NRAW], raw_empty[WG_NRAW], op_full[WG_NOP], op_empty[WG_NOP], done;
     uint32_t tmem, pad;
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx_only(unsigned long long* bar, unsigned bytes) {   // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t umma_idesc_tf32_m64(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
 }
 
-// One producer thread's share of a stage: rows {4 w + rsub, 4 (w + 8) + rsub}, columns {8 g + nsub}.
-__device__ __forceinline__ void wgrad_fill_stage(WStage& st, const WJob& J, long long row0, long long R) {
-    const int t = threadIdx.x, w = t >> 5, lane = t & 31, rsub = lane & 3, nsub = lane >> 2;
-    float gv[2][7];
-    float xv[2][14];
-    long long Rr[2];
-    bool ok[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        Rr[q] = row0 + 4 * (w + 8 * q) + rsub;
-        ok[q] = Rr[q] < R;
+// Unit iterator shared by the three roles.  The R rows are cut into 32-row quarter tiles; CTA b owns a contiguous, balanced
+// range of them and runs every job on each (unit = quarter tile x job).
+struct WUnit {
+    long long qt, qt_end;
+    int j, njobs;
+    __device__ __forceinline__ void init(long long R, int njobs_) {
+        const long long nq = (R + WG_ROWS - 1) / WG_ROWS;
+        qt = nq * blockIdx.x / gridDim.x; qt_end = nq * (blockIdx.x + 1) / gridDim.x;
+        j = 0; njobs = njobs_;
     }
-    // issue every global load of this thread first (independent), then split and store
+    __device__ __forceinline__ bool valid() const { return qt < qt_end; }
+    __device__ __forceinline__ long long row0() const { return qt * WG_ROWS; }
+    __device__ __forceinline__ void next() { if (++j == njobs) { j = 0; ++qt; } }
+};
+
+__device__ __forceinline__ void wgrad_put(float* hi_img, float* lo_img, int off, const float (&v)[4]) {
+    float4 h, l;
+    h.x = tf32_hi(v[0]); h.y = tf32_hi(v[1]); h.z = tf32_hi(v[2]); h.w = tf32_hi(v[3]);
+    l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+    st4(hi_img + off, h); st4(lo_img + off, l);
+}
+// Transposer work items of a unit: item i = (column n = i % ncols, row group rg = i / ncols), rows 4 rg .. 4 rg + 3.  A thread
+// reads the four rows of its column (consecutive lanes = consecutive columns: conflict-free) and writes ONE 16-byte store
+// per image: element (n, 4 rg .. 4 rg + 3) is contiguous in the K-major operand layout.
+template <int NITEMS>
+__device__ __forceinline__ void wgrad_transpose_block(float* hi_img, float* lo_img, int img_rows, int img_col0, const float* src,
+                                                      int pitch, int ncols, int cols_valid, int rows_left) {
+    const int t = threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const float* gp = J.G + Rr[q] * J.g_stride;
+    for (int k = 0; k < NITEMS; ++k) {
+        const int i = t + 256 * k, rg = i / ncols, n = i - rg * ncols;
+        if (rg < 8) {
+            float v[4];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const int n = 8 * c + nsub;
-            gv[q][c] = (ok[q] && n < J.g_cols) ? __ldg(gp + n) : 0.f;
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (s < J.nx) {
-            const WSeg& X = J.x[s];
-            const int ngroups = (X.cols_store + 7) >> 3;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float* xp = X.base + (ok[q] ? (X.offs ? X.offs[Rr[q]] : Rr[q] * X.stride) : 0);
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    const int cc = 8 * c + nsub;
-                    xv[q][7 * s + c] = (c < ngroups && ok[q] && cc < X.cols_valid) ? __ldg(xp + cc) : 0.f;
-                }
+            for (int r = 0; r < 4; ++r) {
+                const float x = src[(4 * rg + r) * pitch + n];
+                v[r] = (4 * rg + r < rows_left && n < cols_valid) ? x : 0.f;
             }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int rg = w + 8 * q;
-        float* ah = st.Ahi + rg * 256 + lane;
-        float* al = st.Alo + rg * 256 + lane;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) {
-            const float v = gv[q][c], hi = tf32_hi(v);
-            ah[32 * c] = hi; al[32 * c] = v - hi;
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        if (s < J.nx) {
-            const WSeg& X = J.x[s];
-            const int ngroups = (X.cols_store + 7) >> 3;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int rg = w + 8 * q;
-                float* bh = st.Bhi + rg * J.nb * 4 + X.col0 * 4 + lane;
-                float* bl = st.Blo + rg * J.nb * 4 + X.col0 * 4 + lane;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) {
-                    if (c < ngroups && 8 * c + nsub < X.cols_store) {
-                        const float v = xv[q][7 * s + c], hi = tf32_hi(v);
-                        bh[32 * c] = hi; bl[32 * c] = v - hi;
-                    }
-                }
-            }
+            wgrad_put(hi_img, lo_img, (rg * img_rows + img_col0 + n) * 4, v);
         }
     }
 }
+// raw blocks -> hi / lo operand images of one operand stage
+__device__ __forceinline__ void wgrad_transpose(WOp& op, const WRaw& raw, const WJob& J, long long row0, long long R) {
+    const int rows_left = (int)min((long long)WG_ROWS, R - row0);       // rows beyond R hold whatever the copy found: zero
+    wgrad_transpose_block<2>(op.Ahi, op.Alo, 64, 0, raw.G, HSLOT, 56, J.g_cols, rows_left);
+    if (J.ngs) wgrad_transpose_block<3>(op.Bhi, op.Blo, 96, 0, raw.X, WG_XG_PITCH, 96, 96, rows_left);   // assembled by the producer warp
+    else wgrad_transpose_block<2>(op.Bhi, op.Blo, J.nb, 0, raw.X, HSLOT, 56, J.x0_valid, rows_left);
+}
 
-// Accumulator row -> the CTA's partial in the tile-major layout of npe_layout.h (what partial_index addresses).
+// Producer warp, gathered jobs: lane = row.  Assembles the 96-column X row in the raw stage (pitch 98 floats):
+//   encoders         [focus window (44) | 0 x 4 | context window (44) | 0 x 4]      (row offsets gs[0].offs / gs[1].offs)
+//   decoder layer 1  [stash row z[0..51] | focus window (44)]                        (stash X0, row offsets gs[0].offs)
+__device__ __forceinline__ void wgrad_assemble(float* xs, const WJob& J, long long row0, long long R) {
+    const int lane = threadIdx.x & 31;
+    const long long row = row0 + lane;
+    const bool ok = row < R;
+    float* o = xs + lane * WG_XG_PITCH;
+    float2 a[26], b[24];
+    const float2 z2 = make_float2(0.f, 0.f);
+    if (J.ngs == 2) {
+        const float* pa = J.gs[0].base + (ok ? J.gs[0].offs[row] : 0);
+        const float* pb = J.gs[1].base + (ok ? J.gs[1].offs[row] : 0);
+#pragma unroll
+        for (int c = 0; c < 24; ++c) { a[c] = (ok && c < 22) ? ld2(pa + 2 * c) : z2; b[c] = (ok && c < 22) ? ld2(pb + 2 * c) : z2; }
+    } else {
+        const float* pa = J.X0 + (ok ? row * HSLOT : 0);
+        const float* pb = J.gs[0].base + (ok ? J.gs[0].offs[row] : 0);
+#pragma unroll
+        for (int c = 0; c < 13; ++c) {
+            const float4 v = ok ? ld4(pa + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            a[2 * c] = make_float2(v.x, v.y); a[2 * c + 1] = make_float2(v.z, v.w);
+        }
+#pragma unroll
+        for (int c = 0; c < 22; ++c) b[c] = ok ? ld2(pb + 2 * c) : z2;
+    }
+    if (J.ngs == 2) {
+#pragma unroll
+        for (int c = 0; c < 24; ++c) { *reinterpret_cast<float2*>(o + 2 * c) = a[c]; *reinterpret_cast<float2*>(o + 48 + 2 * c) = b[c]; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 26; ++c) *reinterpret_cast<float2*>(o + 2 * c) = a[c];
+#pragma unroll
+        for (int c = 0; c < 22; ++c) *reinterpret_cast<float2*>(o + 52 + 2 * c) = b[c];
+    }
+}
+
+// Accumulator row n (d[0 .. nb)) -> the CTA's partial in the tile-major layout of npe_layout.h (what partial_index addresses).
+// All register indices are static (no local memory).
 __device__ __forceinline__ void wgrad_store_rows(float* __restrict__ out, const WJob& J, int n, const float* d, bool zero) {
-    const int nchunks = J.nb >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (J.kind == 2) {   // encoders: G = dz0; rows 0..24 x cols 0..43 -> focus encoder, rows 25..49 x cols 48..91 -> context
         if (n >= H) return;
-        const int nn = n < H2 ? n : n - H2, cb = n < H2 ? 0 : 12;
-        float* o = out + (n < H2 ? PT_ENC_T : PT_ENC_C) + (nn >> 2) * 11 * 16 + 4 * (nn & 3);
-        for (int kc = 0; kc < 11; ++kc) {
-            const float* v = d + 4 * (cb + kc);
-            st4(o + kc * 16, zero ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[0], v[1], v[2], v[3]));
+        if (n < H2) {
+            float* o = out + PT_ENC_T + (n >> 2) * 11 * 16 + 4 * (n & 3);
+#pragma unroll
+            for (int kc = 0; kc < 11; ++kc) st4(o + kc * 16, zero ? z4 : make_float4(d[4 * kc], d[4 * kc + 1], d[4 * kc + 2], d[4 * kc + 3]));
+        } else {
+            const int nn = n - H2;
+            float* o = out + PT_ENC_C + (nn >> 2) * 11 * 16 + 4 * (nn & 3);
+#pragma unroll
+            for (int kc = 0; kc < 11; ++kc)
+                st4(o + kc * 16, zero ? z4 : make_float4(d[48 + 4 * kc], d[49 + 4 * kc], d[50 + 4 * kc], d[51 + 4 * kc]));
         }
         return;
     }
     if (n >= J.n_valid) return;
-    for (int kc = 0; kc < nchunks && kc < J.kt; ++kc) {
-        float* o;
-        if (J.kind == 1) {
-            const int tile = (n >> 2) * 24 + kc;
-            o = out + (tile < NT ? PT_DEC1A + tile * 16 : PT_DEC1B + (tile - NT) * 16) + 4 * (n & 3);
-        } else {
-            o = out + J.pt_base + ((n >> 2) * J.kt + kc) * 16 + 4 * (n & 3);
+    const int nk = min(J.nb >> 2, J.kt);
+#pragma unroll
+    for (int kc = 0; kc < 24; ++kc) {
+        if (kc < nk) {
+            float* o;
+            if (J.kind == 1) {
+                const int tile = (n >> 2) * 24 + kc;
+                o = out + (tile < NT ? PT_DEC1A + tile * 16 : PT_DEC1B + (tile - NT) * 16) + 4 * (n & 3);
+            } else {
+                o = out + J.pt_base + ((n >> 2) * J.kt + kc) * 16 + 4 * (n & 3);
+            }
+            st4(o, zero ? z4 : make_float4(d[4 * kc], d[4 * kc + 1], d[4 * kc + 2], d[4 * kc + 3]));
         }
-        const float* v = d + 4 * kc;
-        st4(o, zero ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
@@ -428,59 +298,78 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
     WgradSmem& S = *reinterpret_cast<WgradSmem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long R = A.nrows_dev ? (long long)*A.nrows_dev : (long long)A.nrows;
-    const int ntiles = (int)((R + 127) / 128);
     if (t == 0) {
-        mbar_init(&S.full[0], 256); mbar_init(&S.full[1], 256);
-        mbar_init(&S.empty[0], 1); mbar_init(&S.empty[1], 1); mbar_init(&S.done, 1);
+        for (int i = 0; i < WG_NRAW; ++i) { mbar_init(&S.raw_full[i], 1); mbar_init(&S.raw_empty[i], 256); }
+        for (int i = 0; i < WG_NOP; ++i) { mbar_init(&S.op_full[i], 256); mbar_init(&S.op_empty[i], 1); }
+        mbar_init(&S.done, 1);
     }
     if (warp == 8) tmem_alloc<512>(&S.tmem);
-    // zero both stages once: image rows / columns that no job writes (A rows 56..63) must read as zero
-    for (int i = t; i < (int)(sizeof(S.st) / 16); i += WG_NT) reinterpret_cast<float4*>(S.st)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // zero the A images once: rows 56..63 are never written and must read as zero
+    for (int i = t; i < WG_NOP * 2 * 64 * WG_ROWS / 4; i += WG_NT) {
+        const int o = i / (2 * 64 * WG_ROWS / 4), r = i - o * (2 * 64 * WG_ROWS / 4);
+        reinterpret_cast<float4*>(S.op[o].Ahi)[r] = make_float4(0.f, 0.f, 0.f, 0.f);      // Ahi and Alo are adjacent
+    }
     proxy_fence_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem;
-    const bool has_work = (int)blockIdx.x < ntiles;
-    if (warp < 8) {
-        int u = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int j = 0; j < A.njobs; ++j) {
-                for (int half = 0; half < 2; ++half, ++u) {
-                    const int s = u & 1;
-                    if (u >= 2) mbar_wait(&S.empty[s], (unsigned)(((u >> 1) - 1) & 1));
-                    wgrad_fill_stage(S.st[s], A.job[j], (long long)tile * 128 + half * WG_ROWS, R);
-                    proxy_fence_async();
-                    mbar_arrive(&S.full[s]);
-                }
+    WUnit it; it.init(R, A.njobs);
+    const bool has_work = it.valid();
+    if (warp == 9) {   // producer: TMA bulk copies of the stash blocks; gathered X rows assembled by the 32 lanes
+        for (int u = 0; it.valid(); it.next(), ++u) {
+            const int s = u % WG_NRAW;
+            const WJob& J = A.job[it.j];
+            if (lane == 0) {
+                if (u >= WG_NRAW) mbar_wait(&S.raw_empty[s], (unsigned)(((u / WG_NRAW) - 1) & 1));
+                mbar_expect_tx_only(&S.raw_full[s], (J.ngs ? 1u : 2u) * WG_BLOCK * 4);
+                bulk_g2s(S.raw[s].G, J.G + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
+                if (!J.ngs) bulk_g2s(S.raw[s].X, J.X0 + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
             }
+            __syncwarp();
+            if (J.ngs) { wgrad_assemble(S.raw[s].X, J, it.row0(), R); __syncwarp(); }
+            if (lane == 0) mbar_arrive(&S.raw_full[s]);
         }
-    } else if (lane == 0) {
-        int u = 0;
+    } else if (warp < 8) {
+        for (int u = 0; it.valid(); it.next(), ++u) {
+            const int s = u % WG_NRAW, o = u % WG_NOP;
+            mbar_wait(&S.raw_full[s], (unsigned)((u / WG_NRAW) & 1));
+            if (u >= WG_NOP) mbar_wait(&S.op_empty[o], (unsigned)(((u / WG_NOP) - 1) & 1));
+            wgrad_transpose(S.op[o], S.raw[s], A.job[it.j], it.row0(), R);
+            proxy_fence_async();
+            mbar_arrive(&S.op_full[o]);
+            mbar_arrive(&S.raw_empty[s]);
+        }
+    } else if (lane == 0) {   // warp 8: MMA issue
         unsigned started = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            for (int j = 0; j < A.njobs; ++j) {
-                const WJob& J = A.job[j];
-                const uint32_t idesc = umma_idesc_tf32_m64(J.nb);
-                for (int half = 0; half < 2; ++half, ++u) {
-                    const int s = u & 1;
-                    mbar_wait(&S.full[s], (unsigned)((u >> 1) & 1));
-                    tc_fence_after();
-                    const uint32_t ah = smem_u32(S.st[s].Ahi), al = smem_u32(S.st[s].Alo);
-                    const uint32_t bh = smem_u32(S.st[s].Bhi), bl = smem_u32(S.st[s].Blo);
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a0 = pass == 2 ? al : ah, b0 = pass == 1 ? bl : bh;
-                        for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-                            const uint64_t da = umma_desc(a0 + 2 * ks * 64 * 16, 64 * 16, 128);
-                            const uint64_t db = umma_desc(b0 + 2 * ks * J.nb * 16, J.nb * 16, 128);
-                            const uint32_t acc = ((started >> j) & 1u) | (uint32_t)(pass | ks);
-                            umma_tf32(tmem + J.tmem_col, da, db, idesc, acc ? 1u : 0u);
-                        }
-                    }
-                    started |= 1u << j;
-                    umma_commit(&S.empty[s]);
+        for (int u = 0; it.valid(); it.next(), ++u) {
+            const WJob& J = A.job[it.j];
+            const int nb = J.nb, o = u % WG_NOP;
+            const uint32_t idesc = umma_idesc_tf32_m64(nb);
+            const uint32_t d_tm = tmem + J.tmem_col;
+            // descriptors: low word = address field | LBO << 16, high word = SBO | version; a K-step advances the address field
+            const uint32_t hiw = (128u >> 4) | (1u << 14);
+            const uint32_t a_lo[2] = {((smem_u32(S.op[o].Ahi) >> 4) & 0x3FFFu) | ((64u * 16u >> 4) << 16),
+                                      ((smem_u32(S.op[o].Alo) >> 4) & 0x3FFFu) | ((64u * 16u >> 4) << 16)};
+            const uint32_t b_lo[2] = {((smem_u32(S.op[o].Bhi) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16),
+                                      ((smem_u32(S.op[o].Blo) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16)};
+            const uint32_t a_step = 2u * 64u * 16u >> 4, b_step = 2u * (uint32_t)nb * 16u >> 4;
+            mbar_wait(&S.op_full[o], (unsigned)((u / WG_NOP) & 1));
+            tc_fence_after();
+            uint32_t acc = (started >> it.j) & 1u;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t a0 = a_lo[pass == 2], b0 = b_lo[pass == 1];
+#pragma unroll
+                for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
+                    const uint64_t da = ((uint64_t)hiw << 32) | (a0 + ks * a_step);
+                    const uint64_t db = ((uint64_t)hiw << 32) | (b0 + ks * b_step);
+                    umma_tf32(d_tm, da, db, idesc, acc);
+                    acc = 1u;
                 }
             }
+            started |= 1u << it.j;
+            umma_commit(&S.op_empty[o]);
         }
         umma_commit(&S.done);
     }

@@ -78,4 +78,54 @@ function model:pull_neighbor_masks()
     return self.neighbor_masks
 end
 
+-- Gradient with respect to the INPUTS (npe.lua:341-384).  Nothing on the north-star path calls it (main.lua / eval.lua -mode
+-- sim never do; the reference version itself returns an undefined `d_input`): explicit error instead of a silent nil.
+function model:bp_input(batch, prediction, sim)
+    error('npe (libnpe_cuda): bp_input is not supported -- input gradients are not part of the training / rollout path')
+end
+
+-- simulate_all_postprocess helpers (eval.lua:170-173).  Host tensors of a few hundred floats: plain torch arithmetic with the
+-- reference's operation order, (p * pnc + v * vnc) / pnc, each op rounded once, so positions stay bit-identical.
+-- this (B, num_past, 22), pred (B, num_future, 22); returns a modified copy of pred.
+
+-- Position of step k+1 = position of step k + velocity of step k, starting from the LAST PAST frame: the predicted
+-- velocity of a step only moves the object one step later (npe.lua:386-419).
+function model:update_position(this, pred)
+    local si = config_args.si
+    local pnc, vnc = config_args.position_normalize_constant, config_args.velocity_normalize_constant
+    local out = pred:clone()
+    local np_, nf = this:size(2), pred:size(2)
+    local pos = this[{{}, {np_}, {si.px, si.py}}]:clone():mul(pnc)           -- (B,1,2) pixels
+    local vel = this[{{}, {np_}, {si.vx, si.vy}}]:clone():mul(vnc)
+    for k = 1, nf do
+        pos = pos + vel                                                       -- integrate the PREVIOUS step's velocity
+        out[{{}, {k}, {si.px, si.py}}] = pos / pnc
+        vel = pred[{{}, {k}, {si.vx, si.vy}}]:clone():mul(vnc)
+    end
+    return out
+end
+
+-- Same recurrence for the angle, wrapped back into (-pi, pi] (npe.lua:422-458): a value above pi loses 2 pi, a value at or
+-- below -pi gains 2 pi, applied to every step of the running sum at once like the reference does.
+function model:update_angle(this, pred)
+    local si = config_args.si
+    local anc = config_args.angle_normalize_constant
+    local out = pred:clone()
+    local np_, nf = this:size(2), pred:size(2)
+    local B = pred:size(1)
+    local ang = torch.Tensor(B, nf + 1, 1):typeAs(pred)
+    ang[{{}, {1}, {}}] = this[{{}, {np_}, {si.a}}]:clone():mul(anc)
+    local av = this[{{}, {np_}, {si.av}}]:clone():mul(anc)
+    for k = 1, nf do
+        ang[{{}, {k + 1}, {}}] = ang[{{}, {k}, {}}] + av
+        av = pred[{{}, {k}, {si.av}}]:clone():mul(anc)
+    end
+    local too_big = ang:gt(math.pi):typeAs(ang)
+    local too_small = ang:le(-math.pi):typeAs(ang)
+    ang = torch.add(ang, -2 * math.pi, too_big)
+    ang = torch.add(ang, 2 * math.pi, too_small)
+    out[{{}, {}, {si.a}}] = ang[{{}, {2, nf + 1}, {}}] / anc
+    return out
+end
+
 return model

@@ -193,6 +193,42 @@ class NPEModel:
         self._ck(self.lib.npe_backward(self.h, divisor_batch))
         return self.get_grads()
 
+    # ---- simulate_all_postprocess helpers (eval.lua:170-173): host tensors, mirrored from lua/npe.lua --------------------
+    PNC, VNC, ANC = np.float32(800.0), np.float32(60.0), np.float32(np.pi)       # config.lua:16-17,51
+
+    def update_position(self, this, pred):
+        """model:update_position (npe.lua:386-419): this (B,num_past,22), pred (B,num_future,22) -> copy of pred whose
+        positions integrate the PREVIOUS step's velocity, starting from the last past frame."""
+        this = L.f32(this); out = L.f32(pred).copy()
+        pos = this[:, -1, 0:2] * self.PNC
+        vel = this[:, -1, 2:4] * self.VNC
+        for k in range(out.shape[1]):
+            pos = (pos + vel).astype(np.float32)
+            vel = out[:, k, 2:4] * self.VNC
+            out[:, k, 0:2] = pos / self.PNC
+        return out
+
+    def update_angle(self, this, pred):
+        """model:update_angle (npe.lua:422-458): running angle sum wrapped back into (-pi, pi]."""
+        this = L.f32(this); out = L.f32(pred).copy()
+        nf = out.shape[1]
+        ang = np.empty((out.shape[0], nf + 1), np.float32)
+        ang[:, 0] = this[:, -1, 4] * self.ANC
+        av = this[:, -1, 5] * self.ANC
+        for k in range(nf):
+            ang[:, k + 1] = ang[:, k] + av
+            av = out[:, k, 5] * self.ANC
+        big = (ang > self.ANC).astype(np.float32); small = (ang <= -self.ANC).astype(np.float32)
+        ang = (ang + np.float32(-2 * np.pi) * big).astype(np.float32)
+        ang = (ang + np.float32(2 * np.pi) * small).astype(np.float32)
+        out[:, :, 4] = ang[:, 1:] / self.ANC
+        return out
+
+    def bp_input(self, batch=None, prediction=None, sim=False):
+        """model:bp_input (npe.lua:341-384) is not on the training / rollout path (and returns an undefined value in the
+        reference): explicit error, as in lua/npe.lua."""
+        raise L.NPEError(-3, "bp_input is not supported: input gradients are not part of the training / rollout path")
+
     def pair_table(self):
         """(closest_indices (F,K) int32, neighbour mask (F,K) uint8, kept count (F)) of the current batch."""
         F, K = self.lib.npe_num_foci(self.h), self.lib.npe_ctx_slots(self.h)

@@ -288,9 +288,8 @@ class Experiment:
         if self.rank != 0:
             return path
         self.say("saving checkpoint to " + path)
-        t7.save(path, {"model": {"theta": {"params": self.model.get_params()}}, "mp": _plain(vars(self.mp)),
-                       "train_losses": list(self.train_losses), "val_losses": list(self.val_losses),
-                       "test_losses": list(self.test_losses), "iters": iters})
+        t7.save_checkpoint(path, self.model.get_params(), mp=_plain(vars(self.mp)), iters=iters,
+                           train_losses=self.train_losses, val_losses=self.val_losses, test_losses=self.test_losses)
         self.say("Saved model")
         return path
 

@@ -279,9 +279,9 @@ int npe_event_record(npe_handle* h, int32_t slot);
 int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* ms_out);
 /*
  * Parity checks of intermediate results (tests only): copies the first nfloats of an internal device buffer of the
- * current batch.  Layouts (csrc/npe_tcbwd.cuh): HACT / DZACT [pair][6][52] = h0..h5 / dz0..dz5 of every active pair in
- * list order; DACT [focus][5][52] = {pair sum | 1 | 0, u1..u4}; DDZ [focus][5][52] = dz1..dz5; DS [focus][52] = gradient
- * into the pair sum; HP [pair][52] = h5.
+ * current batch.  Layouts (layer-major, rows of 56 floats, 52 used; csrc/npe_kernels.cuh): HACT / DZACT [6][rows][56] =
+ * h0..h5 / dz0..dz5 of every active pair in list order, rows = pair capacity rounded up to 128; DACT [5][F][56] =
+ * {pair sum | 1 | 0, u1..u4}; DDZ [5][F][56] = dz1..dz5; DS [F][52] = gradient into the pair sum; HP [pair][52] = h5.
  */
 #define NPE_DBG_HACT 0
 #define NPE_DBG_DZACT 1

@@ -245,18 +245,20 @@ def test_tcgen05_backward_stage_by_stage(s64, trained_like_params):
         act = inter["m"][:, :, 0] > 0                                    # (F, C) active pairs, list order = row-major
         def err(a, b):
             return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
-        dact = m.debug_read("dact", (F, 5, 52))
+        dact = m.debug_read("dact", (5, F, 56)).transpose(1, 0, 2)                # layer-major on the device
         e = {"z": err(dact[:, 0, :50], inter["us"][0][:, :50])}
         assert np.all(dact[:, :, 50] == 1) and np.all(dact[:, :, 51] == 0)
         for i in range(1, 5):
             e[f"u{i}"] = err(dact[:, i, :50], inter["us"][i])
-        ddz = m.debug_read("ddz", (F, 5, 52))
+        ddz = m.debug_read("ddz", (5, F, 56)).transpose(1, 0, 2)
         e["dz5_dec"] = err(ddz[:, 4, :22], inter["dz_dec"][5])
         for i in range(4, 0, -1):
             e[f"dz{i}_dec"] = err(ddz[:, i - 1, :50], inter["dz_dec"][i])
         ds = m.debug_read("ds", (F, 52))
         e["ds"] = err(ds[:, :50], inter["ds"])
-        hact = m.debug_read("hact", (P, 6, 52)); dzact = m.debug_read("dzact", (P, 6, 52))
+        SR = (F * 16 + 127) // 128 * 128                                  # slot capacity: pair capacity (16 per focus) in 128-row tiles
+        hact = m.debug_read("hact", (6, SR, 56))[:, :P].transpose(1, 0, 2)
+        dzact = m.debug_read("dzact", (6, SR, 56))[:, :P].transpose(1, 0, 2)
         # A pre-activation within rounding noise of zero may be > 0 on one side and == 0 on the other; from that layer
         # down the two gradients of that row legitimately differ.  Rows with such a ReLU flip are counted and excluded.
         flip_p = np.zeros(P, bool)

@@ -160,3 +160,30 @@ def test_slot_metrics_reduce_like_eval_lua():
         num = sum((vals[3, t, j] * amask[t, j]).sum() / amask[t, j].sum() for j in range(N) if amask[t, j].sum() > 0)
         den = sum(amask[t, j].sum() / B for j in range(N))
         assert row["cos"][t] == pytest.approx(num / den)
+
+
+def test_update_position_and_angle_mirror_the_reference():
+    """model:update_position / update_angle (npe.lua:386-458; called by eval.lua:170-173) on the drop-in surface: the host
+    mirror (same arithmetic as dynamics_b200/lua/npe.lua) against the oracle's restatement, bit for bit."""
+    from oracle import rollout
+    from dynamics_b200.model import NPEModel
+    rng = np.random.default_rng(3)
+    this = rng.uniform(-1, 1, (64, 2, 22)).astype(np.float32)
+    pred = rng.uniform(-1, 1, (64, 1, 22)).astype(np.float32)
+    this[:8, -1, 4] = 0.99; this[:8, -1, 5] = 0.5            # wraps past +pi
+    this[8:16, -1, 4] = -0.99; this[8:16, -1, 5] = -0.5      # wraps past -pi
+    m = NPEModel.__new__(NPEModel)                            # pure host arithmetic: no device handle needed
+    assert np.array_equal(NPEModel.update_position(m, this, pred), rollout.update_position(this, pred))
+    got = NPEModel.update_angle(m, this, pred)
+    assert np.array_equal(got, rollout.update_angle(this, pred))
+    assert np.all(np.abs(got[:16, 0, 4]) <= 1.0)
+    # several future steps: step k integrates the velocity / angular velocity of step k - 1
+    pred3 = rng.uniform(-1, 1, (64, 3, 22)).astype(np.float32)
+    out = NPEModel.update_position(m, this, pred3)
+    p = this[:, -1, 0:2] * np.float32(800); v = this[:, -1, 2:4] * np.float32(60)
+    for k in range(3):
+        p = p + v; v = pred3[:, k, 2:4] * np.float32(60)
+        assert np.array_equal(out[:, k, 0:2], p / np.float32(800))
+    assert np.array_equal(out[:, :, 2:], pred3[:, :, 2:])
+    with pytest.raises(Exception):
+        NPEModel.bp_input(m)
