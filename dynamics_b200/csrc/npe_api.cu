@@ -104,12 +104,14 @@ struct npe_handle {
     DevBuf<long long> pair_frow;      // focus-window offset of every active pair (encoder weight gradient)
     DevBuf<u64> hmask, umask;         // ReLU bits of h0..h5 per active pair [6][pair_cap] / of u1..u4 per focus [4][F]
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
+    long long* chain_prof_dev = nullptr;
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
     int train_stash = 1;              // forward writes the pair activations for the backward kernels (0: recompute)
     int bwd_tc = 1;                   // large training batches: backward (input + weight gradients) on tcgen05
     int small_batch_max = -1;         // foci up to which the 16-row latency mapping is used (-1: 4 * SM count)
+    int pdl_max_foci = 592;           // batches up to this many foci chain their kernels with programmatic dependent launch
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
     int roll_F = 0;
@@ -286,7 +288,11 @@ cudaError_t launch_pdl(npe_handle* h, void (*kernel)(KArgs...), int grid, int bl
     cfg.attrs = attr;
     // directly after a pair builder: a plain (fully serialised) launch, because the kernels below read the builder's
     // outputs in their prologue, before griddepcontrol.wait
-    cfg.numAttrs = h->after_builder ? 0 : 1;
+    // Programmatic launches pay off in the latency regime (a step of ~25 us made of kernels of a few us).  In the throughput
+    // regime every kernel is a persistent grid that fills the machine: measured on the S-64 step, dependents that become
+    // resident early and sit in griddepcontrol.wait cost 0.420 ms against 0.335 ms with plain launches (tools/s64_time.py).
+    static const bool no_pdl = getenv("NPE_NO_PDL") != nullptr;    // A/B measurements only
+    cfg.numAttrs = (h->after_builder || no_pdl || h->F > h->pdl_max_foci) ? 0 : 1;
     h->after_builder = false;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
@@ -386,6 +392,16 @@ int focus_grid(const npe_handle* h, int F, int rows) {
     return tiles < h->num_sms ? tiles : h->num_sms;
 }
 
+int refresh_wtt(npe_handle* h);
+
+// tools only (NPE_CHAIN_PROF=1): cycle counters of CTA 0 / thread 0 of the pair forward chain, printed at npe_sync
+long long* chain_prof(npe_handle* h) {
+    static const bool want = getenv("NPE_CHAIN_PROF") != nullptr;
+    if (!want) return nullptr;
+    if (!h->chain_prof_dev) { cudaMalloc((void**)&h->chain_prof_dev, 32 * sizeof(long long)); cudaMemset(h->chain_prof_dev, 0, 32 * sizeof(long long)); }
+    return h->chain_prof_dev;
+}
+
 int refresh_wtc(npe_handle* h, int mode) {
     if (mode == NPE_PRECISION_TF32_TC && h->wtc_dirty) {
         k_pack_tc_scatter<<<(NPARAM + 255) / 256, 256, 0, h->stream>>>(h->params, h->wtc);
@@ -431,13 +447,11 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
                                                                        h->pred.p, loss_ex);
         } else {
             // warp-specialised chain kernels (npe_chain.cuh): two tile slots per CTA, two threads per row, one MMA warp
-            k_pair_forward_c2<<<pg, CH_NT, sizeof(PairChainSmem), h->stream>>>(st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
-                                                                              h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash,
-                                                                              dact ? h->hmask.p : nullptr, h->stash_rows);
+            CK(launch_pdl(h, k_pair_forward_c2, pg, CH_NT, sizeof(PairChainSmem), st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                          h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
             if (!skip_decoder)
-                k_dec_forward_c2<<<fg, CH_NT, sizeof(DecChainSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
-                                                                                h->wtc3, y, h->pred.p, loss_ex, dact,
-                                                                                dact ? h->umask.p : nullptr);
+                CK(launch_pdl(h, k_dec_forward_c2, fg, CH_NT, sizeof(DecChainSmem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
+                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr));
         }
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
@@ -475,6 +489,9 @@ int run_forward(npe_handle* h, bool training, bool fused = false) {
         h->dact.ensure((size_t)5 * h->F * HSLOT + 128 * HSLOT) == cudaSuccess && h->umask.ensure((size_t)4 * h->F) == cudaSuccess &&
         h->hmask.ensure((size_t)(NL + 1) * h->stash_rows) == cudaSuccess)
         dact = h->dact.p;
+    // the transposed images of the input-gradient chains are refreshed here, before the forward chain, so that no plain
+    // launch sits between the programmatically chained kernels of the step
+    if (dact && (rc = refresh_wtt(h))) return rc;
     rc = launch_forward_kernels(h, h->states.p, h->F, h->have_y ? h->yptr() : nullptr, h->have_y ? h->loss_ex.p : nullptr, tc,
                                 stash, fused && !dact, dact);
     if (rc) return rc;
@@ -572,15 +589,14 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
     const int gp = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
     {
         ProfScope ps__(h, NPE_K_DEC_BACKWARD);
-        k_dec_dgrad_c2<<<fg, CH_NT, sizeof(DecDgradChainSmem), h->stream>>>(F, h->pred.p, h->yptr(), h->umask.p, h->wtt3, sv, sw,
-                                                                            h->ddz.p, h->ds.p);
+        CK(launch_pdl(h, k_dec_dgrad_c2, fg, CH_NT, sizeof(DecDgradChainSmem), F, h->pred.p, h->yptr(), h->umask.p, h->wtt3, sv, sw,
+                      h->ddz.p, h->ds.p));
         h->launches++;
     }
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
-        k_pair_dgrad_c2<<<pg, CH_NT, sizeof(PairDgradChainSmem), h->stream>>>(h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
-                                                                              h->stash_rows, h->ds.p, h->wtt3, h->dzact.p,
-                                                                              h->pair_frow.p);
+        CK(launch_pdl(h, k_pair_dgrad_c2, pg, CH_NT, sizeof(PairDgradChainSmem), h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
+                      h->stash_rows, h->ds.p, h->wtt3, h->dzact.p, h->pair_frow.p));
         h->launches++;
     }
     {
@@ -595,8 +611,8 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         E.gs[0].base = h->states.p; E.gs[0].offs = h->pair_frow.p; E.gs[0].cols_valid = IN; E.gs[0].cols_store = 48; E.gs[0].col0 = 0;
         E.gs[1].base = h->states.p; E.gs[1].offs = h->pair_crow.p; E.gs[1].cols_valid = IN; E.gs[1].cols_store = 48; E.gs[1].col0 = 48;
         E.ngs = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
-        A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial;
-        k_wgrad_tc<<<gp, WG_NT, sizeof(WgradSmem), h->stream>>>(A);
+        A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial; A.prof = chain_prof(h);
+        CK(launch_pdl(h, k_wgrad_tc, gp, WG_NT, sizeof(WgradSmem), A));
         h->launches++;
         WArgs B = {};
         // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
@@ -612,7 +628,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
         D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
         B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial;
-        k_wgrad_tc<<<gd, WG_NT, sizeof(WgradSmem), h->stream>>>(B);
+        CK(launch_pdl(h, k_wgrad_tc, gd, WG_NT, sizeof(WgradSmem), B));
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -1595,6 +1611,14 @@ int npe_allreduce_grads(npe_handle* h) {
 int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
+    if (h->chain_prof_dev) {
+        long long q[32];
+        cudaMemcpy(q, h->chain_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[pair forward chain, CTA 0 thread 0] gather %lld, wait for MMA %lld, epilogue %lld, total %lld cycles\n", q[0], q[1], q[2], q[3]);
+        fprintf(stderr, "[pair wgrad CTA 0] producer: wait empty %lld of %lld | transposer: wait raw %lld, wait op %lld, work %lld, units %lld, loop %lld | "
+                        "mma: wait %lld, issue %lld, loop %lld | epilogue %lld, kernel body %lld cycles\n",
+                q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[19]);
+    }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;
 }

@@ -74,65 +74,82 @@ __device__ __forceinline__ const float* shfl_ptr(const float* p, int src) {
 }
 // v[0 .. 31] of every lane (= 32 columns of its row) -> global rows: row q of the warp at g + q * gpitch, the first
 // nchunks 16-byte chunks of it; rows >= nrows are skipped.  8 lanes write 128 contiguous bytes of one row.
-__device__ __forceinline__ void warp_store32(float* stg, const float* v, float* __restrict__ g, long long gpitch, int nrows, int nchunks) {
+// Every helper below is written in two phases (all loads, then all stores) so that the loads are in flight together: a
+// store between two loads through pointers the compiler cannot tell apart serialises them.
+__device__ __forceinline__ void warp_store32(float* __restrict__ stg, const float* v, float* __restrict__ g, long long gpitch,
+                                             int nrows, int nchunks) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int c = 0; c < 8; ++c) st4(stg + lane * STG_PITCH + 4 * c, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
     __syncwarp();
     const int ch = lane & 7;
+    float4 x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int q = (lane >> 3) + 4 * i;
-        const float4 x = ld4(stg + q * STG_PITCH + 4 * ch);
-        if (q < nrows && ch < nchunks) st4(g + (long long)q * gpitch + 4 * ch, x);
-    }
+    for (int i = 0; i < 8; ++i) x[i] = ld4(stg + ((lane >> 3) + 4 * i) * STG_PITCH + 4 * ch);
     __syncwarp();
+    if (ch < nchunks) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = (lane >> 3) + 4 * i;
+            if (q < nrows) st4(g + (long long)q * gpitch + 4 * ch, x[i]);
+        }
+    }
 }
 // A full 52-column row per lane (d[0 .. 63], columns >= 52 ignored) -> global rows of pitch gpitch
-__device__ __forceinline__ void warp_store_row52(float* stg, const float* d, float* __restrict__ g, long long gpitch, int nrows) {
+__device__ __forceinline__ void warp_store_row52(float* __restrict__ stg, const float* d, float* __restrict__ g, long long gpitch, int nrows) {
     warp_store32(stg, d, g, gpitch, nrows, 8);
     warp_store32(stg, d + 32, g + 32, gpitch, nrows, 5);
 }
 // inverse: v[0 .. 31] of lane q = the first nchunks chunks (rest zero) of the row at myrow (per-lane pointer, 16-byte aligned)
-__device__ __forceinline__ void warp_load32(float* stg, float* v, const float* myrow, bool live, int nchunks) {
+__device__ __forceinline__ void warp_load32(float* __restrict__ stg, float* v, const float* __restrict__ myrow, bool live, int nchunks) {
     const int lane = threadIdx.x & 31, ch = lane & 7;
+    float4 x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int q = (lane >> 3) + 4 * i;
         const float* rp = shfl_ptr(myrow, q);
         const bool ok = __shfl_sync(0xffffffffu, (int)live, q) != 0;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && ch < nchunks) x = ld4(rp + 4 * ch);
-        st4(stg + q * STG_PITCH + 4 * ch, x);
+        x[i] = (ok && ch < nchunks) ? __ldg(reinterpret_cast<const float4*>(rp + 4 * ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st4(stg + ((lane >> 3) + 4 * i) * STG_PITCH + 4 * ch, x[i]);
     __syncwarp();
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        const float4 x = ld4(stg + lane * STG_PITCH + 4 * c);
-        v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
+        const float4 y = ld4(stg + lane * STG_PITCH + 4 * c);
+        v[4 * c] = y.x; v[4 * c + 1] = y.y; v[4 * c + 2] = y.z; v[4 * c + 3] = y.w;
     }
     __syncwarp();
 }
-// One frame (22 floats, 8-byte aligned) of every lane's window: x[0 .. 21] <- myrow[0 .. 21].  Lane-linear 8-byte accesses:
-// a warp instruction covers 32 consecutive float2 of the (row, column) order, i.e. ~3 rows.
-__device__ __forceinline__ void warp_gather22(float* stg, float* x, const float* myrow, bool live) {
+// The 44-float window (two frames of 22 floats, 8-byte aligned) of every lane's row: x[0 .. 43] <- myrow[0 .. 43].  Lane-linear
+// 8-byte accesses: a warp instruction covers 32 consecutive float2 of the (row, column) order, i.e. ~3 rows.  All 22 loads
+// of a lane are issued before the first staging store.
+__device__ __forceinline__ void warp_gather44(float* __restrict__ stg, float* x, const float* __restrict__ myrow, bool live) {
     const int lane = threadIdx.x & 31;
+    float2 v[22];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-        const int e = k * 32 + lane, q = e / 11, c2 = e - q * 11;
+    for (int k = 0; k < 22; ++k) {
+        const int e = k * 32 + lane, q = e / 22, c2 = e - q * 22;
         const float* rp = shfl_ptr(myrow, q);
         const bool ok = __shfl_sync(0xffffffffu, (int)live, q) != 0;
-        float2 v = make_float2(0.f, 0.f);
-        if (ok) v = ld2(rp + 2 * c2);
-        *reinterpret_cast<float2*>(stg + 2 * e) = v;
+        v[k] = ok ? __ldg(reinterpret_cast<const float2*>(rp + 2 * c2)) : make_float2(0.f, 0.f);
     }
-    __syncwarp();
+    // two rounds through the staging buffer (32 rows x 22 floats each): frame 0 = float2 columns 0..10, frame 1 = 11..21
 #pragma unroll
-    for (int c2 = 0; c2 < 11; ++c2) {
-        const float2 v = *reinterpret_cast<const float2*>(stg + lane * 22 + 2 * c2);
-        x[2 * c2] = v.x; x[2 * c2 + 1] = v.y;
+    for (int f = 0; f < 2; ++f) {
+#pragma unroll
+        for (int k = 0; k < 22; ++k) {
+            const int e = k * 32 + lane, q = e / 22, c2 = e - q * 22;
+            if ((c2 >= 11) == (f == 1)) *reinterpret_cast<float2*>(stg + q * 22 + 2 * (c2 - 11 * f)) = v[k];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c2 = 0; c2 < 11; ++c2) {
+            const float2 y = *reinterpret_cast<const float2*>(stg + lane * 22 + 2 * c2);
+            x[22 * f + 2 * c2] = y.x; x[22 * f + 2 * c2 + 1] = y.y;
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -229,34 +246,33 @@ __global__ void __launch_bounds__(CH_NT, 1)
 k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
                   const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wtc3,
                   const float* __restrict__ wenc, float* __restrict__ Hp, float* __restrict__ hact,
-                  unsigned long long* __restrict__ hmask, long long stash_rows) {
+                  unsigned long long* __restrict__ hmask, long long stash_rows, long long* __restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairChainSmem& S = *reinterpret_cast<PairChainSmem*>(smem_raw);
-    const int P = info[0];
-    if ((int)blockIdx.x * 256 >= P) return;
+    long long pf_gather = 0, pf_wait = 0, pf_epi = 0, pf_t0 = clock64();
+    // Programmatic dependent launch: barrier init, TMEM allocation and the weight staging (the images were written by
+    // kernels that completed long ago) overlap the predecessor's tail; the pair list is read only after the wait.
+    pdl_launch_dependents();
     chain_setup(S.ctl);
-    const int ntiles = (P + 127) / 128;
     const int t = threadIdx.x;
+    if (t == CH_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, (4 * ENC64_SZ + 2 * NL * TC_HID_SZ) * 4);
+        bulk_g2s(S.Ehi, wenc, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+        bulk_g2s(S.Elo, wenc + 2 * ENC64_SZ, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+        bulk_g2s(S.Whi, wtc3 + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
+        bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
+    }
+    pdl_wait();
+    const int P = info[0];
+    const int ntiles = (P + 127) / 128;
     if (t >= CH_EPI) {
         if (t == CH_EPI) {
-            mbar_expect_tx(&S.ctl.wbar, (4 * ENC64_SZ + 2 * NL * TC_HID_SZ) * 4);
-            bulk_g2s(S.Ehi, wenc, 2 * ENC64_SZ * 4, &S.ctl.wbar);
-            bulk_g2s(S.Elo, wenc + 2 * ENC64_SZ, 2 * ENC64_SZ * 4, &S.ctl.wbar);
-            bulk_g2s(S.Whi, wtc3 + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
-            bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
             mbar_wait(&S.ctl.wbar, 0);
             chain_mma_loop<NL + 1>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
                 if (stage == 0) {
                     umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Ehi, S.Elo, 64, 64, 6);
                     // the context encoder accumulates on top (its real rows are 25..49)
-                    const uint32_t idesc = umma_idesc_tf32(64);
-                    const uint32_t bh = smem_u32(S.Ehi + ENC64_SZ), bl = smem_u32(S.Elo + ENC64_SZ);
-                    for (int pass = 0; pass < 3; ++pass) {
-                        const uint32_t a0 = tm + (pass == 2 ? TM_ALO : TM_AHI) + 48;
-                        const uint32_t b0 = pass == 1 ? bl : bh;
-                        for (int s = 0; s < 6; ++s)
-                            umma_tf32_ts(tm + TM_D, a0 + 8 * s, umma_desc(b0 + 2 * s * 64 * 16, 64 * 16, 128), idesc, 1u);
-                    }
+                    umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI + 48, tm + TM_ALO + 48, S.Ehi + ENC64_SZ, S.Elo + ENC64_SZ, 64, 64, 6, true);
                 } else {
                     umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + (stage - 1) * TC_HID_SZ,
                                         S.Wlo + (stage - 1) * TC_HID_SZ, 64, 64, 7);
@@ -273,6 +289,7 @@ k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair
             const int wrows = max(0, min(32, nrows - 32 * c.wq));     // valid rows of this warp
             const size_t p = (size_t)(lo + c.row);
             const size_t pw = (size_t)(lo + 32 * c.wq);               // first row of this warp
+            const long long c_g0 = clock64();
             {   // gather: focus window -> A columns [0, 48), context window -> [48, 96); frame by frame through the staging buffer
                 const float* fw = states, * cw = states;
                 if (live) { fw = states + foc_row[pair_foc[p]]; cw = states + pair_crow[p]; }
@@ -280,16 +297,19 @@ k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair
                 for (int which = 0; which < 2; ++which) {
                     float x[48];
                     const float* wp = which ? cw : fw;
-                    warp_gather22(c.stg, x, wp, live);
-                    warp_gather22(c.stg, x + 22, wp + 22, live);
+                    warp_gather44(c.stg, x, wp, live);
                     x[44] = x[45] = x[46] = x[47] = 0.f;
                     tmem_store_split<6>(c.tm, TM_AHI + 48 * which, TM_ALO + 48 * which, x);
                 }
             }
             chain_publish_a(S.ctl, c.slot);
+            pf_gather += clock64() - c_g0;
 #pragma unroll 1
             for (int l = 0; l <= NL; ++l) {          // epilogue of stage l: h_l
+                const long long c_w0 = clock64();
                 chain_wait_d(S.ctl, c.slot, nd);
+                const long long c_w1 = clock64();
+                pf_wait += c_w1 - c_w0;
                 float d[64];
                 tc_load_relu(c.tm, d);
                 if (hmask && live) hmask[(size_t)l * stash_rows + p] = relu_bits64(d);
@@ -300,8 +320,10 @@ k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair
                 } else {
                     warp_store_row52(c.stg, d, Hp + pw * 52, 52, wrows);
                 }
+                pf_epi += clock64() - c_w1;
             }
         }
+        if (prof && blockIdx.x == 0 && t == 0) { prof[0] = pf_gather; prof[1] = pf_wait; prof[2] = pf_epi; prof[3] = clock64() - pf_t0; }
     }
     chain_teardown(S.ctl);
 }
@@ -324,14 +346,18 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
                  float* __restrict__ dact, unsigned long long* __restrict__ umask) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecChainSmem& S = *reinterpret_cast<DecChainSmem*>(smem_raw);
+    pdl_launch_dependents();
     chain_setup(S.ctl);
     const int ntiles = (F + 127) / 128;
     const int t = threadIdx.x;
+    if (t == CH_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, 2 * TC_DEC_TOTAL * 4);
+        bulk_g2s(S.Whi, wtc3 + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
+        bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
+    }
+    pdl_wait();
     if (t >= CH_EPI) {
         if (t == CH_EPI) {
-            mbar_expect_tx(&S.ctl.wbar, 2 * TC_DEC_TOTAL * 4);
-            bulk_g2s(S.Whi, wtc3 + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
-            bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR_TOTAL, TC_DEC_TOTAL * 4, &S.ctl.wbar);
             mbar_wait(&S.ctl.wbar, 0);
             chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
                 if (stage == 0) umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TC_DEC1, S.Wlo + TC_DEC1, TC_HID_ROWS, 64, 12);
@@ -377,8 +403,7 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
                 x[0] = z[48]; x[1] = z[49]; x[2] = z[50]; x[3] = z[51];
                 const float* wp = live ? states + foc_row[f] : states;
                 float w44[44];
-                warp_gather22(c.stg, w44, wp, live);
-                warp_gather22(c.stg, w44 + 22, wp + 22, live);
+                warp_gather44(c.stg, w44, wp, live);
 #pragma unroll
                 for (int k = 0; k < 44; ++k) x[4 + k] = w44[k];
                 tmem_store_split<6>(c.tm, TM_AHI + 48, TM_ALO + 48, x);
@@ -441,14 +466,18 @@ k_dec_dgrad_c2(int F, const float* __restrict__ pred, const float* __restrict__ 
                float* __restrict__ ds_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecDgradChainSmem& S = *reinterpret_cast<DecDgradChainSmem*>(smem_raw);
+    pdl_launch_dependents();
     chain_setup(S.ctl);
     const int ntiles = (F + 127) / 128;
     const int t = threadIdx.x;
+    if (t == CH_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, 2 * TT_DEC_TOTAL * 4);
+        bulk_g2s(S.Whi, wtt3 + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
+        bulk_g2s(S.Wlo, wtt3 + TT_TOTAL + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
+    }
+    pdl_wait();
     if (t >= CH_EPI) {
         if (t == CH_EPI) {
-            mbar_expect_tx(&S.ctl.wbar, 2 * TT_DEC_TOTAL * 4);
-            bulk_g2s(S.Whi, wtt3 + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
-            bulk_g2s(S.Wlo, wtt3 + TT_TOTAL + TT_PAIR_TOTAL, TT_DEC_TOTAL * 4, &S.ctl.wbar);
             mbar_wait(&S.ctl.wbar, 0);
             chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
                 // stage 0: dz5 W5 (K = 24); stages 1..3: layers 4..2; stage 4: dz1 W1[:, :50]
@@ -526,16 +555,19 @@ k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ 
                 const float* __restrict__ wtt3, float* __restrict__ dzact, long long* __restrict__ pair_frow) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairDgradChainSmem& S = *reinterpret_cast<PairDgradChainSmem*>(smem_raw);
-    const int P = info[0];
-    if ((int)blockIdx.x * 256 >= P) return;
+    pdl_launch_dependents();
     chain_setup(S.ctl);
-    const int ntiles = (P + 127) / 128;
     const int t = threadIdx.x;
+    if (t == CH_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
+        bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
+        bulk_g2s(S.Wlo, wtt3 + TT_TOTAL, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
+    }
+    pdl_wait();
+    const int P = info[0];
+    const int ntiles = (P + 127) / 128;
     if (t >= CH_EPI) {
         if (t == CH_EPI) {
-            mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
-            bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
-            bulk_g2s(S.Wlo, wtt3 + TT_TOTAL, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
             mbar_wait(&S.ctl.wbar, 0);
             chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
                 const int l = NL - stage;            // dh_{l-1} = dz_l W_l

@@ -140,12 +140,13 @@ struct WArgs {
     const int* nrows_dev;         // number of rows R (pairs: info[0]) or nullptr
     int nrows;                    // used when nrows_dev == nullptr
     float* partial;               // [gridDim.x][PT_TOTAL]
+    long long* prof;              // tools only (NPE_CHAIN_PROF): cycle counters of CTA 0, or nullptr
 };
 
 constexpr int WG_ROWS = 32;       // rows per unit: K = 32 = 4 MMA k-steps
 constexpr int WG_NRAW = 4;        // raw ring depth
 constexpr int WG_NOP = 3;         // operand ring depth: transposers run up to 2 units ahead of the MMA warp
-constexpr int WG_NT = 320;        // 8 transposer warps + MMA warp + producer warp
+constexpr int WG_NT = 352;        // 8 transposer warps + MMA warp + TMA warp + gather warp
 constexpr int WG_BLOCK = WG_ROWS * HSLOT;            // floats of one stash block (7168 B)
 constexpr int WG_XG_PITCH = 98;   // floats: pitch of gathered X rows in the raw stage (8-byte stores of 32 lanes: conflict-free)
 struct WRaw { float G[WG_BLOCK]; float X[WG_ROWS * WG_XG_PITCH]; };   // 7168 + 12544 B
@@ -297,9 +298,9 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     WgradSmem& S = *reinterpret_cast<WgradSmem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const long long R = A.nrows_dev ? (long long)*A.nrows_dev : (long long)A.nrows;
+    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail
     if (t == 0) {
-        for (int i = 0; i < WG_NRAW; ++i) { mbar_init(&S.raw_full[i], 1); mbar_init(&S.raw_empty[i], 256); }
+        for (int i = 0; i < WG_NRAW; ++i) { mbar_init(&S.raw_full[i], 2); mbar_init(&S.raw_empty[i], 256); }
         for (int i = 0; i < WG_NOP; ++i) { mbar_init(&S.op_full[i], 256); mbar_init(&S.op_empty[i], 1); }
         mbar_init(&S.done, 1);
     }
@@ -313,33 +314,55 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                // everything below reads the predecessors' stashes
+    const long long R = A.nrows_dev ? (long long)*A.nrows_dev : (long long)A.nrows;
     const uint32_t tmem = S.tmem;
     WUnit it; it.init(R, A.njobs);
     const bool has_work = it.valid();
-    if (warp == 9) {   // producer: TMA bulk copies of the stash blocks; gathered X rows assembled by the 32 lanes
-        for (int u = 0; it.valid(); it.next(), ++u) {
-            const int s = u % WG_NRAW;
-            const WJob& J = A.job[it.j];
-            if (lane == 0) {
+    const bool prof = A.prof && blockIdx.x == 0 && lane == 0;
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pt0 = clock64();
+    if (warp == 9) {   // TMA warp: bulk copies of the stash blocks of every unit
+        if (lane == 0) {
+            for (int u = 0; it.valid(); it.next(), ++u) {
+                const int s = u % WG_NRAW;
+                const WJob& J = A.job[it.j];
+                const long long c0 = clock64();
                 if (u >= WG_NRAW) mbar_wait(&S.raw_empty[s], (unsigned)(((u / WG_NRAW) - 1) & 1));
-                mbar_expect_tx_only(&S.raw_full[s], (J.ngs ? 1u : 2u) * WG_BLOCK * 4);
+                pw0 += clock64() - c0;
+                mbar_expect_tx(&S.raw_full[s], (J.ngs ? 1u : 2u) * WG_BLOCK * 4);      // arrival 1 of 2
                 bulk_g2s(S.raw[s].G, J.G + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
                 if (!J.ngs) bulk_g2s(S.raw[s].X, J.X0 + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
             }
-            __syncwarp();
-            if (J.ngs) { wgrad_assemble(S.raw[s].X, J, it.row0(), R); __syncwarp(); }
+            if (prof) { A.prof[8] = pw0; A.prof[9] = clock64() - pt0; }
+        }
+    } else if (warp == 10) {   // gather warp (lane = row): assembles the X rows of gathered jobs; arrival 2 of 2 of every unit
+        for (int u = 0; it.valid(); it.next(), ++u) {
+            const int s = u % WG_NRAW;
+            const WJob& J = A.job[it.j];
+            // the stage must be free before EITHER arrival of its next use: an early arrival would complete the previous phase
+            if (u >= WG_NRAW) mbar_wait(&S.raw_empty[s], (unsigned)(((u / WG_NRAW) - 1) & 1));
+            if (J.ngs) {
+                wgrad_assemble(S.raw[s].X, J, it.row0(), R);
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive(&S.raw_full[s]);
         }
     } else if (warp < 8) {
-        for (int u = 0; it.valid(); it.next(), ++u) {
+        int u = 0;
+        for (; it.valid(); it.next(), ++u) {
             const int s = u % WG_NRAW, o = u % WG_NOP;
+            const long long c0 = clock64();
             mbar_wait(&S.raw_full[s], (unsigned)((u / WG_NRAW) & 1));
+            const long long c1 = clock64();
             if (u >= WG_NOP) mbar_wait(&S.op_empty[o], (unsigned)(((u / WG_NOP) - 1) & 1));
+            const long long c2 = clock64();
             wgrad_transpose(S.op[o], S.raw[s], A.job[it.j], it.row0(), R);
             proxy_fence_async();
             mbar_arrive(&S.op_full[o]);
             mbar_arrive(&S.raw_empty[s]);
+            pw0 += c1 - c0; pw1 += c2 - c1; pw2 += clock64() - c2;
         }
+        if (prof && warp == 0) { A.prof[10] = pw0; A.prof[11] = pw1; A.prof[12] = pw2; A.prof[13] = u; A.prof[14] = clock64() - pt0; }
     } else if (lane == 0) {   // warp 8: MMA issue
         unsigned started = 0;
         for (int u = 0; it.valid(); it.next(), ++u) {
@@ -354,7 +377,10 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
             const uint32_t b_lo[2] = {((smem_u32(S.op[o].Bhi) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16),
                                       ((smem_u32(S.op[o].Blo) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16)};
             const uint32_t a_step = 2u * 64u * 16u >> 4, b_step = 2u * (uint32_t)nb * 16u >> 4;
+            const long long c0 = clock64();
             mbar_wait(&S.op_full[o], (unsigned)((u / WG_NOP) & 1));
+            pw0 += clock64() - c0;
+            const long long c1 = clock64();
             tc_fence_after();
             uint32_t acc = (started >> it.j) & 1u;
 #pragma unroll
@@ -370,9 +396,12 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
             }
             started |= 1u << it.j;
             umma_commit(&S.op_empty[o]);
+            pw1 += clock64() - c1;
         }
         umma_commit(&S.done);
+        if (prof) { A.prof[15] = pw0; A.prof[16] = pw1; A.prof[17] = clock64() - pt0; }
     }
+    const long long pe0 = clock64();
     // epilogue: warps 0..3 own the four TMEM lane quadrants; an M = 64 accumulator keeps row n in lane (n % 16) + 32 (n / 16)
     if (warp < 4) {
         mbar_wait(&S.done, 0);
@@ -391,6 +420,7 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
             if (lane < 16) wgrad_store_rows(out, J, n, d, !has_work);
         }
     }
+    if (prof && warp == 0) { A.prof[18] = clock64() - pe0; A.prof[19] = clock64() - pt0; }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc<512>(tmem);

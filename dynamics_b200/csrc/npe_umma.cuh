@@ -59,15 +59,25 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // 3xTF32: D (+)= Ahi*Bhi + Ahi*Blo + Alo*Bhi with A (hi at tmem_ahi, lo at tmem_alo) in tensor memory and the two
 // images of B in shared memory.  K = 8 * ksteps.  FP32-grade (1.5e-6 relative in the stand-alone test).  One thread.
+// The issue loop is on the critical path of every layer (one thread, ~20 dependent instructions per MMA when the 64-bit
+// descriptor is rebuilt each time): the descriptor's low word (address field | LBO << 16) advances by a constant per
+// K-step, the high word (SBO | version) is fixed.  `accumulate_first`: add to what the accumulator already holds.
 __device__ __forceinline__ void umma_gemm_tf32x3_ts(uint32_t tmem_d, uint32_t tmem_ahi, uint32_t tmem_alo, const float* sBhi,
-                                                    const float* sBlo, int rows_b, int n, int ksteps) {
+                                                    const float* sBlo, int rows_b, int n, int ksteps, bool accumulate_first = false) {
     const uint32_t idesc = umma_idesc_tf32(n);
-    const uint32_t bh = smem_u32(sBhi), bl = smem_u32(sBlo);
+    const uint32_t lbo = ((uint32_t)rows_b * 16u >> 4) << 16, step = 2u * (uint32_t)rows_b * 16u >> 4;
+    const uint32_t bh = ((smem_u32(sBhi) >> 4) & 0x3FFFu) | lbo, bl = ((smem_u32(sBlo) >> 4) & 0x3FFFu) | lbo;
+    const uint64_t hiw = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         const uint32_t a0 = pass == 2 ? tmem_alo : tmem_ahi;
         const uint32_t b0 = pass == 1 ? bl : bh;
-        for (int s = 0; s < ksteps; ++s)
-            umma_tf32_ts(tmem_d, a0 + 8 * s, umma_desc(b0 + 2 * s * rows_b * 16, rows_b * 16, 128), idesc, (pass | s) ? 1u : 0u);
+#pragma unroll 4
+        for (int s = 0; s < ksteps; ++s) {
+            umma_tf32_ts(tmem_d, a0 + 8 * s, hiw | (uint64_t)(b0 + s * step), idesc, acc);
+            acc = 1u;
+        }
     }
 }
 

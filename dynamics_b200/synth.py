@@ -77,3 +77,38 @@ def reference_batch_schedule(n_scenes_per_set, set_sizes, steps, batch_size, see
         sc.append(scene_offsets[d] + b * batch_size + np.arange(batch_size))
         ob.append(np.full(batch_size, o)); tt.append(np.full(batch_size, t0))
     return (np.concatenate(sc).astype(np.int32), np.concatenate(ob).astype(np.int32), np.concatenate(tt).astype(np.int32))
+
+
+def wall_scenes(n_scenes, T, seed, variant="O", n_balls=2):
+    """configs[2] shape: a ring of static 80-px obstacles (9 x 7 border = 28 blocks, centres x in {80..720}, y in {60..540};
+    Examples.js:2775-2800) plus the variant's inner blocks (L: +1 corner piece of 2, U / I not generated here), then
+    `n_balls` balls bouncing inside.  Object order = walls first, then balls (Examples.js:3124-3200).
+    -> states (S, N, T, 22) float32; obstacles: mass one-hot 1e30 (col 9), oid obstacle (col 11), size 1."""
+    rng = np.random.default_rng(seed)
+    xs = np.arange(80, 721, 80); ys = np.arange(60, 541, 80)
+    ring = [(x, y) for x in xs for y in (ys[0], ys[-1])] + [(x, y) for y in ys[1:-1] for x in (xs[0], xs[-1])]
+    if variant == "L":
+        ring += [(240, 220), (240, 300)]
+    walls = np.asarray(ring, np.float64)
+    W = len(walls)
+    S, N = n_scenes, W + n_balls
+    out = np.zeros((S, N, T, 22), np.float32)
+    out[:, :W, :, 0:2] = (walls / PNC)[None, :, None, :]
+    out[:, :W, :, 9] = 1; out[:, :W, :, 11] = 1
+    out[:, W:, :, 10] = 1
+    mass = rng.choice(np.array([1.0, 5.0, 25.0]), (S, n_balls))
+    for m, col in MASS_COL.items():
+        out[:, W:, :, col] = (mass == m)[:, :, None]
+    out[..., 14] = 1
+    out[..., 16] = out[..., 18] = out[..., 20] = 1
+    lo = np.array([180.0, 160.0]); hi = np.array([620.0, 440.0])          # interior kept clear of the ring
+    pos = lo + rng.random((S, n_balls, 2)) * (hi - lo)
+    vel = rng.integers(-20, 21, (S, n_balls, 2)).astype(np.float64)
+    for t in range(T):
+        out[:, W:, t, 0:2] = pos / PNC
+        out[:, W:, t, 2:4] = vel / VNC
+        pos = pos + vel
+        for ax in (0, 1):
+            vel[..., ax] = np.where(pos[..., ax] < lo[ax], np.abs(vel[..., ax]), vel[..., ax])
+            vel[..., ax] = np.where(pos[..., ax] > hi[ax], -np.abs(vel[..., ax]), vel[..., ax])
+    return out

@@ -294,15 +294,48 @@ class Experiment:
         return path
 
     # ---- main.lua:398-437 ----
+    VAL_GROUP = 64     # reference batches evaluated by ONE device call (forward only, per-example losses back in one copy)
+
+    def _eval_group(self, batches):
+        """model:fp losses (npe.lua:233-246) of several batches from one forward over all their examples.  Per batch the
+        loss is (sum vel + sum angvel) / (3B) with double accumulation, the arithmetic of the device's loss kernel."""
+        m = self.model
+        if not (hasattr(m, "forward_per_example_current") and all(hasattr(b, "select") for b in batches)
+                and len({id(b.store) for b in batches}) == 1):
+            return [float(m.fp(None, b)[0]) for b in batches]
+        batches[0].store.commit()
+        m.upload_foci(np.concatenate([b.scene for b in batches]), np.concatenate([b.obj for b in batches]),
+                      np.concatenate([b.t0 for b in batches]))
+        m.select_foci(0, sum(len(b) for b in batches))
+        _, le = m.forward_per_example_current()
+        out, a = [], 0
+        for b in batches:
+            e = le[a:a + len(b)].astype(np.float64); a += len(b)
+            out.append(float(np.float32((2.0 * e[:, 1].sum() + e[:, 2].sum()) / (3.0 * len(b)))))
+        return out
+
     def test(self, loader, num_batches=None):
+        """test() of main.lua:398-414, sharded: every rank walks the same sequential batch order (so the loaders stay in
+        step), evaluates batches i with i % world == rank in groups of VAL_GROUP, and the per-rank loss sums meet in ONE
+        scalar all-reduce."""
         num_batches = num_batches or loader.num_batches
         if self.mp.fast:
             num_batches = min(5000, num_batches)
         self.say(f"Testing {num_batches} batches")
-        total = 0.0
-        for _ in range(num_batches):
+        total, mine = 0.0, []
+        for i in range(num_batches):
             batch, _ = loader.sample_sequential_batch(False)
-            total += self.model.fp(None, batch)[0]
+            if i % self.world == self.rank:
+                mine.append(batch)
+                if len(mine) == self.VAL_GROUP:
+                    total += sum(self._eval_group(mine)); mine = []
+        if mine:
+            total += sum(self._eval_group(mine))
+        if self.world > 1:
+            import torch
+            t = torch.tensor([total], dtype=torch.float64)
+            self.dist.all_reduce(t)
+            total = float(t[0])
         return total / num_batches
 
     def validate(self):

@@ -51,6 +51,12 @@ def _train_worker(rank, world, port, root, out):
         def attach_data_parallel(self, d, r, w, mode="p2p"):
             DPFake.attached = (r, w, mode)
 
+        fp_calls = 0
+
+        def fp(self, params_, batch, sim=False):
+            DPFake.fp_calls += 1
+            return super().fp(params_, batch, sim)
+
         def train_step(self, opt="adam", lr=3e-4, divisor_batch=0, want_loss=True):
             DPFake.divisors.append(divisor_batch)
             return super().train_step(opt, lr, divisor_batch, want_loss)
@@ -68,7 +74,8 @@ def _train_worker(rank, world, port, root, out):
     e.history = []
     e.run_experiment()
     out[rank] = {"ids": [(h[0], h[1]) for h in e.history], "div": sorted(set(DPFake.divisors) - {0}),
-                 "attached": DPFake.attached, "val": list(e.val_losses), "device": e.mp.device}
+                 "attached": DPFake.attached, "val": list(e.val_losses), "device": e.mp.device, "fp_calls": DPFake.fp_calls,
+                 "val_batches": 2 * (min(5000, e.val_loader.num_batches) + e.val_loader.num_batches + e.test_loader.num_batches)}
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,6 +91,8 @@ def test_training_driver_under_two_ranks(tmp_path):
     assert a["attached"] == (0, 2, "p2p") and b["attached"] == (1, 2, "p2p") and (a["device"], b["device"]) == (0, 1)
     assert a["div"] == [100] and b["div"] == [100]                 # global batch = 2 x 50 is the divisor on both ranks
     assert len(a["ids"]) == len(b["ids"]) == 12 and a["ids"] != b["ids"]   # each rank samples its own batches
-    assert a["val"] == b["val"]                                     # validation walks the same batches everywhere
+    assert a["val"] == b["val"]                                     # one all-reduced loss sum: identical on every rank
+    # validation is sharded (main.lua:398-437 on 2 ranks): each rank evaluated half of the batches of the 2 validations
+    assert a["fp_calls"] + b["fp_calls"] == a["val_batches"] and abs(a["fp_calls"] - b["fp_calls"]) <= 6
     logs = os.listdir(tmp_path / "logs" / "dp")
     assert "train.log" in logs and sum(f.startswith("epoch") for f in logs) == 2   # written once (rank 0)

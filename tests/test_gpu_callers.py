@@ -189,3 +189,40 @@ def test_slot_metrics_reproduce_mixed_validity_average(model, trained_like_param
     assert np.max(np.abs(traj[..., 0:4] - pred_sim[..., 0:4])) < 1e-3
     _, tot = model.rollout(0, steps, use_gt=True)
     assert np.allclose(slots.sum(1), tot, rtol=1e-12)
+
+
+def test_grouped_validation_equals_per_batch_fp(model, trained_like_params, tmp_path):
+    """Experiment.test (main.lua:398-414) evaluates VAL_GROUP reference batches per device call; the per-batch losses it
+    derives from the per-example losses equal what model:fp returns for each batch alone (1e-5: a group of 1 600 examples
+    runs on the 64-row kernels, a single batch of 50 on the 16-row ones), across two datasets with different object
+    counts and a group boundary inside the walk."""
+    _write_dataset(tmp_path, "balls_n3_t60_ex100_m", 3, 100, seed=1)
+    _write_dataset(tmp_path, "balls_n5_t60_ex60_m", 5, 60, seed=2)
+    g = GeneralDataSampler.create("trainset", _args(tmp_path, ["balls_n3_t60_ex100_m", "balls_n5_t60_ex60_m"], model=model))
+    model.set_params(trained_like_params)
+    n = 70
+    single = []
+    for _ in range(n):
+        b, _ = g.sample_sequential_batch(False)
+        single.append(model.fp(None, b)[0])
+    for d in g.datasamplers:
+        d.current_batch = 0
+    g.current_dataset = 1
+
+    class E:                                      # the two attributes Experiment.test / _eval_group read
+        pass
+    e = E(); e.model = model; e.mp = type("mp", (), {"fast": False})(); e.world = 1; e.rank = 0; e.dist = None; e.say = lambda *a: None
+    e.VAL_GROUP = 32
+    e._eval_group = lambda bs: train.Experiment._eval_group(e, bs)
+    mean = train.Experiment.test(e, g, n)
+    groups = []
+    for d in g.datasamplers:
+        d.current_batch = 0
+    g.current_dataset = 1
+    bs = [g.sample_sequential_batch(False)[0] for _ in range(n)]
+    for a in range(0, n, 32):
+        groups += train.Experiment._eval_group(e, bs[a:a + 32])
+    assert np.allclose(groups, single, rtol=1e-5, atol=0)
+    assert abs(mean - float(np.mean(np.asarray(groups, np.float64)))) < 1e-12
+    # a group of ONE batch takes the same kernels as model:fp: the loss arithmetic on the host is the device's, bit for bit
+    assert train.Experiment._eval_group(e, bs[:1]) == [float(single[0])]
