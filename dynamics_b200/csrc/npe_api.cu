@@ -119,7 +119,7 @@ struct npe_handle {
     double* loss_sums_dev = nullptr;
 
     // scenes / foci
-    DevBuf<float> states;
+    DevBuf<float> states, raw_stage;
     DevBuf<int> n_obj;
     int S = 0, Nmax = 0, T = 0;
     std::vector<std::vector<int>> scene_foci;   // non-obstacle objects per scene
@@ -885,7 +885,7 @@ int npe_destroy(npe_handle* h) {
     if (h->loss4_host) cudaFreeHost(h->loss4_host);
     for (int i = 0; i < 2; ++i) { if (h->stage[i]) cudaFreeHost(h->stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
-    h->states.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
+    h->states.release(); h->raw_stage.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
     h->dzact.release(); h->dact.release(); h->ddz.release(); h->pair_frow.release(); h->hmask.release(); h->umask.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
@@ -1034,6 +1034,41 @@ int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, 
     h->batch_form = false; h->have_y = false; h->y_view = nullptr;
     h->pairs_valid = false; h->fwd_valid = false;
     h->win_start.clear();
+    return NPE_OK;
+}
+
+int npe_scenes_upload_raw(npe_handle* h, const float* raw, const int32_t* n_obj, int32_t S, int32_t Nmax, int32_t T) {
+    NEED(h);
+    if (!raw || !n_obj || S <= 0 || Nmax <= 0 || T < 2) return fail(h, NPE_ERR_INVALID, "scenes_upload_raw: bad arguments");
+    if (Nmax > MAXOBJ) return fail(h, NPE_ERR_INVALID, "scenes_upload_raw: at most %d objects per scene", MAXOBJ);
+    CK(cudaStreamSynchronize(h->stream2));
+    const size_t nframes = (size_t)S * Nmax * T;
+    CK(h->states.ensure(nframes * D));
+    CK(h->n_obj.ensure(S));
+    CK(h->raw_stage.ensure(nframes * 12));
+    CK(cudaMemcpyAsync(h->raw_stage.p, raw, nframes * 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->n_obj.p, n_obj, (size_t)S * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->info_dev + 2, 0, sizeof(int), h->stream));
+    k_raw_to_state<<<(unsigned)((nframes + 255) / 256), 256, 0, h->stream>>>(h->raw_stage.p, h->states.p, (long long)nframes, h->info_dev + 2);
+    CKL();
+    h->foci_B = h->foci_N = -1;
+    h->scene_foci.assign(S, {});
+    h->scene_pred_objects = 0;
+    for (int s = 0; s < S; ++s) {
+        if (n_obj[s] < 1 || n_obj[s] > Nmax) return fail(h, NPE_ERR_INVALID, "scenes_upload_raw: n_obj[%d] = %d out of range", s, n_obj[s]);
+        for (int o = 0; o < n_obj[s]; ++o)
+            if (raw[(((size_t)s * Nmax + o) * T) * 12 + 7] != 2.f) h->scene_foci[s].push_back(o);   // objtype 2 = obstacle: never a focus
+        h->scene_pred_objects += (int64_t)h->scene_foci[s].size();
+    }
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, h->info_dev + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->S = S; h->Nmax = Nmax; h->T = T;
+    h->F = 0; h->foc_first = 0;
+    h->batch_form = false; h->have_y = false; h->y_view = nullptr;
+    h->pairs_valid = false; h->fwd_valid = false;
+    h->win_start.clear();
+    if (bad) return fail(h, NPE_ERR_INVALID, "scenes_upload_raw: a mass / objtype / sizemul / flag value is outside its category set");
     return NPE_OK;
 }
 
@@ -1714,6 +1749,7 @@ int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats) {
         case NPE_DBG_DDZ: src = h->ddz.p; cap = h->ddz.cap; break;
         case NPE_DBG_DS: src = h->ds.p; cap = h->ds.cap; break;
         case NPE_DBG_HP: src = h->Hp.p; cap = h->Hp.cap; break;
+        case NPE_DBG_STATES: src = h->states.p; cap = h->states.cap; break;
         default: return fail(h, NPE_ERR_INVALID, "debug_read: unknown buffer %d", which);
     }
     if (!out || nfloats <= 0 || !src || (size_t)nfloats > cap) return fail(h, NPE_ERR_INVALID, "debug_read: buffer %d holds %zu floats", which, cap);

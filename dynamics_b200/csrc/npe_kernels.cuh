@@ -217,10 +217,54 @@ __device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, 
     __shared__ int s_cnt[FPB];
     __shared__ int s_pre[FPB];
     __shared__ u64 s_nbr[FPB];
+    // Position cache: the foci of a CTA come in runs that share (scene, t0) -- all objects of a window are consecutive
+    // foci -- and every focus of a run needs the positions of ALL objects of that scene at frame t0 + 1.  Object rows are
+    // T * 22 floats apart, so each warp-wide position load touches 32 different lines; loading a run's positions ONCE
+    // into shared memory (instead of once per focus) removes the pair builder's dominant cost on large scenes
+    // (64-ball scenes: 64 foci per run).  Same values, same arithmetic: bit-identical tables.
+    __shared__ float2 s_pos[FPB][MAXOBJ];      // [run][object]  (32 KB)
+    __shared__ int s_run[FPB];                 // run index of every focus of this CTA
+    __shared__ int s_head[FPB];                // focus index that opens run r
+    __shared__ int s_nruns;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int GPW = 32 / LANES;                       // foci per warp per pass
     const int nwarps = blockDim.x >> 5;
     const int gl = lane & (LANES - 1), grp = lane / LANES;
+    if (warp < 2) {                                       // warps 0, 1: foci 0..31, 32..63
+        const int fl = threadIdx.x, f = blk * FPB + fl;
+        const bool act = f < src.F;
+        int sc = -1, t0 = -1;
+        if (act) { sc = src.foc_scene[f]; t0 = src.foc_t0[f]; }
+        const int psc = __shfl_up_sync(0xffffffffu, sc, 1), pt0 = __shfl_up_sync(0xffffffffu, t0, 1);
+        bool head = act && (lane == 0 || sc != psc || t0 != pt0);
+        if (act && lane == 0 && warp == 1) {              // run may continue across the warp boundary
+            const int f1 = f - 1;
+            head = src.foc_scene[f1] != sc || src.foc_t0[f1] != t0;
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_cnt[warp] = __popc(hb);          // s_cnt is rewritten below, after the barrier
+        __syncwarp();
+        const int before = __popc(hb & ((2u << lane) - 1u)) - 1;   // runs opened up to and including this focus, minus one
+        s_pre[fl] = before;                               // per-warp run index (warp 1 is shifted below)
+        s_nbr[fl] = head ? 1ull : 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x < FPB) {
+        const int fl = threadIdx.x;
+        const int shift = fl >= 32 ? s_cnt[0] : 0;
+        const int r = s_pre[fl] + shift;
+        s_run[fl] = r;
+        if (s_nbr[fl]) s_head[r] = fl;
+        if (fl == 0) s_nruns = s_cnt[0] + s_cnt[1];
+    }
+    __syncthreads();
+    for (int r = warp; r < s_nruns; r += nwarps) {        // one warp loads the positions of one run
+        const int f = blk * FPB + s_head[r];
+        const int sc = src.foc_scene[f], t0 = src.foc_t0[f], N = src.n_obj[sc];
+        const float* base = src.states + row_off(src, sc, 0, t0 + 1);
+        for (int j = lane; j < N; j += 32) s_pos[r][j] = *reinterpret_cast<const float2*>(base + (size_t)j * src.T * D);
+    }
+    __syncthreads();
     for (int base = 0; base < FPB; base += nwarps * GPW) {
         const int fl = base + warp * GPW + grp;
         const int f = blk * FPB + fl;
@@ -228,16 +272,17 @@ __device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, 
         int c = 0;
         u64 keep = 0, nbr = 0;
         size_t ro = 0;
+        const float* pos = reinterpret_cast<const float*>(s_pos[active ? s_run[fl] : 0]);
         if (LANES == 32) {
             if (active) {
                 const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
-                warp_pairs(src.states + row_off(src, s, 0, t0 + 1), src.T * D, src.n_obj[s], n, kmax, thr_px, keep, nbr);
+                warp_pairs(pos, 2, src.n_obj[s], n, kmax, thr_px, keep, nbr);
                 ro = row_off(src, s, n, t0);
             }
         } else {
             int s = 0, n = 0, t0 = 0, N = 1;
             if (active) { s = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f]; N = src.n_obj[s]; ro = row_off(src, s, n, t0); }
-            group_pairs<LANES>(src.states + row_off(src, s, 0, t0 + 1), src.T * D, N, n, kmax, thr_px, active, keep, nbr);
+            group_pairs<LANES>(pos, 2, N, n, kmax, thr_px, active, keep, nbr);
         }
         if (active) {
             if (y) {
@@ -386,6 +431,48 @@ __global__ void k_expand_pairs(const u64* __restrict__ keep, const u64* __restri
         if (ctx_idx) ctx_idx[(size_t)f * K + slot] = -1;
         if (mask) mask[(size_t)f * K + slot] = 0;
     }
+}
+
+// f1 (the step before the path): raw matter-js state (12 floats: px, py, vx, vy, a, av, mass, oid, size, g, f, p) -> the
+// 22-float normalised one-hot state, on the device.  Follows data_process:normalize (data_process.lua:119-139) and
+// properties2onehotall (:184-207): positions / 800, velocities / 60, angles wrapped (a > pi loses 2 pi) then / pi, each
+// operation rounded once; categorical columns one-hot (mass {1, 5, 25, 1e30}, oid {1, 2, 3}, size {0.5, 1, 2}, flags {0, 1}).
+// A value outside its category set raises *bad.  One thread per object-frame.
+__global__ void k_raw_to_state(const float* __restrict__ raw, float* __restrict__ st, long long n, int* __restrict__ bad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = raw + i * 12;
+    float o[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) o[k] = 0.f;
+    o[0] = __fdiv_rn(r[0], 800.f); o[1] = __fdiv_rn(r[1], 800.f);
+    o[2] = __fdiv_rn(r[2], 60.f); o[3] = __fdiv_rn(r[3], 60.f);
+    const float PI_F = 3.14159274101257324f, M2PI = -6.28318548202514648f;
+#pragma unroll
+    for (int k = 4; k < 6; ++k) {
+        const float a = r[k];
+        o[k] = __fdiv_rn(__fadd_rn(a, __fmul_rn(M2PI, a > PI_F ? 1.f : 0.f)), PI_F);
+    }
+    bool ok = true;
+    const float m = r[6];
+    const int mi = m == 1.f ? 0 : m == 5.f ? 1 : m == 25.f ? 2 : m == 1e30f ? 3 : -1;
+    ok &= mi >= 0; if (mi >= 0) o[6 + mi] = 1.f;
+    const float oid = r[7];
+    const int oi = oid == 1.f ? 0 : oid == 2.f ? 1 : oid == 3.f ? 2 : -1;
+    ok &= oi >= 0; if (oi >= 0) o[10 + oi] = 1.f;
+    const float sz = r[8];
+    const int si = sz == 0.5f ? 0 : sz == 1.f ? 1 : sz == 2.f ? 2 : -1;
+    ok &= si >= 0; if (si >= 0) o[13 + si] = 1.f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float v = r[9 + q];
+        const int bi = v == 0.f ? 0 : v == 1.f ? 1 : -1;
+        ok &= bi >= 0; if (bi >= 0) o[16 + 2 * q + bi] = 1.f;
+    }
+    if (!ok) *bad = 1;
+    float* w = st + i * D;
+#pragma unroll
+    for (int k = 0; k < D; k += 2) *reinterpret_cast<float2*>(w + k) = make_float2(o[k], o[k + 1]);
 }
 
 // Gathered focus rows (F,44) for parity checks.

@@ -43,14 +43,12 @@ def load_data_json(jsonfile_or_obj, gfp=(0, 0, 0)):
             data = json.load(fh)
     tr = data["trajectories"]
     E, N, T = len(tr), len(tr[0]), len(tr[0][0])
-    raw = np.zeros((E, N, T, 12), F32)
-    for e in range(E):
-        for i in range(N):
-            for t in range(T):
-                s = tr[e][i][t]
-                raw[e, i, t] = (s["position"]["x"], s["position"]["y"], s["velocity"]["x"], s["velocity"]["y"], s["angle"],
-                                s["angularVelocity"], s["mass"], OIDS[s["objtype"]], s["sizemul"], gfp[0], gfp[1], gfp[2])
-    return raw
+    # one flat pass over the records and ONE array conversion (the nested assignment loop it replaces spent its time in
+    # per-record numpy row writes); ragged input (an object with fewer frames) fails the reshape loudly
+    g, f, p = (float(v) for v in gfp)
+    flat = [(s["position"]["x"], s["position"]["y"], s["velocity"]["x"], s["velocity"]["y"], s["angle"], s["angularVelocity"],
+             s["mass"], OIDS[s["objtype"]], s["sizemul"], g, f, p) for ex in tr for ob in ex for s in ob]
+    return np.asarray(flat, np.float64).astype(F32).reshape(E, N, T, 12)
 
 
 def raw_to_states(raw, sizes=SIZES):

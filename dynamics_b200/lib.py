@@ -43,6 +43,7 @@ SIGNATURES = {
     "npe_grads_set": (C.c_int, [_H, _fp, C.c_int32]),
     "npe_batch_upload": (C.c_int, [_H, _fp, _fp, _fp, C.c_int32, C.c_int32]),
     "npe_scenes_upload": (C.c_int, [_H, _fp, _ip, C.c_int32, C.c_int32, C.c_int32]),
+    "npe_scenes_upload_raw": (C.c_int, [_H, _fp, _ip, C.c_int32, C.c_int32, C.c_int32]),
     "npe_windows_upload": (C.c_int, [_H, _ip, _ip, C.c_int32]),
     "npe_select_windows": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "npe_foci_upload": (C.c_int, [_H, _ip, _ip, _ip, C.c_int32]),

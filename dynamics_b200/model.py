@@ -283,6 +283,16 @@ class NPEModel:
         self._ck(self.lib.npe_scenes_upload(self.h, L.fptr(states), L.iptr(n_obj), S, Nmax, T))
         self.scene_shape = (S, Nmax, T)
 
+    def upload_scenes_raw(self, raw, n_obj=None):
+        """Raw matter-js states (S,Nmax,T,12) (dataprep.load_data_json): normalisation and one-hot coding happen on the
+        device (data_process.lua:119-139,184-207)."""
+        raw = L.f32(raw)
+        S, Nmax, T, K = raw.shape
+        assert K == 12
+        n_obj = L.i32(np.full(S, Nmax) if n_obj is None else n_obj)
+        self._ck(self.lib.npe_scenes_upload_raw(self.h, L.fptr(raw), L.iptr(n_obj), S, Nmax, T))
+        self.scene_shape = (S, Nmax, T)
+
     def upload_windows(self, scene_ids, t0):
         scene_ids, t0 = L.i32(scene_ids), L.i32(t0)
         self._ck(self.lib.npe_windows_upload(self.h, L.iptr(scene_ids), L.iptr(t0), scene_ids.size))
@@ -358,7 +368,7 @@ class NPEModel:
     def debug_read(self, which, shape):
         """Intermediate device buffer of the current batch (tests): 'hact', 'dzact', 'dact', 'ddz', 'ds', 'hp'."""
         out = np.empty(shape, np.float32)
-        self._ck(self.lib.npe_debug_read(self.h, {"hact": 0, "dzact": 1, "dact": 2, "ddz": 3, "ds": 4, "hp": 5}[which],
+        self._ck(self.lib.npe_debug_read(self.h, {"hact": 0, "dzact": 1, "dact": 2, "ddz": 3, "ds": 4, "hp": 5, "states": 6}[which],
                                          L.fptr(out), out.size))
         return out
 

@@ -104,6 +104,13 @@ int npe_batch_upload(npe_handle* h, const float* this_past, const float* context
  */
 int npe_scenes_upload(npe_handle* h, const float* states, const int32_t* n_obj, int32_t S, int32_t Nmax, int32_t T);
 /*
+ * The same from RAW matter-js states (S,Nmax,T,12) = {px, py, vx, vy, angle, angularVelocity, mass, objtype (1 ball, 2
+ * obstacle, 3 block), sizemul, gravity, friction, pairwise} as json_interface.lua:26-63 reads them: the device does
+ * data_process:normalize (data_process.lua:119-139) and properties2onehotall (:184-207) -- the data-prep step before the
+ * path -- bit-identically (one rounding per operation).  A value outside its category set returns NPE_ERR_INVALID.
+ */
+int npe_scenes_upload_raw(npe_handle* h, const float* raw, const int32_t* n_obj, int32_t S, int32_t Nmax, int32_t T);
+/*
  * Window schedule: W (scene, t0) windows, uploaded once; past = frames t0,t0+1, target = frame t0+2
  * (split_time, data_sampler.lua:83-101).  npe_select_windows makes windows [first, first+count) the current batch:
  * every non-obstacle object of each window becomes a focus (expand_for_each_object, data_process.lua:254-295),
@@ -289,6 +296,7 @@ int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* m
 #define NPE_DBG_DDZ 3
 #define NPE_DBG_DS 4
 #define NPE_DBG_HP 5
+#define NPE_DBG_STATES 6 /* the resident scene tensor (S,Nmax,T,22) */
 int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats);
 /* Counters: kernels launched by this handle since creation; active pairs / foci of the current batch. */
 int64_t npe_launch_count(const npe_handle* h);

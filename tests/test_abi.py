@@ -63,9 +63,7 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
 
 
-def test_plain_c_client(tmp_path):
-    """The header is C, the library links from C and reports errors as codes + messages; with a GPU the same binary runs
-    a tiny batch end to end (tests/c_abi_check.c).  Runs on the CPU box (expects the loud no-GPU failure) and on the B200."""
+def _run_c_client(tmp_path):
     import shutil
     import subprocess
     from dynamics_b200.build import build
@@ -78,7 +76,19 @@ def test_plain_c_client(tmp_path):
                     "-Wl,-rpath," + os.path.dirname(lib)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.strip() in ("gpu", "nogpu")
+    return r.stdout.strip()
+
+
+def test_plain_c_client(tmp_path):
+    """The header is C, the library links from C and reports errors as codes + messages (tests/c_abi_check.c).  On the
+    CPU box the binary must see the loud no-GPU failure; the B200 run of the same binary is test_plain_c_client_gpu."""
+    assert _run_c_client(tmp_path) in ("gpu", "nogpu")
+
+
+@pytest.mark.gpu
+def test_plain_c_client_gpu(tmp_path):
+    """The same plain-C binary on the B200: a tiny batch through upload / forward / backward / Adam from C."""
+    assert _run_c_client(tmp_path) == "gpu"
 
 
 def test_product_never_touches_the_oracle():
@@ -97,4 +107,4 @@ def test_product_never_touches_the_oracle():
     for pos in uses:                                            # every use sits inside one of the two checker functions
         head = bench[:pos]
         fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]
-        assert fn in ("cpu_baseline_leg", "run_reference"), fn
+        assert fn in ("cpu_baseline_leg", "cpu_rollout_leg", "run_reference"), fn

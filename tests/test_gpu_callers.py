@@ -226,3 +226,25 @@ def test_grouped_validation_equals_per_batch_fp(model, trained_like_params, tmp_
     assert abs(mean - float(np.mean(np.asarray(groups, np.float64)))) < 1e-12
     # a group of ONE batch takes the same kernels as model:fp: the loss arithmetic on the host is the device's, bit for bit
     assert train.Experiment._eval_group(e, bs[:1]) == [float(single[0])]
+
+
+def test_device_packer_raw_to_states_is_bit_exact(model):
+    """f1 on the device (npe_scenes_upload_raw): raw matter-js states -> normalised one-hot states, bit for bit the oracle's
+    data_process:normalize + properties2onehotall (oracle/scenes.py raw_to_state), on balls and on walls (static
+    obstacles of mass 1e30), angles beyond pi included; obstacles are contexts, never foci; bad categories are refused."""
+    from dynamics_b200 import NPEError
+    rawb = scenes.gen_balls(12, 5, 6, seed=3)
+    rawb[:, :, :, 4] = np.linspace(-3.5, 3.5, 12 * 5 * 6, dtype=np.float32).reshape(12, 5, 6)      # angles across +-pi
+    rawb[:, :, :, 5] = 0.25
+    raww = scenes.gen_walls(4, 6, seed=5, variant="O")
+    for raw in (rawb, raww):
+        model.upload_scenes_raw(raw)
+        S, N, T, _ = raw.shape
+        got = model.debug_read("states", (S, N, T, 22))
+        assert np.array_equal(got, scenes.raw_to_state(raw))
+    model.upload_windows(np.arange(4), np.zeros(4, np.int32))
+    n_balls = int((raww[0, :, 0, 7] == 1).sum())
+    assert model.select_windows(0, 4) == 4 * n_balls                     # foci = non-obstacle objects only
+    bad = rawb.copy(); bad[0, 0, 0, 6] = 7.0                             # a mass outside {1, 5, 25, 1e30}
+    with pytest.raises(NPEError):
+        model.upload_scenes_raw(bad)

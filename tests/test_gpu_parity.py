@@ -264,13 +264,26 @@ def test_rollout_balls(model, trained_like_params):
     logs = rollout_metrics_to_logs(met_t)
     for k in ("loss", "vel", "angvel", "cos", "mag"):
         assert np.allclose(logs[k], mref_t[k], rtol=2e-3, atol=1e-7), k
-    # free running
+    # free running (SURVEY 8d ii): positions within 1e-3 normalised units on EVERY scene whose neighbourhood-mask sequence
+    # is the same in both runs; a scene whose masks differ somewhere crossed the 210-px threshold on rounding noise and
+    # legitimately diverges afterwards -- those are counted, and must be few
     traj, met = model.rollout(0, steps, use_gt=True, teacher=False)
     ref, mref, masks = rollout.rollout_scenes(trained_like_params, st[:, :, 0:2], np.full(50, 6), steps, gt=st[:, :, 2:],
                                               return_masks=True)
+    # device-side mask sequence, recomputed from the device trajectory with the oracle's mask arithmetic (bit-exact in
+    # float32: positions are the only input, and the builder's masks are tested bit-exact elsewhere)
+    full = np.concatenate([st[:, :, 0:2], traj], axis=2)            # (S, N, 2 + steps, 22) device states
+    flips = np.zeros(50, bool)
+    for (N, t, j, idx, mask) in masks:
+        this = full[:, j, t:t + 2]
+        ctx = np.delete(full[:, :, t:t + 2], j, axis=1)
+        gmask = npe.neighbor_mask(this, ctx, check_focus=False)
+        flips |= (gmask != mask).any(axis=1)
     err = np.abs(traj[..., 0:2] - ref[..., 0:2]).max(axis=(1, 2, 3))
-    good = err <= 1e-3
-    assert good.mean() >= 0.9, f"{(~good).sum()} of 50 scenes diverged"
+    same = ~flips
+    print(f"[rollout n6] scenes with a mask flip: {int(flips.sum())} of 50; max position error on the others {err[same].max():.2e}")
+    assert err[same].max() <= 1e-3
+    assert flips.mean() <= 0.1, f"{int(flips.sum())} of 50 scenes flipped a neighbourhood mask"
     assert np.all(traj[..., 4:6] == 0)                             # balls: a = av = 0 (eval.lua:176-178)
 
 
