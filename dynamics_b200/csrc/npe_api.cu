@@ -430,7 +430,7 @@ float* training_stash(npe_handle* h) {
 // stash: activation stash for a following backward (training) or nullptr; skip_decoder: the fused training step lets
 // k_dec_backward produce pred / losses.
 int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, int tc,
-                           float* stash = nullptr, bool skip_decoder = false, float* dact = nullptr) {
+                           float* stash = nullptr, bool skip_decoder = false, float* dact = nullptr, float* roll = nullptr) {
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
         int rc = refresh_wtc(h, tc);
@@ -451,7 +451,7 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
                           h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
             if (!skip_decoder)
                 CK(launch_pdl(h, k_dec_forward_c2, fg, CH_NT, sizeof(DecChainSmem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
-                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr));
+                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode));
         }
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
@@ -1501,6 +1501,12 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     const float thr = h->cfg.nbrhdsize * 60.f;
     const int nblk = (F + FPB - 1) / FPB;
     const int tc = h->precision;
+    // Scenes in which every object is a focus, no ground truth, no trajectory / metric output (npe_rollout_resident on ball
+    // scenes): the 3xTF32 decoder kernel does the post-process and the window shift itself, no separate pass over the window
+    const bool fused_post = tc == NPE_PRECISION_TF32X3_TC && !use_gt && !want_traj && !want_metrics && !h->want_slots &&
+                            (long long)F == [&] { long long n = 0; for (int s = 0; s < h->S; ++s) n += (long long)h->scene_foci[s].size(); return n; }() &&
+                            [&] { for (int s = 0; s < h->S; ++s) if ((int)h->scene_foci[s].size() != h->Nmax) return false; return true; }() &&
+                            !getenv("NPE_NO_FUSED_POST");
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
@@ -1513,9 +1519,9 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
                 h->launches++;
             }
         }
-        if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc))) return rc;
+        if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc, nullptr, false, nullptr, fused_post ? h->roll.p : nullptr))) return rc;
         A.step = step;
-        {
+        if (!fused_post) {
             ProfScope ps__(h, NPE_K_ROLLOUT);
             k_rollout_post<<<(SN + POST_OBJ - 1) / POST_OBJ, 256, 0, h->stream>>>(A);
             h->launches++;
@@ -1750,6 +1756,7 @@ int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats) {
         case NPE_DBG_DS: src = h->ds.p; cap = h->ds.cap; break;
         case NPE_DBG_HP: src = h->Hp.p; cap = h->Hp.cap; break;
         case NPE_DBG_STATES: src = h->states.p; cap = h->states.cap; break;
+        case NPE_DBG_ROLL: src = h->roll.p; cap = h->roll.cap; break;
         default: return fail(h, NPE_ERR_INVALID, "debug_read: unknown buffer %d", which);
     }
     if (!out || nfloats <= 0 || !src || (size_t)nfloats > cap) return fail(h, NPE_ERR_INVALID, "debug_read: buffer %d holds %zu floats", which, cap);

@@ -152,6 +152,25 @@ __device__ __forceinline__ void warp_gather44(float* __restrict__ stg, float* x,
     }
 }
 
+// reverse of a frame gather: x[0 .. 21] of every lane -> myrow[0 .. 21] (lane-linear 8-byte stores through the staging buffer)
+__device__ __forceinline__ void warp_scatter22(float* __restrict__ stg, const float* x, float* myrow, bool live) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c2 = 0; c2 < 11; ++c2) *reinterpret_cast<float2*>(stg + lane * 22 + 2 * c2) = make_float2(x[2 * c2], x[2 * c2 + 1]);
+    __syncwarp();
+    float2 v[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) v[k] = *reinterpret_cast<const float2*>(stg + 2 * (k * 32 + lane));
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        const int e = k * 32 + lane, q = e / 11, c2 = e - q * 11;
+        float* rp = const_cast<float*>(shfl_ptr(myrow, q));
+        const bool ok = __shfl_sync(0xffffffffu, (int)live, q) != 0;
+        if (ok) *reinterpret_cast<float2*>(rp + 2 * c2) = v[k];
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // slot bookkeeping
 // ----------------------------------------------------------------------------------------------------------------
@@ -343,7 +362,11 @@ __global__ void __launch_bounds__(CH_NT, 1)
 k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
                  const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
                  const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
-                 float* __restrict__ dact, unsigned long long* __restrict__ umask) {
+                 float* __restrict__ dact, unsigned long long* __restrict__ umask, float* roll, int ball_zero) {
+    // roll != nullptr (device-resident rollout of scenes in which every object is a focus, no ground truth, no trajectory
+    // output): `states` IS the two-frame rollout window and this kernel also does simulate_all_postprocess + the window shift
+    // (eval.lua:155-182,379-381; update_position / update_angle npe.lua:386-458) for its foci, in place -- every window is
+    // read by exactly one thread of this kernel, before that thread overwrites it -- instead of a separate pass over HBM.
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DecChainSmem& S = *reinterpret_cast<DecChainSmem*>(smem_raw);
     pdl_launch_dependents();
@@ -377,6 +400,8 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
             const int wrows = max(0, min(32, nf - 32 * c.wq));
             const size_t f = (size_t)(f0 + c.row);
             const size_t fw = (size_t)(f0 + 32 * c.wq);
+            float last[22];                          // the focus's last past frame (kept for the fused rollout post-process)
+            long long foff = 0;
             {   // z = [pair sum (50) | 1 | 0 | focus window (44)]: columns 0..47, then 48..95
                 float z[52];
 #pragma unroll
@@ -401,9 +426,12 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
                 }
                 float x[48];
                 x[0] = z[48]; x[1] = z[49]; x[2] = z[50]; x[3] = z[51];
-                const float* wp = live ? states + foc_row[f] : states;
+                if (live) foff = foc_row[f];
+                const float* wp = states + foff;
                 float w44[44];
                 warp_gather44(c.stg, w44, wp, live);
+#pragma unroll
+                for (int k = 0; k < 22; ++k) last[k] = w44[22 + k];
 #pragma unroll
                 for (int k = 0; k < 44; ++k) x[4 + k] = w44[k];
                 tmem_store_split<6>(c.tm, TM_AHI + 48, TM_ALO + 48, x);
@@ -428,15 +456,37 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
                         const float* yy = y + f * OUT;
                         e2 = o[2] - yy[2]; e3 = o[3] - yy[3]; e5 = o[5] - yy[5];
                     }
+                    if (roll) {
+                        // new state of the focus: position integrates the PREVIOUS velocity, angle likewise and is
+                        // wrapped into (-pi, pi], dynamic columns 2, 3, 5 = relative prediction + last, properties restored
+                        const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
+                        float q[22];
+#pragma unroll
+                        for (int k = 0; k < 22; ++k) q[k] = last[k];
+                        q[0] = __fdiv_rn(__fadd_rn(__fmul_rn(last[0], 800.f), __fmul_rn(last[2], 60.f)), 800.f);
+                        q[1] = __fdiv_rn(__fadd_rn(__fmul_rn(last[1], 800.f), __fmul_rn(last[3], 60.f)), 800.f);
+                        q[2] = __fadd_rn(o[2], last[2]); q[3] = __fadd_rn(o[3], last[3]); q[5] = __fadd_rn(o[5], last[5]);
+                        float ang = __fadd_rn(__fmul_rn(last[4], PI_F), __fmul_rn(last[5], PI_F));
+                        const float gtpi = ang > PI_F ? 1.f : 0.f, lepi = ang <= -PI_F ? 1.f : 0.f;   // both masks on the sum (npe.lua:443-447)
+                        ang = __fadd_rn(ang, __fmul_rn(-TWO_PI_F, gtpi));
+                        ang = __fadd_rn(ang, __fmul_rn(TWO_PI_F, lepi));
+                        q[4] = __fdiv_rn(ang, PI_F);
+                        if (ball_zero && last[10] == 1.f) { q[4] = 0.f; q[5] = 0.f; }
+                        float* wrow = roll + foff;
+                        warp_scatter22(c.stg, last, wrow, live);           // window shift: frame 0 <- old frame 1
+                        warp_scatter22(c.stg, q, wrow + 22, live);         //               frame 1 <- new state
+                    }
 #pragma unroll
                     for (int n = 6; n < OUT; ++n) o[n] = 1.f / (1.f + expf(-o[n]));   // Sigmoid on the property columns (modules.lua:80-86)
-                    // pred rows are dense (22 floats): the warp's 32 rows are 704 consecutive floats -> lane-linear copy
+                    if (!roll) {
+                        // pred rows are dense (22 floats): the warp's 32 rows are 704 consecutive floats -> lane-linear copy
 #pragma unroll
-                    for (int n = 0; n < OUT; ++n) c.stg[lane * OUT + n] = o[n];
-                    __syncwarp();
-                    for (int e = lane; e < wrows * (OUT / 2); e += 32)
-                        *reinterpret_cast<float2*>(pred + fw * OUT + 2 * e) = *reinterpret_cast<const float2*>(c.stg + 2 * e);
-                    __syncwarp();
+                        for (int n = 0; n < OUT; ++n) c.stg[lane * OUT + n] = o[n];
+                        __syncwarp();
+                        for (int e = lane; e < wrows * (OUT / 2); e += 32)
+                            *reinterpret_cast<float2*>(pred + fw * OUT + 2 * e) = *reinterpret_cast<const float2*>(c.stg + 2 * e);
+                        __syncwarp();
+                    }
                     if (live && loss_ex && y) {
                         const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
                         loss_ex[f * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);          // npe.lua:271-274

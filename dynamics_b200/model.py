@@ -368,7 +368,7 @@ class NPEModel:
     def debug_read(self, which, shape):
         """Intermediate device buffer of the current batch (tests): 'hact', 'dzact', 'dact', 'ddz', 'ds', 'hp'."""
         out = np.empty(shape, np.float32)
-        self._ck(self.lib.npe_debug_read(self.h, {"hact": 0, "dzact": 1, "dact": 2, "ddz": 3, "ds": 4, "hp": 5, "states": 6}[which],
+        self._ck(self.lib.npe_debug_read(self.h, {"hact": 0, "dzact": 1, "dact": 2, "ddz": 3, "ds": 4, "hp": 5, "states": 6, "roll": 7}[which],
                                          L.fptr(out), out.size))
         return out
 

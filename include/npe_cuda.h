@@ -297,6 +297,7 @@ int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* m
 #define NPE_DBG_DS 4
 #define NPE_DBG_HP 5
 #define NPE_DBG_STATES 6 /* the resident scene tensor (S,Nmax,T,22) */
+#define NPE_DBG_ROLL 7   /* the two-frame window (S,Nmax,2,22) after a rollout by kernels */
 int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats);
 /* Counters: kernels launched by this handle since creation; active pairs / foci of the current batch. */
 int64_t npe_launch_count(const npe_handle* h);

@@ -287,3 +287,29 @@ def test_tcgen05_backward_stage_by_stage(s64, trained_like_params):
         assert not bad, bad
     finally:
         m.close()
+
+
+def test_resident_rollout_fused_postprocess_equals_separate_pass(trained_like_params):
+    """npe_rollout_resident on ball scenes (every object a focus, no ground truth): the decoder kernel applies
+    simulate_all_postprocess and shifts the window itself.  The window after 6 steps must be the bits of the separate
+    post-process pass (k_rollout_post), which is the one compared with the oracle elsewhere; 2 048 scenes = 16 384 foci."""
+    import os
+    st = scenes.raw_to_state(scenes.gen_balls(2048, 8, 2, seed=31))
+    st[::7, 3, :, 4] = 0.9; st[::7, 3, :, 5] = 0.3            # some angles that wrap (balls: zeroed by ball_zero_mode)
+    m = make_model(12, {})
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.set_precision("tf32x3"); m.set_rollout_mode("kernels")
+        os.environ["NPE_NO_FUSED_POST"] = "1"
+        m.rollout_resident(0, 6)
+        w_sep = m.debug_read("roll", (2048, 8, 2, 22))
+        del os.environ["NPE_NO_FUSED_POST"]
+        m.rollout_resident(0, 6)
+        w_fused = m.debug_read("roll", (2048, 8, 2, 22))
+        assert np.array_equal(w_fused, w_sep)
+        traj, _ = m.rollout(0, 6, use_gt=False, want_metrics=False)       # trajectory output: separate pass again
+        assert np.array_equal(traj[:, :, 5], w_fused[:, :, 1]) and np.array_equal(traj[:, :, 4], w_fused[:, :, 0])
+    finally:
+        os.environ.pop("NPE_NO_FUSED_POST", None)
+        m.close()
