@@ -101,6 +101,13 @@ struct npe_handle {
     float* wtt3 = nullptr;            // hi | lo TRANSPOSED images for the tcgen05 input-gradient chains (2 * TT_TOTAL floats)
     bool wtt3_dirty = true;
     DevBuf<float> dzact, dact, ddz;   // tcgen05 backward: pair gradient stash, decoder activation / gradient stashes
+    // device-side priority sampler (priority_sampler.lua): last loss per batch, scan scratch, draw output
+    static constexpr int PRIO_TABLES = 16;                 // one table per data_sampler (dataset folder)
+    DevBuf<float> prio_w[PRIO_TABLES], prio_vals, prio_out2;
+    DevBuf<double> prio_cum;
+    DevBuf<int> prio_ids;
+    int prio_nb[PRIO_TABLES] = {};
+    float prio_alpha[PRIO_TABLES] = {};
     DevBuf<long long> pair_frow;      // focus-window offset of every active pair (encoder weight gradient)
     DevBuf<u64> hmask, umask;         // ReLU bits of h0..h5 per active pair [6][pair_cap] / of u1..u4 per focus [4][F]
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
@@ -887,6 +894,7 @@ int npe_destroy(npe_handle* h) {
     h->cnt.release(); h->block_sums.release(); h->pair_start.release(); h->pair_foc.release(); h->foc_row.release(); h->pair_crow.release(); h->Hp.release();
     h->states.release(); h->raw_stage.release(); h->n_obj.release(); h->foc_scene.release(); h->foc_obj.release(); h->foc_t0.release();
     h->y.release(); h->pred.release(); h->loss_ex.release(); h->ds.release(); h->hact.release(); h->this_rows.release();
+    for (auto& w : h->prio_w) w.release(); h->prio_vals.release(); h->prio_out2.release(); h->prio_cum.release(); h->prio_ids.release();
     h->dzact.release(); h->dact.release(); h->ddz.release(); h->pair_frow.release(); h->hmask.release(); h->umask.release();
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release(); h->slot_metrics.release();
@@ -1649,6 +1657,76 @@ int npe_allreduce_grads(npe_handle* h) {
     return run_allreduce(h);
 }
 
+#define PRIO_TABLE(fn)                                                                                              \
+    if (table < 0 || table >= npe_handle::PRIO_TABLES) return fail(h, NPE_ERR_INVALID, fn ": table must be in [0, %d)", npe_handle::PRIO_TABLES); \
+    auto& W = h->prio_w[table]; const int NB = h->prio_nb[table];
+
+int npe_priority_init(npe_handle* h, int32_t table, int32_t num_batches, float alpha) {
+    NEED(h);
+    if (table < 0 || table >= npe_handle::PRIO_TABLES) return fail(h, NPE_ERR_INVALID, "priority_init: table must be in [0, %d)", npe_handle::PRIO_TABLES);
+    if (num_batches <= 0 || alpha < 0.f || alpha > 1.f) return fail(h, NPE_ERR_INVALID, "priority_init: bad arguments");
+    CK(h->prio_w[table].ensure(num_batches)); CK(h->prio_cum.ensure(num_batches)); CK(h->prio_out2.ensure(2));
+    CK(cudaMemsetAsync(h->prio_w[table].p, 0, (size_t)num_batches * sizeof(float), h->stream));
+    h->prio_nb[table] = num_batches; h->prio_alpha[table] = alpha;
+    return NPE_OK;
+}
+
+int npe_priority_update(npe_handle* h, int32_t table, const int32_t* ids, const float* weights, int32_t n) {
+    NEED(h);
+    PRIO_TABLE("priority_update")
+    if (!NB) return fail(h, NPE_ERR_STATE, "priority_update: call npe_priority_init first");
+    if (!ids || n <= 0) return fail(h, NPE_ERR_INVALID, "priority_update: bad arguments");
+    CK(h->prio_ids.ensure(n));
+    CK(cudaMemcpyAsync(h->prio_ids.p, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    const float* vals; int stride;
+    if (weights) {
+        CK(h->prio_vals.ensure(n));
+        CK(cudaMemcpyAsync(h->prio_vals.p, weights, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        vals = h->prio_vals.p; stride = 1;
+    } else {   // weights == NULL: the losses of the last npe_train_steps call, step i -> ids[i] (no host round trip of the losses)
+        if (h->loss_hist.cap < (size_t)n * 4) return fail(h, NPE_ERR_STATE, "priority_update: no per-step losses of %d steps on the device", n);
+        vals = h->loss_hist.p; stride = 4;
+    }
+    k_priority_update<<<(n + 255) / 256, 256, 0, h->stream>>>(W.p, NB, h->prio_ids.p, vals, stride, n);
+    CKL();
+    CK(cudaStreamSynchronize(h->stream));   // the host arrays may go out of scope
+    return NPE_OK;
+}
+
+int npe_priority_sample(npe_handle* h, int32_t table, float pow_, uint64_t seed, int32_t n, int32_t* ids_out) {
+    NEED(h);
+    PRIO_TABLE("priority_sample")
+    if (!NB) return fail(h, NPE_ERR_STATE, "priority_sample: call npe_priority_init first");
+    if (!ids_out || n <= 0) return fail(h, NPE_ERR_INVALID, "priority_sample: bad arguments");
+    CK(h->prio_ids.ensure((size_t)n + 1));
+    CK(cudaMemsetAsync(h->prio_ids.p + n, 0, sizeof(int), h->stream));
+    CK(h->prio_cum.ensure(NB));
+    k_priority_sample<<<1, 1024, 0, h->stream>>>(W.p, NB, pow_ > 0.f ? pow_ : 1.f, h->prio_alpha[table], (unsigned long long)seed, n,
+                                                 h->prio_cum.p, h->prio_ids.p, h->prio_ids.p + n);
+    CKL();
+    std::vector<int> tmp((size_t)n + 1);
+    CK(cudaMemcpyAsync(tmp.data(), h->prio_ids.p, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (tmp[(size_t)n]) return fail(h, NPE_ERR_STATE, "priority_sample: the weight table is not full (a batch has weight <= 0); "
+                                                      "the reference asserts here (priority_sampler.lua:24-33)");
+    memcpy(ids_out, tmp.data(), (size_t)n * sizeof(int));
+    return NPE_OK;
+}
+
+int npe_priority_hardest(npe_handle* h, int32_t table, float* weight_out, int32_t* id_out) {
+    NEED(h);
+    PRIO_TABLE("priority_hardest")
+    if (!NB) return fail(h, NPE_ERR_STATE, "priority_hardest: call npe_priority_init first");
+    k_priority_hardest<<<1, 1024, 0, h->stream>>>(W.p, NB, h->prio_out2.p);
+    CKL();
+    float o[2];
+    CK(cudaMemcpyAsync(o, h->prio_out2.p, sizeof o, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (weight_out) *weight_out = o[0];
+    if (id_out) *id_out = (int32_t)o[1];
+    return NPE_OK;
+}
+
 int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
@@ -1657,8 +1735,8 @@ int npe_sync(npe_handle* h) {
         cudaMemcpy(q, h->chain_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[pair forward chain, CTA 0 thread 0] gather %lld, wait for MMA %lld, epilogue %lld, total %lld cycles\n", q[0], q[1], q[2], q[3]);
         fprintf(stderr, "[pair wgrad CTA 0] producer: wait empty %lld of %lld | transposer: wait raw %lld, wait op %lld, work %lld, units %lld, loop %lld | "
-                        "mma: wait %lld, issue %lld, loop %lld | epilogue %lld, kernel body %lld cycles\n",
-                q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[19]);
+                        "mma: wait %lld, issue %lld, loop %lld | epilogue %lld (of which waiting for the last MMAs %lld), kernel body %lld cycles\n",
+                q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[20], q[19]);
     }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;

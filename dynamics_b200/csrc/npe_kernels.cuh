@@ -1235,6 +1235,88 @@ __global__ void k_rmsprop(float* __restrict__ x, const float* __restrict__ g, fl
     wpack[pack_index(i)] = xn;
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Device-side priority sampler (priority_sampler.lua:4-54; the `-rs`-off training path): a table of the last loss seen per
+// batch lives in HBM; a draw is uniform with probability alpha and otherwise multinomial over weight^pow.  One CTA:
+// sharpened weights -> inclusive scan (double) -> `n` draws by binary search, counter-based random numbers (same seed,
+// same draws).  flag[0] = 1 when a non-uniform draw met a table that is not full (a weight <= 0; the reference asserts).
+// ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {      // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long seed, unsigned long long ctr) {
+    return (double)(mix64(seed ^ mix64(ctr)) >> 11) * (1.0 / 9007199254740992.0);
+}
+__global__ void __launch_bounds__(1024) k_priority_sample(const float* __restrict__ w, int nb, float pow_, float alpha,
+                                                          unsigned long long seed, int n, double* __restrict__ cum,
+                                                          int* __restrict__ ids_out, int* __restrict__ flag) {
+    __shared__ double s_part[1024];
+    __shared__ int s_bad;
+    const int t = threadIdx.x;
+    if (t == 0) s_bad = 0;
+    __syncthreads();
+    const int per = (nb + 1023) / 1024, lo = t * per, hi = min(nb, lo + per);
+    double acc = 0.0;
+    bool bad = false;
+    for (int i = lo; i < hi; ++i) {
+        const float wi = w[i];
+        bad |= !(wi > 0.f);
+        acc += (double)powf(wi, pow_);
+    }
+    if (bad) s_bad = 1;
+    s_part[t] = acc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {          // inclusive scan of the 1024 chunk sums
+        const double v = t >= off ? s_part[t - off] : 0.0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    double run = t ? s_part[t - 1] : 0.0;
+    for (int i = lo; i < hi; ++i) { run += (double)powf(w[i], pow_); cum[i] = run; }
+    __syncthreads();
+    const double total = s_part[1023];
+    for (int d = t; d < n; d += 1024) {
+        int id;
+        if (u01(seed, 2ull * d) < (double)alpha) {
+            id = min(nb - 1, (int)(u01(seed, 2ull * d + 1) * nb));
+        } else {
+            if (s_bad) *flag = 1;
+            const double x = u01(seed, 2ull * d + 1) * total;
+            int a = 0, b = nb - 1;                       // first index with cum > x
+            while (a < b) { const int mid = (a + b) >> 1; if (cum[mid] > x) b = mid; else a = mid + 1; }
+            id = a;
+        }
+        ids_out[d] = id + 1;                             // 1-based like the Lua table
+    }
+}
+// weight[ids[i] - 1] = value i; values from a host-provided array or from the per-step losses of npe_train_steps (loss4 rows)
+__global__ void k_priority_update(float* __restrict__ w, int nb, const int* __restrict__ ids, const float* __restrict__ vals, int stride, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int id = ids[i];
+    if (id >= 1 && id <= nb) w[id - 1] = vals[(size_t)i * stride];
+}
+__global__ void __launch_bounds__(1024) k_priority_hardest(const float* __restrict__ w, int nb, float* __restrict__ out2) {
+    __shared__ float sv[1024];
+    __shared__ int si[1024];
+    float best = -1e38f; int bi = 0;
+    for (int i = threadIdx.x; i < nb; i += 1024) if (w[i] > best) { best = w[i]; bi = i; }
+    sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const float o = sv[threadIdx.x + s]; const int oi = si[threadIdx.x + s];
+            if (o > sv[threadIdx.x] || (o == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = o; si[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = sv[0]; out2[1] = (float)(si[0] + 1); }
+}
+
 __global__ void k_fill(float* p, int n, float v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
     if (warp < 4) {
         mbar_wait(&S.done, 0);
         tc_fence_after();
+        if (prof && warp == 0) A.prof[20] = clock64() - pe0;
         float* out = A.partial + (size_t)blockIdx.x * PT_TOTAL;
         const int n = 16 * warp + lane;
         for (int j = 0; j < A.njobs; ++j) {

@@ -74,6 +74,10 @@ SIGNATURES = {
     "npe_allreduce_grads": (C.c_int, [_H]),
     "npe_peer_export": (C.c_int, [_H, C.c_void_p]),
     "npe_peer_attach": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
+    "npe_priority_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_float]),
+    "npe_priority_update": (C.c_int, [_H, C.c_int32, _ip, _fp, C.c_int32]),
+    "npe_priority_sample": (C.c_int, [_H, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _ip]),
+    "npe_priority_hardest": (C.c_int, [_H, C.c_int32, _fp, _ip]),
     "npe_sync": (C.c_int, [_H]),
     "npe_host_alloc": (C.c_void_p, [C.c_size_t]),
     "npe_host_free": (None, [C.c_void_p]),

@@ -25,21 +25,36 @@ MAX_CTX = 12             # data_sampler.lua:169
 
 
 class PrioritySampler:
-    """priority_sampler.lua: a table of the last loss seen per batch; 10 % uniform, else multinomial(weights^pow)."""
+    """priority_sampler.lua: a table of the last loss seen per batch; 10 % uniform, else multinomial(weights^pow).
+    With `model` (an NPEModel) and a table index the weights live on the DEVICE and the draw (scan of weight^pow + binary
+    search, counter-based random numbers) runs there (npe_priority_*); the host keeps only which batches have been seen."""
 
-    def __init__(self, num_batches, rng=None):
+    _next_table = {}
+
+    def __init__(self, num_batches, rng=None, model=None):
         self.batch_weights = np.zeros(num_batches, np.float64)
         self.alpha = 0.1
         self.epc_num = 1
         self.table_is_full = False
         self.num_batches = num_batches
         self.rng = rng or np.random.default_rng(0)
+        self.model, self.table = None, None
+        if model is not None and hasattr(model, "priority_init"):
+            t = PrioritySampler._next_table.get(id(model), 0)
+            if t < 16:
+                PrioritySampler._next_table[id(model)] = t + 1
+                model.priority_init(t, num_batches, self.alpha)
+                self.model, self.table = model, t
 
     def update_batch_weight(self, batch_id, weight):            # 1-based id, priority_sampler.lua:18-22
         self.batch_weights[batch_id - 1] = weight
         self.table_is_full = bool(self.batch_weights.min() > 0)
+        if self.model is not None:
+            self.model.priority_update(self.table, [batch_id], [weight])
 
     def sample(self, pow_=1):                                     # priority_sampler.lua:37-48
+        if self.model is not None:
+            return int(self.model.priority_sample(self.table, pow_ or 1, int(self.rng.integers(0, 2 ** 63)), 1)[0])
         if self.rng.integers(1, 101) / 100.0 < self.alpha:
             return int(self.rng.integers(1, self.num_batches + 1))
         sharpened = np.power(self.batch_weights, pow_ if pow_ else 1)
@@ -49,11 +64,18 @@ class PrioritySampler:
         return int(self.rng.choice(self.num_batches, p=p)) + 1
 
     def get_hardest_batch(self):                                  # priority_sampler.lua:50-54 -> {max, argmax}
+        if self.model is not None:
+            return self.model.priority_hardest(self.table)
         i = int(np.argmax(self.batch_weights))
         return [float(self.batch_weights[i]), i + 1]
 
     def set_alpha(self, v):
         self.alpha = v
+        if self.model is not None:                                 # re-create the device table with the new alpha, same weights
+            self.model.priority_init(self.table, self.num_batches, v)
+            seen = np.nonzero(self.batch_weights)[0]
+            if seen.size:
+                self.model.priority_update(self.table, seen + 1, self.batch_weights[seen])
 
     def set_epcnum(self, v):
         self.epc_num = v
@@ -184,7 +206,9 @@ class DataSampler:
         self.total_batches = self.num_subbatches if self.subdivide else self.num_batches
         self.batch_idxs = (self.rng.permutation(self.total_batches) + 1 if self.shuffle
                            else np.arange(1, self.total_batches + 1))
-        self.priority_sampler = PrioritySampler(self.total_batches, self.rng)
+        # the loss table of priority sampling lives on the device when asked for (train loader of a -rs-off run)
+        self.priority_sampler = PrioritySampler(self.total_batches, self.rng,
+                                                args.get("model") if args.get("device_priority") else None)
         self.current_sampled_id = 0
         self.current_batch = 0
         self.current_subbatch = 0

@@ -376,6 +376,26 @@ class NPEModel:
         """'persistent' (one kernel, window on chip) or 'kernels' (window in HBM, 5 launches per step)."""
         self._ck(self.lib.npe_set_rollout_mode(self.h, {"persistent": 0, "kernels": 1}[mode]))
 
+    # ---- device-side priority sampler (priority_sampler.lua) ---------------------------------------------------
+    def priority_init(self, table, num_batches, alpha=0.1):
+        self._ck(self.lib.npe_priority_init(self.h, table, num_batches, alpha))
+
+    def priority_update(self, table, ids, weights=None):
+        """weights None: the per-step losses the last train_steps call left on the device (step i -> ids[i])."""
+        ids = L.i32(np.atleast_1d(ids))
+        w = None if weights is None else L.f32(np.atleast_1d(weights))
+        self._ck(self.lib.npe_priority_update(self.h, table, L.iptr(ids), L.fptr(w), ids.size))
+
+    def priority_sample(self, table, pow_=1.0, seed=0, n=1):
+        out = np.empty(n, np.int32)
+        self._ck(self.lib.npe_priority_sample(self.h, table, pow_, int(seed) & (2 ** 64 - 1), n, L.iptr(out)))
+        return out
+
+    def priority_hardest(self, table):
+        w = C.c_float(); i = C.c_int32()
+        self._ck(self.lib.npe_priority_hardest(self.h, table, C.byref(w), C.byref(i)))
+        return [float(w.value), int(i.value)]
+
     # ---- misc -------------------------------------------------------------------------------------------------
     def sync(self):
         self._ck(self.lib.npe_sync(self.h))

@@ -170,7 +170,8 @@ class Experiment:
                 "model": self.model, "batch_size": mp.batch_size, "rng": self.rng}
         eval_args = dict(args); eval_args["rng"] = self.rng_eval
         test_args = dict(eval_args); test_args["dataset_folders"] = mp.test_dataset_folders
-        self.train_loader = GeneralDataSampler.create("trainset", dict(args))
+        # without -rs the batch is drawn from the loss table (main.lua:249-253): kept on the device
+        self.train_loader = GeneralDataSampler.create("trainset", dict(args, device_priority=not mp.rs))
         self.val_loader = GeneralDataSampler.create("valset", dict(eval_args))
         self.test_loader = GeneralDataSampler.create("testset", test_args)
         self.train_test_loader = GeneralDataSampler.create("trainset", dict(eval_args))

@@ -252,6 +252,20 @@ int npe_allreduce_grads(npe_handle* h); /* sum of flat gradients (+3 loss sums) 
 int npe_peer_export(npe_handle* h, void* handle64_out);
 int npe_peer_attach(npe_handle* h, int32_t rank, int32_t nranks, const void* all_handles);
 
+/*
+ * Device-side priority sampler (priority_sampler.lua:4-54; main.lua:249-253 when -rs is off): the table of the last loss
+ * per batch lives on the device, one table (0..15) per data sampler / dataset folder.  init: num_batches zero weights, `alpha` = probability of a uniform draw (0.1 in the
+ * reference).  update: weight[ids[i]] = weights[i] (ids 1-based; update_batch_weight, :18-22); weights == NULL takes the
+ * per-step losses the last npe_train_steps call left on the device (step i -> ids[i]).  sample: n draws (uniform with
+ * probability alpha, else multinomial over weight^pow, :37-48) from counter-based random numbers of `seed`; fails with
+ * NPE_ERR_STATE when a multinomial draw meets a table that is not full (the reference asserts).  hardest: {max, argmax}
+ * (get_hardest_batch, :50-54).
+ */
+int npe_priority_init(npe_handle* h, int32_t table, int32_t num_batches, float alpha);
+int npe_priority_update(npe_handle* h, int32_t table, const int32_t* ids, const float* weights, int32_t n);
+int npe_priority_sample(npe_handle* h, int32_t table, float pow_, uint64_t seed, int32_t n, int32_t* ids_out);
+int npe_priority_hardest(npe_handle* h, int32_t table, float* weight_out, int32_t* id_out);
+
 int npe_sync(npe_handle* h);
 /* Page-locked host buffers for callers that stream batches (cudaHostAlloc / cudaFreeHost). */
 void* npe_host_alloc(size_t bytes);

@@ -248,3 +248,37 @@ def test_device_packer_raw_to_states_is_bit_exact(model):
     bad = rawb.copy(); bad[0, 0, 0, 6] = 7.0                             # a mass outside {1, 5, 25, 1e30}
     with pytest.raises(NPEError):
         model.upload_scenes_raw(bad)
+
+
+def test_device_priority_sampler(model):
+    """priority_sampler.lua on the device: update_batch_weight / sample (uniform with probability alpha, else multinomial over
+    weight^pow) / get_hardest_batch; frequencies of 40 000 draws against the exact probabilities; the reference's assert on
+    a table that is not full; the loss of every step of npe_train_steps fed to the table without a host round trip."""
+    from dynamics_b200 import NPEError
+    w = np.array([1.0, 2.0, 3.0, 4.0, 10.0], np.float32)
+    model.priority_init(0, 5, alpha=0.0)
+    with pytest.raises(NPEError):
+        model.priority_sample(0, 1.0, seed=1, n=4)                    # table not full: weights are all zero
+    model.priority_update(0, np.arange(1, 6), w)
+    assert model.priority_hardest(0) == [10.0, 5]
+    for pw in (1.0, 2.0):
+        ids = model.priority_sample(0, pw, seed=7, n=40000)
+        assert ids.min() >= 1 and ids.max() <= 5
+        freq = np.bincount(ids, minlength=6)[1:] / 40000.0
+        p = w.astype(np.float64) ** pw; p /= p.sum()
+        assert np.max(np.abs(freq - p)) < 0.01, (freq, p)
+    assert np.array_equal(model.priority_sample(0, 1.0, seed=7, n=64), model.priority_sample(0, 1.0, seed=7, n=64))   # same seed, same draws
+    model.priority_init(1, 5, alpha=1.0)                              # second table, always uniform: a zero table is fine
+    ids = model.priority_sample(1, 1.0, seed=3, n=20000)
+    assert np.max(np.abs(np.bincount(ids, minlength=6)[1:] / 20000.0 - 0.2)) < 0.015
+    # losses of npe_train_steps -> table, on the device
+    st = scenes.raw_to_state(scenes.gen_balls(100, 4, 12, seed=51))
+    sc = np.arange(100); ob = np.tile(np.arange(4), 25); t0 = (np.arange(100) * 7) % 9
+    model.upload_scenes(st); model.upload_foci(sc, ob, t0)
+    model.set_params(npe.init_params(1234)); model.optim_reset(0.0)
+    losses = model.train_steps(0, 50, 2, "adam", 3e-4, want_losses=True)
+    model.priority_init(2, 4, alpha=0.0)
+    model.priority_update(2, [3, 1])                                  # step 0 -> batch 3, step 1 -> batch 1
+    model.priority_update(2, [2, 4], [1e-9, 1e-9])
+    hw, hid = model.priority_hardest(2)
+    assert hid == (3 if losses[0, 0] >= losses[1, 0] else 1) and abs(hw - max(losses[0, 0], losses[1, 0])) < 1e-12
