@@ -20,6 +20,7 @@
 #include "npe_tc.cuh"
 #include "npe_tcbwd.cuh"
 #include "npe_chain.cuh"
+#include "npe_wgrad.cuh"
 
 using namespace npe;
 
@@ -189,6 +190,10 @@ struct npe_handle {
     cudaEvent_t ring_ev[64] = {};     // npe_train_step_async / npe_loss_wait: one event per ring slot (slot i at loss4_host + 16 + 4 i)
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
+    unsigned* scan_ticket[2] = {nullptr, nullptr};   // chained scan of the throughput pair builder (k_build_pairs_scan):
+    DevBuf<u64> scan_status[2];                      // one state per stream the builder may run on (main, upload)
+    unsigned scan_epoch = 0;
+    bool keep_valid = false;          // the kept-context bits of the current pair table are complete (API view; see warp_pairs)
     // The last launch on the main stream was a pair builder: the next kernel must not be a programmatic dependent of it
     // (it would read the pair tables before griddepcontrol.wait, and only the wait guarantees the builder's writes are
     // visible).  launch_pdl drops the attribute once and clears the flag.
@@ -333,36 +338,88 @@ int ensure_batch_buffers(npe_handle* h, int F) {
     return NPE_OK;
 }
 
-// Pair builder launch: sub-warp variants when every scene has at most 9 / 17 objects.
-template <typename... Args>
-void launch_build_pairs(npe_handle* h, int nblk, int nmax, Args... args) {
-    if (nmax - 1 <= 8) k_build_pairs<8><<<nblk, 512, 0, h->stream>>>(args...);
-    else if (nmax - 1 <= 16) k_build_pairs<16><<<nblk, 1024, 0, h->stream>>>(args...);
-    else k_build_pairs<32><<<nblk, NT_PAIRS, 0, h->stream>>>(args...);
-    h->launches++;
-    h->after_builder = true;
+// Pair builder launch: sub-warp variants when every scene has at most 9 / 17 objects.  One CTA (at most 64 foci): the
+// latency-tuned kernel; more: the single-launch chained-scan kernel.
+// Largest squared distance s whose reference test  fl(800 * fl(sqrt(s))) <= thr  passes (see warp_pairs_core): bisection over
+// the bit patterns of the non-negative floats (the test is monotone in s).  Negative: nothing passes.
+float nbr_threshold_sq(float thr) {
+    auto passes = [thr](uint32_t bits) {
+        float s; memcpy(&s, &bits, 4);
+        volatile float d = sqrtf(s);                      // correctly rounded, like __fsqrt_rn
+        volatile float m = d * 800.f;                     // one rounding, like __fmul_rn
+        return m <= thr;
+    };
+    if (!passes(0u)) return -1.f;
+    uint32_t lo = 0u, hi = 0x7f800000u;                   // passes(lo), !passes(hi) (+inf never passes a finite threshold)
+    if (passes(hi)) hi = 0x7f800001u;
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        if (passes(mid)) lo = mid; else hi = mid;
+    }
+    float s; memcpy(&s, &lo, 4);
+    return s;
 }
 
-int build_pairs(npe_handle* h) {
-    if (h->pairs_valid) return NPE_OK;
+struct PairOut { u64* keep; u64* nbr; int* cnt; int* block_sums; long long* foc_row; float* y; };
+int launch_build_pairs(npe_handle* h, const FocusSrc& src, float thr, const PairOut& o, bool want_keep) {
+    const int nmax = h->Nmax, kmax = h->cfg.max_ctx;
+    if (src.F <= FPB) {
+        if (nmax - 1 <= 8)
+            k_build_pairs<8><<<1, 512, 0, h->stream>>>(src, kmax, thr, o.keep, o.nbr, o.cnt, o.block_sums, o.foc_row, o.y, h->active_total,
+                                                       h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, (int)want_keep);
+        else if (nmax - 1 <= 16)
+            k_build_pairs<16><<<1, 1024, 0, h->stream>>>(src, kmax, thr, o.keep, o.nbr, o.cnt, o.block_sums, o.foc_row, o.y, h->active_total,
+                                                         h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, (int)want_keep);
+        else
+            k_build_pairs<32><<<1, NT_PAIRS, 0, h->stream>>>(src, kmax, thr, o.keep, o.nbr, o.cnt, o.block_sums, o.foc_row, o.y, h->active_total,
+                                                            h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, (int)want_keep);
+    } else {
+        const int nblk = (src.F + NT_SCAN - 1) / NT_SCAN;
+        const int w = h->stream == h->stream2;
+        DevBuf<u64>& status = h->scan_status[w];
+        const size_t had = status.cap;
+        CK(status.ensure((size_t)nblk));
+        if (status.cap != had) CK(cudaMemsetAsync(status.p, 0, status.cap * sizeof(u64), h->stream));
+        if (!h->scan_ticket[w]) {
+            CK(cudaMalloc((void**)&h->scan_ticket[w], sizeof(unsigned)));
+            CK(cudaMemsetAsync(h->scan_ticket[w], 0, sizeof(unsigned), h->stream));
+        }
+        PairScan sc;
+        sc.ticket = h->scan_ticket[w]; sc.status = status.p;
+        sc.epoch = ++h->scan_epoch;
+        if ((sc.epoch & 0x3fffffffu) == 0) sc.epoch = ++h->scan_epoch;      // 0 is what a fresh status array holds
+        sc.nblk = nblk;
+        const int per_sm = o.y ? 4 : 8;                                      // resident CTAs per SM (launch bounds of the two variants)
+        const int grid = nblk < per_sm * h->num_sms ? nblk : per_sm * h->num_sms;
+        if (o.y)
+            k_build_pairs_scan<true><<<grid, NT_SCAN, 0, h->stream>>>(src, kmax, thr, (int)want_keep, o.keep, o.nbr, o.foc_row, o.y, h->active_total,
+                                                                      h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, sc);
+        else
+            k_build_pairs_scan<false><<<grid, NT_SCAN, 0, h->stream>>>(src, kmax, thr, (int)want_keep, o.keep, o.nbr, o.foc_row, o.y, h->active_total,
+                                                                       h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, sc);
+    }
+    h->launches++;
+    h->after_builder = true;
+    return NPE_OK;
+}
+
+// want_keep: the caller reads the trimmed context LIST (npe_build_pairs outputs), not only the neighbour bits.  The hot
+// paths never do, and on scenes of more than 17 objects the complete list costs O(N^2) shuffles per focus (warp_pairs).
+int build_pairs(npe_handle* h, bool want_keep = false) {
+    if (h->pairs_valid && (h->keep_valid || !want_keep)) return NPE_OK;
+    const bool refresh = h->pairs_valid;          // tables are current; only the kept-context bits are incomplete
     if (h->F <= 0) return fail(h, NPE_ERR_STATE, "no batch selected");
-    if (h->F > FPB) CK(cudaMemsetAsync(h->active_total, 0, sizeof(u64), h->stream));   // one CTA stores its total
-    const float thr = h->cfg.nbrhdsize * 60.f;   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
+    const float thr = nbr_threshold_sq(h->cfg.nbrhdsize * 60.f);   // nbrhdsize * object_base_size.ball|block (npe.lua:180-186)
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
-        const int nblk = (h->F + FPB - 1) / FPB;
-        launch_build_pairs(h, nblk, h->Nmax, h->src(), h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
-                           h->foc_row.p, h->batch_form ? nullptr : h->y.p, h->active_total, h->pair_start.p, h->pair_foc.p,
-                           h->pair_crow.p, h->pair_cap, h->info_dev);
-        if (nblk > 1) {
-            k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(h->src(), h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
-                                                              h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
-            h->launches++;
-        }
+        const PairOut o = {h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p, h->foc_row.p, h->batch_form ? nullptr : h->y.p};
+        const int rc = launch_build_pairs(h, h->src(), thr, o, want_keep);
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     h->pairs_valid = true;
-    h->hact_valid = false; h->dact_valid = false;
+    h->keep_valid = want_keep || (h->F <= FPB && h->Nmax - 1 <= 16);   // the sub-warp single-CTA variants rank every context
+    if (!refresh) { h->hact_valid = false; h->dact_valid = false; }   // a refresh rewrites identical tables
     return NPE_OK;
 }
 
@@ -550,12 +607,19 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
 int launch_reduce(npe_handle* h, int gp, int gd, int fuse_opt, float lr, bool want_loss, int peer_opt) {
     ProfScope ps__(h, NPE_K_REDUCE);
     const ReducePlan r = prepare_reduce(h, fuse_opt, lr, want_loss, peer_opt);
-    const int nb = (NPARAM + 255) / 256 + (want_loss ? 1 : 0);
-    if (r.peer && r.opt == 1) CK(launch_pdl(h, k_dp_step<1>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
-    else if (r.peer) CK(launch_pdl(h, k_dp_step<2>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));
-    else if (r.opt == 1) CK(launch_pdl(h, k_reduce_grads<1>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
-    else if (r.opt == 2) CK(launch_pdl(h, k_reduce_grads<2>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
-    else CK(launch_pdl(h, k_reduce_grads<0>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));
+    // many partials (throughput regime: one per SM and part): four lanes per parameter, see ordered_partial_sum
+    const bool split = (gp > gd ? gp : gd) > 32;
+    const int nb = ((split ? 4 : 1) * NPARAM + 255) / 256 + (want_loss ? 1 : 0);
+#define NPE_REDUCE(RS)                                                                                                              \
+    do {                                                                                                                            \
+        if (r.peer && r.opt == 1) CK(launch_pdl(h, k_dp_step<1, RS>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L)); \
+        else if (r.peer) CK(launch_pdl(h, k_dp_step<2, RS>, nb, 256, 0, h->partial, gp, gd, r.P, r.buf, r.stamp, h->grads, r.o, r.L));          \
+        else if (r.opt == 1) CK(launch_pdl(h, k_reduce_grads<1, RS>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));          \
+        else if (r.opt == 2) CK(launch_pdl(h, k_reduce_grads<2, RS>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));          \
+        else CK(launch_pdl(h, k_reduce_grads<0, RS>, nb, 256, 0, h->partial, gp, gd, h->grads, r.o, r.L));                          \
+    } while (0)
+    if (split) NPE_REDUCE(4); else NPE_REDUCE(1);
+#undef NPE_REDUCE
     h->launches++;
     CK(cudaGetLastError());
     return NPE_OK;
@@ -619,7 +683,23 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         E.gs[1].base = h->states.p; E.gs[1].offs = h->pair_crow.p; E.gs[1].cols_valid = IN; E.gs[1].cols_store = 48; E.gs[1].col0 = 48;
         E.ngs = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
         A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial; A.prof = chain_prof(h);
-        CK(launch_pdl(h, k_wgrad_tc, gp, WG_NT, sizeof(WgradSmem), A));
+        static const bool old_wgrad = getenv("NPE_WGRAD_V3") != nullptr;     // A/B measurements only
+        auto stacked = [](const WArgs& W, const int (&ia)[3], const int (&ib)[3]) {
+            WmArgs M = {};
+            for (int p = 0; p < 3; ++p) {
+                WPair& P = M.pair[p];
+                P.a = W.job[ia[p]];
+                P.has_b = ib[p] >= 0;
+                if (P.has_b) P.b = W.job[ib[p]];
+                P.ca = P.a.ngs ? 3 : 2;
+                P.cb = !P.has_b ? 0 : (P.b.ngs ? 3 : 2);
+                P.tmem_col = 128 * p;
+            }
+            M.npairs = 3; M.nrows_dev = W.nrows_dev; M.nrows = W.nrows; M.partial = W.partial; M.prof = W.prof;
+            return M;
+        };
+        if (old_wgrad) CK(launch_pdl(h, k_wgrad_tc, gp, WG_NT, sizeof(WgradSmem), A));
+        else CK(launch_pdl(h, k_wgrad_mn<0>, gp, WM_NT, sizeof(WmSmem) + 1024, stacked(A, {0, 2, 4}, {1, 3, 5})));   // (L5, L4) (L3, L2) (L1, encoders)
         h->launches++;
         WArgs B = {};
         // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
@@ -635,7 +715,8 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
         D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
         B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial;
-        CK(launch_pdl(h, k_wgrad_tc, gd, WG_NT, sizeof(WgradSmem), B));
+        if (old_wgrad) CK(launch_pdl(h, k_wgrad_tc, gd, WG_NT, sizeof(WgradSmem), B));
+        else CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));  // (D5, D4) (D3, D2) (D1)
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -857,6 +938,8 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_wgrad_mn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_wgrad_mn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradChainSmem))) != cudaSuccess ||
@@ -877,6 +960,7 @@ int npe_destroy(npe_handle* h) {
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
+    for (int i = 0; i < 2; ++i) { if (h->scan_ticket[i]) cudaFree(h->scan_ticket[i]); h->scan_status[i].release(); }
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
@@ -1164,7 +1248,7 @@ int npe_batch_download(npe_handle* h, float* this_past_out, float* y_out) {
 
 int npe_build_pairs(npe_handle* h, int32_t* ctx_idx_out, uint8_t* mask_out, int32_t* cnt_out) {
     NEED(h);
-    int rc = build_pairs(h);
+    int rc = build_pairs(h, ctx_idx_out || mask_out || cnt_out);
     if (rc) return rc;
     if (ctx_idx_out || mask_out || cnt_out) {
         const int K = npe_ctx_slots(h);
@@ -1304,7 +1388,7 @@ static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* 
     o.total = q.total.p; o.pair_start = q.pair_start.p; o.pair_foc = q.pair_foc.p; o.pair_crow = q.pair_crow.p; o.info = q.info.p;
     FocusSrc src = h->src();
     src.foc_scene = h->foc_scene.p; src.foc_obj = h->foc_obj.p; src.foc_t0 = h->foc_t0.p;
-    const float thr = h->cfg.nbrhdsize * 60.f;
+    const float thr = nbr_threshold_sq(h->cfg.nbrhdsize * 60.f);
     {
         ProfScope ps__(h, NPE_K_BUILD_PAIRS);
         if (h->Nmax - 1 <= 8) k_build_pairs_sched<8><<<n, 512, 0, h->stream>>>(src, q.step_first.p, q.step_F.p, fmax, cap, h->cfg.max_ctx, thr, o);
@@ -1385,7 +1469,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
                 h->pair_foc.p = q.pair_foc.p + po; h->pair_crow.p = q.pair_crow.p + po; h->info_dev = q.info.p + 2 * i;
                 h->active_total = q.total.p + i;
                 h->pair_cap = cap;
-                h->pairs_valid = true; h->hact_valid = false; h->dact_valid = false;
+                h->pairs_valid = true; h->keep_valid = true; h->hact_valid = false; h->dact_valid = false;
             }
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
@@ -1430,7 +1514,7 @@ static int rollout_impl(npe_handle* h, int t0, int steps, int use_gt, int teache
     A.states = h->states.p; A.n_obj = h->n_obj.p; A.S = h->S; A.Nmax = h->Nmax; A.T = h->T;
     A.t0 = t0; A.steps = steps; A.use_gt = use_gt; A.teacher = teacher;
     A.kmax = h->cfg.max_ctx; A.ball_zero = h->cfg.ball_zero_mode;
-    A.thr_px = h->cfg.nbrhdsize * 60.f;
+    A.thr_s = nbr_threshold_sq(h->cfg.nbrhdsize * 60.f);
     A.wpack = h->wpack;
     A.traj = nullptr; A.metrics = nullptr;
     if (want_traj) {
@@ -1506,7 +1590,7 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     FocusSrc src;
     src.states = h->roll.p; src.n_obj = h->n_obj.p; src.Nmax = h->Nmax; src.T = 2;
     src.foc_scene = h->roll_scene.p; src.foc_obj = h->roll_obj.p; src.foc_t0 = h->roll_t0.p; src.F = F;
-    const float thr = h->cfg.nbrhdsize * 60.f;
+    const float thr = nbr_threshold_sq(h->cfg.nbrhdsize * 60.f);
     const int nblk = (F + FPB - 1) / FPB;
     const int tc = h->precision;
     // Scenes in which every object is a focus, no ground truth, no trajectory / metric output (npe_rollout_resident on ball
@@ -1518,14 +1602,8 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
-            launch_build_pairs(h, nblk, h->Nmax, src, h->cfg.max_ctx, thr, h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p,
-                               h->foc_row.p, (float*)nullptr, h->active_total, h->pair_start.p, h->pair_foc.p, h->pair_crow.p,
-                               h->pair_cap, h->info_dev);
-            if (nblk > 1) {
-                k_expand_pairs_dense<<<nblk, FPB, 0, h->stream>>>(src, h->nbr.p, h->cnt.p, h->block_sums.p, h->pair_start.p,
-                                                                  h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev);
-                h->launches++;
-            }
+            const PairOut o = {h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p, h->foc_row.p, nullptr};
+            if ((rc = launch_build_pairs(h, src, thr, o, false))) return rc;
         }
         if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc, nullptr, false, nullptr, fused_post ? h->roll.p : nullptr))) return rc;
         A.step = step;
@@ -1734,9 +1812,9 @@ int npe_sync(npe_handle* h) {
         long long q[32];
         cudaMemcpy(q, h->chain_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[pair forward chain, CTA 0 thread 0] gather %lld, wait for MMA %lld, epilogue %lld, total %lld cycles\n", q[0], q[1], q[2], q[3]);
-        fprintf(stderr, "[pair wgrad CTA 0] producer: wait empty %lld of %lld | transposer: wait raw %lld, wait op %lld, work %lld, units %lld, loop %lld | "
+        fprintf(stderr, "[pair wgrad CTA 0] loader group 0: issue loads %lld, wait for the stage %lld, data + split + stores %lld, units %lld, loop %lld | "
                         "mma: wait %lld, issue %lld, loop %lld | epilogue %lld (of which waiting for the last MMAs %lld), kernel body %lld cycles\n",
-                q[8], q[9], q[10], q[11], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[20], q[19]);
+                q[11], q[10], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[20], q[19]);
     }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;
@@ -1822,6 +1900,8 @@ int npe_event_elapsed_ms(npe_handle* h, int32_t a, int32_t b, float* ms_out) {
 }
 
 int64_t npe_launch_count(const npe_handle* h) { return h ? h->launches : 0; }
+
+float npe_nbr_threshold_sq(float thr_px) { return nbr_threshold_sq(thr_px); }
 
 int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats) {
     NEED(h);

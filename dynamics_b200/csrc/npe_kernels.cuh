@@ -127,77 +127,120 @@ __device__ __forceinline__ void stage_wait(WeightStage& st) { mbar_wait(&st.bar,
 // distance, then lower index); nbr = kept contexts inside the neighbourhood (npe.lua:170-206).
 // Distance arithmetic follows compute_euc_dist (data_utils.lua:276-285) with one rounding per op: no FMA contraction.
 // ----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, int n, int kmax, float thr_px,
-                                           u64& keep, u64& nbr) {
+// The neighbourhood test of the reference is  fl(800 * fl(sqrt(s))) <= thr  on the squared distance s.  Both roundings
+// are monotone, so the set of s that pass is  s <= thr_s  for ONE float thr_s (the largest s that passes; the host finds
+// it by bisection over the float bit patterns, npe_api.cu nbr_threshold_sq): the same bits without the IEEE square root,
+// which is only taken where contexts have to be RANKED by distance (distinct s can round to equal distances, and ties
+// go to the lower index).
+__device__ __forceinline__ float pair_sqdist(float x, float y, float fx, float fy) {
+    const float dx = __fsub_rn(x, fx), dy = __fsub_rn(y, fy);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+// A set of OBJECTS of a scene (bit o = object o) -> the same set as CONTEXTS of focus n (context c = object c + (c >= n)).
+__device__ __forceinline__ u64 objects_to_contexts(u64 m, int n) {
+    return (m & ((1ull << n) - 1ull)) | (((m >> n) >> 1) << n);
+}
+// One focus per warp, in OBJECT space: lane l holds the squared distances focus -> object l (s[0]) and -> object l + 32
+// (s[1]).  Object order is context order, so ranks and the lower-index tie rule carry over unchanged; the two sets are
+// renumbered to context indices at the end.
+__device__ __forceinline__ void warp_pairs_core(const float (&s)[2], int N, int n, int kmax, float thr_s, u64& keep, u64& nbr,
+                                                bool want_keep) {
     const int lane = threadIdx.x & 31;
     const int Cn = N - 1;
-    const float fx = pos[(size_t)n * stride], fy = pos[(size_t)n * stride + 1];
+    const u64 V = (N >= 64 ? ~0ull : ((1ull << N) - 1ull)) & ~(1ull << n);     // the other objects of the scene
+    bool in[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) in[h] = ((V >> (lane + 32 * h)) & 1ull) && s[h] <= thr_s;
+    const u64 W = (u64)__ballot_sync(0xffffffffu, in[0]) | ((u64)__ballot_sync(0xffffffffu, in[1]) << 32);
+    const int k = (kmax > 0 && kmax < Cn) ? kmax : Cn;
+    if (k >= Cn) { keep = objects_to_contexts(V, n); nbr = objects_to_contexts(W, n); return; }
+    // Trim to the k nearest (ties: lower index first).  The neighbourhood W is a PREFIX of that order, so ranks never
+    // have to be taken over all Cn contexts (O(Cn^2) shuffles per focus):
+    //   |W| >= k : the k nearest all lie in W; rank the members of W among W             (|W| shuffles)
+    //   |W| <  k : every member of W is kept and nbr = W; the kept set also holds the k - |W| nearest OUTSIDE W, which
+    //              only the API view of the pair table shows (want_keep): rank the outsiders among the outsiders
+    const int w = __popcll(W);
+    const bool inside = w >= k;
+    if (!inside && !want_keep) { keep = objects_to_contexts(W, n); nbr = keep; return; }
     float d[2];
     bool valid[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int c = lane + 32 * h;
-        valid[h] = c < Cn;
-        d[h] = __int_as_float(0x7f800000);
-        if (valid[h]) {
-            const int j = c + (c >= n);
-            const float dx = __fsub_rn(pos[(size_t)j * stride], fx);
-            const float dy = __fsub_rn(pos[(size_t)j * stride + 1], fy);
-            d[h] = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        }
+        valid[h] = (V >> (lane + 32 * h)) & 1ull;
+        d[h] = valid[h] ? __fsqrt_rn(s[h]) : __int_as_float(0x7f800000);
     }
-    const int k = (kmax > 0 && kmax < Cn) ? kmax : Cn;
-    bool kp[2] = {valid[0], valid[1]};
-    if (k < Cn) {
-        int rank[2] = {0, 0};
-        for (int cp = 0; cp < Cn; ++cp) {
-            const float dp = __shfl_sync(0xffffffffu, cp < 32 ? d[0] : d[1], cp & 31);
+    u64 bits = inside ? W : (V & ~W);
+    int rank[2] = {0, 0};
+    while (bits) {
+        const int op = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        const float dp = __shfl_sync(0xffffffffu, op < 32 ? d[0] : d[1], op & 31);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = lane + 32 * h;
-                rank[h] += (dp < d[h]) || (dp == d[h] && cp < c);
-            }
+        for (int h = 0; h < 2; ++h) {
+            const int o = lane + 32 * h;
+            rank[h] += (dp < d[h]) || (dp == d[h] && op < o);
         }
-        kp[0] = valid[0] && rank[0] < k;
-        kp[1] = valid[1] && rank[1] < k;
     }
-    const unsigned k0 = __ballot_sync(0xffffffffu, kp[0]), k1 = __ballot_sync(0xffffffffu, kp[1]);
-    const unsigned m0 = __ballot_sync(0xffffffffu, kp[0] && (__fmul_rn(d[0], 800.f) <= thr_px));
-    const unsigned m1 = __ballot_sync(0xffffffffu, kp[1] && (__fmul_rn(d[1], 800.f) <= thr_px));
-    keep = (u64)k0 | ((u64)k1 << 32);
-    nbr = (u64)m0 | ((u64)m1 << 32);
+    bool kp[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) kp[h] = inside ? (in[h] && rank[h] < k) : (in[h] || (valid[h] && rank[h] < k - w));
+    const u64 K = (u64)__ballot_sync(0xffffffffu, kp[0]) | ((u64)__ballot_sync(0xffffffffu, kp[1]) << 32);
+    keep = objects_to_contexts(K, n);
+    nbr = inside ? keep : objects_to_contexts(W, n);
 }
-
+// object j at pos + j * stride (global or shared memory)
+__device__ __forceinline__ void warp_pairs(const float* pos, int stride, int N, int n, int kmax, float thr_s,
+                                           u64& keep, u64& nbr, bool want_keep = true) {
+    const int lane = threadIdx.x & 31;
+    const float fx = pos[(size_t)n * stride], fy = pos[(size_t)n * stride + 1];
+    float s[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int o = lane + 32 * h;
+        s[h] = __int_as_float(0x7f800000);
+        if (o < N) s[h] = pair_sqdist(pos[(size_t)o * stride], pos[(size_t)o * stride + 1], fx, fy);
+    }
+    warp_pairs_core(s, N, n, kmax, thr_s, keep, nbr, want_keep);
+}
 // Sub-warp variant of warp_pairs for small scenes: a group of LANES (8 or 16) lanes handles one focus with at most
 // LANES contexts, so a warp builds 32 / LANES pair tables at once (8-ball scenes: 4 foci per warp instead of 1 with 7
 // of 32 lanes busy).  Same arithmetic, same tie rule, bit-identical results.
 template <int LANES>
-__device__ __forceinline__ void group_pairs(const float* pos, int stride, int N, int n, int kmax, float thr_px, bool active,
-                                            u64& keep, u64& nbr) {
-    const int lane = threadIdx.x & 31, gl = lane & (LANES - 1), gbase = lane & ~(LANES - 1);
-    const int Cn = active ? N - 1 : 0;
-    const bool valid = gl < Cn;
-    float d = __int_as_float(0x7f800000);
-    if (valid) {
-        const float fx = pos[(size_t)n * stride], fy = pos[(size_t)n * stride + 1];
+__device__ __forceinline__ float group_sqdist(const float* pos, int stride, int Cn, int n) {
+    const int gl = threadIdx.x & (LANES - 1);
+    float s = __int_as_float(0x7f800000);
+    if (gl < Cn) {
         const int j = gl + (gl >= n);
-        const float dx = __fsub_rn(pos[(size_t)j * stride], fx);
-        const float dy = __fsub_rn(pos[(size_t)j * stride + 1], fy);
-        d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        s = pair_sqdist(pos[(size_t)j * stride], pos[(size_t)j * stride + 1], pos[(size_t)n * stride], pos[(size_t)n * stride + 1]);
     }
+    return s;
+}
+template <int LANES>
+__device__ __forceinline__ void group_core(float s, int Cn, int kmax, float thr_s, u64& keep, u64& nbr) {
+    const int lane = threadIdx.x & 31, gl = lane & (LANES - 1), gbase = lane & ~(LANES - 1);
+    const bool valid = gl < Cn;
     const int k = (kmax > 0 && kmax < Cn) ? kmax : Cn;
     int rank = 0;
+    if (__any_sync(0xffffffffu, k < Cn)) {                // no group of this warp trims: no ranks, no square root
+        const float d = valid ? __fsqrt_rn(s) : __int_as_float(0x7f800000);
 #pragma unroll
-    for (int cp = 0; cp < LANES; ++cp) {
-        const float dp = __shfl_sync(0xffffffffu, d, gbase + cp);
-        if (cp < Cn) rank += (dp < d) || (dp == d && cp < gl);
+        for (int cp = 0; cp < LANES; ++cp) {
+            const float dp = __shfl_sync(0xffffffffu, d, gbase + cp);
+            if (cp < Cn) rank += (dp < d) || (dp == d && cp < gl);
+        }
     }
     const bool kp = valid && (k >= Cn || rank < k);
     const unsigned bk = __ballot_sync(0xffffffffu, kp);
-    const unsigned bm = __ballot_sync(0xffffffffu, kp && (__fmul_rn(d, 800.f) <= thr_px));
+    const unsigned bm = __ballot_sync(0xffffffffu, kp && s <= thr_s);
     const unsigned gm = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
     keep = (u64)((bk >> gbase) & gm);
     nbr = (u64)((bm >> gbase) & gm);
+}
+template <int LANES>
+__device__ __forceinline__ void group_pairs(const float* pos, int stride, int N, int n, int kmax, float thr_s, bool active,
+                                            u64& keep, u64& nbr) {
+    const int Cn = active ? N - 1 : 0;
+    group_core<LANES>(group_sqdist<LANES>(pos, stride, Cn, n), Cn, kmax, thr_s, keep, nbr);
 }
 
 // K1 (+K7): pair bits, focus row offset, the relative target y = frame(t0+2) with columns 0..5 minus frame(t0+1)
@@ -207,13 +250,13 @@ __device__ __forceinline__ void group_pairs(const float* pos, int stride, int N,
 constexpr int FPB = 64;   // foci per CTA of the pair builder
 constexpr int NT_PAIRS = 1024;
 template <int LANES>
-__device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, float thr_px, u64* __restrict__ keep_out,
+__device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, float thr_s, u64* __restrict__ keep_out,
                                                  u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
                                                  int* __restrict__ block_sums, long long* __restrict__ foc_row,
                                                  float* __restrict__ y, u64* __restrict__ active_total,
                                                  int* __restrict__ pair_start, int* __restrict__ pair_foc,
                                                  long long* __restrict__ pair_crow, int cap, int* __restrict__ info,
-                                                 const int blk, const bool single) {
+                                                 const int blk, const bool single, const bool want_keep) {
     __shared__ int s_cnt[FPB];
     __shared__ int s_pre[FPB];
     __shared__ u64 s_nbr[FPB];
@@ -276,13 +319,13 @@ __device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, 
         if (LANES == 32) {
             if (active) {
                 const int s = src.foc_scene[f], n = src.foc_obj[f], t0 = src.foc_t0[f];
-                warp_pairs(pos, 2, src.n_obj[s], n, kmax, thr_px, keep, nbr);
+                warp_pairs(pos, 2, src.n_obj[s], n, kmax, thr_s, keep, nbr, want_keep);
                 ro = row_off(src, s, n, t0);
             }
         } else {
             int s = 0, n = 0, t0 = 0, N = 1;
             if (active) { s = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f]; N = src.n_obj[s]; ro = row_off(src, s, n, t0); }
-            group_pairs<LANES>(pos, 2, N, n, kmax, thr_px, active, keep, nbr);
+            group_pairs<LANES>(pos, 2, N, n, kmax, thr_s, active, keep, nbr);
         }
         if (active) {
             if (y) {
@@ -338,14 +381,14 @@ __device__ __forceinline__ void build_pairs_body(const FocusSrc& src, int kmax, 
 }
 
 template <int LANES>
-__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_px, u64* __restrict__ keep_out,
+__global__ void __launch_bounds__(NT_PAIRS) k_build_pairs(FocusSrc src, int kmax, float thr_s, u64* __restrict__ keep_out,
                                                           u64* __restrict__ nbr_out, int* __restrict__ local_prefix,
                                                           int* __restrict__ block_sums, long long* __restrict__ foc_row,
                                                           float* __restrict__ y, u64* __restrict__ active_total,
                                                           int* __restrict__ pair_start, int* __restrict__ pair_foc,
-                                                          long long* __restrict__ pair_crow, int cap, int* __restrict__ info) {
-    build_pairs_body<LANES>(src, kmax, thr_px, keep_out, nbr_out, local_prefix, block_sums, foc_row, y, active_total, pair_start,
-                            pair_foc, pair_crow, cap, info, (int)blockIdx.x, gridDim.x == 1);
+                                                          long long* __restrict__ pair_crow, int cap, int* __restrict__ info, int want_keep) {
+    build_pairs_body<LANES>(src, kmax, thr_s, keep_out, nbr_out, local_prefix, block_sums, foc_row, y, active_total, pair_start,
+                            pair_foc, pair_crow, cap, info, (int)blockIdx.x, gridDim.x == 1, want_keep != 0);
 }
 
 // The batcher for a whole SCHEDULE of small batches (train(): main.lua:299-304 over a device-resident schedule): CTA s
@@ -358,54 +401,225 @@ struct SchedOut {
 template <int LANES>
 __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs_sched(FocusSrc src, const int* __restrict__ step_first,
                                                                 const int* __restrict__ step_F, int fmax, int cap, int kmax,
-                                                                float thr_px, SchedOut o) {
+                                                                float thr_s, SchedOut o) {
     const int s = blockIdx.x;
     const int first = step_first[s];
     src.foc_scene += first; src.foc_obj += first; src.foc_t0 += first; src.F = step_F[s];
     const size_t fo = (size_t)s * fmax, po = (size_t)s * cap;
-    build_pairs_body<LANES>(src, kmax, thr_px, o.keep + fo, o.nbr + fo, o.cnt + fo, o.block_sums + s, o.foc_row + fo, o.y + fo * D,
+    build_pairs_body<LANES>(src, kmax, thr_s, o.keep + fo, o.nbr + fo, o.cnt + fo, o.block_sums + s, o.foc_row + fo, o.y + fo * D,
                             o.total + s, o.pair_start + (size_t)s * (fmax + 1), o.pair_foc + po, o.pair_crow + po, cap,
-                            o.info + 2 * s, 0, true);
+                            o.info + 2 * s, 0, true, true);
 }
 
-// K1b: second level of the scan + the dense pair list: for pair p of focus f (contexts in ascending index order)
-// pair_foc[p] = f and pair_crow[p] = float offset of the context's window.  One CTA per 64 foci; each CTA sums the
-// totals of the CTAs before it.  Pairs beyond `cap` are dropped and flagged.
-__global__ void __launch_bounds__(FPB) k_expand_pairs_dense(FocusSrc src, const u64* __restrict__ nbr,
-                                                           const int* __restrict__ local_prefix,
-                                                           const int* __restrict__ block_sums, int* __restrict__ pair_start,
-                                                           int* __restrict__ pair_foc, long long* __restrict__ pair_crow,
-                                                           int cap, int* __restrict__ info) {
-    __shared__ int s_part[2];
-    const int t = threadIdx.x, lane = t & 31;
-    int part = 0;
-    for (int b = t; b < (int)blockIdx.x; b += FPB) part += block_sums[b];
-    for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-    if (lane == 0) s_part[t >> 5] = part;
+// K1 for more than one CTA of foci -- the throughput regime (S-64: 65 536 foci, configs[4] rollout: 524 288 per step).
+// One launch builds the pair bits AND the dense pair list: for pair p of focus f (contexts in ascending index order)
+// pair_foc[p] = f, pair_crow[p] = float offset of the context's window; pairs beyond `cap` are dropped and flagged.
+// History, from ncu: the first generation (a warp per focus, 1024-thread CTAs, second kernel for the list) ran its phases
+// one after the other with most warps parked at a barrier, 3.5 waves of 8 us; a warp per focus costs ~130 warp
+// instructions per focus whatever the helper (shuffles, ballots, 64-bit mask arithmetic for 2 pair tests per lane), and a
+// 32-wide look-back walked the predecessors of the last of 1024 blocks in 30 serial L2 round trips.  Now:
+//   * a THREAD per focus: it walks the objects of its scene (positions: broadcast / L1-resident loads, the loop is
+//     uniform for the foci of a window) and keeps the neighbourhood as a 64-bit object set; ~10 instructions per pair
+//     test for 32 foci at once.  The k-nearest trim only runs where more than k objects are inside the neighbourhood (or
+//     for the API view of the kept set), thread-locally.
+//   * blocks of 256 foci; the relative targets are written by a warp per 32 foci, coalesced
+//   * the scan across blocks is a chained scan with look-back by the whole CTA (256 predecessors per round) inside the
+//     launch.  Blocks are handed out by TICKET (start order), a CTA draws the ticket of its next block while it works on
+//     the current one, so the minimum unfinished ticket is always some resident CTA's current block and a CTA only ever
+//     waits for smaller tickets.  Status words carry the launch epoch (no clearing between launches); the last draw
+//     resets the ticket counter.
+// Same arithmetic, order and tie rule as the first generation (bit-identical tables).
+constexpr int NT_SCAN = 256;               // threads = foci per block
+struct PairScan {
+    unsigned* ticket;     // zero between launches
+    u64* status;          // [blocks]: epoch (30 bits) | flag (2: 1 = own count, 2 = inclusive prefix) | value (32)
+    unsigned epoch;       // differs from the previous launch on the same status array
+    int nblk;             // blocks of NT_SCAN foci
+};
+__device__ __forceinline__ u64 scan_pack(unsigned epoch, unsigned flag, unsigned v) {
+    return ((u64)epoch << 34) | ((u64)flag << 32) | (u64)v;
+}
+// The `need` nearest members of the object set `cand` (ties: lower index), thread-local: O(|cand|^2) distance evaluations
+// from L1.  Distances are the reference's: sqrt of the squared distance, one rounding per operation.
+__device__ __noinline__ u64 nearest_of(const float* pos, int stride, float fx, float fy, u64 cand, int need) {
+    u64 out = 0;
+    for (u64 a = cand; a; a &= a - 1) {
+        const int o = __ffsll((long long)a) - 1;
+        const float d = __fsqrt_rn(pair_sqdist(pos[(size_t)o * stride], pos[(size_t)o * stride + 1], fx, fy));
+        int rank = 0;
+        for (u64 b = cand; b; b &= b - 1) {
+            const int p = __ffsll((long long)b) - 1;
+            const float dp = __fsqrt_rn(pair_sqdist(pos[(size_t)p * stride], pos[(size_t)p * stride + 1], fx, fy));
+            rank += (dp < d) || (dp == d && p < o);
+        }
+        if (rank < need) out |= 1ull << o;
+    }
+    return out;
+}
+template <bool HAS_Y>     // training batches also get their relative targets (28 more registers: 4 CTAs per SM instead of 8)
+__global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(FocusSrc src, int kmax, float thr_s, int want_keep,
+                                                                 u64* __restrict__ keep_out, u64* __restrict__ nbr_out,
+                                                                 long long* __restrict__ foc_row, float* __restrict__ y,
+                                                                 u64* __restrict__ active_total, int* __restrict__ pair_start,
+                                                                 int* __restrict__ pair_foc, long long* __restrict__ pair_crow,
+                                                                 int cap, int* __restrict__ info, PairScan sc) {
+    __shared__ int s_tk[2], s_wtot[NT_SCAN / 32];
+    __shared__ unsigned s_full[NT_SCAN / 32], s_part[NT_SCAN / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int stride = src.T * D;
+    const unsigned draws = (unsigned)sc.nblk + gridDim.x; // every CTA draws one ticket past the end
+    const unsigned ep = sc.epoch & 0x3fffffffu;
+    volatile u64* st = sc.status;
+    unsigned next = 0;
+    if (t == 0) {
+        next = atomicAdd(sc.ticket, 1u);
+        if (next == draws - 1) *sc.ticket = 0;
+        s_tk[0] = (int)next;
+    }
     __syncthreads();
-    const int blk_base = s_part[0] + s_part[1];
-    const int f = blockIdx.x * FPB + t;
-    if (f < src.F) {
-        int base = blk_base + local_prefix[f];
-        pair_start[f] = min(base, cap);
-        u64 bits = nbr[f];
-        const int fo = src.foc_obj[f];
-        const long long sbase = (long long)row_off(src, src.foc_scene[f], 0, src.foc_t0[f]);
-        const int objstride = src.T * D;
-        while (bits) {
-            const int c = __ffsll((long long)bits) - 1;
-            bits &= bits - 1;
-            if (base < cap) {
-                pair_foc[base] = f;
-                pair_crow[base] = sbase + (long long)(c + (c >= fo)) * objstride;
+    int blk = s_tk[0];
+    for (int it = 0; blk < sc.nblk; ++it) {
+        if (t == 0) {                                     // ticket of the next block: its round trip hides behind this block
+            next = atomicAdd(sc.ticket, 1u);
+            if (next == draws - 1) *sc.ticket = 0;
+        }
+        // ---- this thread's focus ----
+        const int f = blk * NT_SCAN + t;
+        const bool active = f < src.F;
+        int scn = 0, n = 0, t0 = 0, N = 1;
+        long long ro = 0;
+        if (active) {
+            scn = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f];
+            N = src.n_obj[scn];
+            ro = (long long)row_off(src, scn, n, t0);
+            foc_row[f] = ro;
+        }
+        // relative target: frame(t0 + 2), columns 0..5 minus frame(t0 + 1) (relative_pair, data_process.lua:87-96).  All 14
+        // loads of the row are issued here and consumed after the pair test (a loop over the columns waited for one
+        // HBM round trip per iteration: 40 % of the kernel's stall samples)
+        float2 ya[HAS_Y ? 11 : 1], yb[HAS_Y ? 3 : 1];
+        if (HAS_Y && active) {
+            const float* p = src.states + ro;
+#pragma unroll
+            for (int k2 = 0; k2 < 11; ++k2) ya[k2] = ld2(p + 2 * D + 2 * k2);
+#pragma unroll
+            for (int k2 = 0; k2 < 3; ++k2) yb[k2] = ld2(p + D + 2 * k2);
+        }
+        // ---- neighbourhood as an object set: bit o = object o of the scene is inside ----
+        const float* pos = src.states + row_off(src, scn, 0, t0 + 1);
+        unsigned m_lo = 0, m_hi = 0;
+        float fx = 0.f, fy = 0.f;
+        if (active) {
+            const float2 fp = *reinterpret_cast<const float2*>(pos + (size_t)n * stride);
+            fx = fp.x; fy = fp.y;
+            const int n_lo = N < 32 ? N : 32;
+#pragma unroll 4
+            for (int o = 0; o < n_lo; ++o) {
+                const float2 q = *reinterpret_cast<const float2*>(pos + (size_t)o * stride);
+                m_lo |= (unsigned)(pair_sqdist(q.x, q.y, fx, fy) <= thr_s) << o;
             }
-            ++base;
+#pragma unroll 4
+            for (int o = 32; o < N; ++o) {
+                const float2 q = *reinterpret_cast<const float2*>(pos + (size_t)o * stride);
+                m_hi |= (unsigned)(pair_sqdist(q.x, q.y, fx, fy) <= thr_s) << (o - 32);
+            }
         }
-        if (f == src.F - 1) {
-            pair_start[src.F] = min(base, cap);
-            info[0] = min(base, cap);      // P
-            info[1] = base > cap;          // overflow flag
+        const int Cn = N - 1;
+        const u64 V = active ? ((N >= 64 ? ~0ull : ((1ull << N) - 1ull)) & ~(1ull << n)) : 0ull;   // the other objects of the scene
+        const u64 W = (((u64)m_hi << 32) | m_lo) & V;
+        const int k = (kmax > 0 && kmax < Cn) ? kmax : Cn;
+        u64 K = V, Nb = W;                                 // kept set, neighbours (object space)
+        if (k < Cn) {
+            // Trim to the k nearest (ties: lower index).  The neighbourhood is a PREFIX of that order, so:
+            //   |W| >= k : the k nearest all lie in W                       -> rank W among itself (only if |W| > k)
+            //   |W| <  k : all of W is kept and nbr = W; the kept set also holds the k - |W| nearest outsiders, which
+            //              only the API view of the pair table shows (want_keep)
+            const int w = __popcll(W);
+            if (w > k) { K = nearest_of(pos, stride, fx, fy, W, k); Nb = K; }
+            else if (w == k || !want_keep) K = W;
+            else K = W | nearest_of(pos, stride, fx, fy, V & ~W, k - w);
         }
+        const u64 keep = objects_to_contexts(K, n), nbr = objects_to_contexts(Nb, n);
+        const int c = __popcll(nbr);
+        if (active) { keep_out[f] = keep; nbr_out[f] = nbr; }
+        if (HAS_Y && active) {
+            float* yo = y + (size_t)f * D;
+#pragma unroll
+            for (int k2 = 0; k2 < 11; ++k2) {
+                float2 v = ya[k2];
+                if (k2 < 3) { v.x = __fsub_rn(v.x, yb[k2].x); v.y = __fsub_rn(v.y, yb[k2].y); }
+                *reinterpret_cast<float2*>(yo + 2 * k2) = v;
+            }
+        }
+        // ---- scan inside the block ----
+        int incl = c;
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        int wbase = 0, agg = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) { const int v = s_wtot[w8]; if (w8 < warp) wbase += v; agg += v; }
+        if (t == 0) st[blk] = scan_pack(ep, blk == 0 ? 2u : 1u, (unsigned)agg);
+        // ---- across blocks: look back over 256 predecessors a round ----
+        unsigned excl = 0;
+        for (int idx = blk - 1; idx >= 0; idx -= NT_SCAN) {
+            const int j = idx - t;
+            u64 v = 0;
+            if (j >= 0) {
+                int spins = 0;
+                while (true) {
+                    v = st[j];
+                    if ((unsigned)(v >> 34) == ep && ((v >> 32) & 3u) != 0u) break;
+                    if (++spins > (1 << 20)) __trap();        // a predecessor never published (cannot happen: smaller tickets run first)
+                    __nanosleep(100);                         // do not take issue slots from the warps that still compute
+                }
+            }
+            const unsigned full = __ballot_sync(0xffffffffu, j >= 0 && ((v >> 32) & 3u) == 2u);
+            if (lane == 0) s_full[warp] = full;
+            __syncthreads();
+            int stop = NT_SCAN;                               // nearest predecessor that already holds an inclusive prefix
+#pragma unroll
+            for (int w8 = NT_SCAN / 32 - 1; w8 >= 0; --w8) if (s_full[w8]) stop = 32 * w8 + __ffs(s_full[w8]) - 1;
+            unsigned part = (j >= 0 && t <= stop) ? (unsigned)v : 0u;
+            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+            if (lane == 0) s_part[warp] = part;
+            __syncthreads();
+#pragma unroll
+            for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) excl += s_part[w8];
+            if (stop < NT_SCAN) break;
+            __syncthreads();                                  // s_full / s_part are rewritten by the next round
+        }
+        if (t == 0) {
+            if (blk > 0) st[blk] = scan_pack(ep, 2u, excl + (unsigned)agg);
+            s_tk[(it + 1) & 1] = (int)next;
+        }
+        // ---- this focus's rows of the tables and its part of the dense pair list ----
+        if (active) {
+            int base = (int)excl + wbase + incl - c;
+            pair_start[f] = min(base, cap);
+            const long long sbase = (long long)row_off(src, scn, 0, t0);
+            u64 bits = nbr;
+            while (bits) {
+                const int cc = __ffsll((long long)bits) - 1;
+                bits &= bits - 1;
+                if (base < cap) {
+                    pair_foc[base] = f;
+                    pair_crow[base] = sbase + (long long)(cc + (cc >= n)) * stride;
+                }
+                ++base;
+            }
+            if (f == src.F - 1) {
+                pair_start[src.F] = min(base, cap);
+                info[0] = min(base, cap);      // P
+                info[1] = base > cap;          // overflow flag
+                *active_total = (u64)base;
+            }
+        }
+        __syncthreads();                                  // s_tk is visible; the next block overwrites the shared records
+        blk = s_tk[(it + 1) & 1];
     }
 }
 
@@ -1084,36 +1298,47 @@ __device__ __forceinline__ int partial_index(int i) {
     return base + ((n >> 2) * kt + (k >> 2)) * 16 + 4 * (n & 3) + (k & 3);
 }
 
-// Sum of partial[b][i] over b < np in CTA order (deterministic), sixteen loads in flight at a time: the additions keep
-// their sequential order (padding with +0 does not change a sum), only the L2 latencies overlap.
-__device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i) {
-    const float* src = partial + partial_index(i);
+// Sum of partial[b][i] over b < np in a fixed order (deterministic), sixteen loads in flight at a time: the additions keep
+// their order (padding with +0 does not change a sum), only the L2 latencies overlap.  RS = 1: one thread per parameter,
+// CTA order.  RS = 4 (many partials: 148 per part in the throughput regime, i.e. ten dependent rounds of L2 latency for one
+// thread): four adjacent lanes sum a contiguous quarter of the partials each, then (q0 + q1) + (q2 + q3).
+template <int RS>
+__device__ __forceinline__ float ordered_partial_sum(const float* __restrict__ partial, int np, int i, int sub, bool live) {
     float a = 0.f;
-    for (int b0 = 0; b0 < np; b0 += 16) {
-        float v[16];
+    if (live) {
+        const float* src = partial + partial_index(i);
+        const int chunk = (np + RS - 1) / RS, b_lo = sub * chunk, b_hi = min(np, b_lo + chunk);
+        for (int b0 = b_lo; b0 < b_hi; b0 += 16) {
+            float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = (b0 + j < np) ? __ldcg(src + (size_t)(b0 + j) * PT_TOTAL) : 0.f;
+            for (int j = 0; j < 16; ++j) v[j] = (b0 + j < b_hi) ? __ldcg(src + (size_t)(b0 + j) * PT_TOTAL) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a += v[j];
+            for (int j = 0; j < 16; ++j) a += v[j];
+        }
+    }
+    if (RS == 4) {
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
     }
     return a;
 }
 
-template <int OPT>
+template <int OPT, int RS>
 __global__ void k_reduce_grads(const float* __restrict__ partial, int nparts_pair, int nparts_dec, float* __restrict__ grad, OptArgs o,
                                LossArgs L) {
     // dependents are released at once: the pair forward kernel of the next step loads its (static) pair list and state
     // rows while this kernel runs and touches the weight image only after its own griddepcontrol.wait
     pdl_launch_dependents();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, i = gid / RS, sub = gid % RS;
     const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
+    const bool live = !loss_block && i < NPARAM, owner = live && sub == 0;
     OptState st{0.f, 0.f, 0.f};
-    if (!loss_block && i < NPARAM) st = opt_load<OPT>(i, o);
+    if (owner) st = opt_load<OPT>(i, o);
     pdl_wait();
     if (loss_block) { block_loss_reduce(L); return; }
-    if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-    const float a = ordered_partial_sum(partial, np, i);
+    const float a = ordered_partial_sum<RS>(partial, np, i, sub, live);
+    if (!owner) return;
     grad[i] = a;
     opt_update<OPT>(i, a, o, st);
 }
@@ -1189,19 +1414,20 @@ __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, 
     return g;
 }
 
-template <int OPT>
+template <int OPT, int RS>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
     pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, i = gid / RS, sub = gid % RS;
     const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
+    const bool live = !loss_block && i < NPARAM, owner = live && sub == 0;
     OptState st{0.f, 0.f, 0.f};
-    if (!loss_block && i < NPARAM) st = opt_load<OPT>(i, o);
+    if (owner) st = opt_load<OPT>(i, o);
     pdl_wait();
     if (loss_block) { block_loss_reduce(L); return; }
-    if (i >= NPARAM) return;
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
-    float a = ordered_partial_sum(partial, np, i);
+    float a = ordered_partial_sum<RS>(partial, np, i, sub, live);
+    if (!owner) return;
     a = peer_exchange(i, a, P, buf, stamp);
     grad[i] = a;
     opt_update<OPT>(i, a, o, st);

@@ -43,7 +43,7 @@ struct RollArgs {
     const int* n_obj;
     int S, Nmax, T;
     int t0, steps, use_gt, teacher, kmax, ball_zero;
-    float thr_px;
+    float thr_s;
     const float* wpack;       // packed weight image
     float* traj;              // (S, Nmax, steps, 22) or null
     double* metrics;          // (steps, 7) or null
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NT, 1) k_rollout(RollArgs A) {
                 u64 keep = 0, nbr = 0;
                 if (S.kind[r] == 1) {
                     const int g = r / A.Nmax, o = r - g * A.Nmax;
-                    warp_pairs(S.Z + (g * A.Nmax) * LD1 + ZCOL_F + D, LD1, A.n_obj[s0 + g], o, A.kmax, A.thr_px, keep, nbr);
+                    warp_pairs(S.Z + (g * A.Nmax) * LD1 + ZCOL_F + D, LD1, A.n_obj[s0 + g], o, A.kmax, A.thr_s, keep, nbr, false);
                 }
                 if (lane == 0) S.M.nbr[r] = nbr;
             }

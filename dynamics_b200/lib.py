@@ -89,6 +89,7 @@ SIGNATURES = {
     "npe_event_elapsed_ms": (C.c_int, [_H, C.c_int32, C.c_int32, _fp]),
     "npe_launch_count": (C.c_int64, [_H]),
     "npe_debug_read": (C.c_int, [_H, C.c_int32, _fp, C.c_int64]),
+    "npe_nbr_threshold_sq": (C.c_float, [C.c_float]),
     "npe_batch_stats": (C.c_int, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 

@@ -313,6 +313,12 @@ int npe_event_elapsed_ms(npe_handle* h, int32_t slot_a, int32_t slot_b, float* m
 #define NPE_DBG_STATES 6 /* the resident scene tensor (S,Nmax,T,22) */
 #define NPE_DBG_ROLL 7   /* the two-frame window (S,Nmax,2,22) after a rollout by kernels */
 int npe_debug_read(npe_handle* h, int32_t which, float* out, int64_t nfloats);
+
+/* The pair builder's form of the neighbourhood test.  The reference keeps context c of a focus when
+ * fl(800 * fl(sqrt(s))) <= thr_px on the squared (normalised) distance s (npe.lua:170-206 over data_utils.lua:276-285);
+ * both roundings are monotone, so that set is s <= s* for one float s*, which this returns (negative: nothing passes).
+ * Pure host arithmetic, no GPU: exported so that the equivalence can be tested exhaustively around the threshold. */
+float npe_nbr_threshold_sq(float thr_px);
 /* Counters: kernels launched by this handle since creation; active pairs / foci of the current batch. */
 int64_t npe_launch_count(const npe_handle* h);
 int npe_batch_stats(npe_handle* h, int64_t* foci_out, int64_t* active_pairs_out);

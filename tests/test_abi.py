@@ -45,6 +45,26 @@ def test_config_struct_matches_header(lib):
     assert lib.npe_param_count(None) == 28222
 
 
+def test_neighbourhood_threshold_on_squared_distances(lib):
+    """The pair builder tests s <= s* instead of fl(800 * fl(sqrt(s))) <= thr (npe_nbr_threshold_sq): the two must agree for
+    EVERY float; checked on the 2^16 floats either side of s*, on random magnitudes and at the extremes (host arithmetic)."""
+    import numpy as np
+    def reference(s, thr):                                 # one rounding per operation, float32 throughout
+        return np.sqrt(s.astype(np.float32)) * np.float32(800.0) <= np.float32(thr)
+    rng = np.random.default_rng(0)
+    for thr in (210.0, 3.5 * 60, 60.0, 1.0, 799.99, 1e-3, 5e4):
+        f = getattr(lib.dll, "npe_nbr_threshold_sq")
+        sstar = np.float32(f(ctypes.c_float(thr)))
+        assert sstar > 0
+        bits = np.array([sstar], np.float32).view(np.uint32)[0]
+        near = (np.arange(-65536, 65536, dtype=np.int64) + int(bits)).astype(np.uint32).view(np.float32)
+        wide = np.abs(rng.standard_normal(200000).astype(np.float32)) * np.float32(10.0) ** rng.integers(-12, 6, 200000).astype(np.float32)
+        edge = np.array([0.0, np.finfo(np.float32).tiny, 1e-45, np.finfo(np.float32).max, np.inf], np.float32)
+        for s in (near, wide, edge):
+            assert np.array_equal(reference(s, thr), s <= sstar)
+    assert lib.dll.npe_nbr_threshold_sq(ctypes.c_float(-1.0)) < 0      # nothing is within a negative radius
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_fails_loudly_without_gpu(lib):
     from dynamics_b200 import NPEError, NPEModel
