@@ -462,7 +462,7 @@ int refresh_wtt(npe_handle* h);
 long long* chain_prof(npe_handle* h) {
     static const bool want = getenv("NPE_CHAIN_PROF") != nullptr;
     if (!want) return nullptr;
-    if (!h->chain_prof_dev) { cudaMalloc((void**)&h->chain_prof_dev, 32 * sizeof(long long)); cudaMemset(h->chain_prof_dev, 0, 32 * sizeof(long long)); }
+    if (!h->chain_prof_dev) { cudaMalloc((void**)&h->chain_prof_dev, 64 * sizeof(long long)); cudaMemset(h->chain_prof_dev, 0, 64 * sizeof(long long)); }
     return h->chain_prof_dev;
 }
 
@@ -599,7 +599,18 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
     } else if (r.opt == 2) {
         o.m = h->rms_m; o.b1 = 0.99f; o.omb1 = (float)(1.0 - 0.99);
     }
-    if (r.opt) { h->wtc_dirty = true; h->wtc3_dirty = true; h->wtt3_dirty = true; }
+    o.wtc3_hi = o.wtc3_lo = o.wtt3_hi = o.wtt3_lo = o.wenc_hi = o.wenc_lo = nullptr;
+    if (r.opt) {
+        // the step that ends here ran on the tcgen05 images (both are current): the optimiser keeps them current
+        const bool through = !h->wtc3_dirty && !h->wtt3_dirty && h->wtc3 && h->wtt3 && h->wenc;
+        if (through) {
+            o.wtc3_hi = h->wtc3; o.wtc3_lo = h->wtc3 + TC_TOTAL;
+            o.wtt3_hi = h->wtt3; o.wtt3_lo = h->wtt3 + TT_TOTAL;
+            o.wenc_hi = h->wenc; o.wenc_lo = h->wenc + 2 * ENC64_SZ;
+        }
+        h->wtc_dirty = true;
+        if (!through) { h->wtc3_dirty = true; h->wtt3_dirty = true; }
+    }
     return r;
 }
 
@@ -714,7 +725,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         D1.X0 = h->dact.p; D1.x0_valid = 52; D1.x0_store = 52;
         D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
         D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
-        B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial;
+        B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial; B.prof = chain_prof(h) ? chain_prof(h) + 32 : nullptr;
         if (old_wgrad) CK(launch_pdl(h, k_wgrad_tc, gd, WG_NT, sizeof(WgradSmem), B));
         else CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));  // (D5, D4) (D3, D2) (D1)
         h->launches++;
@@ -1809,12 +1820,15 @@ int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
     if (h->chain_prof_dev) {
-        long long q[32];
+        long long q[64];
         cudaMemcpy(q, h->chain_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[pair forward chain, CTA 0 thread 0] gather %lld, wait for MMA %lld, epilogue %lld, total %lld cycles\n", q[0], q[1], q[2], q[3]);
-        fprintf(stderr, "[pair wgrad CTA 0] loader group 0: issue loads %lld, wait for the stage %lld, data + split + stores %lld, units %lld, loop %lld | "
-                        "mma: wait %lld, issue %lld, loop %lld | epilogue %lld (of which waiting for the last MMAs %lld), kernel body %lld cycles\n",
-                q[11], q[10], q[12], q[13], q[14], q[15], q[16], q[17], q[18], q[20], q[19]);
+        for (int part = 0; part < 2; ++part) {
+            const long long* w = q + 32 * part;
+            fprintf(stderr, "[%s weight gradients, CTA 0] loader group 0: issue loads %lld, wait for the stage %lld, data + split + stores %lld, units %lld, loop %lld | "
+                            "mma: wait %lld, issue %lld, loop %lld | epilogue %lld (of which waiting for the last MMAs %lld), kernel body %lld cycles\n",
+                    part ? "decoder" : "pair", w[11], w[10], w[12], w[13], w[14], w[15], w[16], w[17], w[18], w[20], w[19]);
+        }
     }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;

@@ -54,11 +54,14 @@ __device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned pari
 }
 
 // ---- 64-row encoder images (hi | lo): [focus encoder: rows 0..24 | context encoder: rows 25..49], K = 44 (+ pad to 48) ----
+__host__ __device__ __forceinline__ int enc64_index(int i) {   // i < OFF_PAIR: flat index of an encoder weight -> offset in the hi (or lo) image pair
+    const int which = i >= OFF_ENC_C, r = i - which * OFF_ENC_C, n = r / IN, k = r - n * IN;
+    return which * ENC64_SZ + ((k >> 2) * 64 + (n + which * H2)) * 4 + (k & 3);
+}
 __global__ void k_pack_enc64(const float* __restrict__ params, float* __restrict__ w) {   // w: hi T | hi C | lo T | lo C
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= OFF_PAIR) return;
-    const int which = i >= OFF_ENC_C, r = i - which * OFF_ENC_C, n = r / IN, k = r - n * IN;
-    const int o = which * ENC64_SZ + ((k >> 2) * 64 + (n + which * H2)) * 4 + (k & 3);
+    const int o = enc64_index(i);
     const float x = params[i], h = tf32_hi(x);
     w[o] = h;
     w[2 * ENC64_SZ + o] = x - h;

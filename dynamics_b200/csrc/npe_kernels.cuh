@@ -1211,7 +1211,22 @@ k_pair_backward(const float* __restrict__ states, const int* __restrict__ pair_f
 struct OptArgs {
     float* x; float* m; float* v; float* wpack;
     float b1, omb1, b2, omb2, eps, step;   // adam: step = lr * sqrt(1 - b2^t) / (1 - b1^t); rmsprop: b1 = alpha, step = lr
+    // hi / lo TF32 weight images of the tcgen05 kernels, written through like wpack when the step uses them (else nullptr):
+    // three re-packing launches per training step (4 us each, latency-bound) disappear
+    float* wtc3_hi; float* wtc3_lo; float* wtt3_hi; float* wtt3_lo; float* wenc_hi; float* wenc_lo;
 };
+__host__ __device__ __forceinline__ int tc_index(int i);      // npe_tc.cuh: forward / K-major image
+__host__ __device__ __forceinline__ int tt_index(int i);      // npe_tcbwd.cuh: transposed image of the input-gradient chains (-1: not part of it)
+__host__ __device__ __forceinline__ int enc64_index(int i);   // npe_chain.cuh: 64-row encoder images
+__device__ __forceinline__ void opt_write_images(int i, float xn, const OptArgs& o) {
+    if (!o.wtc3_hi) return;
+    const float hi = __uint_as_float(__float_as_uint(xn) & 0xFFFFE000u), lo = xn - hi;
+    const int a = tc_index(i);
+    o.wtc3_hi[a] = hi; o.wtc3_lo[a] = lo;
+    const int b = tt_index(i);
+    if (b >= 0) { o.wtt3_hi[b] = hi; o.wtt3_lo[b] = lo; }
+    if (i < OFF_PAIR) { const int e = enc64_index(i); o.wenc_hi[e] = hi; o.wenc_lo[e] = lo; }
+}
 // Last block (index gridDim.x - 1, launched as an extra block) optionally reduces the per-example losses and publishes
 // {loss, vel, angvel, overflow flag} to `loss4_out` (device or host-mapped memory): saves a launch and a copy per step.
 struct LossArgs {
@@ -1261,12 +1276,14 @@ __device__ __forceinline__ void opt_update(int i, float a, const OptArgs& o, con
         const float xn = __fsub_rn(s.x, __fdiv_rn(__fmul_rn(o.step, mi), __fadd_rn(__fsqrt_rn(vi), o.eps)));
         o.x[i] = xn;
         o.wpack[pack_index(i)] = xn;
+        opt_write_images(i, xn, o);
     } else if (OPT == 2) {
         const float mi = __fadd_rn(__fmul_rn(o.b1, s.m), __fmul_rn(o.omb1, __fmul_rn(a, a)));
         o.m[i] = mi;
         const float xn = __fsub_rn(s.x, __fdiv_rn(__fmul_rn(o.step, a), __fadd_rn(__fsqrt_rn(mi), o.eps)));
         o.x[i] = xn;
         o.wpack[pack_index(i)] = xn;
+        opt_write_images(i, xn, o);
     }
 }
 

@@ -313,3 +313,29 @@ def test_resident_rollout_fused_postprocess_equals_separate_pass(trained_like_pa
     finally:
         os.environ.pop("NPE_NO_FUSED_POST", None)
         m.close()
+
+
+def test_weight_images_follow_the_optimiser(n8, trained_like_params):
+    """Large-batch training keeps the hi / lo TF32 weight images of the tcgen05 kernels current from inside the optimiser
+    kernel (no re-packing launches between steps).  Three steps in a row must give the SAME BITS as three steps with the
+    images re-packed from the parameter vector before every step (npe_set_params marks them stale)."""
+    st, _ = n8
+    S = 1024
+    out = []
+    for repack in (False, True):
+        m = make_model(12, DISPATCH["default"])
+        try:
+            m.set_params(trained_like_params); m.optim_reset(0.0)
+            m.upload_scenes(st[:S])
+            m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+            losses = []
+            for step in range(3):
+                if repack and step:
+                    m.set_params(m.get_params())
+                assert m.select_windows(0, S) == S * 8
+                losses.append(m.train_step("adam", 1e-3))
+            out.append((m.get_params(), np.array(losses)))
+        finally:
+            m.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert not np.array_equal(out[0][0], trained_like_params)
