@@ -58,13 +58,19 @@ NCU_TRAFFIC_COLD_BYTES = {"step_fused": 287488}      # profiles/r1_final_step_fu
 ALG_BYTES_PER_STEP = lambda F, P: (176 + 88) * F + 176 * P + 112888      # focus window + target, context windows, gradient
 
 
+HBM_PEAK_GBS = None       # MEASURED_PEAKS.json hbm_gbs (copy bandwidth, read + write bytes)
+HBM_PEAK_SOURCE = None
+
+
 def _load_peaks():
-    global TF32_PEAK_TFLOPS
+    global TF32_PEAK_TFLOPS, HBM_PEAK_GBS, HBM_PEAK_SOURCE
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         TF32_PEAK_TFLOPS = pk["bf16_tflops"] / 2.0
+        HBM_PEAK_GBS = float(pk["hbm_gbs"]); HBM_PEAK_SOURCE = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth on this pool's B200): of measured"
     except Exception:
         TF32_PEAK_TFLOPS = 1590.0 / 2.0      # B200_PROFILING.md fallback (of fallback)
+        HBM_PEAK_GBS = 6650.0; HBM_PEAK_SOURCE = "B200_PROFILING.md fallback 6.65 TB/s (MEASURED_PEAKS.json absent): of fallback"
 
 
 _load_peaks()
@@ -327,13 +333,24 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
         # ALGORITHMIC FLOP rate against the TF32 dense peak (bf16 measured / 2); the 3-way split issues 3x these MMAs and
         # 64-padded tiles another 1.6x, so `issued_frac` is the tensor pipe's own view
         names = {"forward": "k_pair_forward_c2 + k_dec_forward_c2", "dec_backward": "k_dec_dgrad_c2", "pair_backward": "k_pair_dgrad_c2",
-                 "wgrad": "k_wgrad_tc (pair part + decoder part)"}
+                 "wgrad": "k_wgrad_mn (pair part + decoder part)"}
         flops = {"forward": KERNEL_FLOPS["forward"](F, P), "dec_backward": 22200.0 * F, "pair_backward": 25000.0 * P,
                  "wgrad": (26600.0 + 2200.0) * F + 27200.0 * P}      # dgrad of decoder / pair chain; all weight gradients
         dom = max(names, key=lambda k: kern[k])
         ach = flops[dom] / (kern[dom] * 1e-3) / 1e12
         step_ach = STEP_FLOPS(F, P) / (out["ms_per_step"] * 1e-3) / 1e12
         out["kernel_ms"] = kern
+        # the weight-gradient kernels are bound by HBM, not by the tensor pipe: they read every stash exactly once
+        # (G and X of 6 pair layers / encoders per active pair and of 5 decoder layers per focus, 56-float slots) plus
+        # the gathered state windows (2 x 44 floats per pair, 44 per focus); ncu (profiles/r2_stress64_kernels.md) counts
+        # the same bytes in dram__bytes_read, i.e. no re-reads
+        wg_bytes = (P * 6 + F * 5) * 2 * 56 * 4 + (2 * P + F) * 44 * 4
+        wg_ach = wg_bytes / (kern["wgrad"] * 1e-3) / 1e9 if kern["wgrad"] > 0 else 0.0
+        out["roofline_wgrad"] = {"kernel": names["wgrad"], "bound": "hbm", "achieved": wg_ach, "peak": HBM_PEAK_GBS, "unit": "GB/s",
+                                 "frac": wg_ach / HBM_PEAK_GBS, "traffic": 275.6e6, "algorithmic_bytes": wg_bytes,
+                                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the two launches, ncu --set full "
+                                                   "(profiles/r2_stress64_kernels.md), F = 65536, P = 40918",
+                                 "peak_source": HBM_PEAK_SOURCE}
         out["roofline"] = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": TF32_PEAK_TFLOPS, "unit": "TFLOP/s",
                            "frac": ach / TF32_PEAK_TFLOPS, "traffic": None,
                            "step": {"achieved": step_ach, "frac": step_ach / TF32_PEAK_TFLOPS,

@@ -694,7 +694,6 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         E.gs[1].base = h->states.p; E.gs[1].offs = h->pair_crow.p; E.gs[1].cols_valid = IN; E.gs[1].cols_store = 48; E.gs[1].col0 = 48;
         E.ngs = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
         A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial; A.prof = chain_prof(h);
-        static const bool old_wgrad = getenv("NPE_WGRAD_V3") != nullptr;     // A/B measurements only
         auto stacked = [](const WArgs& W, const int (&ia)[3], const int (&ib)[3]) {
             WmArgs M = {};
             for (int p = 0; p < 3; ++p) {
@@ -709,8 +708,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
             M.npairs = 3; M.nrows_dev = W.nrows_dev; M.nrows = W.nrows; M.partial = W.partial; M.prof = W.prof;
             return M;
         };
-        if (old_wgrad) CK(launch_pdl(h, k_wgrad_tc, gp, WG_NT, sizeof(WgradSmem), A));
-        else CK(launch_pdl(h, k_wgrad_mn<0>, gp, WM_NT, sizeof(WmSmem) + 1024, stacked(A, {0, 2, 4}, {1, 3, 5})));   // (L5, L4) (L3, L2) (L1, encoders)
+        CK(launch_pdl(h, k_wgrad_mn<0>, gp, WM_NT, sizeof(WmSmem) + 1024, stacked(A, {0, 2, 4}, {1, 3, 5})));   // (L5, L4) (L3, L2) (L1, encoders)
         h->launches++;
         WArgs B = {};
         // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
@@ -726,8 +724,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
         D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
         B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial; B.prof = chain_prof(h) ? chain_prof(h) + 32 : nullptr;
-        if (old_wgrad) CK(launch_pdl(h, k_wgrad_tc, gd, WG_NT, sizeof(WgradSmem), B));
-        else CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));  // (D5, D4) (D3, D2) (D1)
+        CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));  // (D5, D4) (D3, D2) (D1)
         h->launches++;
     }
     CK(cudaGetLastError());
@@ -948,7 +945,6 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RollSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairTcSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecTcSmem))) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WgradSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_wgrad_mn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_wgrad_mn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairChainSmem))) != cudaSuccess ||

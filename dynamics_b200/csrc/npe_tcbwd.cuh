@@ -104,18 +104,10 @@ __device__ __forceinline__ void relu_mask50(float* d, unsigned long long bits) {
 }
 
 // ----------------------------------------------------------------------------------------------------------------
-// weight gradients: dW_j[n][k] = sum_r G_j[r][n] * X_j[r][k] for a list of jobs that share the row index r.
-//
-// Pipeline per CTA (persistent over 128-row tiles; unit = 32 rows of one job):
-//   TMA warp        one thread issues cp.async.bulk for the unit's G block and stash X block (32 rows x 224 B, contiguous in the
-//                   layer-major stashes) into a 6-deep raw ring in shared memory (raw_full / raw_empty mbarriers)
-//   8 transposer    read the raw blocks (conflict-free: pitch 56), split hi / lo and store them TRANSPOSED into the K-major
-//   warps           operand images of a 2-deep operand ring; lane mapping 4 rows x 8 columns per instruction, so every store
-//                   instruction writes 32 consecutive floats.  Gathered X segments (state windows addressed through a row
-//                   offset table) are fetched with LDG one unit ahead.
-//   MMA warp        12 x tcgen05.mma.kind::tf32 (M = 64, N = 56 / 96, K = 8; hi*hi + hi*lo + lo*hi) per unit into the job's
-//                   accumulator in tensor memory; tcgen05.commit frees the operand stage
-// The accumulators of all jobs stay in TMEM across the CTA's tiles; one epilogue writes them to the CTA's partial.
+// weight gradients: dW_j[n][k] = sum_r G_j[r][n] * X_j[r][k] for a list of jobs (layers) that share the row index r.
+// The job tables below describe where G and X of every layer live and where the result goes; the kernel is in
+// npe_wgrad.cuh (operands stay row-major / MN-major, two layers per MMA, accumulators in tensor memory for the whole
+// kernel, one epilogue into the CTA's tile-major partial).
 // ----------------------------------------------------------------------------------------------------------------
 struct WGather {
     const float* base;            // value(R, c) = base[offs[R] + c]
@@ -143,36 +135,14 @@ struct WArgs {
     long long* prof;              // tools only (NPE_CHAIN_PROF): cycle counters of CTA 0, or nullptr
 };
 
-constexpr int WG_ROWS = 32;       // rows per unit: K = 32 = 4 MMA k-steps
-constexpr int WG_NRAW = 4;        // raw ring depth
-constexpr int WG_NOP = 3;         // operand ring depth: transposers run up to 2 units ahead of the MMA warp
-constexpr int WG_NT = 352;        // 8 transposer warps + MMA warp + TMA warp + gather warp
-constexpr int WG_BLOCK = WG_ROWS * HSLOT;            // floats of one stash block (7168 B)
-constexpr int WG_XG_PITCH = 98;   // floats: pitch of gathered X rows in the raw stage (8-byte stores of 32 lanes: conflict-free)
-struct WRaw { float G[WG_BLOCK]; float X[WG_ROWS * WG_XG_PITCH]; };   // 7168 + 12544 B
-struct WOp {
-    float Ahi[64 * WG_ROWS], Alo[64 * WG_ROWS];       // G^T: [r / 4][n (64)][r % 4]
-    float Bhi[96 * WG_ROWS], Blo[96 * WG_ROWS];       // X^T: [r / 4][k (nb)][r % 4]
-};
-struct WgradSmem {
-    WOp op[WG_NOP];                                   // 3 x 40960 B
-    WRaw raw[WG_NRAW];                                // 4 x 19712 B
-    unsigned long long raw_full[WG_NRAW], raw_empty[WG_NRAW], op_full[WG_NOP], op_empty[WG_NOP], done;
-    uint32_t tmem, pad;
-};
+constexpr int WG_ROWS = 32;       // rows per unit of the weight-gradient kernel: K = 32 = 4 MMA k-steps
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx_only(unsigned long long* bar, unsigned bytes) {   // no arrival
-    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t umma_idesc_tf32_m64(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
-}
 
-// Unit iterator shared by the three roles.  The R rows are cut into 32-row quarter tiles; CTA b owns a contiguous, balanced
-// range of them and runs every job on each (unit = quarter tile x job).
+// Unit iterator shared by the roles of the weight-gradient kernel (npe_wgrad.cuh).  The R rows are cut into 32-row quarter
+// tiles; CTA b owns a contiguous, balanced range of them and runs every job on each (unit = quarter tile x job).
 struct WUnit {
     long long qt, qt_end;
     int j, njobs;
@@ -185,78 +155,6 @@ struct WUnit {
     __device__ __forceinline__ long long row0() const { return qt * WG_ROWS; }
     __device__ __forceinline__ void next() { if (++j == njobs) { j = 0; ++qt; } }
 };
-
-__device__ __forceinline__ void wgrad_put(float* hi_img, float* lo_img, int off, const float (&v)[4]) {
-    float4 h, l;
-    h.x = tf32_hi(v[0]); h.y = tf32_hi(v[1]); h.z = tf32_hi(v[2]); h.w = tf32_hi(v[3]);
-    l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
-    st4(hi_img + off, h); st4(lo_img + off, l);
-}
-// Transposer work items of a unit: item i = (column n = i % ncols, row group rg = i / ncols), rows 4 rg .. 4 rg + 3.  A thread
-// reads the four rows of its column (consecutive lanes = consecutive columns: conflict-free) and writes ONE 16-byte store
-// per image: element (n, 4 rg .. 4 rg + 3) is contiguous in the K-major operand layout.
-template <int NITEMS>
-__device__ __forceinline__ void wgrad_transpose_block(float* hi_img, float* lo_img, int img_rows, int img_col0, const float* src,
-                                                      int pitch, int ncols, int cols_valid, int rows_left) {
-    const int t = threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < NITEMS; ++k) {
-        const int i = t + 256 * k, rg = i / ncols, n = i - rg * ncols;
-        if (rg < 8) {
-            float v[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float x = src[(4 * rg + r) * pitch + n];
-                v[r] = (4 * rg + r < rows_left && n < cols_valid) ? x : 0.f;
-            }
-            wgrad_put(hi_img, lo_img, (rg * img_rows + img_col0 + n) * 4, v);
-        }
-    }
-}
-// raw blocks -> hi / lo operand images of one operand stage
-__device__ __forceinline__ void wgrad_transpose(WOp& op, const WRaw& raw, const WJob& J, long long row0, long long R) {
-    const int rows_left = (int)min((long long)WG_ROWS, R - row0);       // rows beyond R hold whatever the copy found: zero
-    wgrad_transpose_block<2>(op.Ahi, op.Alo, 64, 0, raw.G, HSLOT, 56, J.g_cols, rows_left);
-    if (J.ngs) wgrad_transpose_block<3>(op.Bhi, op.Blo, 96, 0, raw.X, WG_XG_PITCH, 96, 96, rows_left);   // assembled by the producer warp
-    else wgrad_transpose_block<2>(op.Bhi, op.Blo, J.nb, 0, raw.X, HSLOT, 56, J.x0_valid, rows_left);
-}
-
-// Producer warp, gathered jobs: lane = row.  Assembles the 96-column X row in the raw stage (pitch 98 floats):
-//   encoders         [focus window (44) | 0 x 4 | context window (44) | 0 x 4]      (row offsets gs[0].offs / gs[1].offs)
-//   decoder layer 1  [stash row z[0..51] | focus window (44)]                        (stash X0, row offsets gs[0].offs)
-__device__ __forceinline__ void wgrad_assemble(float* xs, const WJob& J, long long row0, long long R) {
-    const int lane = threadIdx.x & 31;
-    const long long row = row0 + lane;
-    const bool ok = row < R;
-    float* o = xs + lane * WG_XG_PITCH;
-    float2 a[26], b[24];
-    const float2 z2 = make_float2(0.f, 0.f);
-    if (J.ngs == 2) {
-        const float* pa = J.gs[0].base + (ok ? J.gs[0].offs[row] : 0);
-        const float* pb = J.gs[1].base + (ok ? J.gs[1].offs[row] : 0);
-#pragma unroll
-        for (int c = 0; c < 24; ++c) { a[c] = (ok && c < 22) ? ld2(pa + 2 * c) : z2; b[c] = (ok && c < 22) ? ld2(pb + 2 * c) : z2; }
-    } else {
-        const float* pa = J.X0 + (ok ? row * HSLOT : 0);
-        const float* pb = J.gs[0].base + (ok ? J.gs[0].offs[row] : 0);
-#pragma unroll
-        for (int c = 0; c < 13; ++c) {
-            const float4 v = ok ? ld4(pa + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            a[2 * c] = make_float2(v.x, v.y); a[2 * c + 1] = make_float2(v.z, v.w);
-        }
-#pragma unroll
-        for (int c = 0; c < 22; ++c) b[c] = ok ? ld2(pb + 2 * c) : z2;
-    }
-    if (J.ngs == 2) {
-#pragma unroll
-        for (int c = 0; c < 24; ++c) { *reinterpret_cast<float2*>(o + 2 * c) = a[c]; *reinterpret_cast<float2*>(o + 48 + 2 * c) = b[c]; }
-    } else {
-#pragma unroll
-        for (int c = 0; c < 26; ++c) *reinterpret_cast<float2*>(o + 2 * c) = a[c];
-#pragma unroll
-        for (int c = 0; c < 22; ++c) *reinterpret_cast<float2*>(o + 52 + 2 * c) = b[c];
-    }
-}
 
 // Accumulator row n (d[0 .. nb)) -> the CTA's partial in the tile-major layout of npe_layout.h (what partial_index addresses).
 // All register indices are static (no local memory).
@@ -292,139 +190,6 @@ __device__ __forceinline__ void wgrad_store_rows(float* __restrict__ out, const 
             st4(o, zero ? z4 : make_float4(d[4 * kc], d[4 * kc + 1], d[4 * kc + 2], d[4 * kc + 3]));
         }
     }
-}
-
-__global__ void __launch_bounds__(WG_NT, 1) k_wgrad_tc(WArgs A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WgradSmem& S = *reinterpret_cast<WgradSmem*>(smem_raw);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    pdl_launch_dependents();   // the next kernel's prologue may overlap this kernel's tail
-    if (t == 0) {
-        for (int i = 0; i < WG_NRAW; ++i) { mbar_init(&S.raw_full[i], 2); mbar_init(&S.raw_empty[i], 256); }
-        for (int i = 0; i < WG_NOP; ++i) { mbar_init(&S.op_full[i], 256); mbar_init(&S.op_empty[i], 1); }
-        mbar_init(&S.done, 1);
-    }
-    if (warp == 8) tmem_alloc<512>(&S.tmem);
-    // zero the A images once: rows 56..63 are never written and must read as zero
-    for (int i = t; i < WG_NOP * 2 * 64 * WG_ROWS / 4; i += WG_NT) {
-        const int o = i / (2 * 64 * WG_ROWS / 4), r = i - o * (2 * 64 * WG_ROWS / 4);
-        reinterpret_cast<float4*>(S.op[o].Ahi)[r] = make_float4(0.f, 0.f, 0.f, 0.f);      // Ahi and Alo are adjacent
-    }
-    proxy_fence_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    pdl_wait();                // everything below reads the predecessors' stashes
-    const long long R = A.nrows_dev ? (long long)*A.nrows_dev : (long long)A.nrows;
-    const uint32_t tmem = S.tmem;
-    WUnit it; it.init(R, A.njobs);
-    const bool has_work = it.valid();
-    const bool prof = A.prof && blockIdx.x == 0 && lane == 0;
-    long long pw0 = 0, pw1 = 0, pw2 = 0, pt0 = clock64();
-    if (warp == 9) {   // TMA warp: bulk copies of the stash blocks of every unit
-        if (lane == 0) {
-            for (int u = 0; it.valid(); it.next(), ++u) {
-                const int s = u % WG_NRAW;
-                const WJob& J = A.job[it.j];
-                const long long c0 = clock64();
-                if (u >= WG_NRAW) mbar_wait(&S.raw_empty[s], (unsigned)(((u / WG_NRAW) - 1) & 1));
-                pw0 += clock64() - c0;
-                mbar_expect_tx(&S.raw_full[s], (J.ngs ? 1u : 2u) * WG_BLOCK * 4);      // arrival 1 of 2
-                bulk_g2s(S.raw[s].G, J.G + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
-                if (!J.ngs) bulk_g2s(S.raw[s].X, J.X0 + it.row0() * HSLOT, WG_BLOCK * 4, &S.raw_full[s]);
-            }
-            if (prof) { A.prof[8] = pw0; A.prof[9] = clock64() - pt0; }
-        }
-    } else if (warp == 10) {   // gather warp (lane = row): assembles the X rows of gathered jobs; arrival 2 of 2 of every unit
-        for (int u = 0; it.valid(); it.next(), ++u) {
-            const int s = u % WG_NRAW;
-            const WJob& J = A.job[it.j];
-            // the stage must be free before EITHER arrival of its next use: an early arrival would complete the previous phase
-            if (u >= WG_NRAW) mbar_wait(&S.raw_empty[s], (unsigned)(((u / WG_NRAW) - 1) & 1));
-            if (J.ngs) {
-                wgrad_assemble(S.raw[s].X, J, it.row0(), R);
-                __syncwarp();
-            }
-            if (lane == 0) mbar_arrive(&S.raw_full[s]);
-        }
-    } else if (warp < 8) {
-        int u = 0;
-        for (; it.valid(); it.next(), ++u) {
-            const int s = u % WG_NRAW, o = u % WG_NOP;
-            const long long c0 = clock64();
-            mbar_wait(&S.raw_full[s], (unsigned)((u / WG_NRAW) & 1));
-            const long long c1 = clock64();
-            if (u >= WG_NOP) mbar_wait(&S.op_empty[o], (unsigned)(((u / WG_NOP) - 1) & 1));
-            const long long c2 = clock64();
-            wgrad_transpose(S.op[o], S.raw[s], A.job[it.j], it.row0(), R);
-            proxy_fence_async();
-            mbar_arrive(&S.op_full[o]);
-            mbar_arrive(&S.raw_empty[s]);
-            pw0 += c1 - c0; pw1 += c2 - c1; pw2 += clock64() - c2;
-        }
-        if (prof && warp == 0) { A.prof[10] = pw0; A.prof[11] = pw1; A.prof[12] = pw2; A.prof[13] = u; A.prof[14] = clock64() - pt0; }
-    } else if (lane == 0) {   // warp 8: MMA issue
-        unsigned started = 0;
-        for (int u = 0; it.valid(); it.next(), ++u) {
-            const WJob& J = A.job[it.j];
-            const int nb = J.nb, o = u % WG_NOP;
-            const uint32_t idesc = umma_idesc_tf32_m64(nb);
-            const uint32_t d_tm = tmem + J.tmem_col;
-            // descriptors: low word = address field | LBO << 16, high word = SBO | version; a K-step advances the address field
-            const uint32_t hiw = (128u >> 4) | (1u << 14);
-            const uint32_t a_lo[2] = {((smem_u32(S.op[o].Ahi) >> 4) & 0x3FFFu) | ((64u * 16u >> 4) << 16),
-                                      ((smem_u32(S.op[o].Alo) >> 4) & 0x3FFFu) | ((64u * 16u >> 4) << 16)};
-            const uint32_t b_lo[2] = {((smem_u32(S.op[o].Bhi) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16),
-                                      ((smem_u32(S.op[o].Blo) >> 4) & 0x3FFFu) | (((uint32_t)nb * 16u >> 4) << 16)};
-            const uint32_t a_step = 2u * 64u * 16u >> 4, b_step = 2u * (uint32_t)nb * 16u >> 4;
-            const long long c0 = clock64();
-            mbar_wait(&S.op_full[o], (unsigned)((u / WG_NOP) & 1));
-            pw0 += clock64() - c0;
-            const long long c1 = clock64();
-            tc_fence_after();
-            uint32_t acc = (started >> it.j) & 1u;
-#pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t a0 = a_lo[pass == 2], b0 = b_lo[pass == 1];
-#pragma unroll
-                for (int ks = 0; ks < WG_ROWS / 8; ++ks) {
-                    const uint64_t da = ((uint64_t)hiw << 32) | (a0 + ks * a_step);
-                    const uint64_t db = ((uint64_t)hiw << 32) | (b0 + ks * b_step);
-                    umma_tf32(d_tm, da, db, idesc, acc);
-                    acc = 1u;
-                }
-            }
-            started |= 1u << it.j;
-            umma_commit(&S.op_empty[o]);
-            pw1 += clock64() - c1;
-        }
-        umma_commit(&S.done);
-        if (prof) { A.prof[15] = pw0; A.prof[16] = pw1; A.prof[17] = clock64() - pt0; }
-    }
-    const long long pe0 = clock64();
-    // epilogue: warps 0..3 own the four TMEM lane quadrants; an M = 64 accumulator keeps row n in lane (n % 16) + 32 (n / 16)
-    if (warp < 4) {
-        mbar_wait(&S.done, 0);
-        tc_fence_after();
-        if (prof && warp == 0) A.prof[20] = clock64() - pe0;
-        float* out = A.partial + (size_t)blockIdx.x * PT_TOTAL;
-        const int n = 16 * warp + lane;
-        for (int j = 0; j < A.njobs; ++j) {
-            const WJob& J = A.job[j];
-            float d[96];
-            if (has_work) {
-                tmem_ld16(tmem + J.tmem_col, 0, d); tmem_ld16(tmem + J.tmem_col, 16, d + 16);
-                tmem_ld16(tmem + J.tmem_col, 32, d + 32); tmem_ld16(tmem + J.tmem_col, 48, d + 48);
-                if (J.nb > 64) { tmem_ld16(tmem + J.tmem_col, 64, d + 64); tmem_ld16(tmem + J.tmem_col, 80, d + 80); }
-                tmem_ld_wait();
-            }
-            if (lane < 16) wgrad_store_rows(out, J, n, d, !has_work);
-        }
-    }
-    if (prof && warp == 0) { A.prof[18] = clock64() - pe0; A.prof[19] = clock64() - pt0; }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace npe
