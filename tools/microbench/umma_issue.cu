@@ -74,6 +74,59 @@ __global__ void __launch_bounds__(128, 1) k_issue(long long* out, int M, int N, 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
+// Same, but TWO threads (lane 0 of warps 0 and 1) issue concurrently into different accumulators: is the ~58-cycle cost a
+// limit of the issuing thread or of the SM?
+__global__ void __launch_bounds__(128, 1) k_issue2(long long* out, int M, int N, int reps, int nthreads) {
+    extern __shared__ __align__(1024) unsigned char raw[];
+    Smem& S = *reinterpret_cast<Smem*>(raw);
+    __shared__ unsigned long long bar2[2];
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int i = t; i < (int)(sizeof(S.A) / 4); i += 128) S.A[i] = 0.f;
+    for (int i = t; i < (int)(sizeof(S.B) / 4); i += 128) S.B[i] = 0.f;
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&S.tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = S.tmem_slot;
+    const long long t0 = clock64();
+    if ((t & 31) == 0 && warp < nthreads) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint32_t d = tmem + (uint32_t)(warp * 256);
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int s = 0; s < KSTEPS; ++s) {
+                const uint64_t da = make_desc(smem_u32(S.A) + 2 * s * M * 16, M * 16, 128);
+                const uint64_t db = make_desc(smem_u32(S.B) + 2 * s * N * 16, N * 16, 128);
+                const uint32_t acc = (r > 0 || s > 0);
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                    ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[warp])) : "memory");
+    }
+    for (int w = 0; w < nthreads; ++w)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+            ::"r"(smem_u32(&bar2[w])) : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const long long t2 = clock64();
+    if (t == 0) out[0] = t2 - t0;
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
 int main() {
     long long* dc; cudaMalloc(&dc, 16);
     cudaFuncSetAttribute(k_issue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
@@ -93,6 +146,19 @@ int main() {
             const double n = reps * KSTEPS;
             printf("M=%3d N=%3d accumulators=%d: issue %.1f cycles/MMA, issue+drain %.1f cycles/MMA (floor max(M,128)*N/256 = %.1f)\n",
                    sh[0], sh[1], naccs, c[0] / n, c[1] / n, 128.0 * sh[1] / 256.0);
+        }
+    cudaFuncSetAttribute(k_issue2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+    for (int n : {56, 64, 112})
+        for (int nth : {1, 2}) {
+            long long c = 0;
+            for (int rep = 0; rep < 3; ++rep) {
+                k_issue2<<<1, 128, sizeof(Smem) + 1024>>>(dc, 128, n == 56 ? 64 : n, 24, nth);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("k_issue2: %s\n", cudaGetErrorString(e)); return 1; }
+                cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+            }
+            printf("M=128 N=%3d, %d issuing thread(s), 24 x 8 MMAs each: %.1f cycles per MMA of ONE thread's stream (wall %lld)\n",
+                   n == 56 ? 64 : n, nth, c / (24.0 * KSTEPS), c);
         }
     return 0;
 }
