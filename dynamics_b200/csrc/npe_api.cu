@@ -166,6 +166,8 @@ struct npe_handle {
     } alt;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t slot_ready = nullptr;          // upload + pair table of the current slot complete (stream2)
+    cudaEvent_t wg_fork = nullptr, wg_join = nullptr;   // large-batch backward: decoder weight gradients on a side stream
+    cudaStream_t stream3 = nullptr;
     cudaEvent_t slot_free[2] = {nullptr, nullptr};   // main-stream work on that slot enqueued so far is complete
     int slot = 0;
     bool slot_free_valid[2] = {false, false};
@@ -675,10 +677,54 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
                       h->ddz.p, h->ds.p));
         h->launches++;
     }
+    auto stacked = [](const WArgs& W, const int (&ia)[3], const int (&ib)[3]) {
+        WmArgs M = {};
+        for (int p = 0; p < 3; ++p) {
+            WPair& P = M.pair[p];
+            P.a = W.job[ia[p]];
+            P.has_b = ib[p] >= 0;
+            if (P.has_b) P.b = W.job[ib[p]];
+            P.ca = P.a.ngs ? 3 : 2;
+            P.cb = !P.has_b ? 0 : (P.b.ngs ? 3 : 2);
+            P.tmem_col = 128 * p;
+        }
+        M.npairs = 3; M.nrows_dev = W.nrows_dev; M.nrows = W.nrows; M.partial = W.partial; M.prof = W.prof;
+        return M;
+    };
+    // decoder part of the weight gradients.  Layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1};
+    // column 50 of X is the constant 1, i.e. accumulator column 50 is the bias gradient
+    WArgs B = {};
+    const size_t FS = (size_t)F * HSLOT;
+    B.job[0] = wjob_layer(h->ddz.p + 4 * FS, 24, h->dact.p + 4 * FS, 0, PT_DEC5, OUT);
+    for (int l = 4; l >= 2; --l)
+        B.job[5 - l] = wjob_layer(h->ddz.p + (l - 1) * FS, 52, h->dact.p + (l - 1) * FS, 64 * (5 - l), PT_DEC2 + (l - 2) * PT_LAYER, H);
+    WJob& D1 = B.job[4];            // layer 1: G = dz1, X = z = [pair sum (50) | 1 | 0 | focus window (44)]
+    D1 = WJob{};
+    D1.G = h->ddz.p; D1.g_cols = 52;
+    D1.X0 = h->dact.p; D1.x0_valid = 52; D1.x0_store = 52;
+    D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
+    D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
+    B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial; B.prof = chain_prof(h) ? chain_prof(h) + 32 : nullptr;
+    // That part only needs what exists now (dz of the decoder chain, forward stashes): in the throughput regime it goes to a
+    // low-priority side stream and fills the SMs that the pair input-gradient chain leaves idle in its last round of tiles
+    // (S-64: 320 pair tiles on 296 tile slots -- the second round keeps 12 of 148 SMs busy), then runs beside the pair part.
+    static const bool side_ok = getenv("NPE_NO_WGRAD_SIDE_STREAM") == nullptr;   // A/B measurements
+    const bool fork = side_ok && h->prof_kernel < 0 && h->F > h->pdl_max_foci;   // kernel brackets (tools) time ONE stream
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
+        if (fork) CK(cudaEventRecord(h->wg_fork, h->stream));
         CK(launch_pdl(h, k_pair_dgrad_c2, pg, CH_NT, sizeof(PairDgradChainSmem), h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
                       h->stash_rows, h->ds.p, h->wtt3, h->dzact.p, h->pair_frow.p));
+        h->launches++;
+    }
+    if (fork) {
+        CK(cudaStreamWaitEvent(h->stream3, h->wg_fork, 0));
+        cudaStream_t main_stream = h->stream;
+        h->stream = h->stream3;
+        const cudaError_t e = launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1}));   // (D5, D4) (D3, D2) (D1)
+        h->stream = main_stream;
+        CK(e);
+        CK(cudaEventRecord(h->wg_join, h->stream3));
         h->launches++;
     }
     {
@@ -694,38 +740,14 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
         E.gs[1].base = h->states.p; E.gs[1].offs = h->pair_crow.p; E.gs[1].cols_valid = IN; E.gs[1].cols_store = 48; E.gs[1].col0 = 48;
         E.ngs = 2; E.nb = 96; E.tmem_col = 64 * NL; E.kind = 2; E.n_valid = H;
         A.njobs = NL + 1; A.nrows_dev = h->info_dev; A.nrows = 0; A.partial = h->partial; A.prof = chain_prof(h);
-        auto stacked = [](const WArgs& W, const int (&ia)[3], const int (&ib)[3]) {
-            WmArgs M = {};
-            for (int p = 0; p < 3; ++p) {
-                WPair& P = M.pair[p];
-                P.a = W.job[ia[p]];
-                P.has_b = ib[p] >= 0;
-                if (P.has_b) P.b = W.job[ib[p]];
-                P.ca = P.a.ngs ? 3 : 2;
-                P.cb = !P.has_b ? 0 : (P.b.ngs ? 3 : 2);
-                P.tmem_col = 128 * p;
-            }
-            M.npairs = 3; M.nrows_dev = W.nrows_dev; M.nrows = W.nrows; M.partial = W.partial; M.prof = W.prof;
-            return M;
-        };
         CK(launch_pdl(h, k_wgrad_mn<0>, gp, WM_NT, sizeof(WmSmem) + 1024, stacked(A, {0, 2, 4}, {1, 3, 5})));   // (L5, L4) (L3, L2) (L1, encoders)
         h->launches++;
-        WArgs B = {};
-        // decoder layer 5: G = dz5 (22 of 24 columns), X = u4; layers 4..2: G = dz_l, X = u_{l-1}; column 50 of X is the
-        // constant 1, i.e. accumulator column 50 is the bias gradient
-        const size_t FS = (size_t)F * HSLOT;
-        B.job[0] = wjob_layer(h->ddz.p + 4 * FS, 24, h->dact.p + 4 * FS, 0, PT_DEC5, OUT);
-        for (int l = 4; l >= 2; --l)
-            B.job[5 - l] = wjob_layer(h->ddz.p + (l - 1) * FS, 52, h->dact.p + (l - 1) * FS, 64 * (5 - l), PT_DEC2 + (l - 2) * PT_LAYER, H);
-        WJob& D1 = B.job[4];            // layer 1: G = dz1, X = z = [pair sum (50) | 1 | 0 | focus window (44)]
-        D1 = WJob{};
-        D1.G = h->ddz.p; D1.g_cols = 52;
-        D1.X0 = h->dact.p; D1.x0_valid = 52; D1.x0_store = 52;
-        D1.gs[0].base = h->states.p; D1.gs[0].offs = h->foc_row.p; D1.gs[0].cols_valid = IN; D1.gs[0].cols_store = IN; D1.gs[0].col0 = ZCOL_F;
-        D1.ngs = 1; D1.nb = 96; D1.tmem_col = 256; D1.kind = 1; D1.kt = 24; D1.n_valid = H;
-        B.njobs = 5; B.nrows_dev = nullptr; B.nrows = F; B.partial = h->partial; B.prof = chain_prof(h) ? chain_prof(h) + 32 : nullptr;
-        CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));  // (D5, D4) (D3, D2) (D1)
-        h->launches++;
+        if (fork) {
+            CK(cudaStreamWaitEvent(h->stream, h->wg_join, 0));      // the reduce kernel needs both parts
+        } else {
+            CK(launch_pdl(h, k_wgrad_mn<1>, gd, WM_NT, sizeof(WmSmem) + 1024, stacked(B, {0, 2, 4}, {1, 3, -1})));
+            h->launches++;
+        }
     }
     CK(cudaGetLastError());
     *gp_out = gp; *gd_out = gd;
@@ -925,6 +947,10 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     cudaMemset(h->alt.active_total, 0, sizeof(u64));
     if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->slot_ready, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->wg_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->wg_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    { int lo_pri = 0, hi_pri = 0; cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);   // numerically greatest = lowest priority
+      if ((e = cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, lo_pri)) != cudaSuccess) return bail("cudaStreamCreate", e); }
     for (int i = 0; i < 2; ++i)
         if ((e = cudaEventCreateWithFlags(&h->slot_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc((void**)&h->loss4_host, (16 + 4 * LOSS_RING) * sizeof(float), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
@@ -977,6 +1003,9 @@ int npe_destroy(npe_handle* h) {
       a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release();
       a.n_obj.release(); a.foc_scene.release(); a.foc_obj.release(); a.foc_t0.release(); }
     if (h->slot_ready) cudaEventDestroy(h->slot_ready);
+    if (h->wg_fork) cudaEventDestroy(h->wg_fork);
+    if (h->wg_join) cudaEventDestroy(h->wg_join);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
     for (int i = 0; i < 2; ++i) if (h->slot_free[i]) cudaEventDestroy(h->slot_free[i]);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     for (int i = 0; i < LOSS_RING; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
