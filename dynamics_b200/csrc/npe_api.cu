@@ -668,7 +668,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
     const int ftiles = (F + 127) / 128;
     const long long ptiles = ((long long)h->pair_cap + 127) / 128;
     const int fg = (ftiles + 1) / 2 < h->num_sms ? (ftiles + 1) / 2 : h->num_sms;
-    const int pg = (int)((ptiles + 1) / 2 < h->num_sms ? ((ptiles + 1) / 2 > 0 ? (ptiles + 1) / 2 : 1) : h->num_sms);
+    const int pg = (int)((ptiles + P3_SLOTS - 1) / P3_SLOTS < h->num_sms ? ((ptiles + P3_SLOTS - 1) / P3_SLOTS > 0 ? (ptiles + P3_SLOTS - 1) / P3_SLOTS : 1) : h->num_sms);   // three tile slots per SM
     const int gd = ftiles < h->num_sms ? ftiles : h->num_sms;
     const int gp = (int)(ptiles < h->num_sms ? (ptiles > 0 ? ptiles : 1) : h->num_sms);
     {
@@ -713,7 +713,7 @@ int run_backward_tc(npe_handle* h, float sv, float sw, int* gp_out, int* gd_out)
     {
         ProfScope ps__(h, NPE_K_PAIR_BACKWARD);
         if (fork) CK(cudaEventRecord(h->wg_fork, h->stream));
-        CK(launch_pdl(h, k_pair_dgrad_c2, pg, CH_NT, sizeof(PairDgradChainSmem), h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
+        CK(launch_pdl(h, k_pair_dgrad_c2, pg, P3_NT, sizeof(PairDgradChainSmem), h->pair_foc.p, h->foc_row.p, h->info_dev, h->hmask.p,
                       h->stash_rows, h->ds.p, h->wtt3, h->dzact.p, h->pair_frow.p));
         h->launches++;
     }

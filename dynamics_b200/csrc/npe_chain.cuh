@@ -595,23 +595,43 @@ k_dec_dgrad_c2(int F, const float* __restrict__ pred, const float* __restrict__ 
 // dzact[l][stash_rows][HSLOT] = dz_l.  CAddTable backward = copy; apply_mask is the identity on the active list
 // (npe.lua:326-328).
 // ================================================================================================================
+// THREE tile slots per SM.  With two, S-64's 320 pair tiles need two rounds of the per-tile latency chain on 296 slots, the
+// second with 12 of 148 SMs busy.  This chain only has 56-wide operands (no encoder stage), so a slot fits 168 tensor-memory
+// columns -- [0,56) accumulator (N = 56 MMAs; the 50 real columns), [56,112) A hi, [112,168) A lo -- and three slots 504.
+constexpr int P3_SLOTS = 3;
+constexpr int P3_EPI = P3_SLOTS * 128, P3_NT = P3_EPI + 32;
+constexpr int P3_D = 0, P3_AHI = 56, P3_ALO = 112, P3_GROUP = 168;
+struct Chain3Ctl {
+    unsigned long long wbar;
+    unsigned long long a_ready[P3_SLOTS];
+    unsigned long long d_ready[P3_SLOTS];
+    uint32_t tmem, pad;
+};
 struct PairDgradChainSmem {
     float Whi[TT_PAIR_TOTAL];      // 71680 B
     float Wlo[TT_PAIR_TOTAL];      // 71680 B
-    float stg[8 * STG_FLOATS];
-    ChainCtl ctl;
+    float stg[(P3_EPI / 32) * STG_FLOATS];
+    Chain3Ctl ctl;
 };
+static_assert(sizeof(PairDgradChainSmem) <= 232448, "pair input-gradient chain exceeds shared memory");
 
-__global__ void __launch_bounds__(CH_NT, 1)
+__global__ void __launch_bounds__(P3_NT, 1)
 k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ foc_row, const int* __restrict__ info,
                 const unsigned long long* __restrict__ hmask, long long stash_rows, const float* __restrict__ ds_in,
                 const float* __restrict__ wtt3, float* __restrict__ dzact, long long* __restrict__ pair_frow) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairDgradChainSmem& S = *reinterpret_cast<PairDgradChainSmem*>(smem_raw);
     pdl_launch_dependents();
-    chain_setup(S.ctl);
     const int t = threadIdx.x;
-    if (t == CH_EPI) {
+    if (t == 0) {
+        mbar_init(&S.ctl.wbar, 1);
+        for (int i = 0; i < P3_SLOTS; ++i) { mbar_init(&S.ctl.a_ready[i], 128); mbar_init(&S.ctl.d_ready[i], 1); }
+    }
+    if ((t >> 5) == P3_EPI / 32) tmem_alloc<TM_COLS>(&S.ctl.tmem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (t == P3_EPI) {
         mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
         bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
         bulk_g2s(S.Wlo, wtt3 + TT_TOTAL, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
@@ -619,25 +639,48 @@ k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ 
     pdl_wait();
     const int P = info[0];
     const int ntiles = (P + 127) / 128;
-    if (t >= CH_EPI) {
-        if (t == CH_EPI) {
+    const int step = P3_SLOTS * gridDim.x;
+    if (t >= P3_EPI) {
+        if (t == P3_EPI) {
             mbar_wait(&S.ctl.wbar, 0);
-            chain_mma_loop<NL>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
-                const int l = NL - stage;            // dh_{l-1} = dz_l W_l
-                umma_gemm_tf32x3_ts(tm + TM_D, tm + TM_AHI, tm + TM_ALO, S.Whi + TT_PAIR + (l - 1) * TC_HID_SZ,
-                                    S.Wlo + TT_PAIR + (l - 1) * TC_HID_SZ, 64, 64, 7);
-            });
+            // MMA-warp scheduler: stage after stage of the three slots in the order their A operands become ready
+            int tiles[P3_SLOTS], stage[P3_SLOTS];
+            unsigned ka[P3_SLOTS];
+            int left = 0;
+#pragma unroll
+            for (int sl = 0; sl < P3_SLOTS; ++sl) {
+                const int first = P3_SLOTS * blockIdx.x + sl;
+                tiles[sl] = first < ntiles ? (ntiles - 1 - first) / step + 1 : 0;
+                stage[sl] = 0; ka[sl] = 0u; left += tiles[sl];
+            }
+            while (left > 0) {
+#pragma unroll
+                for (int sl = 0; sl < P3_SLOTS; ++sl) {
+                    if (tiles[sl] > 0 && mbar_test(&S.ctl.a_ready[sl], ka[sl] & 1u)) {
+                        tc_fence_after();
+                        const int l = NL - stage[sl];            // dh_{l-1} = dz_l W_l
+                        const uint32_t tm = S.ctl.tmem + sl * P3_GROUP;
+                        umma_gemm_tf32x3_ts(tm + P3_D, tm + P3_AHI, tm + P3_ALO, S.Whi + TT_PAIR + (l - 1) * TC_HID_SZ,
+                                            S.Wlo + TT_PAIR + (l - 1) * TC_HID_SZ, 64, 56, 7);
+                        umma_commit(&S.ctl.d_ready[sl]);
+                        ++ka[sl];
+                        if (++stage[sl] == NL) { stage[sl] = 0; --tiles[sl]; --left; }
+                    }
+                }
+            }
         }
     } else {
-        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        const int slot = t >> 7, row = t & 127, wq = (t >> 5) & 3;
+        const uint32_t tm = S.ctl.tmem + slot * P3_GROUP;
+        float* stg = S.stg + (t >> 5) * STG_FLOATS;
         unsigned nd = 0;
-        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+        for (int tile = P3_SLOTS * blockIdx.x + slot; tile < ntiles; tile += step) {
             const int lo = tile * 128;
             const int nrows = min(128, P - lo);
-            const bool live = c.row < nrows;
-            const int wrows = max(0, min(32, nrows - 32 * c.wq));
-            const size_t p = (size_t)(lo + c.row);
-            const size_t pw = (size_t)(lo + 32 * c.wq);
+            const bool live = row < nrows;
+            const int wrows = max(0, min(32, nrows - 32 * wq));
+            const size_t p = (size_t)(lo + row);
+            const size_t pw = (size_t)(lo + 32 * wq);
             unsigned long long hm[NL + 1];
 #pragma unroll
             for (int l = 0; l <= NL; ++l) hm[l] = live ? hmask[(size_t)l * stash_rows + p] : 0ull;
@@ -649,28 +692,39 @@ k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ 
                     pair_frow[p] = foc_row[pf];                   // focus-window offset for the encoder weight gradient
                     src = ds_in + (size_t)pf * 52;
                 }
-                warp_load32(c.stg, d, src, live, 8);
-                warp_load32(c.stg, d + 32, src + 32, live, 5);
+                warp_load32(stg, d, src, live, 8);
+                warp_load32(stg, d + 32, src + 32, live, 5);
                 relu_mask50(d, hm[NL]);
-                warp_store_row52(c.stg, d, dzact + ((size_t)NL * stash_rows + pw) * HSLOT, HSLOT, wrows);
-                tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
+                warp_store_row52(stg, d, dzact + ((size_t)NL * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                tmem_store_split<7>(tm, P3_AHI, P3_ALO, d);
             }
-            chain_publish_a(S.ctl, c.slot);
+            tmem_st_wait(); tc_fence_before(); mbar_arrive(&S.ctl.a_ready[slot]);
 #pragma unroll 1
             for (int st = 0; st < NL; ++st) {        // epilogue of stage st: dz_{4 - st}
-                chain_wait_d(S.ctl, c.slot, nd);
+                mbar_wait(&S.ctl.d_ready[slot], nd & 1u); ++nd; tc_fence_after();
                 float d[64];
-                tc_load64(c.tm, d);
+                tmem_ld16(tm, 0, d); tmem_ld16(tm, 16, d + 16); tmem_ld16(tm, 32, d + 32);
+                {   // columns 48..55 (the accumulator is 56 wide: no x16 load across its end)
+                    uint32_t r[8];
+                    const uint32_t taddr = tm + ((uint32_t)wq * 32u << 16) + 48u;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { d[48 + i] = __uint_as_float(r[i]); d[56 + i] = 0.f; }
+                }
                 relu_mask50(d, st == 0 ? hm[4] : st == 1 ? hm[3] : st == 2 ? hm[2] : st == 3 ? hm[1] : hm[0]);
-                warp_store_row52(c.stg, d, dzact + ((size_t)(NL - 1 - st) * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                warp_store_row52(stg, d, dzact + ((size_t)(NL - 1 - st) * stash_rows + pw) * HSLOT, HSLOT, wrows);
                 if (st < NL - 1) {
-                    tmem_store_split<7>(c.tm, TM_AHI, TM_ALO, d);
-                    chain_publish_a(S.ctl, c.slot);
+                    tmem_store_split<7>(tm, P3_AHI, P3_ALO, d);
+                    tmem_st_wait(); tc_fence_before(); mbar_arrive(&S.ctl.a_ready[slot]);
                 }
             }
         }
     }
-    chain_teardown(S.ctl);
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == P3_EPI / 32) tmem_dealloc<TM_COLS>(S.ctl.tmem);
 }
 
 }  // namespace npe
