@@ -512,7 +512,16 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
             k_dec_forward_tc<<<fg, NT, sizeof(DecTcSmem), h->stream>>>(st, h->foc_row.p, F, h->pair_start.p, h->Hp.p, h->wtc, y,
                                                                        h->pred.p, loss_ex);
         } else {
-            // warp-specialised chain kernels (npe_chain.cuh): two tile slots per CTA, two threads per row, one MMA warp
+            // warp-specialised chain kernels (npe_chain.cuh): tile slots of 128 row-owner threads + one MMA warp per CTA; the
+            // pair kernel runs three slots, the decoder kernel two
+            // training batches take the three-slot variant of the pair kernel (fewer ROUNDS of the per-tile latency chain when
+            // an SM sees only a few tiles); inference and the rollout (many tiles per SM) the two-slot one
+            const long long pt3 = (((long long)h->pair_cap + 127) / 128 + P3_SLOTS - 1) / P3_SLOTS;
+            const int pg3 = (int)(pt3 < h->num_sms ? (pt3 > 0 ? pt3 : 1) : h->num_sms);
+            if (stash)
+                CK(launch_pdl(h, k_pair_forward_c3, pg3, P3_NT, sizeof(Pair3ChainSmem), st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
+                              h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
+            else
             CK(launch_pdl(h, k_pair_forward_c2, pg, CH_NT, sizeof(PairChainSmem), st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
                           h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
             if (!skip_decoder)
@@ -974,6 +983,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_wgrad_mn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_wgrad_mn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmSmem) + 1024)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairChainSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pair_forward_c3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pair3ChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairDgradChainSmem))) != cudaSuccess)

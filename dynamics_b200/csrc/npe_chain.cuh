@@ -251,10 +251,80 @@ __device__ __forceinline__ int chain_tiles(int ntiles, int s) {
     return first < ntiles ? (ntiles - 1 - first) / step + 1 : 0;
 }
 
+// The PAIR kernels run THREE tile slots per SM.  With two, S-64's 320 pair tiles need two rounds of the per-tile latency chain
+// on 296 slots, the second with 12 of 148 SMs busy.  Their operands are at most 56 wide (the forward feeds its 2 x 48-wide
+// encoder input in two K-halves), so a slot fits 168 tensor-memory columns -- [0,56) accumulator (N = 56 MMAs; the 50 real
+// columns), [56,112) A hi, [112,168) A lo -- and three slots 504.
+constexpr int P3_SLOTS = 3;
+constexpr int P3_EPI = P3_SLOTS * 128, P3_NT = P3_EPI + 32;
+constexpr int P3_D = 0, P3_AHI = 56, P3_ALO = 112, P3_GROUP = 168;
+struct Chain3Ctl {
+    unsigned long long wbar;
+    unsigned long long a_ready[P3_SLOTS];
+    unsigned long long d_ready[P3_SLOTS];
+    uint32_t tmem, pad;
+};
+// accumulator columns 0..55 of this thread's row (d[56..63] = 0): no 16-column load across the end of the 56-wide accumulator
+__device__ __forceinline__ void p3_load56(uint32_t tm, float* d) {
+    tmem_ld16(tm, 0, d); tmem_ld16(tm, 16, d + 16); tmem_ld16(tm, 32, d + 32);
+    uint32_t r[8];
+    const uint32_t taddr = tm + ((uint32_t)((threadIdx.x >> 5) & 3) * 32u << 16) + 48u;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { d[48 + i] = __uint_as_float(r[i]); d[56 + i] = 0.f; }
+}
+__device__ __forceinline__ void p3_setup(Chain3Ctl& ctl) {
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(&ctl.wbar, 1);
+        for (int i = 0; i < P3_SLOTS; ++i) { mbar_init(&ctl.a_ready[i], 128); mbar_init(&ctl.d_ready[i], 1); }
+    }
+    if ((t >> 5) == P3_EPI / 32) tmem_alloc<TM_COLS>(&ctl.tmem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+}
+__device__ __forceinline__ void p3_teardown(Chain3Ctl& ctl) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == P3_EPI / 32) tmem_dealloc<TM_COLS>(ctl.tmem);
+}
+__device__ __forceinline__ void p3_publish(Chain3Ctl& ctl, int slot) { tmem_st_wait(); tc_fence_before(); mbar_arrive(&ctl.a_ready[slot]); }
+__device__ __forceinline__ void p3_wait(Chain3Ctl& ctl, int slot, unsigned& nd) { mbar_wait(&ctl.d_ready[slot], nd & 1u); ++nd; tc_fence_after(); }
+// MMA-warp scheduler: stage after stage of the three slots in the order their A operands become ready
+template <int NSTAGE, typename IssueFn>
+__device__ __forceinline__ void p3_mma_loop(Chain3Ctl& ctl, int ntiles, IssueFn issue) {
+    const int step = P3_SLOTS * gridDim.x;
+    int tiles[P3_SLOTS], stage[P3_SLOTS];
+    unsigned ka[P3_SLOTS];
+    int left = 0;
+#pragma unroll
+    for (int sl = 0; sl < P3_SLOTS; ++sl) {
+        const int first = P3_SLOTS * blockIdx.x + sl;
+        tiles[sl] = first < ntiles ? (ntiles - 1 - first) / step + 1 : 0;
+        stage[sl] = 0; ka[sl] = 0u; left += tiles[sl];
+    }
+    while (left > 0) {
+#pragma unroll
+        for (int sl = 0; sl < P3_SLOTS; ++sl) {
+            if (tiles[sl] > 0 && mbar_test(&ctl.a_ready[sl], ka[sl] & 1u)) {
+                tc_fence_after();
+                issue(stage[sl], ctl.tmem + sl * P3_GROUP);
+                umma_commit(&ctl.d_ready[sl]);
+                ++ka[sl];
+                if (++stage[sl] == NSTAGE) { stage[sl] = 0; --tiles[sl]; --left; }
+            }
+        }
+    }
+}
+
 // ================================================================================================================
 // pair MLP forward: tiles of 128 active pairs.  Stage 0: both encoders into one accumulator; stages 1..5: pairwise layers.
 // Training (hact != nullptr): h0..h5 go to the layer-major stash hact[l][stash_rows][HSLOT], their ReLU bits to hmask[l][stash_rows].
 // ================================================================================================================
+// Two-slot variant (inference and the rollout: many tiles per SM, steady state).
 struct PairChainSmem {
     float Ehi[2 * ENC64_SZ];              // 24576 B   focus | context encoder, 64-row images
     float Elo[2 * ENC64_SZ];              // 24576 B
@@ -348,6 +418,107 @@ k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair
         if (prof && blockIdx.x == 0 && t == 0) { prof[0] = pf_gather; prof[1] = pf_wait; prof[2] = pf_epi; prof[3] = clock64() - pf_t0; }
     }
     chain_teardown(S.ctl);
+}
+
+constexpr int P3_HID_ROWS = 56;                         // rows of a pairwise layer's shared-memory image (the global one has 64)
+constexpr int P3_HID_SZ = TC_HID_KC * P3_HID_ROWS * 4;  // 3136 floats
+struct Pair3ChainSmem {
+    float Ehi[2 * ENC64_SZ];              // 24576 B   focus | context encoder, 64-row images
+    float Elo[2 * ENC64_SZ];              // 24576 B
+    float Whi[NL * P3_HID_SZ];            // 62720 B   56 of the 64 rows of every K-chunk
+    float Wlo[NL * P3_HID_SZ];            // 62720 B
+    float stg[(P3_EPI / 32) * STG_FLOATS];   // 55296 B
+    Chain3Ctl ctl;
+};
+static_assert(sizeof(Pair3ChainSmem) <= 232448, "pair forward chain exceeds shared memory");
+
+// Three-slot variant (training batches: few tiles per SM, the number of ROUNDS of the per-tile latency chain is what counts).
+__global__ void __launch_bounds__(P3_NT, 1)
+k_pair_forward_c3(const float* __restrict__ states, const int* __restrict__ pair_foc, const long long* __restrict__ pair_crow,
+                  const long long* __restrict__ foc_row, const int* __restrict__ info, const float* __restrict__ wtc3,
+                  const float* __restrict__ wenc, float* __restrict__ Hp, float* __restrict__ hact,
+                  unsigned long long* __restrict__ hmask, long long stash_rows, long long* __restrict__ prof) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Pair3ChainSmem& S = *reinterpret_cast<Pair3ChainSmem*>(smem_raw);
+    long long pf_gather = 0, pf_wait = 0, pf_epi = 0, pf_t0 = clock64();
+    pdl_launch_dependents();
+    p3_setup(S.ctl);
+    const int t = threadIdx.x;
+    if (t == P3_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, (4 * ENC64_SZ + 2 * NL * P3_HID_SZ) * 4);
+        bulk_g2s(S.Ehi, wenc, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+        bulk_g2s(S.Elo, wenc + 2 * ENC64_SZ, 2 * ENC64_SZ * 4, &S.ctl.wbar);
+        for (int kc = 0; kc < NL * TC_HID_KC; ++kc) {      // 56 of the 64 rows of every K-chunk of every layer
+            bulk_g2s(S.Whi + kc * P3_HID_ROWS * 4, wtc3 + TC_PAIR + kc * TC_HID_ROWS * 4, P3_HID_ROWS * 16, &S.ctl.wbar);
+            bulk_g2s(S.Wlo + kc * P3_HID_ROWS * 4, wtc3 + TC_TOTAL + TC_PAIR + kc * TC_HID_ROWS * 4, P3_HID_ROWS * 16, &S.ctl.wbar);
+        }
+    }
+    pdl_wait();
+    const int P = info[0];
+    const int ntiles = (P + 127) / 128;
+    if (t >= P3_EPI) {
+        if (t == P3_EPI) {
+            mbar_wait(&S.ctl.wbar, 0);
+            // stages: 0 = focus half of the encoder input, 1 = context half (accumulates: its real rows are 25..49), 2..6 = layers
+            p3_mma_loop<NL + 2>(S.ctl, ntiles, [&](int stage, uint32_t tm) {
+                if (stage == 0) umma_gemm_tf32x3_ts(tm + P3_D, tm + P3_AHI, tm + P3_ALO, S.Ehi, S.Elo, 64, 56, 6);
+                else if (stage == 1) umma_gemm_tf32x3_ts(tm + P3_D, tm + P3_AHI, tm + P3_ALO, S.Ehi + ENC64_SZ, S.Elo + ENC64_SZ, 64, 56, 6, true);
+                else umma_gemm_tf32x3_ts(tm + P3_D, tm + P3_AHI, tm + P3_ALO, S.Whi + (stage - 2) * P3_HID_SZ,
+                                         S.Wlo + (stage - 2) * P3_HID_SZ, P3_HID_ROWS, 56, 7);
+            });
+        }
+    } else {
+        const int slot = t >> 7, row = t & 127, wq = (t >> 5) & 3;
+        const uint32_t tm = S.ctl.tmem + slot * P3_GROUP;
+        float* stg = S.stg + (t >> 5) * STG_FLOATS;
+        unsigned nd = 0;
+        for (int tile = P3_SLOTS * blockIdx.x + slot; tile < ntiles; tile += P3_SLOTS * gridDim.x) {
+            const int lo = tile * 128;
+            const int nrows = min(128, P - lo);
+            const bool live = row < nrows;
+            const int wrows = max(0, min(32, nrows - 32 * wq));       // valid rows of this warp
+            const size_t p = (size_t)(lo + row);
+            const size_t pw = (size_t)(lo + 32 * wq);                 // first row of this warp
+            const long long c_g0 = clock64();
+            {   // gather: the two 44-float state windows go through the 48-wide A operand one after the other
+                const float* fw = states, * cw = states;
+                if (live) { fw = states + foc_row[pair_foc[p]]; cw = states + pair_crow[p]; }
+                float x[48];
+                warp_gather44(stg, x, fw, live);
+                x[44] = x[45] = x[46] = x[47] = 0.f;
+                tmem_store_split<6>(tm, P3_AHI, P3_ALO, x);
+                p3_publish(S.ctl, slot);
+                warp_gather44(stg, x, cw, live);                      // fetched while the focus half runs
+                x[44] = x[45] = x[46] = x[47] = 0.f;
+                p3_wait(S.ctl, slot, nd);                             // the focus half has consumed the operand
+                tmem_store_split<6>(tm, P3_AHI, P3_ALO, x);
+                p3_publish(S.ctl, slot);
+            }
+            pf_gather += clock64() - c_g0;
+#pragma unroll 1
+            for (int l = 0; l <= NL; ++l) {          // epilogue of stage l + 1: h_l
+                const long long c_w0 = clock64();
+                p3_wait(S.ctl, slot, nd);
+                const long long c_w1 = clock64();
+                pf_wait += c_w1 - c_w0;
+                float d[64];
+                p3_load56(tm, d);
+#pragma unroll
+                for (int k = 0; k < 56; ++k) d[k] = relu(d[k]);
+                if (hmask && live) hmask[(size_t)l * stash_rows + p] = relu_bits64(d);
+                if (hact) warp_store_row52(stg, d, hact + ((size_t)l * stash_rows + pw) * HSLOT, HSLOT, wrows);
+                if (l < NL) {
+                    tmem_store_split<7>(tm, P3_AHI, P3_ALO, d);
+                    p3_publish(S.ctl, slot);
+                } else {
+                    warp_store_row52(stg, d, Hp + pw * 52, 52, wrows);
+                }
+                pf_epi += clock64() - c_w1;
+            }
+        }
+        if (prof && blockIdx.x == 0 && t == 0) { prof[0] = pf_gather; prof[1] = pf_wait; prof[2] = pf_epi; prof[3] = clock64() - pf_t0; }
+    }
+    p3_teardown(S.ctl);
 }
 
 // ================================================================================================================
@@ -595,18 +766,6 @@ k_dec_dgrad_c2(int F, const float* __restrict__ pred, const float* __restrict__ 
 // dzact[l][stash_rows][HSLOT] = dz_l.  CAddTable backward = copy; apply_mask is the identity on the active list
 // (npe.lua:326-328).
 // ================================================================================================================
-// THREE tile slots per SM.  With two, S-64's 320 pair tiles need two rounds of the per-tile latency chain on 296 slots, the
-// second with 12 of 148 SMs busy.  This chain only has 56-wide operands (no encoder stage), so a slot fits 168 tensor-memory
-// columns -- [0,56) accumulator (N = 56 MMAs; the 50 real columns), [56,112) A hi, [112,168) A lo -- and three slots 504.
-constexpr int P3_SLOTS = 3;
-constexpr int P3_EPI = P3_SLOTS * 128, P3_NT = P3_EPI + 32;
-constexpr int P3_D = 0, P3_AHI = 56, P3_ALO = 112, P3_GROUP = 168;
-struct Chain3Ctl {
-    unsigned long long wbar;
-    unsigned long long a_ready[P3_SLOTS];
-    unsigned long long d_ready[P3_SLOTS];
-    uint32_t tmem, pad;
-};
 struct PairDgradChainSmem {
     float Whi[TT_PAIR_TOTAL];      // 71680 B
     float Wlo[TT_PAIR_TOTAL];      // 71680 B
@@ -622,15 +781,8 @@ k_pair_dgrad_c2(const int* __restrict__ pair_foc, const long long* __restrict__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PairDgradChainSmem& S = *reinterpret_cast<PairDgradChainSmem*>(smem_raw);
     pdl_launch_dependents();
+    p3_setup(S.ctl);
     const int t = threadIdx.x;
-    if (t == 0) {
-        mbar_init(&S.ctl.wbar, 1);
-        for (int i = 0; i < P3_SLOTS; ++i) { mbar_init(&S.ctl.a_ready[i], 128); mbar_init(&S.ctl.d_ready[i], 1); }
-    }
-    if ((t >> 5) == P3_EPI / 32) tmem_alloc<TM_COLS>(&S.ctl.tmem);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
     if (t == P3_EPI) {
         mbar_expect_tx(&S.ctl.wbar, 2 * TT_PAIR_TOTAL * 4);
         bulk_g2s(S.Whi, wtt3, TT_PAIR_TOTAL * 4, &S.ctl.wbar);
