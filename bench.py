@@ -332,7 +332,7 @@ def bench_stress64(model_cls, mp_cls, device, steps=10, warmup=3, scenes_per_ste
         # the whole step runs on the tensor pipe (3xTF32 chains + weight-gradient kernels): its roofline is the step's
         # ALGORITHMIC FLOP rate against the TF32 dense peak (bf16 measured / 2); the 3-way split issues 3x these MMAs and
         # 64-padded tiles another 1.6x, so `issued_frac` is the tensor pipe's own view
-        names = {"forward": "k_pair_forward_c2 + k_dec_forward_c2", "dec_backward": "k_dec_dgrad_c2", "pair_backward": "k_pair_dgrad_c2",
+        names = {"forward": "k_pair_forward_c3 + k_dec_forward_c2", "dec_backward": "k_dec_dgrad_c2", "pair_backward": "k_pair_dgrad_c2",
                  "wgrad": "k_wgrad_mn (pair part + decoder part)"}
         flops = {"forward": KERNEL_FLOPS["forward"](F, P), "dec_backward": 22200.0 * F, "pair_backward": 25000.0 * P,
                  "wgrad": (26600.0 + 2200.0) * F + 27200.0 * P}      # dgrad of decoder / pair chain; all weight gradients
