@@ -26,7 +26,7 @@ struct FocusSrc {
     const float* states;   // (S, Nmax, T, 22)
     const int* n_obj;      // (S)
     int Nmax, T;
-    const int* foc_scene;  // (F)
+    const int* foc_scene;  // (F); nullptr (k_build_pairs_scan only): focus f = object f % Nmax of scene f / Nmax at t0 = 0, all scenes full
     const int* foc_obj;    // (F)
     const int* foc_t0;     // (F)
     int F;
@@ -489,8 +489,8 @@ __global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(Foc
         int scn = 0, n = 0, t0 = 0, N = 1;
         long long ro = 0;
         if (active) {
-            scn = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f];
-            N = src.n_obj[scn];
+            if (src.foc_scene) { scn = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f]; N = src.n_obj[scn]; }
+            else { scn = f / src.Nmax; n = f - scn * src.Nmax; t0 = 0; N = src.Nmax; }   // dense: every object of every (full) scene, in order
             ro = (long long)row_off(src, scn, n, t0);
             foc_row[f] = ro;
         }

@@ -8,7 +8,7 @@ m = NPEModel(ModelParams())
 st = synth.ball_scenes(65536, 8, 2, seed=5)
 m.set_params(init_params()); m.upload_scenes(st)
 m.set_precision("tf32x3"); m.set_rollout_mode("kernels")
-m.rollout_resident(0, 5); m.sync()
+m.rollout_resident(0, 400); m.sync()   # past the dense early steps
 out = {}
 for k in ("build_pairs", "forward", "rollout"):
     m.profile_select(k)
