@@ -339,3 +339,96 @@ def test_weight_images_follow_the_optimiser(n8, trained_like_params):
             m.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert not np.array_equal(out[0][0], trained_like_params)
+
+
+@pytest.mark.parametrize("n_obj,n_scenes", [(33, 27), (14, 61), (64, 11)])
+def test_throughput_pair_builder_trim_and_ties(n_obj, n_scenes):
+    """k_build_pairs_scan (more than 64 foci: a thread per focus, chained scan across blocks) with the 12-nearest trim ACTIVE
+    on an 80-px lattice (equidistant contexts everywhere, more than 12 inside many neighbourhoods): kept-context lists
+    (the on-demand path of npe_build_pairs), neighbourhood masks, the active-pair count and the dense pair list that the
+    forward consumes == the oracle.  Block counts: 891 / 854 / 704 foci = 4 / 4 / 3 blocks, the last one partial."""
+    from oracle import batcher
+    rng = np.random.default_rng(1000 + n_obj)
+    pos = (rng.integers(0, 5, (n_scenes, n_obj, 2)) * 80).astype(np.float32) / np.float32(800)   # 5 x 5 lattice: dense, many exact ties
+    st = np.zeros((n_scenes, n_obj, 3, 22), np.float32)
+    st[:, :, :, 0:2] = pos[:, :, None, :]
+    st[..., 2:4] = (rng.standard_normal((n_scenes, n_obj, 1, 2)) * 0.1).astype(np.float32)
+    st[..., 6] = 1; st[..., 10] = 1; st[..., 14] = 1; st[..., 16] = 1; st[..., 18] = 1; st[..., 20] = 1
+    this, ctx, y = scene_examples(st, 0)
+    oidx, omask, tctx = None, None, None
+    idx_o, d = batcher.k_nearest_indices(this, ctx, 12)
+    tctx = np.take_along_axis(ctx, idx_o[:, :, None, None], axis=1)
+    omask = npe.neighbor_mask(this, tctx, check_focus=False)
+    params = npe.init_params(1)
+    m = make_model(12, {})
+    try:
+        m.set_params(params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(n_scenes), np.zeros(n_scenes, np.int32))
+        F = m.select_windows(0, n_scenes)
+        assert F == n_scenes * n_obj and F > 592
+        # the hot path first: it only needs the neighbour bits (the kept-context list is completed on demand below)
+        pred, loss3 = m.forward_current()
+        f, p = m.batch_stats()
+        assert p == int(omask.sum())
+        pred_o = npe.forward(params, this.reshape(F, -1), tctx.reshape(F, tctx.shape[1], -1), omask)
+        assert rel_err(pred[:, :6], pred_o[:, :6]) < TOL
+        idx, mask, cnt = m.pair_table()
+        k = idx_o.shape[1]
+        assert np.all(cnt == k) and np.array_equal(idx[:, :k], idx_o.astype(np.int32))
+        assert np.array_equal(mask[:, :k], omask.astype(np.uint8))
+        # and the tables are the same after the list was completed (a refresh rewrites identical tables)
+        pred2, _ = m.forward_current()
+        assert np.array_equal(pred2, pred)
+        # the trim really cut INSIDE neighbourhoods (more than 12 contexts within 210 px before the trim)
+        assert npe.neighbor_mask(this, ctx, check_focus=False).sum(1).max() > 12
+    finally:
+        m.close()
+
+
+def test_throughput_pair_builder_ragged_scenes(trained_like_params):
+    """The same kernel on a padded scene tensor with variable object counts, obstacles that are contexts but never foci
+    (wall scenes: 28 obstacles + 2 balls, trim to the 12 nearest active) and a focus count that is no multiple of the
+    256-focus blocks: prediction and pair count per focus against the oracle, focus by focus."""
+    nw, nb = 120, 70
+    sw = scenes.raw_to_state(scenes.gen_walls(nw, 6, seed=5, variant="O"))        # N = 30, 2 foci per scene
+    sb = scenes.raw_to_state(scenes.gen_balls(nb, 7, 6, seed=6))                   # N = 7, 7 foci per scene
+    Nmax = 30
+    S = nw + nb
+    st = np.zeros((S, Nmax, 6, 22), np.float32)
+    order = np.random.default_rng(3).permutation(S)                                # interleave the two kinds of scenes
+    n_obj = np.zeros(S, np.int32)
+    for dst, src in enumerate(order):
+        if src < nw: st[dst] = sw[src]; n_obj[dst] = 30
+        else: st[dst, :7] = sb[src - nw]; n_obj[dst] = 7
+    m = make_model(12, {})
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st, n_obj)
+        m.upload_windows(np.arange(S), np.ones(S, np.int32))
+        F = m.select_windows(0, S)
+        assert F == nw * 2 + nb * 7 and F > 592 and F % 256 != 0
+        pred_g, _ = m.forward_current()
+        idx_g, mask_g, cnt_g = m.pair_table()
+        row, pairs = 0, 0
+        for s in range(S):
+            N = n_obj[s]
+            for o in range(N):
+                if st[s, o, 0, 11] == 1:
+                    continue
+                this = st[s:s + 1, o, 1:3]; ctx = np.delete(st[s:s + 1, :N], o, axis=1)[:, :, 1:3]
+                idx, d = batcher.k_nearest_indices(this, ctx, 12)
+                tctx = np.take_along_axis(ctx, idx[:, :, None, None], axis=1)
+                mask = npe.neighbor_mask(this, tctx, check_focus=False)
+                k = idx.shape[1]
+                assert cnt_g[row] == k and np.array_equal(idx_g[row, :k], idx[0].astype(np.int32)), (s, o)
+                assert np.array_equal(mask_g[row, :k], mask[0].astype(np.uint8)), (s, o)
+                if row % 7 == 0:      # the forward on a sample of the foci (the oracle is a Python loop here)
+                    pr = npe.forward(trained_like_params, this.reshape(1, -1), tctx.reshape(1, k, -1), mask)
+                    assert rel_err(pred_g[row, :6], pr[0, :6]) < TOL, (s, o)
+                pairs += int(mask.sum())
+                row += 1
+        assert row == F
+        assert m.batch_stats() == (F, pairs)
+    finally:
+        m.close()
