@@ -12,7 +12,7 @@ m.rollout_resident(0, 400); m.sync()   # past the dense early steps
 out = {}
 for k in ("build_pairs", "forward", "rollout"):
     m.profile_select(k)
-    m.rollout_resident(0, 16)
+    m.rollout_resident(0, 1000)
     n, tot = m.profile_read()
     out[k] = (n, round(1e3 * tot / max(n, 1), 1))
 m.profile_select(None)
