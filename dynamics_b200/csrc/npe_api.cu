@@ -122,6 +122,7 @@ struct npe_handle {
     int pdl_max_foci = 592;           // batches up to this many foci chain their kernels with programmatic dependent launch
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
+    DevBuf<float2> roll_pos;          // fused rollout: last-frame positions per focus, written by the decoder kernel for the next builder
     int roll_F = 0;
     float* loss3_dev = nullptr;
     double* loss_sums_dev = nullptr;
@@ -192,8 +193,9 @@ struct npe_handle {
     cudaEvent_t ring_ev[64] = {};     // npe_train_step_async / npe_loss_wait: one event per ring slot (slot i at loss4_host + 16 + 4 i)
     u64* active_total = nullptr;
     bool pairs_valid = false, fwd_valid = false;
-    unsigned* scan_ticket[2] = {nullptr, nullptr};   // chained scan of the throughput pair builder (k_build_pairs_scan):
-    DevBuf<u64> scan_status[2];                      // one state per stream the builder may run on (main, upload)
+    DevBuf<unsigned> scan_count[2];   // throughput pair builder (k_build_pairs_scan): block counts and grid-barrier words,
+    unsigned* scan_bar[2] = {nullptr, nullptr};   // one set per stream the builder may run on (main, upload)
+    int scan_ctas_per_sm[2] = {0, 0}; // resident CTAs per SM of its two variants (occupancy query, cached)
     unsigned scan_epoch = 0;
     bool keep_valid = false;          // the kept-context bits of the current pair table are complete (API view; see warp_pairs)
     // The last launch on the main stream was a pair builder: the next kernel must not be a programmatic dependent of it
@@ -362,6 +364,7 @@ float nbr_threshold_sq(float thr) {
     return s;
 }
 
+long long* chain_prof(npe_handle* h);
 struct PairOut { u64* keep; u64* nbr; int* cnt; int* block_sums; long long* foc_row; float* y; };
 int launch_build_pairs(npe_handle* h, const FocusSrc& src, float thr, const PairOut& o, bool want_keep) {
     const int nmax = h->Nmax, kmax = h->cfg.max_ctx;
@@ -378,27 +381,29 @@ int launch_build_pairs(npe_handle* h, const FocusSrc& src, float thr, const Pair
     } else {
         const int nblk = (src.F + NT_SCAN - 1) / NT_SCAN;
         const int w = h->stream == h->stream2;
-        DevBuf<u64>& status = h->scan_status[w];
-        const size_t had = status.cap;
-        CK(status.ensure((size_t)nblk));
-        if (status.cap != had) CK(cudaMemsetAsync(status.p, 0, status.cap * sizeof(u64), h->stream));
-        if (!h->scan_ticket[w]) {
-            CK(cudaMalloc((void**)&h->scan_ticket[w], sizeof(unsigned)));
-            CK(cudaMemsetAsync(h->scan_ticket[w], 0, sizeof(unsigned), h->stream));
+        DevBuf<unsigned>& cnt = h->scan_count[w];
+        CK(cnt.ensure((size_t)nblk));
+        if (!h->scan_bar[w]) {
+            CK(cudaMalloc((void**)&h->scan_bar[w], 128 * sizeof(unsigned)));
+            CK(cudaMemsetAsync(h->scan_bar[w], 0, 128 * sizeof(unsigned), h->stream));
         }
-        PairScan sc;
-        sc.ticket = h->scan_ticket[w]; sc.status = status.p;
-        sc.epoch = ++h->scan_epoch;
-        if ((sc.epoch & 0x3fffffffu) == 0) sc.epoch = ++h->scan_epoch;      // 0 is what a fresh status array holds
-        sc.nblk = nblk;
-        const int per_sm = o.y ? 4 : 8;                                      // resident CTAs per SM (launch bounds of the two variants)
+        ScanArgs A;
+        A.src = src; A.kmax = kmax; A.thr_s = thr; A.want_keep = (int)want_keep;
+        A.keep = o.keep; A.nbr = o.nbr; A.foc_row = o.foc_row; A.y = o.y; A.active_total = h->active_total;
+        A.pair_start = h->pair_start.p; A.pair_foc = h->pair_foc.p; A.pair_crow = h->pair_crow.p; A.cap = h->pair_cap; A.info = h->info_dev;
+        A.sc.count = cnt.p; A.sc.bar = h->scan_bar[w];
+        A.sc.epoch = ++h->scan_epoch;
+        if (A.sc.epoch == 0) A.sc.epoch = ++h->scan_epoch;                      // 0 is what fresh barrier words hold
+        A.sc.nblk = nblk;
+        A.sc.prof = chain_prof(h) ? chain_prof(h) + 64 : nullptr;
+        // cooperative launch: the grid never exceeds what is resident at once (occupancy x SMs), see the kernel
+        const void* fn = o.y ? (const void*)k_build_pairs_scan<true> : (const void*)k_build_pairs_scan<false>;
+        int& per_sm = h->scan_ctas_per_sm[o.y ? 1 : 0];
+        if (per_sm == 0) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT_SCAN, 0));
+        if (per_sm < 1) return fail(h, NPE_ERR_CUDA, "pair builder: kernel does not fit an SM");
         const int grid = nblk < per_sm * h->num_sms ? nblk : per_sm * h->num_sms;
-        if (o.y)
-            k_build_pairs_scan<true><<<grid, NT_SCAN, 0, h->stream>>>(src, kmax, thr, (int)want_keep, o.keep, o.nbr, o.foc_row, o.y, h->active_total,
-                                                                      h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, sc);
-        else
-            k_build_pairs_scan<false><<<grid, NT_SCAN, 0, h->stream>>>(src, kmax, thr, (int)want_keep, o.keep, o.nbr, o.foc_row, o.y, h->active_total,
-                                                                       h->pair_start.p, h->pair_foc.p, h->pair_crow.p, h->pair_cap, h->info_dev, sc);
+        void* args[] = {(void*)&A};
+        CK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT_SCAN), args, 0, h->stream));
     }
     h->launches++;
     h->after_builder = true;
@@ -464,7 +469,7 @@ int refresh_wtt(npe_handle* h);
 long long* chain_prof(npe_handle* h) {
     static const bool want = getenv("NPE_CHAIN_PROF") != nullptr;
     if (!want) return nullptr;
-    if (!h->chain_prof_dev) { cudaMalloc((void**)&h->chain_prof_dev, 64 * sizeof(long long)); cudaMemset(h->chain_prof_dev, 0, 64 * sizeof(long long)); }
+    if (!h->chain_prof_dev) { cudaMalloc((void**)&h->chain_prof_dev, 96 * sizeof(long long)); cudaMemset(h->chain_prof_dev, 0, 96 * sizeof(long long)); }
     return h->chain_prof_dev;
 }
 
@@ -496,7 +501,8 @@ float* training_stash(npe_handle* h) {
 // stash: activation stash for a following backward (training) or nullptr; skip_decoder: the fused training step lets
 // k_dec_backward produce pred / losses.
 int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y, float* loss_ex, int tc,
-                           float* stash = nullptr, bool skip_decoder = false, float* dact = nullptr, float* roll = nullptr) {
+                           float* stash = nullptr, bool skip_decoder = false, float* dact = nullptr, float* roll = nullptr,
+                           float2* roll_pos = nullptr) {
     ProfScope ps__(h, NPE_K_FORWARD);
     if (tc) {
         int rc = refresh_wtc(h, tc);
@@ -526,7 +532,7 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
                           h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
             if (!skip_decoder)
                 CK(launch_pdl(h, k_dec_forward_c2, fg, CH_NT, sizeof(DecChainSmem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
-                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode));
+                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode, roll_pos));
         }
         h->launches += (skip_decoder && tc == NPE_PRECISION_TF32X3_TC) ? 1 : 2;
     } else {
@@ -1003,7 +1009,7 @@ int npe_destroy(npe_handle* h) {
     for (float* b : bufs) if (b) cudaFree(b);
     if (h->loss_sums_dev) cudaFree(h->loss_sums_dev);
     if (h->active_total) cudaFree(h->active_total);
-    for (int i = 0; i < 2; ++i) { if (h->scan_ticket[i]) cudaFree(h->scan_ticket[i]); h->scan_status[i].release(); }
+    for (int i = 0; i < 2; ++i) { h->scan_count[i].release(); if (h->scan_bar[i]) cudaFree(h->scan_bar[i]); }
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
@@ -1029,7 +1035,7 @@ int npe_destroy(npe_handle* h) {
     h->keep.release(); h->nbr.release(); h->ctx_idx_out.release(); h->cnt_out.release(); h->mask_out.release();
     h->traj.release(); h->metrics.release(); h->slot_metrics.release();
     { auto& q = h->sched; q.keep.release(); q.nbr.release(); q.total.release(); q.cnt.release(); q.block_sums.release(); q.pair_start.release(); q.pair_foc.release(); q.info.release(); q.step_first.release(); q.step_F.release(); q.foc_row.release(); q.pair_crow.release(); q.y.release(); }
-    h->roll.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
+    h->roll.release(); h->roll_pos.release(); h->roll_scene.release(); h->roll_obj.release(); h->roll_t0.release(); h->foc_of_obj.release();
     for (auto& ev : h->events) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->prof_events) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1651,13 +1657,19 @@ static int rollout_by_kernels(npe_handle* h, int t0, int steps, int use_gt, int 
                             (long long)F == [&] { long long n = 0; for (int s = 0; s < h->S; ++s) n += (long long)h->scene_foci[s].size(); return n; }() &&
                             [&] { for (int s = 0; s < h->S; ++s) if ((int)h->scene_foci[s].size() != h->Nmax) return false; return true; }() &&
                             !getenv("NPE_NO_FUSED_POST");
+    // fused post-process + dense focus list over scenes of 2^k <= 32 objects: the decoder kernel also keeps the new positions as
+    // a contiguous array for the next step's pair builder (k_build_pairs_scan, by_shuffle)
+    const bool compact = fused_post && dense && (h->Nmax & (h->Nmax - 1)) == 0 && h->Nmax <= 32;
+    if (compact) CK(h->roll_pos.ensure((size_t)F));
     for (int step = 0; step < steps; ++step) {
         {
             ProfScope ps__(h, NPE_K_BUILD_PAIRS);
             const PairOut o = {h->keep.p, h->nbr.p, h->cnt.p, h->block_sums.p, h->foc_row.p, nullptr};
             if ((rc = launch_build_pairs(h, src, thr, o, false))) return rc;
         }
-        if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc, nullptr, false, nullptr, fused_post ? h->roll.p : nullptr))) return rc;
+        if ((rc = launch_forward_kernels(h, h->roll.p, F, nullptr, nullptr, tc, nullptr, false, nullptr, fused_post ? h->roll.p : nullptr,
+                                         compact ? h->roll_pos.p : nullptr))) return rc;
+        if (compact) src.pos_compact = h->roll_pos.p;                 // the next step's builder reads what this decoder kernel wrote
         A.step = step;
         if (!fused_post) {
             ProfScope ps__(h, NPE_K_ROLLOUT);
@@ -1861,8 +1873,15 @@ int npe_sync(npe_handle* h) {
     NEED(h);
     CK(cudaStreamSynchronize(h->stream));
     if (h->chain_prof_dev) {
-        long long q[64];
+        long long q[96];
         cudaMemcpy(q, h->chain_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
+        for (int w = 0; w < 2; ++w) {
+            const long long* b = q + 64 + 12 * w;
+            if (b[0]) fprintf(stderr, "[pair builder, %s CTA, ns after its start] block 1: bits %lld, count stored %lld | block 2: start %lld, bits %lld, count stored %lld | "
+                                      "arrives at the barrier %lld, passes it %lld | lists written %lld / %lld | barrier released by CTA %lld at %lld (first CTA's clock)\n",
+                              w ? "last" : "first", b[2] - b[0], b[3] - b[0], b[6] - b[0], b[7] - b[0], b[8] - b[0], b[11] - b[0], b[4] - b[0], b[5] - b[0],
+                              b[10] - b[0], q[64 + 31], q[64 + 30] - q[64]);
+        }
         fprintf(stderr, "[pair forward chain, CTA 0 thread 0] gather %lld, wait for MMA %lld, epilogue %lld, total %lld cycles\n", q[0], q[1], q[2], q[3]);
         for (int part = 0; part < 2; ++part) {
             const long long* w = q + 32 * part;

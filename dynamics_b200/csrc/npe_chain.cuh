@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(CH_NT, 1)
 k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
                  const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
                  const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
-                 float* __restrict__ dact, unsigned long long* __restrict__ umask, float* roll, int ball_zero) {
+                 float* __restrict__ dact, unsigned long long* __restrict__ umask, float* roll, int ball_zero, float2* __restrict__ roll_pos) {
     // roll != nullptr (device-resident rollout of scenes in which every object is a focus, no ground truth, no trajectory
     // output): `states` IS the two-frame rollout window and this kernel also does simulate_all_postprocess + the window shift
     // (eval.lua:155-182,379-381; update_position / update_angle npe.lua:386-458) for its foci, in place -- every window is
@@ -649,6 +649,7 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
                         float* wrow = roll + foff;
                         warp_scatter22(c.stg, last, wrow, live);           // window shift: frame 0 <- old frame 1
                         warp_scatter22(c.stg, q, wrow + 22, live);         //               frame 1 <- new state
+                        if (roll_pos && live) roll_pos[f] = make_float2(q[0], q[1]);   // compact positions for the next pair builder
                     }
 #pragma unroll
                     for (int n = 6; n < OUT; ++n) o[n] = 1.f / (1.f + expf(-o[n]));   // Sigmoid on the property columns (modules.lua:80-86)

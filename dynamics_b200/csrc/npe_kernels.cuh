@@ -30,6 +30,7 @@ struct FocusSrc {
     const int* foc_obj;    // (F)
     const int* foc_t0;     // (F)
     int F;
+    const float2* pos_compact = nullptr;   // dense lists only (rollout): positions of the last frame per focus, contiguous; or nullptr
 };
 
 __device__ __forceinline__ size_t row_off(const FocusSrc& s, int scene, int obj, int t) {
@@ -422,23 +423,28 @@ __global__ void __launch_bounds__(NT_PAIRS) k_build_pairs_sched(FocusSrc src, co
 //     uniform for the foci of a window) and keeps the neighbourhood as a 64-bit object set; ~10 instructions per pair
 //     test for 32 foci at once.  The k-nearest trim only runs where more than k objects are inside the neighbourhood (or
 //     for the API view of the kept set), thread-locally.
-//   * blocks of 256 foci; the relative targets are written by a warp per 32 foci, coalesced
-//   * the scan across blocks is a chained scan with look-back by the whole CTA (256 predecessors per round) inside the
-//     launch.  Blocks are handed out by TICKET (start order), a CTA draws the ticket of its next block while it works on
-//     the current one, so the minimum unfinished ticket is always some resident CTA's current block and a CTA only ever
-//     waits for smaller tickets.  Status words carry the launch epoch (no clearing between launches); the last draw
-//     resets the ticket counter.
+//   * blocks of 256 foci; the relative targets are 14 loads per thread issued before the pair loop
+//   * two phases around ONE grid barrier (the launch is cooperative): every block writes its pair count, then every block
+//     sums the counts of its predecessors (a coalesced read of at most a few thousand words) and writes its part of the list
 // Same arithmetic, order and tie rule as the first generation (bit-identical tables).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr int NT_SCAN = 256;               // threads = foci per block
 struct PairScan {
-    unsigned* ticket;     // zero between launches
-    u64* status;          // [blocks]: epoch (30 bits) | flag (2: 1 = own count, 2 = inclusive prefix) | value (32)
-    unsigned epoch;       // differs from the previous launch on the same status array
+    unsigned* count;      // [blocks]: active pairs of every block of 256 foci (phase 1 -> phase 2)
+    unsigned* bar;        // grid barrier: [0] top counter, [1] release word (= epoch of the last launch), [2 ..] group counters; zero / stale between launches
+    unsigned epoch;       // differs from the previous launch on the same barrier words
     int nblk;             // blocks of NT_SCAN foci
+    long long* prof;      // tools only (NPE_CHAIN_PROF): phase time stamps of CTA 0 and of the last CTA
 };
-__device__ __forceinline__ u64 scan_pack(unsigned epoch, unsigned flag, unsigned v) {
-    return ((u64)epoch << 34) | ((u64)flag << 32) | (u64)v;
-}
+struct ScanArgs {          // one parameter block: the kernel is launched with cudaLaunchCooperativeKernel
+    FocusSrc src; int kmax; float thr_s; int want_keep;
+    u64* keep; u64* nbr; long long* foc_row; float* y; u64* active_total; int* pair_start; int* pair_foc; long long* pair_crow;
+    int cap; int* info; PairScan sc;
+};
 // The `need` nearest members of the object set `cand` (ties: lower index), thread-local: O(|cand|^2) distance evaluations
 // from L1.  Distances are the reference's: sqrt of the squared distance, one rounding per operation.
 __device__ __noinline__ u64 nearest_of(const float* pos, int stride, float fx, float fy, u64 cand, int need) {
@@ -457,32 +463,31 @@ __device__ __noinline__ u64 nearest_of(const float* pos, int stride, float fx, f
     return out;
 }
 template <bool HAS_Y>     // training batches also get their relative targets (28 more registers: 4 CTAs per SM instead of 8)
-__global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(FocusSrc src, int kmax, float thr_s, int want_keep,
-                                                                 u64* __restrict__ keep_out, u64* __restrict__ nbr_out,
-                                                                 long long* __restrict__ foc_row, float* __restrict__ y,
-                                                                 u64* __restrict__ active_total, int* __restrict__ pair_start,
-                                                                 int* __restrict__ pair_foc, long long* __restrict__ pair_crow,
-                                                                 int cap, int* __restrict__ info, PairScan sc) {
-    __shared__ int s_tk[2], s_wtot[NT_SCAN / 32];
-    __shared__ unsigned s_full[NT_SCAN / 32], s_part[NT_SCAN / 32];
+__global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(const ScanArgs A) {
+    const FocusSrc& src = A.src;
+    const int kmax = A.kmax, want_keep = A.want_keep, cap = A.cap;
+    const float thr_s = A.thr_s;
+    u64* __restrict__ keep_out = A.keep; u64* __restrict__ nbr_out = A.nbr;
+    long long* __restrict__ foc_row = A.foc_row; float* __restrict__ y = A.y;
+    u64* __restrict__ active_total = A.active_total; int* __restrict__ pair_start = A.pair_start;
+    int* __restrict__ pair_foc = A.pair_foc; long long* __restrict__ pair_crow = A.pair_crow; int* __restrict__ info = A.info;
+    const PairScan& sc = A.sc;
+    __shared__ int s_wtot[NT_SCAN / 32];
+    __shared__ unsigned s_part[NT_SCAN / 32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int stride = src.T * D;
-    const unsigned draws = (unsigned)sc.nblk + gridDim.x; // every CTA draws one ticket past the end
-    const unsigned ep = sc.epoch & 0x3fffffffu;
-    volatile u64* st = sc.status;
-    unsigned next = 0;
-    if (t == 0) {
-        next = atomicAdd(sc.ticket, 1u);
-        if (next == draws - 1) *sc.ticket = 0;
-        s_tk[0] = (int)next;
-    }
-    __syncthreads();
-    int blk = s_tk[0];
-    for (int it = 0; blk < sc.nblk; ++it) {
-        if (t == 0) {                                     // ticket of the next block: its round trip hides behind this block
-            next = atomicAdd(sc.ticket, 1u);
-            if (next == draws - 1) *sc.ticket = 0;
-        }
+    const bool stamp = sc.prof && t == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    long long* pf = sc.prof + (blockIdx.x == 0 ? 0 : 12);
+    if (stamp) pf[0] = (long long)global_ns();
+    // ================= phase 1: pair bits, tables, targets and the pair COUNT of every block of this CTA =================
+    // Static assignment: CTA b takes blocks b, b + G, b + 2G, ...; the launch is COOPERATIVE (all G CTAs resident), which is
+    // what makes the grid barrier below legal.  History: a chained scan with look-back (status words polled by the
+    // successors) spent most of the kernel waiting -- 300 k threads polling 128 cache lines delay the very stores they wait
+    // for, whichever way the polling was organised (32 / 256 / 1024 predecessors per round, CTA-wide or one warp); handing the
+    // blocks out through an atomic ticket cost 15 us for 2 x 1184 same-address atomics.
+    int it = 0;
+    for (int blk = blockIdx.x; blk < sc.nblk; blk += gridDim.x, ++it) {
+        if (stamp && it < 2) pf[1 + 5 * it] = (long long)global_ns();
         // ---- this thread's focus ----
         const int f = blk * NT_SCAN + t;
         const bool active = f < src.F;
@@ -509,7 +514,22 @@ __global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(Foc
         const float* pos = src.states + row_off(src, scn, 0, t0 + 1);
         unsigned m_lo = 0, m_hi = 0;
         float fx = 0.f, fy = 0.f;
-        if (active) {
+        // dense focus lists over scenes of 2^k <= 32 objects (the configs[4] rollout): the objects of a scene are adjacent lanes,
+        // so a thread loads ITS position only and takes the others by shuffle -- one HBM round trip instead of three
+        const bool by_shuffle = !src.foc_scene && (src.Nmax & (src.Nmax - 1)) == 0 && src.Nmax <= 32;
+        if (by_shuffle) {
+            // the fused rollout keeps the positions of the last frame as a contiguous float2 array (written by the decoder kernel):
+            // a coalesced 8-byte load instead of one 32-byte sector per object out of the 176-byte window rows
+            if (active) {
+                const float2 fp = src.pos_compact ? src.pos_compact[f] : *reinterpret_cast<const float2*>(pos + (size_t)n * stride);
+                fx = fp.x; fy = fp.y;
+            }
+            const int base = lane & ~(src.Nmax - 1);
+            for (int o = 0; o < src.Nmax; ++o) {
+                const float qx = __shfl_sync(0xffffffffu, fx, base + o), qy = __shfl_sync(0xffffffffu, fy, base + o);
+                m_lo |= (unsigned)(pair_sqdist(qx, qy, fx, fy) <= thr_s) << o;
+            }
+        } else if (active) {
             const float2 fp = *reinterpret_cast<const float2*>(pos + (size_t)n * stride);
             fx = fp.x; fy = fp.y;
             const int n_lo = N < 32 ? N : 32;
@@ -551,7 +571,66 @@ __global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(Foc
                 *reinterpret_cast<float2*>(yo + 2 * k2) = v;
             }
         }
-        // ---- scan inside the block ----
+        if (stamp && it < 2) pf[2 + 5 * it] = (long long)global_ns();
+        // ---- the block's pair count ----
+        int tot = c;
+        for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
+        if (lane == 0) s_wtot[warp] = tot;
+        __syncthreads();
+        if (t == 0) {
+            int agg = 0;
+#pragma unroll
+            for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) agg += s_wtot[w8];
+            sc.count[blk] = (unsigned)agg;
+        }
+        __syncthreads();                                  // s_wtot is rewritten by the next block
+        if (stamp && it < 2) pf[3 + 5 * it] = (long long)global_ns();
+    }
+    // ================= grid barrier: every block count of the launch is in memory =================
+    // Hierarchical arrival (groups of 32 CTAs on their own counters, the last of a group arrives at the top counter): 1184
+    // same-address atomics cost ~7 us on this part, 32 + 37 of them well under one.  The last arrivers reset the counters; one
+    // thread per CTA polls the release word (= launch epoch), with a back-off.
+    if (t == 0) {
+        __threadfence();
+        if (stamp) pf[11] = (long long)global_ns();
+        const int G = (int)gridDim.x, g = (int)blockIdx.x >> 5, gsize = min(32, G - 32 * g), ngroups = (G + 31) >> 5;
+        volatile unsigned* rel = sc.bar + 1;
+        if (atomicAdd(sc.bar + 2 + g, 1u) == (unsigned)gsize - 1u) {
+            sc.bar[2 + g] = 0u;
+            if (atomicAdd(sc.bar, 1u) == (unsigned)ngroups - 1u) {
+                sc.bar[0] = 0u;
+                __threadfence();
+                *rel = sc.epoch;
+                if (sc.prof) { sc.prof[30] = (long long)global_ns(); sc.prof[31] = blockIdx.x; }
+            }
+        }
+        int spins = 0;
+        while (*rel != sc.epoch) {
+            if (++spins > (1 << 20)) __trap();            // cannot happen: cooperative launch, every CTA is resident
+            __nanosleep(200);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (stamp) pf[4] = (long long)global_ns();
+    // ================= phase 2: exclusive prefix of the block counts, then every focus writes its part of the pair list =========
+    it = 0;
+    for (int blk = blockIdx.x; blk < sc.nblk; blk += gridDim.x, ++it) {
+        unsigned part = 0;
+        for (int j = t; j < blk; j += NT_SCAN) part += __ldcg(sc.count + j);
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (lane == 0) s_part[warp] = part;
+        // this thread's focus again: its neighbour bits come back from the table it wrote in phase 1
+        const int f = blk * NT_SCAN + t;
+        const bool active = f < src.F;
+        int scn = 0, n = 0, t0 = 0;
+        u64 nbr = 0;
+        if (active) {
+            if (src.foc_scene) { scn = src.foc_scene[f]; n = src.foc_obj[f]; t0 = src.foc_t0[f]; }
+            else { scn = f / src.Nmax; n = f - scn * src.Nmax; }
+            nbr = nbr_out[f];
+        }
+        const int c = __popcll(nbr);
         int incl = c;
         for (int off = 1; off < 32; off <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, off);
@@ -559,44 +638,10 @@ __global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(Foc
         }
         if (lane == 31) s_wtot[warp] = incl;
         __syncthreads();
-        int wbase = 0, agg = 0;
-#pragma unroll
-        for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) { const int v = s_wtot[w8]; if (w8 < warp) wbase += v; agg += v; }
-        if (t == 0) st[blk] = scan_pack(ep, blk == 0 ? 2u : 1u, (unsigned)agg);
-        // ---- across blocks: look back over 256 predecessors a round ----
         unsigned excl = 0;
-        for (int idx = blk - 1; idx >= 0; idx -= NT_SCAN) {
-            const int j = idx - t;
-            u64 v = 0;
-            if (j >= 0) {
-                int spins = 0;
-                while (true) {
-                    v = st[j];
-                    if ((unsigned)(v >> 34) == ep && ((v >> 32) & 3u) != 0u) break;
-                    if (++spins > (1 << 20)) __trap();        // a predecessor never published (cannot happen: smaller tickets run first)
-                    __nanosleep(100);                         // do not take issue slots from the warps that still compute
-                }
-            }
-            const unsigned full = __ballot_sync(0xffffffffu, j >= 0 && ((v >> 32) & 3u) == 2u);
-            if (lane == 0) s_full[warp] = full;
-            __syncthreads();
-            int stop = NT_SCAN;                               // nearest predecessor that already holds an inclusive prefix
+        int wbase = 0;
 #pragma unroll
-            for (int w8 = NT_SCAN / 32 - 1; w8 >= 0; --w8) if (s_full[w8]) stop = 32 * w8 + __ffs(s_full[w8]) - 1;
-            unsigned part = (j >= 0 && t <= stop) ? (unsigned)v : 0u;
-            for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
-            if (lane == 0) s_part[warp] = part;
-            __syncthreads();
-#pragma unroll
-            for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) excl += s_part[w8];
-            if (stop < NT_SCAN) break;
-            __syncthreads();                                  // s_full / s_part are rewritten by the next round
-        }
-        if (t == 0) {
-            if (blk > 0) st[blk] = scan_pack(ep, 2u, excl + (unsigned)agg);
-            s_tk[(it + 1) & 1] = (int)next;
-        }
-        // ---- this focus's rows of the tables and its part of the dense pair list ----
+        for (int w8 = 0; w8 < NT_SCAN / 32; ++w8) { excl += s_part[w8]; if (w8 < warp) wbase += s_wtot[w8]; }
         if (active) {
             int base = (int)excl + wbase + incl - c;
             pair_start[f] = min(base, cap);
@@ -618,8 +663,8 @@ __global__ void __launch_bounds__(NT_SCAN, HAS_Y ? 4 : 8) k_build_pairs_scan(Foc
                 *active_total = (u64)base;
             }
         }
-        __syncthreads();                                  // s_tk is visible; the next block overwrites the shared records
-        blk = s_tk[(it + 1) & 1];
+        if (stamp && it < 2) pf[5 + 5 * it] = (long long)global_ns();
+        __syncthreads();                                  // s_part / s_wtot are rewritten by the next block
     }
 }
 
@@ -1383,11 +1428,6 @@ struct DpArgs {
     int* abort;                           // info[1]: set to 3 when a peer's cell does not arrive within timeout_ns
     unsigned long long timeout_ns;
 };
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ void st_cell(uint2* p, float v, unsigned stamp) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(stamp) : "memory");
 }
