@@ -334,9 +334,15 @@ class NPEModel:
         return f.value, p.value
 
     # ---- rollout (eval.lua:237-454) ---------------------------------------------------------------------------
-    def rollout(self, t0, steps, use_gt=True, teacher=False, want_traj=True, want_metrics=True):
+    def rollout(self, t0, steps, use_gt=True, teacher=False, want_traj=True, want_metrics=True, traj_out=None):
+        """traj_out: optional caller-owned (S, Nmax, steps, 22) float32 array for the trajectories, e.g. page-locked memory
+        from lib.pinned_array (the device-to-host copy then runs at link speed instead of through pageable staging)."""
         S, Nmax, T = self.scene_shape
-        traj = np.empty((S, Nmax, steps, L.OBJ_DIM), np.float32) if want_traj else None
+        if traj_out is not None:
+            assert want_traj and traj_out.shape == (S, Nmax, steps, L.OBJ_DIM) and traj_out.dtype == np.float32 and traj_out.flags.c_contiguous
+            traj = traj_out
+        else:
+            traj = np.empty((S, Nmax, steps, L.OBJ_DIM), np.float32) if want_traj else None
         met = np.zeros((steps, 7), np.float64) if want_metrics else None
         mp = met.ctypes.data_as(C.POINTER(C.c_double)) if met is not None else None
         self._ck(self.lib.npe_rollout(self.h, t0, steps, int(use_gt), int(teacher), L.fptr(traj), mp))
