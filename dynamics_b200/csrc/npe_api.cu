@@ -530,7 +530,11 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
             else
             CK(launch_pdl(h, k_pair_forward_c2, pg, CH_NT, sizeof(PairChainSmem), st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
                           h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
-            if (!skip_decoder)
+            static const int decs2 = getenv("NPE_DEC_S2") ? atoi(getenv("NPE_DEC_S2")) : 1;   // A/B: 0 never, 1 inference / rollout, 2 always
+            if (!skip_decoder && (decs2 == 2 || (decs2 == 1 && !dact)))
+                CK(launch_pdl(h, k_dec_forward_s2, fg, CH_NT, sizeof(DecS2Smem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
+                              h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode, roll_pos));
+            else if (!skip_decoder)
                 CK(launch_pdl(h, k_dec_forward_c2, fg, CH_NT, sizeof(DecChainSmem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
                               h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode, roll_pos));
         }
@@ -991,6 +995,7 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
         (e = cudaFuncSetAttribute(k_pair_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_forward_c3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Pair3ChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_forward_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecChainSmem))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_dec_forward_s2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecS2Smem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_dec_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecDgradChainSmem))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pair_dgrad_c2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairDgradChainSmem))) != cudaSuccess)
         return bail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize)", e);

@@ -675,6 +675,189 @@ k_dec_forward_c2(const float* __restrict__ states, const long long* __restrict__
     chain_teardown(S.ctl);
 }
 
+// Stacked-image variant (inference and the rollout, whose steady state is this kernel: 185 of 225 us per step at configs[4],
+// more than half of it MMA issue time).  hi and lo weight images stacked along N (umma_gemm_tf32x3_ts_stacked): 80 instead of
+// 120 MMAs per tile.  TMEM per slot: [0,128) accumulator (hi x hi + lo x hi | hi x lo), [128,184) A hi, [192,248) A lo; the
+// 96-wide input of layer 1 goes through the 56-wide operand in two K-halves (pair sum first; the focus window is gathered
+// while that half runs).
+constexpr int S2_D = 0, S2_AHI = 128, S2_ALO = 192;
+constexpr int S2_DEC1 = 0, S2_DEC2 = 2 * TC_DEC2, S2_DEC5 = 2 * TC_DEC5;      // offsets in the stacked image (2 x the plain ones)
+struct DecS2Smem {
+    float W[2 * TC_DEC_TOTAL];     // 149504 B   [k-chunk][hi rows | lo rows][4] per matrix
+    float stg[8 * STG_FLOATS];     // 36864 B
+    ChainCtl ctl;
+};
+
+__global__ void __launch_bounds__(CH_NT, 1)
+k_dec_forward_s2(const float* __restrict__ states, const long long* __restrict__ foc_row, int F,
+                 const int* __restrict__ pair_start, const float* __restrict__ Hp, const float* __restrict__ wtc3,
+                 const float* __restrict__ y, float* __restrict__ pred, float* __restrict__ loss_ex,
+                 float* __restrict__ dact, unsigned long long* __restrict__ umask, float* roll, int ball_zero, float2* __restrict__ roll_pos) {
+    // roll != nullptr (device-resident rollout of scenes in which every object is a focus, no ground truth, no trajectory
+    // output): `states` IS the two-frame rollout window and this kernel also does simulate_all_postprocess + the window shift
+    // (eval.lua:155-182,379-381; update_position / update_angle npe.lua:386-458) for its foci, in place -- every window is
+    // read by exactly one thread of this kernel, before that thread overwrites it -- instead of a separate pass over HBM.
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    DecS2Smem& S = *reinterpret_cast<DecS2Smem*>(smem_raw);
+    pdl_launch_dependents();
+    chain_setup(S.ctl);
+    const int ntiles = (F + 127) / 128;
+    const int t = threadIdx.x;
+    if (t == CH_EPI) {
+        mbar_expect_tx(&S.ctl.wbar, 2 * TC_DEC_TOTAL * 4);
+        const float* ghi = wtc3 + TC_PAIR_TOTAL, * glo = wtc3 + TC_TOTAL + TC_PAIR_TOTAL;
+        // every K-chunk of every matrix: its hi rows, then its lo rows
+        auto stage = [&](int src, int dst, int rows, int chunks) {
+            for (int kc = 0; kc < chunks; ++kc) {
+                bulk_g2s(S.W + dst + kc * 2 * rows * 4, ghi + src + kc * rows * 4, rows * 16, &S.ctl.wbar);
+                bulk_g2s(S.W + dst + kc * 2 * rows * 4 + rows * 4, glo + src + kc * rows * 4, rows * 16, &S.ctl.wbar);
+            }
+        };
+        stage(TC_DEC1, S2_DEC1, TC_HID_ROWS, TC_D1_KC);
+        for (int l = 0; l < 3; ++l) stage(TC_DEC2 + l * TC_HID_SZ, S2_DEC2 + 2 * l * TC_HID_SZ, TC_HID_ROWS, TC_HID_KC);
+        stage(TC_DEC5, S2_DEC5, TC_OUT_ROWS, TC_HID_KC);
+    }
+    pdl_wait();
+    if (t >= CH_EPI) {
+        if (t == CH_EPI) {
+            mbar_wait(&S.ctl.wbar, 0);
+            // stages: 0 = pair-sum half of layer 1, 1 = focus-window half (accumulates), 2..4 = layers 2..4, 5 = output layer
+            chain_mma_loop<NL + 1>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
+                if (stage == 0) umma_gemm_tf32x3_ts_stacked(tm + S2_D, tm + S2_AHI, tm + S2_ALO, S.W + S2_DEC1, TC_HID_ROWS, 6);
+                else if (stage == 1) umma_gemm_tf32x3_ts_stacked(tm + S2_D, tm + S2_AHI, tm + S2_ALO, S.W + S2_DEC1 + 12 * 2 * TC_HID_ROWS * 4, TC_HID_ROWS, 6, true);
+                else if (stage < NL) umma_gemm_tf32x3_ts_stacked(tm + S2_D, tm + S2_AHI, tm + S2_ALO, S.W + S2_DEC2 + 2 * (stage - 2) * TC_HID_SZ, TC_HID_ROWS, 7);
+                else umma_gemm_tf32x3_ts_stacked(tm + S2_D, tm + S2_AHI, tm + S2_ALO, S.W + S2_DEC5, TC_OUT_ROWS, 7);
+            });
+        }
+    } else {
+        const ChainThread c = chain_thread(S.ctl.tmem, S.stg);
+        const int lane = t & 31;
+        unsigned nd = 0;
+        for (int tile = 2 * blockIdx.x + c.slot; tile < ntiles; tile += 2 * gridDim.x) {
+            const int f0 = tile * 128;
+            const int nf = min(128, F - f0);
+            const bool live = c.row < nf;
+            const int wrows = max(0, min(32, nf - 32 * c.wq));
+            const size_t f = (size_t)(f0 + c.row);
+            const size_t fw = (size_t)(f0 + 32 * c.wq);
+            float last[22];                          // the focus's last past frame (kept for the fused rollout post-process)
+            long long foff = 0;
+            {   // z = [pair sum (50) | 1 | 0 | focus window (44)]: columns 0..47, then 48..95
+                float z[52];
+#pragma unroll
+                for (int k = 0; k < 52; ++k) z[k] = 0.f;
+                if (live) {   // per-focus sum of its pairs' h5 rows in list order (fixed order: deterministic)
+                    const int p0 = pair_start[f], p1 = pair_start[f + 1];
+                    for (int p = p0; p < p1; ++p) {
+#pragma unroll
+                        for (int q = 0; q < 13; ++q) {
+                            const float4 h = ld4(Hp + (size_t)p * 52 + 4 * q);
+                            z[4 * q] += h.x; z[4 * q + 1] += h.y; z[4 * q + 2] += h.z; z[4 * q + 3] += h.w;
+                        }
+                    }
+                    z[50] = 1.f; z[51] = 0.f;
+                }
+                tmem_store_split<6>(c.tm, S2_AHI, S2_ALO, z);
+                chain_publish_a(S.ctl, c.slot);
+                if (dact) {   // stash slot 0 = z[0..51]
+                    float zz[64];
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) zz[k] = k < 52 ? z[k] : 0.f;
+                    warp_store_row52(c.stg, zz, dact + fw * HSLOT, HSLOT, wrows);
+                }
+                float x[48];
+                x[0] = z[48]; x[1] = z[49]; x[2] = z[50]; x[3] = z[51];
+                if (live) foff = foc_row[f];
+                const float* wp = states + foff;
+                float w44[44];
+                warp_gather44(c.stg, w44, wp, live);
+#pragma unroll
+                for (int k = 0; k < 22; ++k) last[k] = w44[22 + k];
+#pragma unroll
+                for (int k = 0; k < 44; ++k) x[4 + k] = w44[k];
+                chain_wait_d(S.ctl, c.slot, nd);                      // the pair-sum half has consumed the operand
+                tmem_store_split<6>(c.tm, S2_AHI, S2_ALO, x);
+            }
+            chain_publish_a(S.ctl, c.slot);
+#pragma unroll 1
+            for (int l = 0; l < NL; ++l) {
+                chain_wait_d(S.ctl, c.slot, nd);
+                if (l < NL - 1) {
+                    float d[64];
+                    {   // d = relu(D[0,56) + D[64,120)), 32 columns at a time
+                        float e[32];
+                        tmem_ld16(c.tm, 0, d); tmem_ld16(c.tm, 16, d + 16); tmem_ld16(c.tm, 64, e); tmem_ld16(c.tm, 80, e + 16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) d[k] = relu(d[k] + e[k]);
+                        tmem_ld16(c.tm, 32, d + 32); tmem_ld16(c.tm, 48, d + 48); tmem_ld16(c.tm, 96, e); tmem_ld16(c.tm, 112, e + 16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) d[32 + k] = k < 24 ? relu(d[32 + k] + e[k]) : 0.f;
+                    }
+                    if (umask && live) umask[(size_t)l * F + f] = relu_bits64(d);                  // ReLU bits of u_{l+1}
+                    if (dact) warp_store_row52(c.stg, d, dact + ((size_t)(l + 1) * F + fw) * HSLOT, HSLOT, wrows);
+                    tmem_store_split<7>(c.tm, S2_AHI, S2_ALO, d);
+                    chain_publish_a(S.ctl, c.slot);
+                } else {
+                    float o[32];
+                    {   // o = D[0,32) + D[32,64)
+                        float e[32];
+                        tmem_ld16(c.tm, 0, o); tmem_ld16(c.tm, 16, o + 16); tmem_ld16(c.tm, 32, e); tmem_ld16(c.tm, 48, e + 16);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) o[k] += e[k];
+                    }
+                    float e2 = 0.f, e3 = 0.f, e5 = 0.f;
+                    if (live && loss_ex && y) {
+                        const float* yy = y + f * OUT;
+                        e2 = o[2] - yy[2]; e3 = o[3] - yy[3]; e5 = o[5] - yy[5];
+                    }
+                    if (roll) {
+                        // new state of the focus: position integrates the PREVIOUS velocity, angle likewise and is
+                        // wrapped into (-pi, pi], dynamic columns 2, 3, 5 = relative prediction + last, properties restored
+                        const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
+                        float q[22];
+#pragma unroll
+                        for (int k = 0; k < 22; ++k) q[k] = last[k];
+                        q[0] = __fdiv_rn(__fadd_rn(__fmul_rn(last[0], 800.f), __fmul_rn(last[2], 60.f)), 800.f);
+                        q[1] = __fdiv_rn(__fadd_rn(__fmul_rn(last[1], 800.f), __fmul_rn(last[3], 60.f)), 800.f);
+                        q[2] = __fadd_rn(o[2], last[2]); q[3] = __fadd_rn(o[3], last[3]); q[5] = __fadd_rn(o[5], last[5]);
+                        float ang = __fadd_rn(__fmul_rn(last[4], PI_F), __fmul_rn(last[5], PI_F));
+                        const float gtpi = ang > PI_F ? 1.f : 0.f, lepi = ang <= -PI_F ? 1.f : 0.f;   // both masks on the sum (npe.lua:443-447)
+                        ang = __fadd_rn(ang, __fmul_rn(-TWO_PI_F, gtpi));
+                        ang = __fadd_rn(ang, __fmul_rn(TWO_PI_F, lepi));
+                        q[4] = __fdiv_rn(ang, PI_F);
+                        if (ball_zero && last[10] == 1.f) { q[4] = 0.f; q[5] = 0.f; }
+                        float* wrow = roll + foff;
+                        warp_scatter22(c.stg, last, wrow, live);           // window shift: frame 0 <- old frame 1
+                        warp_scatter22(c.stg, q, wrow + 22, live);         //               frame 1 <- new state
+                        if (roll_pos && live) roll_pos[f] = make_float2(q[0], q[1]);   // compact positions for the next pair builder
+                    }
+#pragma unroll
+                    for (int n = 6; n < OUT; ++n) o[n] = 1.f / (1.f + expf(-o[n]));   // Sigmoid on the property columns (modules.lua:80-86)
+                    if (!roll) {
+                        // pred rows are dense (22 floats): the warp's 32 rows are 704 consecutive floats -> lane-linear copy
+#pragma unroll
+                        for (int n = 0; n < OUT; ++n) c.stg[lane * OUT + n] = o[n];
+                        __syncwarp();
+                        for (int e = lane; e < wrows * (OUT / 2); e += 32)
+                            *reinterpret_cast<float2*>(pred + fw * OUT + 2 * e) = *reinterpret_cast<const float2*>(c.stg + 2 * e);
+                        __syncwarp();
+                    }
+                    if (live && loss_ex && y) {
+                        const float lv = __fadd_rn(__fmul_rn(e2, e2), __fmul_rn(e3, e3)), lw = __fmul_rn(e5, e5);
+                        loss_ex[f * 3 + 0] = __fdiv_rn(__fadd_rn(lv, lw), 3.f);          // npe.lua:271-274
+                        loss_ex[f * 3 + 1] = __fdiv_rn(lv, 2.f);
+                        loss_ex[f * 3 + 2] = lw;
+                    }
+                }
+            }
+        }
+    }
+    chain_teardown(S.ctl);
+}
+
 // ================================================================================================================
 // decoder input-gradient chain (d_pred -> dz5 -> ... -> dz1 -> ds), tiles of 128 foci; ddz[slot][F][HSLOT] = dz1..dz5
 // ================================================================================================================

@@ -81,6 +81,26 @@ __device__ __forceinline__ void umma_gemm_tf32x3_ts(uint32_t tmem_d, uint32_t tm
     }
 }
 
+// 3xTF32 with the hi and lo images of B STACKED along N in one shared-memory image ([k-chunk][hi rows (R) | lo rows (R)][4]):
+//     D[0, R) (+)= Ahi Bhi + Alo Bhi        D[R, 2R) (+)= Ahi Blo             (the epilogue adds the two halves)
+// i.e. 2 MMAs per K-step instead of 3.  A tcgen05.mma kind::tf32 costs ~58 cycles whatever its shape up to N = 112 and
+// 65 at N = 128 (tools/microbench/umma_issue.cu), so the wide one is almost free.
+__device__ __forceinline__ void umma_gemm_tf32x3_ts_stacked(uint32_t tmem_d, uint32_t tmem_ahi, uint32_t tmem_alo, const float* sW, int R,
+                                                            int ksteps, bool accumulate_first = false) {
+    const uint32_t idesc2 = umma_idesc_tf32(2 * R), idesc1 = umma_idesc_tf32(R);
+    const uint32_t lbo = ((uint32_t)(2 * R) * 16u >> 4) << 16, step = 2u * (uint32_t)(2 * R) * 16u >> 4;
+    const uint32_t b = ((smem_u32(sW) >> 4) & 0x3FFFu) | lbo;
+    const uint64_t hiw = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+    uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll 4
+    for (int s = 0; s < ksteps; ++s) {
+        umma_tf32_ts(tmem_d, tmem_ahi + 8 * s, hiw | (uint64_t)(b + s * step), idesc2, acc);
+        acc = 1u;
+    }
+#pragma unroll 4
+    for (int s = 0; s < ksteps; ++s) umma_tf32_ts(tmem_d, tmem_alo + 8 * s, hiw | (uint64_t)(b + s * step), idesc1, 1u);
+}
+
 // This thread's row: 8 consecutive 32-bit columns starting at `col` of tensor memory.
 __device__ __forceinline__ void tmem_st8(uint32_t tmem_base, int col, const float* v) {
     const uint32_t taddr = tmem_base + ((uint32_t)((threadIdx.x >> 5) & 3) * 32u << 16) + (uint32_t)col;
