@@ -119,6 +119,7 @@ struct npe_handle {
     int train_stash = 1;              // forward writes the pair activations for the backward kernels (0: recompute)
     int bwd_tc = 1;                   // large training batches: backward (input + weight gradients) on tcgen05
     int small_batch_max = -1;         // foci up to which the 16-row latency mapping is used (-1: 4 * SM count)
+    int dec_stacked = 0;              // NPE_OPT_DEC_STACKED: 0 automatic, 1 always, 2 never
     int pdl_max_foci = 592;           // batches up to this many foci chain their kernels with programmatic dependent launch
     DevBuf<float> roll;               // rollout-by-kernels window (S, Nmax, 2, 22)
     DevBuf<int> roll_scene, roll_obj, roll_t0, foc_of_obj;
@@ -530,8 +531,12 @@ int launch_forward_kernels(npe_handle* h, const float* st, int F, const float* y
             else
             CK(launch_pdl(h, k_pair_forward_c2, pg, CH_NT, sizeof(PairChainSmem), st, h->pair_foc.p, h->pair_crow.p, h->foc_row.p,
                           h->info_dev, h->wtc3, h->wenc, h->Hp.p, stash, dact ? h->hmask.p : nullptr, h->stash_rows, chain_prof(h)));
-            static const int decs2 = getenv("NPE_DEC_S2") ? atoi(getenv("NPE_DEC_S2")) : 1;   // A/B: 0 never, 1 inference / rollout, 2 always
-            if (!skip_decoder && (decs2 == 2 || (decs2 == 1 && !dact)))
+            // stacked images pay in the steady state (many tiles per tile slot: the MMA issue rate counts); with a round or two
+            // of tiles the per-tile latency chain counts, and the two K-halves of layer 1 lengthen it.  Training keeps the plain
+            // kernel (it also writes the stashes).
+            const bool many_tiles = (F + 127) / 128 >= 4 * 2 * h->num_sms;
+            const bool stacked = !dact && (h->dec_stacked == 1 || (h->dec_stacked == 0 && many_tiles));
+            if (!skip_decoder && stacked)
                 CK(launch_pdl(h, k_dec_forward_s2, fg, CH_NT, sizeof(DecS2Smem), st, h->foc_row.p, F, h->pair_start.p, h->Hp.p,
                               h->wtc3, y, h->pred.p, loss_ex, dact, dact ? h->umask.p : nullptr, roll, h->cfg.ball_zero_mode, roll_pos));
             else if (!skip_decoder)
@@ -1909,6 +1914,7 @@ int npe_set_option(npe_handle* h, int32_t option, int32_t value) {
             if (value < 1) return fail(h, NPE_ERR_INVALID, "set_option: peer timeout must be >= 1 ms");
             h->peer_timeout_ms = value; break;
         case NPE_OPT_SMALL_BATCH_MAX: h->small_batch_max = value; break;
+        case NPE_OPT_DEC_STACKED: if (value < 0 || value > 2) return fail(h, NPE_ERR_INVALID, "set_option: dec_stacked is 0, 1 or 2"); h->dec_stacked = value; break;
         default: return fail(h, NPE_ERR_INVALID, "set_option: unknown option %d", option);
     }
     h->fwd_valid = false; h->hact_valid = false; h->dact_valid = false;

@@ -128,7 +128,7 @@ def load_library(path=LIB_PATH):
     return _LIB
 
 
-OPTIONS = {"train_fwd_tc": 0, "train_stash": 1, "bwd_tc": 2, "peer_timeout_ms": 3, "small_batch_max": 4}
+OPTIONS = {"train_fwd_tc": 0, "train_stash": 1, "bwd_tc": 2, "peer_timeout_ms": 3, "small_batch_max": 4, "dec_stacked": 5}
 KERNEL_IDS = {"build_pairs": 0, "forward": 1, "dec_backward": 2, "pair_backward": 3, "reduce": 4, "optim": 5,
               "rollout": 6, "targets": 7, "step_fused": 8, "wgrad": 9}
 

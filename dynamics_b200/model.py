@@ -368,7 +368,7 @@ class NPEModel:
 
     def set_option(self, name, value):
         """Kernel-dispatch switches (include/npe_cuda.h NPE_OPT_*): 'train_fwd_tc', 'train_stash', 'bwd_tc',
-        'peer_timeout_ms', 'small_batch_max'."""
+        'peer_timeout_ms', 'small_batch_max', 'dec_stacked'."""
         self._ck(self.lib.npe_set_option(self.h, L.OPTIONS[name], int(value)))
 
     def debug_read(self, which, shape):

@@ -227,12 +227,15 @@ int npe_set_rollout_mode(npe_handle* h, int32_t mode);
  *   NPE_OPT_BWD_TC           1 (default): large batches run input- and weight-gradients on tcgen05 (3xTF32); 0: FFMA kernels
  *   NPE_OPT_PEER_TIMEOUT_MS  how long the data-parallel step waits for a peer's gradient before failing (default 10000)
  *   NPE_OPT_SMALL_BATCH_MAX  foci up to which the 16-row latency mapping is used (-1 = default, 4 x SM count)
+ *   NPE_OPT_DEC_STACKED      decoder forward of inference / rollout with stacked hi | lo weight images (2 MMAs per K-step):
+ *                            0 = automatic (from 8 tiles per SM on), 1 = always, 2 = never
  */
 #define NPE_OPT_TRAIN_FWD_TC 0
 #define NPE_OPT_TRAIN_STASH 1
 #define NPE_OPT_BWD_TC 2
 #define NPE_OPT_PEER_TIMEOUT_MS 3
 #define NPE_OPT_SMALL_BATCH_MAX 4
+#define NPE_OPT_DEC_STACKED 5
 int npe_set_option(npe_handle* h, int32_t option, int32_t value);
 
 /* Data-parallel: one handle per GPU/process.  id = 128-byte ncclUniqueId from npe_comm_unique_id on rank 0. */

@@ -432,3 +432,44 @@ def test_throughput_pair_builder_ragged_scenes(trained_like_params):
         assert m.batch_stats() == (F, pairs)
     finally:
         m.close()
+
+
+def test_stacked_decoder_forward(n8, trained_like_params):
+    """k_dec_forward_s2 (hi and lo weight images stacked along N: 2 MMAs per K-step, layer-1 input in two K-halves) is what
+    the rollout's steady state runs on; it is chosen automatically from 8 tiles per SM on and forced here
+    (NPE_OPT_DEC_STACKED = 1).  Same three products per K-step as the plain 3xTF32 kernel: the FP32-grade tolerances hold
+    for the inference forward on 40 960 foci (predictions, per-example losses) and for the fused rollout (window after 6
+    steps against the plain kernel with the separate post-process pass, which other tests compare with the oracle:
+    positions bit-exact, velocities within 1e-4)."""
+    st, ref = n8
+    S = st.shape[0]
+    m = make_model(12, {})
+    try:
+        m.set_params(trained_like_params)
+        m.upload_scenes(st)
+        m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+        m.select_windows(0, S)
+        m.set_precision("tf32x3")
+        m.set_option("dec_stacked", 2)
+        pred_plain, le_plain = m.forward_per_example_current()
+        m.set_option("dec_stacked", 1)
+        pred, le = m.forward_per_example_current()
+        assert rel_err(pred[:, :6], ref["pred"][:, :6]) < TOL and float(np.max(np.abs(le - ref["le"]))) < 1e-6
+        assert rel_err(pred[:, :6], pred_plain[:, :6]) < 2e-5
+        assert np.max(np.abs(pred[:, 6:] - pred_plain[:, 6:])) < 1e-5      # sigmoid columns
+        # fused rollout on ball scenes
+        m.set_rollout_mode("kernels")
+        sb = scenes.raw_to_state(scenes.gen_balls(2048, 8, 2, seed=31))
+        m.upload_scenes(sb)
+        m.set_option("dec_stacked", 2)
+        m.rollout_resident(0, 6)
+        w_plain = m.debug_read("roll", (2048, 8, 2, 22))
+        m.set_option("dec_stacked", 1)
+        m.rollout_resident(0, 6)
+        w = m.debug_read("roll", (2048, 8, 2, 22))
+        vs = np.abs(w_plain[..., 2:6]).max()
+        assert float(np.max(np.abs(w[..., 2:6] - w_plain[..., 2:6])) / vs) < 1e-4
+        assert float(np.max(np.abs(w[..., 0:2] - w_plain[..., 0:2]))) < 1e-5   # positions integrate velocities of earlier steps
+        assert np.array_equal(w[..., 6:], w_plain[..., 6:])                     # properties are copied
+    finally:
+        m.close()
