@@ -347,18 +347,21 @@ k_pair_forward_c2(const float* __restrict__ states, const int* __restrict__ pair
     pdl_launch_dependents();
     chain_setup(S.ctl);
     const int t = threadIdx.x;
-    if (t == CH_EPI) {
+    pdl_wait();
+    const int P = info[0];
+    const int ntiles = (P + 127) / 128;
+    // a CTA without tiles stages nothing (late rollout steps have a handful of active pairs: 190 KB of weight images per
+    // idle CTA were most of that launch)
+    const bool has_tiles = 2 * (int)blockIdx.x < ntiles;
+    if (t == CH_EPI && has_tiles) {
         mbar_expect_tx(&S.ctl.wbar, (4 * ENC64_SZ + 2 * NL * TC_HID_SZ) * 4);
         bulk_g2s(S.Ehi, wenc, 2 * ENC64_SZ * 4, &S.ctl.wbar);
         bulk_g2s(S.Elo, wenc + 2 * ENC64_SZ, 2 * ENC64_SZ * 4, &S.ctl.wbar);
         bulk_g2s(S.Whi, wtc3 + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
         bulk_g2s(S.Wlo, wtc3 + TC_TOTAL + TC_PAIR, NL * TC_HID_SZ * 4, &S.ctl.wbar);
     }
-    pdl_wait();
-    const int P = info[0];
-    const int ntiles = (P + 127) / 128;
     if (t >= CH_EPI) {
-        if (t == CH_EPI) {
+        if (t == CH_EPI && has_tiles) {
             mbar_wait(&S.ctl.wbar, 0);
             chain_mma_loop<NL + 1>(S.ctl, S.ctl.tmem, chain_tiles(ntiles, 0), chain_tiles(ntiles, 1), [&](int stage, uint32_t tm) {
                 if (stage == 0) {
