@@ -166,6 +166,21 @@ struct npe_handle {
         int* info_dev = nullptr;
         u64* active_total = nullptr;
     } alt;
+    // Scene form, throughput regime: the pair tables are double-buffered.  npe_select_windows builds the tables of the batch
+    // it selects at once, on `stream2`, into the table set that the step in flight does NOT use; the builder is gated by an
+    // event recorded just before that step's reduce + optimiser launch, so it runs BESIDE that (light) kernel instead of
+    // after it -- and not under the chain / weight-gradient kernels, which own every SM (tried: it only delays them).
+    struct TableSet {
+        DevBuf<u64> keep, nbr;
+        DevBuf<int> cnt, block_sums, pair_start, pair_foc;
+        DevBuf<long long> foc_row, pair_crow;
+        DevBuf<float> y;
+        int* info_dev = nullptr;
+        u64* active_total = nullptr;
+    } tab_alt;
+    cudaEvent_t tab_free[2] = {nullptr, nullptr}, tab_ready = nullptr, pre_reduce = nullptr;
+    bool tab_free_valid[2] = {false, false}, pre_reduce_valid = false;
+    int tab_cur = 0;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t slot_ready = nullptr;          // upload + pair table of the current slot complete (stream2)
     cudaEvent_t wg_fork = nullptr, wg_join = nullptr;   // large-batch backward: decoder weight gradients on a side stream
@@ -793,6 +808,7 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
         int gpt = 0, gdt = 0;
         const int rc = run_backward_tc(h, sv, sw, &gpt, &gdt);
         if (rc) return rc;
+        if (h->prof_kernel < 0) { CK(cudaEventRecord(h->pre_reduce, h->stream)); h->pre_reduce_valid = true; }   // gate of the next pair builder
         return launch_reduce(h, gpt, gdt, fuse_opt, lr, want_loss, peer_opt);
     }
     const int rows = small ? 16 : 64;
@@ -969,6 +985,14 @@ int npe_create(const npe_config* cfg, npe_handle** out) {
     if ((e = cudaMalloc((void**)&h->alt.info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
     cudaMemset(h->alt.info_dev, 0, 4 * sizeof(int));
     cudaMemset(h->alt.active_total, 0, sizeof(u64));
+    if ((e = cudaMalloc((void**)&h->tab_alt.active_total, sizeof(u64))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&h->tab_alt.info_dev, 4 * sizeof(int))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(h->tab_alt.info_dev, 0, 4 * sizeof(int));
+    cudaMemset(h->tab_alt.active_total, 0, sizeof(u64));
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaEventCreateWithFlags(&h->tab_free[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->tab_ready, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&h->pre_reduce, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->slot_ready, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&h->wg_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1025,6 +1049,12 @@ int npe_destroy(npe_handle* h) {
     if (h->step_flags) cudaFree(h->step_flags);
     if (h->step_trace) cudaFree(h->step_trace);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
+    if (h->tab_alt.info_dev) cudaFree(h->tab_alt.info_dev);
+    if (h->tab_alt.active_total) cudaFree(h->tab_alt.active_total);
+    for (int i = 0; i < 2; ++i) if (h->tab_free[i]) cudaEventDestroy(h->tab_free[i]);
+    if (h->tab_ready) cudaEventDestroy(h->tab_ready);
+    if (h->pre_reduce) cudaEventDestroy(h->pre_reduce);
+    { auto& a = h->tab_alt; a.keep.release(); a.nbr.release(); a.cnt.release(); a.block_sums.release(); a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release(); a.y.release(); }
     { auto& a = h->alt; a.states.release(); a.keep.release(); a.nbr.release(); a.cnt.release(); a.block_sums.release();
       a.pair_start.release(); a.pair_foc.release(); a.foc_row.release(); a.pair_crow.release();
       a.n_obj.release(); a.foc_scene.release(); a.foc_obj.release(); a.foc_t0.release(); }
@@ -1259,10 +1289,37 @@ int npe_select_windows(npe_handle* h, int32_t first, int32_t count) {
     h->foc_first = h->win_start[first];
     h->F = h->win_start[first + count] - h->foc_first;
     if (h->F <= 0) return fail(h, NPE_ERR_INVALID, "select_windows: empty batch");
-    int rc = ensure_batch_buffers(h, h->F);
-    if (rc) return rc;
     h->have_y = true;   // relative targets are written by the pair builder (K1 + K7)
     h->pairs_valid = false; h->fwd_valid = false;
+    static const bool eager_ok = getenv("NPE_NO_EAGER_PAIRS") == nullptr;    // A/B measurements
+    if (eager_ok && h->F > h->pdl_max_foci && h->pre_reduce_valid && h->prof_kernel < 0) {
+        // a large-batch step is in flight: build the tables of this batch now, on the upload stream, beside its reduce kernel
+        auto& a = h->tab_alt;
+        CK(cudaEventRecord(h->tab_free[h->tab_cur], h->stream));            // everything enqueued so far used the current set
+        h->tab_free_valid[h->tab_cur] = true;
+        std::swap(h->keep, a.keep); std::swap(h->nbr, a.nbr); std::swap(h->cnt, a.cnt); std::swap(h->block_sums, a.block_sums);
+        std::swap(h->pair_start, a.pair_start); std::swap(h->pair_foc, a.pair_foc); std::swap(h->foc_row, a.foc_row);
+        std::swap(h->pair_crow, a.pair_crow); std::swap(h->y, a.y);
+        std::swap(h->info_dev, a.info_dev); std::swap(h->active_total, a.active_total);
+        h->tab_cur ^= 1;
+        int rc = ensure_batch_buffers(h, h->F);
+        if (rc) return rc;
+        CK(cudaStreamWaitEvent(h->stream2, h->pre_reduce, 0));
+        h->pre_reduce_valid = false;
+        if (h->tab_free_valid[h->tab_cur]) CK(cudaStreamWaitEvent(h->stream2, h->tab_free[h->tab_cur], 0));
+        cudaStream_t main_stream = h->stream;
+        h->stream = h->stream2;
+        rc = build_pairs(h);
+        cudaError_t e = rc == NPE_OK ? cudaEventRecord(h->tab_ready, h->stream) : cudaSuccess;
+        h->stream = main_stream;
+        h->after_builder = false;                                            // the event wait below is a full dependency
+        if (rc) return rc;
+        CK(e);
+        CK(cudaStreamWaitEvent(h->stream, h->tab_ready, 0));                 // later work on the main stream sees the tables
+        return NPE_OK;
+    }
+    int rc = ensure_batch_buffers(h, h->F);
+    if (rc) return rc;
     return NPE_OK;
 }
 

@@ -473,3 +473,30 @@ def test_stacked_decoder_forward(n8, trained_like_params):
         assert np.array_equal(w[..., 6:], w_plain[..., 6:])                     # properties are copied
     finally:
         m.close()
+
+
+def test_overlapped_launches_do_not_change_results(n8, trained_like_params):
+    """In the throughput regime a training loop overlaps three things: the decoder weight gradients run on a side stream
+    beside the pair input-gradient chain, the NEXT batch's pair tables are built on the upload stream beside the reduce
+    kernel (double-buffered tables), and the optimiser writes the weight images through.  With a kernel class selected for
+    event bracketing (npe_profile_select) the first two are switched off (one stream, tables built lazily): four steps over
+    alternating batches must give the same bits either way."""
+    st, _ = n8
+    S = 2048
+    out = []
+    for bracket in (False, True):
+        m = make_model(12, DISPATCH["default"])
+        try:
+            m.set_params(trained_like_params); m.optim_reset(0.0)
+            m.upload_scenes(st[:S])
+            m.upload_windows(np.arange(S), np.zeros(S, np.int32))
+            if bracket:
+                m.profile_select("reduce")
+            losses = []
+            for step in range(4):
+                assert m.select_windows((step % 2) * (S // 2), S // 2) == (S // 2) * 8
+                losses.append(m.train_step("adam", 1e-3))
+            out.append((m.get_params(), np.array(losses), m.get_grads()))
+        finally:
+            m.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
