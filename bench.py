@@ -443,7 +443,7 @@ def bench_rollout(model_cls, mp_cls, device, total_scenes=ROLL_SCENES, balls=ROL
         # headline rollout number: the fastest FP32-grade variant (tf32 single pass is reported beside it)
         best = max(("fp32_persistent", "tf32x3_tcgen05"), key=lambda k: out[k]["value"])
         out["value"] = out[best]["value"]; out["unit"] = "object-steps/s"; out["best"] = best
-        out["roofline"] = dict(out[best]["roofline"], kernel="rollout step = k_build_pairs + k_pair_forward_c2 + k_dec_forward_c2 + k_rollout_post"
+        out["roofline"] = dict(out[best]["roofline"], kernel="rollout step = k_build_pairs_scan + k_pair_forward_c2 + k_dec_forward_s2 (post-process fused)"
                                if best != "fp32_persistent" else "k_rollout")
         if rank == 0 and world == 1 and cpu_seconds > 0:
             out["cpu_baseline"] = cpu_rollout_leg(st, cpu_seconds)

@@ -1445,34 +1445,46 @@ __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, 
         st_cell(P.region[q] + mine, a, stamp);
     }
     const uint2* in = P.region[P.rank] + (size_t)buf * MAX_PEERS * DP_NPAD + i;
-    float g = 0.f;
-    for (int r = 0; r < P.nranks; ++r) {                 // rank order
-        float v = a;
-        if (r != P.rank) {
-            // Bounded wait (like wait_flags of the one-grid step): a peer that faulted, stopped stepping or issued a
-            // different number of steps must surface as an error on this rank, not as a wedged GPU.  Ranks have to issue
-            // the same number of npe_train_step calls.
-            uint2 c = ld_cell(in + (size_t)r * DP_NPAD);
-            if (c.y != stamp) {
-                const unsigned long long t0 = global_ns();
-                int spins = 0;
-                while ((c = ld_cell(in + (size_t)r * DP_NPAD)).y != stamp) {
-                    if (++spins > 64) {
-                        __nanosleep(64);
-                        if ((spins & 255) == 0 &&
-                            (*(volatile int*)P.abort == 3 || global_ns() - t0 > P.timeout_ns)) { *P.abort = 3; break; }
-                    }
-                }
-            }
-            v = __uint_as_float(c.x);
-        }
-        g += v;
+    // All peers' cells are read TOGETHER (one L2 round trip for the common case that they have all arrived; polling them
+    // one after the other costs nranks - 1 dependent round trips), then only the missing ones are polled again.
+    uint2 c[MAX_PEERS];
+    unsigned missing = 0;
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r) {
+        c[r] = make_uint2(__float_as_uint(a), stamp);
+        if (r < P.nranks && r != P.rank) c[r] = ld_cell(in + (size_t)r * DP_NPAD);
     }
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r) missing |= (c[r].y != stamp ? 1u : 0u) << r;
+    if (missing) {
+        // Bounded wait (like wait_flags of the one-grid step): a peer that faulted, stopped stepping or issued a different
+        // number of steps must surface as an error on this rank, not as a wedged GPU.  Ranks have to issue the same number
+        // of npe_train_step calls.
+        const unsigned long long t0 = global_ns();
+        int spins = 0;
+        while (missing) {
+#pragma unroll
+            for (int r = 0; r < MAX_PEERS; ++r)
+                if (missing >> r & 1u) {
+                    c[r] = ld_cell(in + (size_t)r * DP_NPAD);
+                    if (c[r].y == stamp) missing &= ~(1u << r);
+                }
+            if (missing && ++spins > 64) {
+                __nanosleep(64);
+                if ((spins & 255) == 0 &&
+                    (*(volatile int*)P.abort == 3 || global_ns() - t0 > P.timeout_ns)) { *P.abort = 3; break; }
+            }
+        }
+    }
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r)                  // rank order: the same sum on every rank
+        if (r < P.nranks) g += __uint_as_float(c[r].x);
     return g;
 }
 
 template <int OPT, int RS>
-__global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, DpArgs P, int buf,
+__global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, const __grid_constant__ DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
     pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, i = gid / RS, sub = gid % RS;
