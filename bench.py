@@ -567,7 +567,7 @@ def run_ours(args):
         dist.init_process_group("gloo", rank=rank, world_size=world)
     barrier = (lambda: dist.barrier()) if dist else (lambda: None)
 
-    states, n_obj, offs = make_training_data(rank)
+    states, n_obj, offs = make_training_data(0 if os.environ.get("NPE_BENCH_SAME_BATCHES") else rank)
     total = args.warmup + args.steps
     # schedule = [W warm-up + K timed steps | PREWARM steps]: the untimed pre-warm / kernel-timing passes run on the TAIL,
     # i.e. on batches disjoint from the timed ones

@@ -113,6 +113,7 @@ struct npe_handle {
     DevBuf<u64> hmask, umask;         // ReLU bits of h0..h5 per active pair [6][pair_cap] / of u1..u4 per focus [4][F]
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
     long long* chain_prof_dev = nullptr;
+    long long* dp_prof_dev = nullptr;    // tools only: k_dp_step stamps (NPE_CHAIN_PROF)
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
@@ -628,6 +629,11 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
     r.P.nranks = h->nranks; r.P.rank = h->rank;
     r.P.abort = h->info_dev + 1; r.P.timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
     for (int q = 0; q < MAX_PEERS; ++q) r.P.region[q] = (r.peer && q < h->nranks) ? (uint2*)h->peer_ptr[q] : nullptr;
+    r.P.prof = nullptr;
+    if (r.peer && chain_prof(h)) {
+        if (!h->dp_prof_dev) { cudaMalloc((void**)&h->dp_prof_dev, 4 * DP_NBLK * sizeof(long long)); cudaMemset(h->dp_prof_dev, 0, 4 * DP_NBLK * sizeof(long long)); }
+        r.P.prof = h->dp_prof_dev;
+    }
     if (r.peer) {
         r.buf = (int)(h->peer_step & 1u);
         r.stamp = h->peer_step + 1u;
@@ -1956,6 +1962,17 @@ int npe_sync(npe_handle* h) {
                             "mma: wait %lld, issue %lld, loop %lld | epilogue %lld (of which waiting for the last MMAs %lld), kernel body %lld cycles\n",
                     part ? "decoder" : "pair", w[11], w[10], w[12], w[13], w[14], w[15], w[16], w[17], w[18], w[20], w[19]);
         }
+    }
+    if (h->dp_prof_dev) {
+        static long long q[4 * DP_NBLK];
+        cudaMemcpy(q, h->dp_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
+        long long t0 = q[0], lo[4], hi[4];
+        for (int b = 0; b < DP_NBLK - 1; ++b) t0 = q[4 * b] && q[4 * b] < t0 ? q[4 * b] : t0;
+        for (int k = 0; k < 4; ++k) { lo[k] = 1ll << 62; hi[k] = 0; }
+        for (int b = 0; b < DP_NBLK - 1; ++b)
+            for (int k = 0; k < 4; ++k) if (q[4 * b + k]) { lo[k] = std::min(lo[k], q[4 * b + k] - t0); hi[k] = std::max(hi[k], q[4 * b + k] - t0); }
+        fprintf(stderr, "[k_dp_step rank %d, last launch with stamp %% 512 == 300, ns after the first CTA passed its wait; first .. last CTA] wait passed %lld..%lld | local sum done %lld..%lld | "
+                        "peers' values in %lld..%lld | optimiser done %lld..%lld\n", h->rank, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]);
     }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;

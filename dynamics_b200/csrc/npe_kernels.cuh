@@ -1427,6 +1427,7 @@ struct DpArgs {
     int nranks, rank;
     int* abort;                           // info[1]: set to 3 when a peer's cell does not arrive within timeout_ns
     unsigned long long timeout_ns;
+    long long* prof;                      // tools only (NPE_CHAIN_PROF): 4 globaltimer stamps per CTA
 };
 __device__ __forceinline__ void st_cell(uint2* p, float v, unsigned stamp) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(stamp) : "memory");
@@ -1494,12 +1495,17 @@ __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ parti
     if (owner) st = opt_load<OPT>(i, o);
     pdl_wait();
     if (loss_block) { block_loss_reduce(L); return; }
+    const bool stamp_it = P.prof && threadIdx.x == 0 && (stamp & 511u) == 300u;      // a step in the middle of a free-running loop
+    if (stamp_it) P.prof[4 * blockIdx.x] = (long long)global_ns();
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     float a = ordered_partial_sum<RS>(partial, np, i, sub, live);
+    if (stamp_it) P.prof[4 * blockIdx.x + 1] = (long long)global_ns();
     if (!owner) return;
     a = peer_exchange(i, a, P, buf, stamp);
+    if (stamp_it) P.prof[4 * blockIdx.x + 2] = (long long)global_ns();
     grad[i] = a;
     opt_update<OPT>(i, a, o, st);
+    if (stamp_it) P.prof[4 * blockIdx.x + 3] = (long long)global_ns();
 }
 
 // ----------------------------------------------------------------------------------------------------------------
