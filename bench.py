@@ -640,6 +640,8 @@ def run_ours(args):
     m.sync()
     barrier()
     ms = m.event_elapsed_ms(0, 1)
+    if os.environ.get("NPE_DP_DEBUG"):      # exchange experiments: per-rank step time
+        print(f"[rank {rank}] {1e3 * ms / args.steps:.2f} us per step", file=sys.stderr)
     clk = clocks.stop()
     launches = (m.launch_count() - launches0) * args.steps // total
     if dist:

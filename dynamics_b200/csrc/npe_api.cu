@@ -114,6 +114,8 @@ struct npe_handle {
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
     long long* chain_prof_dev = nullptr;
     long long* dp_prof_dev = nullptr;    // tools only: k_dp_step stamps (NPE_CHAIN_PROF)
+    cudaGraphExec_t step_exec = nullptr;   // npe_train_steps: executable graph of the last STEP_GRAPH steps (updated in place)
+    bool graph_warm[2] = {false, false};   // npe_train_steps: a step with this optimiser has run outside a stream capture
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
     int precision = 0, rollout_mode = 0;
     int train_fwd_tc = 1;             // large training batches: pair forward on the 3xTF32 tcgen05 kernel
@@ -630,8 +632,12 @@ ReducePlan prepare_reduce(npe_handle* h, int fuse_opt, float lr, bool want_loss,
     r.P.abort = h->info_dev + 1; r.P.timeout_ns = (unsigned long long)h->peer_timeout_ms * 1000000ull;
     for (int q = 0; q < MAX_PEERS; ++q) r.P.region[q] = (r.peer && q < h->nranks) ? (uint2*)h->peer_ptr[q] : nullptr;
     r.P.prof = nullptr;
+    {   // timing experiments only: NPE_DP_DEBUG = one digit per rank ("12": rank 0 pushes without waiting, rank 1 does neither)
+        const char* dbg = getenv("NPE_DP_DEBUG");
+        r.P.debug_mode = (dbg && (int)strlen(dbg) > h->rank) ? dbg[h->rank] - '0' : (dbg && *dbg ? dbg[0] - '0' : 0);
+    }
     if (r.peer && chain_prof(h)) {
-        if (!h->dp_prof_dev) { cudaMalloc((void**)&h->dp_prof_dev, 4 * DP_NBLK * sizeof(long long)); cudaMemset(h->dp_prof_dev, 0, 4 * DP_NBLK * sizeof(long long)); }
+        if (!h->dp_prof_dev) { cudaMalloc((void**)&h->dp_prof_dev, 8 * DP_NBLK * sizeof(long long)); cudaMemset(h->dp_prof_dev, 0, 8 * DP_NBLK * sizeof(long long)); }
         r.P.prof = h->dp_prof_dev;
     }
     if (r.peer) {
@@ -850,6 +856,12 @@ int run_backward(npe_handle* h, int divisor_batch, int fuse_opt = 0, float lr = 
 
 // Forward + backward of a small batch as ONE grid of tiles (npe_step16.cuh) followed by the reduce kernel.  Taken by
 // npe_train_step when every pair tile and decoder tile gets its own SM; same results as run_forward + run_backward.
+// npe_train_steps runs its steps as graphs when the data-parallel exchange writes into peer memory (see there); NPE_STEP_GRAPH=1
+// forces graphs for a single GPU as well (A/B measurements).
+bool step_graph_wanted(const npe_handle* h) {
+    static const bool force = getenv("NPE_STEP_GRAPH") != nullptr;
+    return (h->peer_ready || force) && (h->peer_ready || !h->comm);      // not with ncclAllReduce in the loop
+}
 bool step_fused_ok(const npe_handle* h) {
     if (!small_batch(h, h->F) || !h->have_y) return false;
     static const bool off = getenv("NPE_NO_FUSED_STEP") != nullptr;   // A/B measurements only
@@ -1053,6 +1065,7 @@ int npe_destroy(npe_handle* h) {
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
+    if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
     if (h->step_trace) cudaFree(h->step_trace);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
     if (h->tab_alt.info_dev) cudaFree(h->tab_alt.info_dev);
@@ -1485,6 +1498,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
 // Pair tables of steps [s0, s0 + n) of the schedule in one launch (CTA s = step s); false when a step does not fit one
 // builder CTA (more than 64 foci), in which case the caller builds the tables step by step.
 constexpr int SCHED_CHUNK = 1024;
+constexpr int STEP_GRAPH = 64;        // steps per captured graph inside a chunk (npe_train_steps)
 static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* fmax_out, int* cap_out) {
     std::vector<int> sf((size_t)n), sF((size_t)n);
     int fmax = 0;
@@ -1583,8 +1597,45 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         long long* const b_row = h->foc_row.p; float* const b_y = h->y.p; int* const b_ps = h->pair_start.p;
         int* const b_pf = h->pair_foc.p; long long* const b_pc = h->pair_crow.p; int* const b_info = h->info_dev;
         u64* const b_tot = h->active_total;
+        // The steps of a chunk run as CUDA graphs of STEP_GRAPH steps each (stream capture of the very same launches): a grid
+        // that has written into a PEER's memory pays a system-scope flush when it completes as a stream launch -- +2.2 us
+        // per grid, +3.8 us when its dependent is a programmatic launch (tools/microbench/nvlink_ipc_store.cu) -- and none
+        // as a node of a graph, whose edges stay on the device.  The host builds graph k + 1 while graph k runs.
+        static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
+        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h);
+        std::vector<cudaGraphExec_t> execs;
+        bool capturing = false;
+        auto end_capture = [&](bool launch) -> int {
+            capturing = false;
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+            if (e != cudaSuccess || !g) { cudaGetLastError(); return launch ? fail(h, NPE_ERR_CUDA, "train_steps: stream capture failed: %s", cudaGetErrorString(e)) : NPE_OK; }
+            int r = NPE_OK;
+            if (launch) {
+                // The executable graph of the previous STEP_GRAPH steps has the same topology (same kernels, other arguments):
+                // updating it costs a fraction of an instantiation, and launches already enqueued keep their arguments.
+                bool have = false;
+                if (h->step_exec) {
+                    cudaGraphExecUpdateResultInfo info;
+                    if (cudaGraphExecUpdate(h->step_exec, g, &info) == cudaSuccess) have = true;
+                    else { cudaGetLastError(); execs.push_back(h->step_exec); h->step_exec = nullptr; }    // other shape: released after the chunk
+                }
+                e = cudaSuccess;
+                if (!have) e = cudaGraphInstantiate(&h->step_exec, g, 0);
+                if (e == cudaSuccess) e = cudaGraphLaunch(h->step_exec, h->stream);
+                if (e != cudaSuccess) r = fail(h, NPE_ERR_CUDA, "train_steps: graph launch failed: %s", cudaGetErrorString(e));
+            }
+            cudaGraphDestroy(g);
+            return r;
+        };
         for (int i = 0; i < n && rc == NPE_OK; ++i) {
             const int s = s0 + i;
+            if (use_graph && !capturing && h->graph_warm[opt & 1]) {
+                // relaxed mode: this thread's other runtime calls (tools-only allocations, lazy module loads) stay legal
+                const cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
+                if (e != cudaSuccess) { rc = fail(h, NPE_ERR_CUDA, "train_steps: cudaStreamBeginCapture: %s", cudaGetErrorString(e)); break; }
+                capturing = true;
+            }
             if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
             if (sched) {
                 auto& q = h->sched;
@@ -1598,11 +1649,18 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             }
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
+            if (capturing && rc == NPE_OK && ((i + 1) % STEP_GRAPH == 0 || i + 1 == n)) rc = end_capture(true);
+            if (!capturing && rc == NPE_OK) h->graph_warm[opt & 1] = true;      // every kernel of a step has been launched (and loaded) once
         }
+        if (capturing) end_capture(false);          // a step failed while the stream was capturing: leave capture mode
         h->loss4_override = nullptr;   // only the npe_train_step calls above may see it (every return path below is clean)
         h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
         h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
         if (sched) { h->pairs_valid = false; h->fwd_valid = false; h->F = 0; }
+        if (!execs.empty()) {
+            cudaStreamSynchronize(h->stream);        // (the check below synchronises anyway) the graphs have run: release them
+            for (cudaGraphExec_t ge : execs) cudaGraphExecDestroy(ge);
+        }
         if (sched && rc == NPE_OK) {
             // one look at the chunk's {P, flag} words: a dropped pair (1) or a timed-out hand-over (2) must not pass silently
             std::vector<int> info((size_t)2 * n);
@@ -1964,15 +2022,31 @@ int npe_sync(npe_handle* h) {
         }
     }
     if (h->dp_prof_dev) {
-        static long long q[4 * DP_NBLK];
+        // the last two k_dp_step launches (by stamp parity) and, when npe_step_trace is armed, the last k_step_fused: absolute
+        // globaltimer values (ns, last 9 digits) so that the two kernels of one step can be put on one time line
+        static long long q[8 * DP_NBLK];
         cudaMemcpy(q, h->dp_prof_dev, sizeof q, cudaMemcpyDeviceToHost);
-        long long t0 = q[0], lo[4], hi[4];
-        for (int b = 0; b < DP_NBLK - 1; ++b) t0 = q[4 * b] && q[4 * b] < t0 ? q[4 * b] : t0;
-        for (int k = 0; k < 4; ++k) { lo[k] = 1ll << 62; hi[k] = 0; }
-        for (int b = 0; b < DP_NBLK - 1; ++b)
-            for (int k = 0; k < 4; ++k) if (q[4 * b + k]) { lo[k] = std::min(lo[k], q[4 * b + k] - t0); hi[k] = std::max(hi[k], q[4 * b + k] - t0); }
-        fprintf(stderr, "[k_dp_step rank %d, last launch with stamp %% 512 == 300, ns after the first CTA passed its wait; first .. last CTA] wait passed %lld..%lld | local sum done %lld..%lld | "
-                        "peers' values in %lld..%lld | optimiser done %lld..%lld\n", h->rank, lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]);
+        for (int half = 0; half < 2; ++half) {
+            long long lo[4], hi[4];
+            for (int k = 0; k < 4; ++k) { lo[k] = 1ll << 62; hi[k] = 0; }
+            for (int b = 0; b < DP_NBLK - 1; ++b)
+                for (int k = 0; k < 4; ++k) { const long long v = q[half * 4 * DP_NBLK + 4 * b + k]; if (v) { lo[k] = std::min(lo[k], v); hi[k] = std::max(hi[k], v); } }
+            fprintf(stderr, "[k_dp_step rank %d, stamp parity %d, absolute ns mod 1e9, first .. last CTA] wait passed %lld..%lld | local sum done %lld..%lld | "
+                            "peers' values in %lld..%lld | optimiser done %lld..%lld\n", h->rank, half, lo[0] % 1000000000, hi[0] % 1000000000,
+                    lo[1] % 1000000000, hi[1] % 1000000000, lo[2] % 1000000000, hi[2] % 1000000000, lo[3] % 1000000000, hi[3] % 1000000000);
+        }
+        if (h->step_trace) {
+            static unsigned long long tr[64 * 8];
+            cudaMemcpy(tr, h->step_trace, sizeof tr, cudaMemcpyDeviceToHost);
+            unsigned long long lo[6], hi[6];
+            for (int k = 0; k < 6; ++k) { lo[k] = ~0ull; hi[k] = 0; }
+            for (int b = 0; b < 64; ++b)
+                for (int k = 0; k < 6; ++k) { const unsigned long long v = tr[b * 8 + k]; if (v) { lo[k] = std::min(lo[k], v); hi[k] = std::max(hi[k], v); } }
+            fprintf(stderr, "[k_step_fused rank %d, last launch, absolute ns mod 1e9, first .. last CTA] static loads done %llu..%llu | wait passed %llu..%llu | "
+                            "hand-over 1 %llu..%llu | hand-over 2 %llu..%llu | gradients done %llu..%llu | partials stored %llu..%llu\n", h->rank,
+                    lo[0] % 1000000000, hi[0] % 1000000000, lo[1] % 1000000000, hi[1] % 1000000000, lo[2] % 1000000000, hi[2] % 1000000000,
+                    lo[3] % 1000000000, hi[3] % 1000000000, lo[4] % 1000000000, hi[4] % 1000000000, lo[5] % 1000000000, hi[5] % 1000000000);
+        }
     }
     if (h->peer_ready) return check_peer_timeout(h);
     return NPE_OK;

@@ -1428,6 +1428,7 @@ struct DpArgs {
     int* abort;                           // info[1]: set to 3 when a peer's cell does not arrive within timeout_ns
     unsigned long long timeout_ns;
     long long* prof;                      // tools only (NPE_CHAIN_PROF): 4 globaltimer stamps per CTA
+    int debug_mode;                       // tools only (NPE_DP_DEBUG): 1 = push but do not wait (WRONG sums), 2 = neither push nor wait
 };
 __device__ __forceinline__ void st_cell(uint2* p, float v, unsigned stamp) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(stamp) : "memory");
@@ -1441,10 +1442,14 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
 // Pushes this rank's value of parameter i into every peer's region and returns the rank-order sum over all ranks.
 __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, int buf, unsigned stamp) {
     const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
+    if (P.debug_mode == 2 || P.debug_mode == 3) return a;
+    if (P.debug_mode == 5 && (threadIdx.x & 7)) return a;
     for (int r = 1; r < P.nranks; ++r) {                 // remote ranks
         const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
+        if (P.debug_mode == 4) { *(P.region[q] + mine) = make_uint2(__float_as_uint(a), stamp); continue; }      // weak 8-byte store
         st_cell(P.region[q] + mine, a, stamp);
     }
+    if (P.debug_mode == 1 || P.debug_mode == 4 || P.debug_mode == 5 || P.debug_mode == 7) return a;
     const uint2* in = P.region[P.rank] + (size_t)buf * MAX_PEERS * DP_NPAD + i;
     // All peers' cells are read TOGETHER (one L2 round trip for the common case that they have all arrived; polling them
     // one after the other costs nranks - 1 dependent round trips), then only the missing ones are polled again.
@@ -1487,7 +1492,7 @@ __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, 
 template <int OPT, int RS>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, const __grid_constant__ DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
-    pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
+    if (P.debug_mode < 6) pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, i = gid / RS, sub = gid % RS;
     const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
     const bool live = !loss_block && i < NPARAM, owner = live && sub == 0;
@@ -1495,17 +1500,26 @@ __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ parti
     if (owner) st = opt_load<OPT>(i, o);
     pdl_wait();
     if (loss_block) { block_loss_reduce(L); return; }
-    const bool stamp_it = P.prof && threadIdx.x == 0 && (stamp & 511u) == 300u;      // a step in the middle of a free-running loop
-    if (stamp_it) P.prof[4 * blockIdx.x] = (long long)global_ns();
+    const bool stamp_it = P.prof && threadIdx.x == 0;
+    long long* const prof = P.prof + (stamp & 1u) * 4 * DP_NBLK;      // the last TWO launches stay readable
+    if (stamp_it) prof[4 * blockIdx.x] = (long long)global_ns();
     const int np = (i < NPARAM_PAIR) ? nparts_pair : nparts_dec;
     float a = ordered_partial_sum<RS>(partial, np, i, sub, live);
-    if (stamp_it) P.prof[4 * blockIdx.x + 1] = (long long)global_ns();
+    if (stamp_it) prof[4 * blockIdx.x + 1] = (long long)global_ns();
     if (!owner) return;
     a = peer_exchange(i, a, P, buf, stamp);
-    if (stamp_it) P.prof[4 * blockIdx.x + 2] = (long long)global_ns();
+    if (P.debug_mode >= 6) pdl_launch_dependents();      // experiment: release the next grid only after the push (6) 
+    if (stamp_it) prof[4 * blockIdx.x + 2] = (long long)global_ns();
     grad[i] = a;
     opt_update<OPT>(i, a, o, st);
-    if (stamp_it) P.prof[4 * blockIdx.x + 3] = (long long)global_ns();
+    if (P.debug_mode == 3) {      // experiment: the push as the LAST stores of the thread
+        const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
+        for (int r = 1; r < P.nranks; ++r) {
+            const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
+            st_cell(P.region[q] + mine, a, stamp);
+        }
+    }
+    if (stamp_it) prof[4 * blockIdx.x + 3] = (long long)global_ns();
 }
 
 // ----------------------------------------------------------------------------------------------------------------

@@ -71,6 +71,18 @@ __global__ void k_idle_pingpong(int side, uint2* mine, uint2* peer, int rounds, 
     if (side == 0 && cell == 0) { out[0] = acc; out[1] = (unsigned long long)fails; }
 }
 
+// What does a grid that ends with posted stores into PEER memory cost at its boundary?  1000 dependent launches of a grid
+// whose only work is one 8-byte store per thread, into local or into peer memory.
+__global__ void k_store_exit(uint2* dst, unsigned r) { st_cell(dst + blockIdx.x * blockDim.x + threadIdx.x, 7u, r); }
+
+// the same with programmatic dependent launch: every grid releases its dependent at once and waits for its predecessor
+// (griddepcontrol.wait: "all memory operations of the prerequisite grid performed") before it stores
+__global__ void k_store_exit_pdl(uint2* dst, unsigned r) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    st_cell(dst + blockIdx.x * blockDim.x + threadIdx.x, 7u, r);
+}
+
 int main() {
     int n = 0;
     CK(cudaGetDeviceCount(&n));
@@ -103,6 +115,52 @@ int main() {
         CK(cudaStreamSynchronize(st[1]));
         printf("%3d CTAs x %3d threads, %2d lanes per warp (%5d cells): round trip %.2f us, one way %.2f us (%llu timeouts)\n", sh[0], sh[1], sh[2],
                sh[0] * sh[1] / 32 * sh[2], out[0] / 1e3 / (rounds - 10), out[0] / 2e3 / (rounds - 10), out[1]);
+    }
+    {
+        CK(cudaSetDevice(0));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int where = 0; where < 2; ++where) {
+            // a graph of 500 dependent launches, so that the host's launch rate is not what is measured
+            cudaGraph_t g; cudaGraphExec_t ge;
+            CK(cudaStreamBeginCapture(st[0], cudaStreamCaptureModeGlobal));
+            for (int r = 0; r < 500; ++r) k_store_exit<<<111, 256, 0, st[0]>>>(cell[where], 0u);
+            CK(cudaStreamEndCapture(st[0], &g));
+            CK(cudaGraphInstantiate(&ge, g, 0));
+            CK(cudaGraphLaunch(ge, st[0]));
+            CK(cudaEventRecord(e0, st[0]));
+            for (int r = 0; r < 4; ++r) CK(cudaGraphLaunch(ge, st[0]));
+            CK(cudaEventRecord(e1, st[0]));
+            CK(cudaStreamSynchronize(st[0]));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("2000 dependent grids (graph) of one store per thread into %s memory: %.2f us per grid\n", where ? "PEER" : "local", ms / 2.0f);
+        }
+    }
+    {
+        CK(cudaSetDevice(0));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int where = 0; where < 2; ++where) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(111); cfg.blockDim = dim3(256); cfg.stream = st[0];
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaGraph_t g; cudaGraphExec_t ge;
+            CK(cudaStreamBeginCapture(st[0], cudaStreamCaptureModeGlobal));
+            for (int r = 0; r < 500; ++r) CK(cudaLaunchKernelEx(&cfg, k_store_exit_pdl, cell[where], 0u));
+            CK(cudaStreamEndCapture(st[0], &g));
+            CK(cudaGraphInstantiate(&ge, g, 0));
+            CK(cudaGraphLaunch(ge, st[0]));
+            CK(cudaEventRecord(e0, st[0]));
+            for (int r = 0; r < 4; ++r) CK(cudaGraphLaunch(ge, st[0]));
+            CK(cudaEventRecord(e1, st[0]));
+            CK(cudaStreamSynchronize(st[0]));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            printf("2000 programmatic-dependent grids (graph) of one store per thread into %s memory: %.2f us per grid\n", where ? "PEER" : "local", ms / 2.0f);
+        }
     }
     // The exchange sends one burst per ~30-us training step.  Does an idle link answer as fast as a busy one?  Side 0 sleeps
     // `idle` ns before every round; optionally it sends a dummy store `lead` ns before the measured one.
