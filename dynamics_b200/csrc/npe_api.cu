@@ -114,7 +114,10 @@ struct npe_handle {
     bool dact_valid = false;          // the decoder stash holds the current batch (forward ran with the tcgen05 backward in mind)
     long long* chain_prof_dev = nullptr;
     long long* dp_prof_dev = nullptr;    // tools only: k_dp_step stamps (NPE_CHAIN_PROF)
-    cudaGraphExec_t step_exec = nullptr;   // npe_train_steps: executable graph of the last STEP_GRAPH steps (updated in place)
+    cudaGraphExec_t step_exec[4] = {nullptr, nullptr, nullptr, nullptr};   // npe_train_steps: ring of executable graphs (updated in place)
+    cudaEvent_t step_exec_ev[4] = {nullptr, nullptr, nullptr, nullptr};    // ... and the end of each one's last launch
+    int step_exec_next = 0;
+    int* sched_host = nullptr;             // page-locked staging of a chunk's {first focus, foci} per step (sched_build)
     bool graph_warm[2] = {false, false};   // npe_train_steps: a step with this optimiser has run outside a stream capture
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
     int precision = 0, rollout_mode = 0;
@@ -1065,7 +1068,8 @@ int npe_destroy(npe_handle* h) {
     if (h->info_dev) cudaFree(h->info_dev);
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
-    if (h->step_exec) cudaGraphExecDestroy(h->step_exec);
+    if (h->sched_host) cudaFreeHost(h->sched_host);
+    for (int k = 0; k < 4; ++k) { if (h->step_exec[k]) cudaGraphExecDestroy(h->step_exec[k]); if (h->step_exec_ev[k]) cudaEventDestroy(h->step_exec_ev[k]); }
     if (h->step_trace) cudaFree(h->step_trace);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
     if (h->tab_alt.info_dev) cudaFree(h->tab_alt.info_dev);
@@ -1498,16 +1502,24 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
 // Pair tables of steps [s0, s0 + n) of the schedule in one launch (CTA s = step s); false when a step does not fit one
 // builder CTA (more than 64 foci), in which case the caller builds the tables step by step.
 constexpr int SCHED_CHUNK = 1024;
-constexpr int STEP_GRAPH = 64;        // steps per captured graph inside a chunk (npe_train_steps)
+constexpr int STEP_GRAPH = 8;         // npe_train_steps: steps per captured graph,
+constexpr int STEP_PLAIN = 4;         // plain launches at the start of a chunk (the GPU works while the first graph is captured),
+constexpr int STEP_EXECS = 4;         // executable graphs in the ring,
+constexpr int STEP_GRAPH_MIN = 48;    // and only for chunks at least this long: building a graph costs the host ~13 us per kernel node,
+                                      // which a short call cannot hide behind running steps
 static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* fmax_out, int* cap_out) {
-    std::vector<int> sf((size_t)n), sF((size_t)n);
+    // page-locked staging (one allocation per handle): the copies below are asynchronous and nothing waits for them -- a
+    // pageable source plus a stream synchronisation here was a ~20-us bubble at the head of every npe_train_steps call.
+    // The previous user of the staging area (the previous chunk) ended with a stream synchronisation.
+    if (!h->sched_host) CK(cudaHostAlloc((void**)&h->sched_host, (size_t)2 * SCHED_CHUNK * sizeof(int), cudaHostAllocDefault));
+    int* const sf = h->sched_host; int* const sF = h->sched_host + SCHED_CHUNK;
     int fmax = 0;
     for (int i = 0; i < n; ++i) {
         const int w = first + (s0 + i) * batch;
-        sf[(size_t)i] = h->win_start[(size_t)w];
-        sF[(size_t)i] = h->win_start[(size_t)w + batch] - sf[(size_t)i];
-        if (sF[(size_t)i] <= 0) return fail(h, NPE_ERR_INVALID, "train_steps: empty batch");
-        fmax = sF[(size_t)i] > fmax ? sF[(size_t)i] : fmax;
+        sf[i] = h->win_start[(size_t)w];
+        sF[i] = h->win_start[(size_t)w + batch] - sf[i];
+        if (sF[i] <= 0) return fail(h, NPE_ERR_INVALID, "train_steps: empty batch");
+        fmax = sF[i] > fmax ? sF[i] : fmax;
     }
     int per = ctx_slots(h);
     per = per > 16 ? 16 : (per < 1 ? 1 : per);
@@ -1518,10 +1530,9 @@ static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* 
     CK(q.block_sums.ensure(n)); CK(q.total.ensure(n)); CK(q.info.ensure((size_t)2 * n));
     CK(q.pair_start.ensure((size_t)n * (fmax + 1))); CK(q.pair_foc.ensure(np)); CK(q.pair_crow.ensure(np));
     CK(q.step_first.ensure(n)); CK(q.step_F.ensure(n));
-    CK(cudaMemcpyAsync(q.step_first.p, sf.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(q.step_F.p, sF.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(q.step_first.p, sf, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(q.step_F.p, sF, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(q.total.p, 0, (size_t)n * sizeof(u64), h->stream));
-    CK(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
     SchedOut o;
     o.keep = q.keep.p; o.nbr = q.nbr.p; o.cnt = q.cnt.p; o.block_sums = q.block_sums.p; o.foc_row = q.foc_row.p; o.y = q.y.p;
     o.total = q.total.p; o.pair_start = q.pair_start.p; o.pair_foc = q.pair_foc.p; o.pair_crow = q.pair_crow.p; o.info = q.info.p;
@@ -1600,10 +1611,12 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         // The steps of a chunk run as CUDA graphs of STEP_GRAPH steps each (stream capture of the very same launches): a grid
         // that has written into a PEER's memory pays a system-scope flush when it completes as a stream launch -- +2.2 us
         // per grid, +3.8 us when its dependent is a programmatic launch (tools/microbench/nvlink_ipc_store.cu) -- and none
-        // as a node of a graph, whose edges stay on the device.  The host builds graph k + 1 while graph k runs.
+        // as a node of a graph, whose edges stay on the device.  The first STEP_PLAIN steps of a chunk are plain launches, so
+        // that the GPU has work while the host captures the first graph; after that the host builds graph k + 1 while graph
+        // k runs.  A ring of STEP_EXECS executable graphs is UPDATED in place (same topology, other arguments: a fraction
+        // of an instantiation); an executable is touched again only after its previous launch has finished (event).
         static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
-        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h);
-        std::vector<cudaGraphExec_t> execs;
+        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= STEP_GRAPH_MIN;
         bool capturing = false;
         auto end_capture = [&](bool launch) -> int {
             capturing = false;
@@ -1612,29 +1625,36 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             if (e != cudaSuccess || !g) { cudaGetLastError(); return launch ? fail(h, NPE_ERR_CUDA, "train_steps: stream capture failed: %s", cudaGetErrorString(e)) : NPE_OK; }
             int r = NPE_OK;
             if (launch) {
-                // The executable graph of the previous STEP_GRAPH steps has the same topology (same kernels, other arguments):
-                // updating it costs a fraction of an instantiation, and launches already enqueued keep their arguments.
-                bool have = false;
-                if (h->step_exec) {
-                    cudaGraphExecUpdateResultInfo info;
-                    if (cudaGraphExecUpdate(h->step_exec, g, &info) == cudaSuccess) have = true;
-                    else { cudaGetLastError(); execs.push_back(h->step_exec); h->step_exec = nullptr; }    // other shape: released after the chunk
-                }
+                const int k = h->step_exec_next;
+                h->step_exec_next = (k + 1) % STEP_EXECS;
                 e = cudaSuccess;
-                if (!have) e = cudaGraphInstantiate(&h->step_exec, g, 0);
-                if (e == cudaSuccess) e = cudaGraphLaunch(h->step_exec, h->stream);
+                if (!h->step_exec_ev[k]) e = cudaEventCreateWithFlags(&h->step_exec_ev[k], cudaEventDisableTiming);
+                else if (h->step_exec[k]) e = cudaEventSynchronize(h->step_exec_ev[k]);
+                if (e == cudaSuccess && h->step_exec[k]) {
+                    cudaGraphExecUpdateResultInfo info;
+                    if (cudaGraphExecUpdate(h->step_exec[k], g, &info) != cudaSuccess) {     // another shape of step: start over
+                        cudaGetLastError();
+                        cudaGraphExecDestroy(h->step_exec[k]);
+                        h->step_exec[k] = nullptr;
+                    }
+                }
+                if (e == cudaSuccess && !h->step_exec[k]) e = cudaGraphInstantiate(&h->step_exec[k], g, 0);
+                if (e == cudaSuccess) e = cudaGraphLaunch(h->step_exec[k], h->stream);
+                if (e == cudaSuccess) e = cudaEventRecord(h->step_exec_ev[k], h->stream);
                 if (e != cudaSuccess) r = fail(h, NPE_ERR_CUDA, "train_steps: graph launch failed: %s", cudaGetErrorString(e));
             }
             cudaGraphDestroy(g);
             return r;
         };
+        int graph_end = -1;          // index of the last step of the graph being captured
         for (int i = 0; i < n && rc == NPE_OK; ++i) {
             const int s = s0 + i;
-            if (use_graph && !capturing && h->graph_warm[opt & 1]) {
+            if (use_graph && !capturing && h->graph_warm[opt & 1] && i >= STEP_PLAIN && n - i >= STEP_GRAPH) {
                 // relaxed mode: this thread's other runtime calls (tools-only allocations, lazy module loads) stay legal
                 const cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
                 if (e != cudaSuccess) { rc = fail(h, NPE_ERR_CUDA, "train_steps: cudaStreamBeginCapture: %s", cudaGetErrorString(e)); break; }
                 capturing = true;
+                graph_end = i + STEP_GRAPH - 1;
             }
             if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
             if (sched) {
@@ -1649,7 +1669,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             }
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
-            if (capturing && rc == NPE_OK && ((i + 1) % STEP_GRAPH == 0 || i + 1 == n)) rc = end_capture(true);
+            if (capturing && rc == NPE_OK && i == graph_end) rc = end_capture(true);
             if (!capturing && rc == NPE_OK) h->graph_warm[opt & 1] = true;      // every kernel of a step has been launched (and loaded) once
         }
         if (capturing) end_capture(false);          // a step failed while the stream was capturing: leave capture mode
@@ -1657,10 +1677,6 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
         h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
         if (sched) { h->pairs_valid = false; h->fwd_valid = false; h->F = 0; }
-        if (!execs.empty()) {
-            cudaStreamSynchronize(h->stream);        // (the check below synchronises anyway) the graphs have run: release them
-            for (cudaGraphExec_t ge : execs) cudaGraphExecDestroy(ge);
-        }
         if (sched && rc == NPE_OK) {
             // one look at the chunk's {P, flag} words: a dropped pair (1) or a timed-out hand-over (2) must not pass silently
             std::vector<int> info((size_t)2 * n);

@@ -1442,14 +1442,12 @@ __device__ __forceinline__ uint2 ld_cell(const uint2* p) {
 // Pushes this rank's value of parameter i into every peer's region and returns the rank-order sum over all ranks.
 __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, int buf, unsigned stamp) {
     const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
-    if (P.debug_mode == 2 || P.debug_mode == 3) return a;
-    if (P.debug_mode == 5 && (threadIdx.x & 7)) return a;
+    if (P.debug_mode == 2) return a;
     for (int r = 1; r < P.nranks; ++r) {                 // remote ranks
         const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
-        if (P.debug_mode == 4) { *(P.region[q] + mine) = make_uint2(__float_as_uint(a), stamp); continue; }      // weak 8-byte store
         st_cell(P.region[q] + mine, a, stamp);
     }
-    if (P.debug_mode == 1 || P.debug_mode == 4 || P.debug_mode == 5 || P.debug_mode == 7) return a;
+    if (P.debug_mode == 1) return a;
     const uint2* in = P.region[P.rank] + (size_t)buf * MAX_PEERS * DP_NPAD + i;
     // All peers' cells are read TOGETHER (one L2 round trip for the common case that they have all arrived; polling them
     // one after the other costs nranks - 1 dependent round trips), then only the missing ones are polled again.
@@ -1492,7 +1490,7 @@ __device__ __forceinline__ float peer_exchange(int i, float a, const DpArgs& P, 
 template <int OPT, int RS>
 __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ partial, int nparts_pair, int nparts_dec, const __grid_constant__ DpArgs P, int buf,
                                                  unsigned stamp, float* __restrict__ grad, OptArgs o, LossArgs L) {
-    if (P.debug_mode < 6) pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
+    pdl_launch_dependents();   // as in k_reduce_grads: the next kernel stages the weight image only after its wait
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, i = gid / RS, sub = gid % RS;
     const bool loss_block = L.loss4_out && blockIdx.x == gridDim.x - 1;
     const bool live = !loss_block && i < NPARAM, owner = live && sub == 0;
@@ -1508,17 +1506,9 @@ __global__ void __launch_bounds__(256) k_dp_step(const float* __restrict__ parti
     if (stamp_it) prof[4 * blockIdx.x + 1] = (long long)global_ns();
     if (!owner) return;
     a = peer_exchange(i, a, P, buf, stamp);
-    if (P.debug_mode >= 6) pdl_launch_dependents();      // experiment: release the next grid only after the push (6) 
     if (stamp_it) prof[4 * blockIdx.x + 2] = (long long)global_ns();
     grad[i] = a;
     opt_update<OPT>(i, a, o, st);
-    if (P.debug_mode == 3) {      // experiment: the push as the LAST stores of the thread
-        const size_t mine = ((size_t)buf * MAX_PEERS + P.rank) * DP_NPAD + i;
-        for (int r = 1; r < P.nranks; ++r) {
-            const int q = P.rank + r < P.nranks ? P.rank + r : P.rank + r - P.nranks;
-            st_cell(P.region[q] + mine, a, stamp);
-        }
-    }
     if (stamp_it) prof[4 * blockIdx.x + 3] = (long long)global_ns();
 }
 
