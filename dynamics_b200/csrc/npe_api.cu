@@ -11,6 +11,7 @@
 #include <cstring>
 #include <string>
 #include <utility>
+#include <tuple>
 #include <vector>
 
 #include "../../include/npe_cuda.h"
@@ -117,6 +118,14 @@ struct npe_handle {
     cudaGraphExec_t step_exec[4] = {nullptr, nullptr, nullptr, nullptr};   // npe_train_steps: ring of executable graphs (updated in place)
     cudaEvent_t step_exec_ev[4] = {nullptr, nullptr, nullptr, nullptr};    // ... and the end of each one's last launch
     int step_exec_next = 0;
+    cudaGraph_t step_graph[4] = {nullptr, nullptr, nullptr, nullptr};      // the captured graphs the executables came from (own the node handles)
+    std::vector<cudaGraphNode_t> step_nodes[4];                            // their kernel nodes in launch order
+    int step_exec_opt[4] = {-1, -1, -1, -1};                               // optimiser the slot was captured with
+    // launch_pdl modes inside npe_train_steps: 0 = launch, 1 = launch into a capturing stream and note the node, 2 = no launch:
+    // write the kernel's parameters into node sink_idx of an executable graph (cudaGraphExecKernelNodeSetParams)
+    int sink_mode = 0, sink_slot = 0, sink_idx = 0;
+    bool sink_ok = true;
+    long long graphs_captured = 0, graphs_set = 0, graphs_replayed = 0;      // statistics (NPE_CHAIN_PROF)
     int* sched_host = nullptr;             // page-locked staging of a chunk's {first focus, foci} per step (sched_build)
     bool graph_warm[2] = {false, false};   // npe_train_steps: a step with this optimiser has run outside a stream capture
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
@@ -332,7 +341,33 @@ cudaError_t launch_pdl(npe_handle* h, void (*kernel)(KArgs...), int grid, int bl
     static const bool no_pdl = getenv("NPE_NO_PDL") != nullptr;    // A/B measurements only
     cfg.numAttrs = (h->after_builder || no_pdl || h->F > h->pdl_max_foci) ? 0 : 1;
     h->after_builder = false;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (h->sink_mode == 2) {
+        // the launch becomes the parameters of an existing kernel node (same place in the chain, same kind of edge)
+        auto& nodes = h->step_nodes[h->sink_slot];
+        if (h->sink_idx >= (int)nodes.size() || cfg.numAttrs != 1) { h->sink_ok = false; return cudaSuccess; }
+        std::tuple<KArgs...> held(static_cast<KArgs>(args)...);
+        void* ptrs[sizeof...(KArgs) > 0 ? sizeof...(KArgs) : 1];
+        int k = 0;
+        std::apply([&](auto&... a) { ((ptrs[k++] = (void*)&a), ...); }, held);
+        cudaKernelNodeParams kp = {};
+        kp.func = (void*)kernel; kp.gridDim = cfg.gridDim; kp.blockDim = cfg.blockDim; kp.sharedMemBytes = (unsigned)smem;
+        kp.kernelParams = ptrs; kp.extra = nullptr;
+        if (cudaGraphExecKernelNodeSetParams(h->step_exec[h->sink_slot], nodes[(size_t)h->sink_idx], &kp) != cudaSuccess) {
+            cudaGetLastError();
+            h->sink_ok = false;
+        }
+        h->sink_idx++;
+        return cudaSuccess;
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (h->sink_mode == 1 && e == cudaSuccess) {
+        // capturing: the node just added is the stream's current dependency
+        cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; const cudaGraphEdgeData* ed = nullptr; size_t nd = 0;
+        if (cudaStreamGetCaptureInfo_v3(h->stream, &st, nullptr, nullptr, &deps, &ed, &nd) == cudaSuccess && nd == 1 && cfg.numAttrs == 1)
+            h->step_nodes[h->sink_slot].push_back(deps[0]);
+        else { cudaGetLastError(); h->sink_ok = false; }
+    }
+    return e;
 }
 
 int ctx_slots(const npe_handle* h) {
@@ -1069,7 +1104,7 @@ int npe_destroy(npe_handle* h) {
     if (h->alt.active_total) cudaFree(h->alt.active_total);
     if (h->step_flags) cudaFree(h->step_flags);
     if (h->sched_host) cudaFreeHost(h->sched_host);
-    for (int k = 0; k < 4; ++k) { if (h->step_exec[k]) cudaGraphExecDestroy(h->step_exec[k]); if (h->step_exec_ev[k]) cudaEventDestroy(h->step_exec_ev[k]); }
+    for (int k = 0; k < 4; ++k) { if (h->step_exec[k]) cudaGraphExecDestroy(h->step_exec[k]); if (h->step_graph[k]) cudaGraphDestroy(h->step_graph[k]); if (h->step_exec_ev[k]) cudaEventDestroy(h->step_exec_ev[k]); }
     if (h->step_trace) cudaFree(h->step_trace);
     if (h->alt.info_dev) cudaFree(h->alt.info_dev);
     if (h->tab_alt.info_dev) cudaFree(h->tab_alt.info_dev);
@@ -1505,8 +1540,8 @@ constexpr int SCHED_CHUNK = 1024;
 constexpr int STEP_GRAPH = 8;         // npe_train_steps: steps per captured graph,
 constexpr int STEP_PLAIN = 4;         // plain launches at the start of a chunk (the GPU works while the first graph is captured),
 constexpr int STEP_EXECS = 4;         // executable graphs in the ring,
-constexpr int STEP_GRAPH_MIN = 48;    // and only for chunks at least this long: building a graph costs the host ~13 us per kernel node,
-                                      // which a short call cannot hide behind running steps
+constexpr int STEP_GRAPH_MIN = 48;    // and only for chunks at least this long: preparing a graph costs the host 50-100 us, which a
+                                      // 20-step call cannot hide behind its 4 plain steps (measured: 35.7 against 33.1 us per step at N = 2)
 static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* fmax_out, int* cap_out) {
     // page-locked staging (one allocation per handle): the copies below are asynchronous and nothing waits for them -- a
     // pageable source plus a stream synchronisation here was a ~20-us bubble at the head of every npe_train_steps call.
@@ -1608,53 +1643,71 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         long long* const b_row = h->foc_row.p; float* const b_y = h->y.p; int* const b_ps = h->pair_start.p;
         int* const b_pf = h->pair_foc.p; long long* const b_pc = h->pair_crow.p; int* const b_info = h->info_dev;
         u64* const b_tot = h->active_total;
-        // The steps of a chunk run as CUDA graphs of STEP_GRAPH steps each (stream capture of the very same launches): a grid
-        // that has written into a PEER's memory pays a system-scope flush when it completes as a stream launch -- +2.2 us
-        // per grid, +3.8 us when its dependent is a programmatic launch (tools/microbench/nvlink_ipc_store.cu) -- and none
-        // as a node of a graph, whose edges stay on the device.  The first STEP_PLAIN steps of a chunk are plain launches, so
-        // that the GPU has work while the host captures the first graph; after that the host builds graph k + 1 while graph
-        // k runs.  A ring of STEP_EXECS executable graphs is UPDATED in place (same topology, other arguments: a fraction
-        // of an instantiation); an executable is touched again only after its previous launch has finished (event).
+        // The steps of a chunk run as CUDA graphs of STEP_GRAPH steps each: a grid that has written into a PEER's memory pays
+        // a system-scope flush when it completes as a stream launch -- +2.2 us per grid, +3.8 us when its dependent is a
+        // programmatic launch (tools/microbench/nvlink_ipc_store.cu) -- and none as a node of a graph, whose edges stay on the
+        // device.  A ring of STEP_EXECS executable graphs: a slot is CAPTURED once (the very same launches into a capturing
+        // stream; launch_pdl notes the kernel nodes) and from then on its nodes just get the parameters of the launches
+        // (launch_pdl in sink mode: cudaGraphExecKernelNodeSetParams, ~1-2 us per node against ~13 us for capture +
+        // cudaGraphExecUpdate), after an event says the slot's previous launch has finished.  The first STEP_PLAIN steps of
+        // a chunk are plain launches, so that the GPU has work while the host prepares the first graph.
         static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
         const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= STEP_GRAPH_MIN;
-        bool capturing = false;
-        auto end_capture = [&](bool launch) -> int {
-            capturing = false;
+        int group_first = -1, group_end = -1, plain_until = -1;      // the group being built; steps replayed as plain launches
+        struct { unsigned step_stamp, peer_step; int adam_t; int64_t launches; } snap = {0, 0, 0, 0};
+        auto leave_capture = [&]() {          // error path: the stream must not stay in capture mode
             cudaGraph_t g = nullptr;
-            cudaError_t e = cudaStreamEndCapture(h->stream, &g);
-            if (e != cudaSuccess || !g) { cudaGetLastError(); return launch ? fail(h, NPE_ERR_CUDA, "train_steps: stream capture failed: %s", cudaGetErrorString(e)) : NPE_OK; }
-            int r = NPE_OK;
-            if (launch) {
-                const int k = h->step_exec_next;
-                h->step_exec_next = (k + 1) % STEP_EXECS;
-                e = cudaSuccess;
-                if (!h->step_exec_ev[k]) e = cudaEventCreateWithFlags(&h->step_exec_ev[k], cudaEventDisableTiming);
-                else if (h->step_exec[k]) e = cudaEventSynchronize(h->step_exec_ev[k]);
-                if (e == cudaSuccess && h->step_exec[k]) {
-                    cudaGraphExecUpdateResultInfo info;
-                    if (cudaGraphExecUpdate(h->step_exec[k], g, &info) != cudaSuccess) {     // another shape of step: start over
-                        cudaGetLastError();
-                        cudaGraphExecDestroy(h->step_exec[k]);
-                        h->step_exec[k] = nullptr;
-                    }
-                }
-                if (e == cudaSuccess && !h->step_exec[k]) e = cudaGraphInstantiate(&h->step_exec[k], g, 0);
-                if (e == cudaSuccess) e = cudaGraphLaunch(h->step_exec[k], h->stream);
-                if (e == cudaSuccess) e = cudaEventRecord(h->step_exec_ev[k], h->stream);
-                if (e != cudaSuccess) r = fail(h, NPE_ERR_CUDA, "train_steps: graph launch failed: %s", cudaGetErrorString(e));
-            }
-            cudaGraphDestroy(g);
-            return r;
+            cudaStreamEndCapture(h->stream, &g);
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            h->step_nodes[h->sink_slot].clear();
         };
-        int graph_end = -1;          // index of the last step of the graph being captured
+        // finishes the group in slot k: 0 = launched, 1 = the sink did not fit (replay the group as plain launches), < 0 = error
+        auto finish_group = [&]() -> int {
+            const int k = h->sink_slot, mode = h->sink_mode;
+            h->sink_mode = 0;
+            cudaError_t e = cudaSuccess;
+            if (mode == 1) {
+                cudaGraph_t g = nullptr;
+                e = cudaStreamEndCapture(h->stream, &g);
+                if (e != cudaSuccess || !g) { cudaGetLastError(); return fail(h, NPE_ERR_CUDA, "train_steps: stream capture failed: %s", cudaGetErrorString(e)); }
+                size_t nn = 0;
+                cudaGraphGetNodes(g, nullptr, &nn);
+                if (!h->sink_ok || nn != h->step_nodes[k].size()) h->step_nodes[k].clear();     // not a pure chain of programmatic launches: capture it every time
+                h->step_graph[k] = g;
+                h->step_exec_opt[k] = opt;
+                e = cudaGraphInstantiate(&h->step_exec[k], g, 0);
+                h->graphs_captured++;
+            } else if (!h->sink_ok || h->sink_idx != (int)h->step_nodes[k].size()) {
+                h->step_nodes[k].clear();         // next time this slot is captured again
+                h->graphs_replayed++;
+                return 1;
+            } else h->graphs_set++;
+            if (e == cudaSuccess) e = cudaGraphLaunch(h->step_exec[k], h->stream);
+            if (e == cudaSuccess && !h->step_exec_ev[k]) e = cudaEventCreateWithFlags(&h->step_exec_ev[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(h->step_exec_ev[k], h->stream);
+            if (e != cudaSuccess) return fail(h, NPE_ERR_CUDA, "train_steps: graph launch failed: %s", cudaGetErrorString(e));
+            h->step_exec_next = (k + 1) % STEP_EXECS;
+            return 0;
+        };
         for (int i = 0; i < n && rc == NPE_OK; ++i) {
             const int s = s0 + i;
-            if (use_graph && !capturing && h->graph_warm[opt & 1] && i >= STEP_PLAIN && n - i >= STEP_GRAPH) {
-                // relaxed mode: this thread's other runtime calls (tools-only allocations, lazy module loads) stay legal
-                const cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
-                if (e != cudaSuccess) { rc = fail(h, NPE_ERR_CUDA, "train_steps: cudaStreamBeginCapture: %s", cudaGetErrorString(e)); break; }
-                capturing = true;
-                graph_end = i + STEP_GRAPH - 1;
+            if (use_graph && h->sink_mode == 0 && h->graph_warm[opt & 1] && i >= STEP_PLAIN && i > plain_until && n - i >= STEP_GRAPH) {
+                const int k = h->step_exec_next;
+                cudaError_t e = cudaSuccess;
+                if (h->step_exec[k] && h->step_exec_ev[k]) e = cudaEventSynchronize(h->step_exec_ev[k]);    // its previous launch has finished
+                const bool reuse = e == cudaSuccess && h->step_exec[k] && !h->step_nodes[k].empty() && h->step_exec_opt[k] == opt;
+                if (e == cudaSuccess && !reuse) {
+                    if (h->step_exec[k]) { cudaGraphExecDestroy(h->step_exec[k]); h->step_exec[k] = nullptr; }
+                    if (h->step_graph[k]) { cudaGraphDestroy(h->step_graph[k]); h->step_graph[k] = nullptr; }
+                    h->step_nodes[k].clear();
+                    // relaxed mode: this thread's other runtime calls (tools-only allocations, lazy module loads) stay legal
+                    e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
+                }
+                if (e != cudaSuccess) { rc = fail(h, NPE_ERR_CUDA, "train_steps: graph slot: %s", cudaGetErrorString(e)); break; }
+                h->sink_mode = reuse ? 2 : 1; h->sink_slot = k; h->sink_idx = 0; h->sink_ok = true;
+                group_first = i; group_end = i + STEP_GRAPH - 1;
+                snap = {h->step_stamp, h->peer_step, h->adam_t, h->launches};
             }
             if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
             if (sched) {
@@ -1669,10 +1722,22 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             }
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
-            if (capturing && rc == NPE_OK && i == graph_end) rc = end_capture(true);
-            if (!capturing && rc == NPE_OK) h->graph_warm[opt & 1] = true;      // every kernel of a step has been launched (and loaded) once
+            if (h->sink_mode != 0 && rc == NPE_OK && i == group_end) {
+                const int r = finish_group();
+                if (r < 0) rc = r;
+                else if (r == 1) {
+                    // the launches of these steps were not what the slot's nodes hold: nothing has been enqueued for them;
+                    // put the step counters back and run the group again as plain launches
+                    h->step_stamp = snap.step_stamp; h->peer_step = snap.peer_step; h->adam_t = snap.adam_t; h->launches = snap.launches;
+                    plain_until = group_end;
+                    i = group_first - 1;
+                }
+            } else if (h->sink_mode == 0 && rc == NPE_OK) {
+                h->graph_warm[opt & 1] = true;      // every kernel of a step has been launched (and loaded) once
+            }
         }
-        if (capturing) end_capture(false);          // a step failed while the stream was capturing: leave capture mode
+        if (h->sink_mode == 1) leave_capture();      // a step failed while the stream was capturing
+        h->sink_mode = 0;
         h->loss4_override = nullptr;   // only the npe_train_step calls above may see it (every return path below is clean)
         h->keep.p = b_keep; h->nbr.p = b_nbr; h->cnt.p = b_cnt; h->block_sums.p = b_bs; h->foc_row.p = b_row; h->y.p = b_y;
         h->pair_start.p = b_ps; h->pair_foc.p = b_pf; h->pair_crow.p = b_pc; h->info_dev = b_info; h->active_total = b_tot;
@@ -2037,6 +2102,9 @@ int npe_sync(npe_handle* h) {
                     part ? "decoder" : "pair", w[11], w[10], w[12], w[13], w[14], w[15], w[16], w[17], w[18], w[20], w[19]);
         }
     }
+    if (chain_prof(h) && (h->graphs_captured || h->graphs_set))
+        fprintf(stderr, "[npe_train_steps rank %d] step graphs: %lld captured + instantiated, %lld re-parameterised in place, %lld groups replayed as plain launches; slot nodes %zu %zu %zu %zu\n",
+                h->rank, h->graphs_captured, h->graphs_set, h->graphs_replayed, h->step_nodes[0].size(), h->step_nodes[1].size(), h->step_nodes[2].size(), h->step_nodes[3].size());
     if (h->dp_prof_dev) {
         // the last two k_dp_step launches (by stamp parity) and, when npe_step_trace is armed, the last k_step_fused: absolute
         // globaltimer values (ns, last 9 digits) so that the two kernels of one step can be put on one time line
