@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -126,6 +127,7 @@ struct npe_handle {
     int sink_mode = 0, sink_slot = 0, sink_idx = 0;
     bool sink_ok = true;
     long long graphs_captured = 0, graphs_set = 0, graphs_replayed = 0;      // statistics (NPE_CHAIN_PROF)
+    double graph_fill_us = 0.0, graph_launch_us = 0.0;                        // host time of the re-parameterised groups: steps, launch
     int* sched_host = nullptr;             // page-locked staging of a chunk's {first focus, foci} per step (sched_build)
     bool graph_warm[2] = {false, false};   // npe_train_steps: a step with this optimiser has run outside a stream capture
     long long stash_rows = 0;         // row capacity of one slot of the layer-major pair stashes (pair_cap rounded up to 128)
@@ -1654,6 +1656,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
         const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= STEP_GRAPH_MIN;
         int group_first = -1, group_end = -1, plain_until = -1;      // the group being built; steps replayed as plain launches
+        std::chrono::steady_clock::time_point group_t0;
         struct { unsigned step_stamp, peer_step; int adam_t; int64_t launches; } snap = {0, 0, 0, 0};
         auto leave_capture = [&]() {          // error path: the stream must not stay in capture mode
             cudaGraph_t g = nullptr;
@@ -1708,6 +1711,7 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
                 h->sink_mode = reuse ? 2 : 1; h->sink_slot = k; h->sink_idx = 0; h->sink_ok = true;
                 group_first = i; group_end = i + STEP_GRAPH - 1;
                 snap = {h->step_stamp, h->peer_step, h->adam_t, h->launches};
+                group_t0 = std::chrono::steady_clock::now();
             }
             if ((rc = npe_select_windows(h, first + s * batch, batch))) break;
             if (sched) {
@@ -1723,7 +1727,13 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
             h->loss4_override = losses_out ? h->loss_hist.p + (size_t)s * 4 : nullptr;
             rc = npe_train_step(h, opt, lr, divisor_batch, nullptr);
             if (h->sink_mode != 0 && rc == NPE_OK && i == group_end) {
+                const bool set_mode = h->sink_mode == 2;
+                const auto t1 = std::chrono::steady_clock::now();
                 const int r = finish_group();
+                if (set_mode && r == 0) {
+                    h->graph_fill_us += std::chrono::duration<double, std::micro>(t1 - group_t0).count();
+                    h->graph_launch_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t1).count();
+                }
                 if (r < 0) rc = r;
                 else if (r == 1) {
                     // the launches of these steps were not what the slot's nodes hold: nothing has been enqueued for them;
@@ -2103,8 +2113,8 @@ int npe_sync(npe_handle* h) {
         }
     }
     if (chain_prof(h) && (h->graphs_captured || h->graphs_set))
-        fprintf(stderr, "[npe_train_steps rank %d] step graphs: %lld captured + instantiated, %lld re-parameterised in place, %lld groups replayed as plain launches; slot nodes %zu %zu %zu %zu\n",
-                h->rank, h->graphs_captured, h->graphs_set, h->graphs_replayed, h->step_nodes[0].size(), h->step_nodes[1].size(), h->step_nodes[2].size(), h->step_nodes[3].size());
+        fprintf(stderr, "[npe_train_steps rank %d] step graphs: %lld captured + instantiated, %lld re-parameterised in place, %lld groups replayed as plain launches; host time per re-parameterised group: %.1f us for its 8 steps + %.1f us for the launch; slot nodes %zu %zu %zu %zu\n",
+                h->rank, h->graphs_captured, h->graphs_set, h->graphs_replayed, h->graph_fill_us / (double)std::max(1ll, h->graphs_set), h->graph_launch_us / (double)std::max(1ll, h->graphs_set), h->step_nodes[0].size(), h->step_nodes[1].size(), h->step_nodes[2].size(), h->step_nodes[3].size());
     if (h->dp_prof_dev) {
         // the last two k_dp_step launches (by stamp parity) and, when npe_step_trace is armed, the last k_step_fused: absolute
         // globaltimer values (ns, last 9 digits) so that the two kernels of one step can be put on one time line
