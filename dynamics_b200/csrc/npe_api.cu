@@ -1542,8 +1542,9 @@ constexpr int SCHED_CHUNK = 1024;
 constexpr int STEP_GRAPH = 8;         // npe_train_steps: steps per captured graph,
 constexpr int STEP_PLAIN = 4;         // plain launches at the start of a chunk (the GPU works while the first graph is captured),
 constexpr int STEP_EXECS = 4;         // executable graphs in the ring,
-constexpr int STEP_GRAPH_MIN = 48;    // and only for chunks at least this long: preparing a graph costs the host 50-100 us, which a
-                                      // 20-step call cannot hide behind its 4 plain steps (measured: 35.7 against 33.1 us per step at N = 2)
+constexpr int STEP_GRAPH_MIN = STEP_PLAIN + STEP_GRAPH;    // shortest chunk that gets a graph.  A slot's FIRST use captures and
+                                      // instantiates (~0.2 ms, once per handle and optimiser); after that a 20-step call at N = 2
+                                      // runs 30.0-30.7 us per step against 32.9 with plain launches (profiles/r2_dp_exchange.md)
 static int sched_build(npe_handle* h, int first, int batch, int s0, int n, int* fmax_out, int* cap_out) {
     // page-locked staging (one allocation per handle): the copies below are asynchronous and nothing waits for them -- a
     // pageable source plus a stream synchronisation here was a ~20-us bubble at the head of every npe_train_steps call.
@@ -1654,7 +1655,8 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         // cudaGraphExecUpdate), after an event says the slot's previous launch has finished.  The first STEP_PLAIN steps of
         // a chunk are plain launches, so that the GPU has work while the host prepares the first graph.
         static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
-        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= STEP_GRAPH_MIN;
+        static const int graph_min = getenv("NPE_STEP_GRAPH_MIN") ? atoi(getenv("NPE_STEP_GRAPH_MIN")) : STEP_GRAPH_MIN;    // experiments
+        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= graph_min;
         int group_first = -1, group_end = -1, plain_until = -1;      // the group being built; steps replayed as plain launches
         std::chrono::steady_clock::time_point group_t0;
         struct { unsigned step_stamp, peer_step; int adam_t; int64_t launches; } snap = {0, 0, 0, 0};
