@@ -167,7 +167,7 @@ int npe_train_step(npe_handle* h, int32_t opt, float lr, int32_t divisor_batch, 
  * [first + s*batch, first + (s+1)*batch) of the uploaded focus/window schedule.  One host call enqueues all `nsteps`
  * steps (no host round trip between steps).  losses_out (nsteps,3) or NULL: per-step {loss, vel_loss, angvel_loss},
  * copied back once at the end.  With the peer-memory exchange attached (npe_peer_attach) the steps are captured into CUDA
- * graphs of 64 steps each: same launches, same results (a stream launch that wrote into a peer's memory pays a
+ * graphs of 8 steps each: same launches, same results (a stream launch that wrote into a peer's memory pays a
  * system-scope flush at its end, a graph node does not).
  */
 int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps, int32_t opt, float lr,
