@@ -1656,7 +1656,13 @@ int npe_train_steps(npe_handle* h, int32_t first, int32_t batch, int32_t nsteps,
         // a chunk are plain launches, so that the GPU has work while the host prepares the first graph.
         static const bool graph_ok = getenv("NPE_NO_STEP_GRAPH") == nullptr;    // A/B measurements
         static const int graph_min = getenv("NPE_STEP_GRAPH_MIN") ? atoi(getenv("NPE_STEP_GRAPH_MIN")) : STEP_GRAPH_MIN;    // experiments
-        const bool use_graph = graph_ok && sched && h->prof_kernel < 0 && step_graph_wanted(h) && n >= graph_min;
+        // only for chunks whose every step is the one-grid step (k_step_fused + the reduce / exchange kernel, both through
+        // launch_pdl): other paths enqueue work that the sink mode of launch_pdl does not see
+        static const bool fused_off = getenv("NPE_NO_FUSED_STEP") != nullptr;
+        const int gp_c = (cap + SR - 1) / SR, gd_c = (fmax + SR - 1) / SR;
+        const bool fused_chunk = !fused_off && small_batch(h, fmax) && (h->peer_ready || !h->comm) && gp_c >= 1 &&
+                                 gp_c + gd_c <= h->num_sms && gp_c + gd_c <= 500;
+        const bool use_graph = graph_ok && sched && fused_chunk && h->prof_kernel < 0 && step_graph_wanted(h) && n >= graph_min;
         int group_first = -1, group_end = -1, plain_until = -1;      // the group being built; steps replayed as plain launches
         std::chrono::steady_clock::time_point group_t0;
         struct { unsigned step_stamp, peer_step; int adam_t; int64_t launches; } snap = {0, 0, 0, 0};
